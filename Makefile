@@ -1,0 +1,35 @@
+# Builds the C-ABI library (CUDA kernels for sm_100a + host half) and the host tools, in-tree.
+#   make            -> gappadder_b200/libgappadder_b200.so, build/ContigsMerger_b200, build/microbench_int
+#   make oracle     -> oracle/_build/liboverlap_oracle.so (+ oracle/_ref/ when /root/reference exists)
+NVCC ?= nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall -Iinclude
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -Wextra -Iinclude
+CSRC := gappadder_b200/csrc
+LIB := gappadder_b200/libgappadder_b200.so
+
+all: $(LIB) build/microbench_int
+
+build:
+	mkdir -p build
+
+build/gp_api.o: $(CSRC)/gp_api.cu $(CSRC)/common.cuh $(CSRC)/overlap_wf32.cuh $(CSRC)/overlap_wf16.cuh include/gappadder_b200.h | build
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/gp_api.ptxas.log || (cat build/gp_api.ptxas.log; false)
+
+build/gp_host.o: $(CSRC)/gp_host.cpp include/gappadder_b200.h | build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(LIB): build/gp_api.o build/gp_host.o
+	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
+
+build/microbench_int: tools/microbench_int.cu | build
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
+
+oracle:
+	$(MAKE) -C oracle all
+	./oracle/build_ref.sh
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all oracle clean

@@ -1,0 +1,251 @@
+"""ctypes binding of include/gappadder_b200.h (one function per exported symbol)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+lib_path = os.path.join(_HERE, "libgappadder_b200.so")
+
+# every symbol include/gappadder_b200.h declares (tests check that each one is exported)
+EXPORTS = [
+    "gp_create", "gp_destroy", "gp_last_error", "gp_abi_version", "gp_stream",
+    "gp_packed_size", "gp_pack_sequences", "gp_set_sequences", "gp_overlap_pairs", "gp_overlap_batch",
+    "gp_upload_pairs", "gp_launch_resident", "gp_fetch_results", "gp_kernel_launches", "gp_pair_stats",
+    "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
+    "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp",
+]
+
+
+class GpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("gappadder_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Pair(C.Structure):
+    _fields_ = [("row_seq", C.c_uint32), ("col_seq", C.c_uint32)]
+
+
+class Result(C.Structure):
+    _fields_ = [("score", C.c_int32), ("row_end", C.c_int32), ("col_end", C.c_int32),
+                ("nclip", C.c_int32), ("flags", C.c_uint32)]
+
+
+class DpParams(C.Structure):
+    _fields_ = [("mismatch", C.c_int32), ("indel", C.c_int32), ("max_clip", C.c_int32)]
+
+
+class Thresholds(C.Structure):
+    _fields_ = [("fraction_loss_score", C.c_double), ("frac_min_overlap", C.c_double),
+                ("min_overlap_len", C.c_double), ("min_overlap_len_with_scaffold", C.c_double)]
+
+
+RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
+PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
+FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16 = 1, 2, 4, 8
+
+# GAPPadder's command line (MergeContigs.py:85): -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1
+GAPPADDER_DP = DpParams(-2, -2, 50)
+
+
+def gappadder_thresholds() -> Thresholds:
+    # -s and -x pass through a float in CM/main.cpp:91-93,108-111; -c and -z keep their defaults
+    return Thresholds(float(np.float32(0.4)), 0.005, float(np.float32(12)), 6.0)
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    """Loads libgappadder_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(lib_path):
+            raise GpError(-100, "%s not found: run `make` (or __graft_entry__.build()) first; there is no CPU fallback" % lib_path)
+        L = C.CDLL(lib_path)
+        L.gp_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.gp_destroy.argtypes = [C.c_void_p]
+        L.gp_destroy.restype = None
+        L.gp_last_error.argtypes = [C.c_void_p]
+        L.gp_last_error.restype = C.c_char_p
+        L.gp_stream.argtypes = [C.c_void_p]
+        L.gp_stream.restype = C.c_void_p
+        L.gp_packed_size.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_packed_size.restype = C.c_size_t
+        L.gp_pack_sequences.argtypes = [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.gp_set_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.gp_overlap_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(DpParams), C.c_void_p]
+        L.gp_overlap_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(DpParams), C.c_void_p]
+        L.gp_upload_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(DpParams)]
+        L.gp_launch_resident.argtypes = [C.c_void_p]
+        L.gp_fetch_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.gp_kernel_launches.argtypes = [C.c_void_p]
+        L.gp_kernel_launches.restype = C.c_uint64
+        L.gp_pair_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.gp_is_score_significant.argtypes = [C.POINTER(Thresholds)] + [C.c_int32] * 6
+        L.gp_is_containment.argtypes = [C.c_int32, C.c_int32, C.POINTER(Result)]
+        L.gp_merged_length.argtypes = [C.c_int32, C.c_int32, C.POINTER(Result)]
+        L.gp_merged_length.restype = C.c_int32
+        L.gp_merged_concat.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.POINTER(Result), C.c_char_p]
+        L.gp_merged_concat.restype = C.c_int32
+        L.gp_overlap_size.argtypes = [C.c_int32, C.c_int32, C.POINTER(Result)]
+        L.gp_overlap_size.restype = C.c_int32
+        L.gp_candidate_pairs.argtypes = [C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
+        L.gp_candidate_pairs.restype = C.c_int64
+        L.gp_revcomp.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
+        L.gp_revcomp.restype = None
+        _lib = L
+    return _lib
+
+
+def _seq_arrays(seqs: Sequence[bytes]):
+    n = len(seqs)
+    arr = (C.c_char_p * n)(*seqs)
+    lens = np.array([len(s) for s in seqs], dtype=np.uint32)
+    return arr, lens
+
+
+def pack_sequences(seqs: Sequence[bytes]) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    """-> (packed uint32 words, word offsets, lengths, n_symbols)"""
+    L = lib()
+    arr, lens = _seq_arrays(seqs)
+    nbytes = L.gp_packed_size(lens.ctypes.data, len(seqs))
+    packed = np.zeros(nbytes // 4, dtype=np.uint32)
+    off = np.zeros(len(seqs), dtype=np.uint32)
+    nsym = C.c_uint32(0)
+    rc = L.gp_pack_sequences(arr, lens.ctypes.data, len(seqs), packed.ctypes.data, off.ctypes.data, C.byref(nsym))
+    if rc != 0:
+        raise GpError(rc, "gp_pack_sequences")
+    return packed, off, lens, int(nsym.value)
+
+
+def candidate_pairs(nodes: Sequence[bytes], k: int = 10) -> np.ndarray:
+    L = lib()
+    arr, lens = _seq_arrays(nodes)
+    n = len(nodes)
+    cap = n * (n + 1) // 2
+    out = np.zeros(cap, dtype=PAIR_DTYPE)
+    cnt = L.gp_candidate_pairs(arr, lens.ctypes.data, n, k, out.ctypes.data, cap)
+    if cnt < 0:
+        raise GpError(int(cnt), "gp_candidate_pairs")
+    return out[:cnt]
+
+
+def revcomp(s: bytes) -> bytes:
+    out = C.create_string_buffer(len(s) + 1)
+    lib().gp_revcomp(s, len(s), out)
+    return out.raw[:len(s)]
+
+
+def is_score_significant(t: Thresholds, score, len1, len2, row_end, col_end, nclip) -> int:
+    return lib().gp_is_score_significant(C.byref(t), score, len1, len2, row_end, col_end, nclip)
+
+
+def _as_result(r) -> Result:
+    return Result(int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]), int(r["flags"]))
+
+
+def merged_concat(s1: bytes, s2: bytes, r) -> bytes:
+    res = _as_result(r)
+    out = C.create_string_buffer(len(s1) + len(s2) + 1)
+    n = lib().gp_merged_concat(s1, len(s1), s2, len(s2), C.byref(res), out)
+    return out.raw[:n]
+
+
+def is_containment(len1: int, len2: int, r) -> bool:
+    res = _as_result(r)
+    return bool(lib().gp_is_containment(len1, len2, C.byref(res)))
+
+
+def overlap_size(len1: int, len2: int, r) -> int:
+    res = _as_result(r)
+    return int(lib().gp_overlap_size(len1, len2, C.byref(res)))
+
+
+class Context:
+    """One gp_ctx (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.gp_create(device, C.byref(h))
+        if rc != 0:
+            raise GpError(rc, (self._L.gp_last_error(None) or b"").decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise GpError(rc, (self._L.gp_last_error(self._h) or b"").decode())
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.gp_stream(self._h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.gp_kernel_launches(self._h))
+
+    def pair_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.gp_pair_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(cells=a.value, pairs16=b.value, pairs32=c.value)
+
+    def set_sequences(self, packed: np.ndarray, off: np.ndarray, lens: np.ndarray, n_symbols: int):
+        self._check(self._L.gp_set_sequences(self._h, packed.ctypes.data, packed.nbytes, off.ctypes.data,
+                                             lens.ctypes.data, len(lens), n_symbols))
+
+    def upload_pairs(self, pairs: np.ndarray, params: DpParams = GAPPADDER_DP):
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        self._check(self._L.gp_upload_pairs(self._h, pairs.ctypes.data, len(pairs), C.byref(params)))
+        self._n_pairs = len(pairs)
+
+    def launch_resident(self):
+        self._check(self._L.gp_launch_resident(self._h))
+
+    def fetch_results(self) -> np.ndarray:
+        out = np.zeros(self._n_pairs, dtype=RESULT_DTYPE)
+        self._check(self._L.gp_fetch_results(self._h, out.ctypes.data, self._n_pairs))
+        return out
+
+    def overlap_pairs(self, pairs: np.ndarray, params: DpParams = GAPPADDER_DP) -> np.ndarray:
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        out = np.zeros(len(pairs), dtype=RESULT_DTYPE)
+        self._check(self._L.gp_overlap_pairs(self._h, pairs.ctypes.data, len(pairs), C.byref(params), out.ctypes.data))
+        return out
+
+    def overlap_batch(self, seqs: Sequence[bytes], pairs, params: DpParams = GAPPADDER_DP) -> np.ndarray:
+        """The call a user makes: host ASCII sequences + (row, col) index pairs -> results."""
+        arr, lens = _seq_arrays(seqs)
+        p = np.zeros(len(pairs), dtype=PAIR_DTYPE)
+        if len(pairs):
+            pa = np.asarray(pairs)
+            if pa.dtype == PAIR_DTYPE:
+                p = np.ascontiguousarray(pa)
+            else:
+                p["row_seq"] = pa[:, 0]
+                p["col_seq"] = pa[:, 1]
+        out = np.zeros(len(p), dtype=RESULT_DTYPE)
+        self._check(self._L.gp_overlap_batch(self._h, arr, lens.ctypes.data, len(seqs), p.ctypes.data, len(p),
+                                             C.byref(params), out.ctypes.data))
+        return out

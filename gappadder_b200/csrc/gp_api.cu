@@ -1,0 +1,294 @@
+// gp_api.cu -- CUDA half of the C ABI (include/gappadder_b200.h): context, device buffers, pair
+// classification and kernel launches for the overlap DP (ContigsCompactor::Evaluate,
+// ContigsCompactor-v0.2.0/ContigsMerger/ContigsCompactor.cpp:1572-1873).  sm_100a only.
+#include "gappadder_b200.h"
+#include "common.cuh"
+#include "overlap_wf32.cuh"
+#include "overlap_wf16.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostBuf {   // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct gp_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+
+    // sequence table
+    DeviceBuf d_packed;
+    std::vector<uint32_t> seq_off, seq_len;
+    uint32_t n_symbols = 0;
+
+    // pair work lists
+    DeviceBuf d_pairs, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16;
+    HostBuf h_stage;
+    uint64_t n_pairs = 0, n16 = 0, n32 = 0, cells = 0;
+    uint32_t max_n16 = 0, max_n32 = 0;
+    gp_dp_params params{};
+    gp::Wf16Params p16{};
+
+    int fail(int code, const char* fmt, ...)
+    {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        error = buf;
+        return code;
+    }
+};
+
+#define GP_CUDA(ctx, call)                                                                        \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return (ctx)->fail(GP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" {
+
+int gp_create(int device, gp_ctx** out)
+{
+    if (!out) return GP_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return GP_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { g_create_error = "device index out of range"; return GP_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GP_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (this library is built for B200 only, no fallback)";
+        return GP_ERR_NO_DEVICE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return GP_ERR_CUDA; }
+    gp_ctx* c = new (std::nothrow) gp_ctx();
+    if (!c) return GP_ERR_NOMEM;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete c; return GP_ERR_CUDA;
+    }
+    if ((e = gp::wf16_configure()) != cudaSuccess) {
+        g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
+        cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA;
+    }
+    *out = c;
+    return GP_OK;
+}
+
+void gp_destroy(gp_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->d_packed.release(); c->d_pairs.release(); c->d_order16.release(); c->d_order32.release();
+    c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
+    c->h_stage.release();
+    delete c;
+}
+
+const char* gp_last_error(const gp_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+void* gp_stream(gp_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t gp_kernel_launches(const gp_ctx* c) { return c ? c->launches : 0; }
+
+int gp_pair_stats(const gp_ctx* c, uint64_t* cells, uint64_t* pairs16, uint64_t* pairs32)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (cells) *cells = c->cells;
+    if (pairs16) *pairs16 = c->n16;
+    if (pairs32) *pairs32 = c->n32;
+    return GP_OK;
+}
+
+int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, const uint32_t* seq_word_off,
+                     const uint32_t* seq_len, uint32_t n_seq, uint32_t n_symbols)
+{
+    if (!c) return GP_ERR_INVALID;
+    if ((!packed || !seq_word_off || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequence table");
+    if (n_symbols > 16) return c->fail(GP_ERR_ALPHABET, "more than 16 symbols");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, c->d_packed.reserve(packed_bytes ? packed_bytes : 16));
+    if (packed_bytes) GP_CUDA(c, cudaMemcpyAsync(c->d_packed.p, packed, packed_bytes, cudaMemcpyHostToDevice, c->stream));
+    c->seq_off.assign(seq_word_off, seq_word_off + n_seq);
+    c->seq_len.assign(seq_len, seq_len + n_seq);
+    c->n_symbols = n_symbols;
+    c->n_pairs = 0;
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));   // caller may reuse `packed` after return
+    return GP_OK;
+}
+
+int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (!params || (!pairs && n_pairs)) return c->fail(GP_ERR_INVALID, "null pairs/params");
+    if (params->max_clip < 0) return c->fail(GP_ERR_INVALID, "max_clip must be >= 0");
+    if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    c->params = *params;
+    c->n_pairs = n_pairs; c->n16 = c->n32 = 0; c->cells = 0; c->max_n16 = c->max_n32 = 0;
+    if (n_pairs == 0) return GP_OK;
+
+    const uint32_t n_seq = (uint32_t)c->seq_len.size();
+    const bool params16 = gp::wf16_params_ok(params->mismatch, params->indel) && c->n_symbols <= 8;
+    if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip);
+
+    // stage: [PairDesc n][order16 n][order32 n]
+    const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
+    const size_t ord_bytes = n_pairs * sizeof(uint32_t);
+    GP_CUDA(c, c->h_stage.reserve(desc_bytes + 2 * ord_bytes));
+    gp::PairDesc* hd = (gp::PairDesc*)c->h_stage.p;
+    uint32_t* ho16 = (uint32_t*)((char*)c->h_stage.p + desc_bytes);
+    uint32_t* ho32 = ho16 + n_pairs;
+    uint64_t max_total = 0;
+    for (uint64_t i = 0; i < n_pairs; ++i) {
+        const uint32_t a = pairs[i].row_seq, b = pairs[i].col_seq;
+        if (a >= n_seq || b >= n_seq) return c->fail(GP_ERR_INVALID, "pair %llu references sequence out of range", (unsigned long long)i);
+        const uint32_t m = c->seq_len[a], n = c->seq_len[b];
+        hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
+        c->cells += (uint64_t)m * n;
+        max_total = std::max<uint64_t>(max_total, (uint64_t)m + n);
+        if (params16 && gp::wf16_pair_ok(m, n)) { ho16[c->n16++] = (uint32_t)i; c->max_n16 = std::max(c->max_n16, n); }
+        else { ho32[c->n32++] = (uint32_t)i; c->max_n32 = std::max(c->max_n32, n); }
+    }
+    // 28-bit score field / 30-bit rank field of the kernels
+    const uint64_t amax = (uint64_t)std::max(std::max(std::abs(params->mismatch), std::abs(params->indel)), 1);
+    if (amax * max_total >= (1ull << 26) || (uint64_t)(params->max_clip + 1) * (max_total + 2) >= (1ull << 30))
+        return c->fail(GP_ERR_RANGE, "sequence lengths / penalties / max_clip exceed the kernels' score or rank range");
+    // longest first: the tail of the queue is then made of short pairs (load balance)
+    auto by_cells = [&](uint32_t x, uint32_t y) {
+        const uint64_t cx = (uint64_t)hd[x].m * hd[x].n, cy = (uint64_t)hd[y].m * hd[y].n;
+        return cx != cy ? cx > cy : x < y;
+    };
+    std::sort(ho16, ho16 + c->n16, by_cells);
+    std::sort(ho32, ho32 + c->n32, by_cells);
+
+    GP_CUDA(c, c->d_pairs.reserve(desc_bytes));
+    GP_CUDA(c, c->d_order16.reserve(ord_bytes));
+    GP_CUDA(c, c->d_order32.reserve(ord_bytes));
+    GP_CUDA(c, c->d_results.reserve(n_pairs * sizeof(gp::DevResult)));
+    GP_CUDA(c, c->d_queue.reserve(64));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hd, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->n16) GP_CUDA(c, cudaMemcpyAsync(c->d_order16.p, ho16, c->n16 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    if (c->n32) GP_CUDA(c, cudaMemcpyAsync(c->d_order32.p, ho32, c->n32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GP_OK;
+}
+
+int gp_launch_resident(gp_ctx* c)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (c->n_pairs == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+    unsigned int* queue = (unsigned int*)c->d_queue.p;
+    if (c->n16) {
+        int rc = gp::wf16_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
+                                 (const uint32_t*)c->d_order16.p, (uint32_t)c->n16, queue, c->p16, c->max_n16,
+                                 &c->d_scratch16.p, &c->d_scratch16.cap, (gp::DevResult*)c->d_results.p);
+        if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16 launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+    }
+    if (c->n32) {
+        constexpr int R = 8, THREADS = 128;
+        const int blocks = c->sm_count * 8;
+        const uint32_t warps = (uint32_t)blocks * (THREADS / 32);
+        const uint32_t stride = (c->max_n32 + 1 + 31) & ~31u;
+        GP_CUDA(c, c->d_scratch32.reserve((size_t)warps * stride * sizeof(int32_t)));
+        gp::overlap_wf32_kernel<R><<<blocks, THREADS, 0, c->stream>>>(
+            (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p, (const uint32_t*)c->d_order32.p,
+            (uint32_t)c->n32, queue + 8, c->params.mismatch, c->params.indel, c->params.max_clip,
+            (int32_t*)c->d_scratch32.p, stride, (gp::DevResult*)c->d_results.p);
+        GP_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return GP_OK;
+}
+
+int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n_pairs)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (n_pairs != c->n_pairs) return c->fail(GP_ERR_INVALID, "n_pairs does not match the uploaded batch");
+    if (n_pairs == 0) return GP_OK;
+    if (!out) return c->fail(GP_ERR_INVALID, "null output");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    static_assert(sizeof(gp_result) == sizeof(gp::DevResult), "result layouts must match");
+    GP_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, n_pairs * sizeof(gp_result), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    return GP_OK;
+}
+
+int gp_overlap_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params, gp_result* out)
+{
+    int rc = gp_upload_pairs(c, pairs, n_pairs, params);
+    if (rc != GP_OK) return rc;
+    if ((rc = gp_launch_resident(c)) != GP_OK) return rc;
+    return gp_fetch_results(c, out, n_pairs);
+}
+
+int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len, uint32_t n_seq,
+                     const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params, gp_result* out)
+{
+    if (!c) return GP_ERR_INVALID;
+    if ((!seqs || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequences");
+    const size_t bytes = gp_packed_size(seq_len, n_seq);
+    std::vector<uint32_t> off(n_seq);
+    HostBuf pinned;
+    {
+        cudaError_t e = pinned.reserve(bytes ? bytes : 16);
+        if (e != cudaSuccess) return c->fail(GP_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(e));
+    }
+    uint32_t nsym = 0;
+    int rc = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)pinned.p, off.data(), &nsym);
+    if (rc != GP_OK) { pinned.release(); return c->fail(rc, rc == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed"); }
+    rc = gp_set_sequences(c, (const uint32_t*)pinned.p, bytes, off.data(), seq_len, n_seq, nsym);
+    pinned.release();
+    if (rc != GP_OK) return rc;
+    return gp_overlap_pairs(c, pairs, n_pairs, params, out);
+}
+
+} // extern "C"

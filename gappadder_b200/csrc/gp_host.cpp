@@ -1,0 +1,228 @@
+// gp_host.cpp -- host-side half of the C ABI (include/gappadder_b200.h): sequence packing, the
+// candidate filter and the exact integer/double epilogue of Evaluate.  No CUDA in this file.
+// file:line citations are relative to /root/reference/ContigsCompactor-v0.2.0/ContigsMerger/.
+#include "gappadder_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+
+int gp_abi_version(void) { return GP_ABI_VERSION; }
+
+static inline size_t words_for(uint32_t len)
+{
+    // eight 4-bit codes per word, rounded up to 4 words (16 bytes) so every sequence can be read
+    // with aligned 128-bit loads; always at least one block so empty sequences own an address.
+    size_t w = ((size_t)len + 7) / 8;
+    w = (w + 3) & ~(size_t)3;
+    return w ? w : 4;
+}
+
+size_t gp_packed_size(const uint32_t *seq_len, uint32_t n_seq)
+{
+    size_t words = 0;
+    for (uint32_t i = 0; i < n_seq; ++i) words += words_for(seq_len[i]);
+    return words * sizeof(uint32_t);
+}
+
+int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
+                      uint32_t *packed, uint32_t *seq_word_off, uint32_t *n_symbols)
+{
+    if ((!seqs || !seq_len || !packed || !seq_word_off) && n_seq) return GP_ERR_INVALID;
+    // byte -> code.  Equality of codes == equality of bytes (ContigsCompactor.cpp:1641).
+    int16_t code[256];
+    for (int i = 0; i < 256; ++i) code[i] = -1;
+    code[(unsigned char)'A'] = 0; code[(unsigned char)'C'] = 1;
+    code[(unsigned char)'G'] = 2; code[(unsigned char)'T'] = 3; code[(unsigned char)'N'] = 4;
+    int next = 5;
+    size_t off = 0;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        const unsigned char *p = (const unsigned char *)seqs[s];
+        const uint32_t len = seq_len[s];
+        if (!p && len) return GP_ERR_INVALID;
+        const size_t nw = words_for(len);
+        seq_word_off[s] = (uint32_t)off;
+        uint32_t *dst = packed + off;
+        uint32_t i = 0;
+        for (size_t w = 0; w < nw; ++w) {
+            uint32_t word = 0;
+            for (int k = 0; k < 8 && i < len; ++k, ++i) {
+                int c = code[p[i]];
+                if (c < 0) {
+                    if (next >= 16) return GP_ERR_ALPHABET;
+                    c = code[p[i]] = (int16_t)next++;
+                }
+                word |= (uint32_t)c << (4 * k);
+            }
+            dst[w] = word;
+        }
+        off += nw;
+        if (off > 0xffffffffull) return GP_ERR_RANGE;
+    }
+    // ACGT+N always count: their codes are fixed
+    if (n_symbols) *n_symbols = (uint32_t)next;
+    return GP_OK;
+}
+
+/* ContigsCompactor::IsScoreSignificant, ContigsCompactor.cpp:1876-1976 (doubles, as there). */
+int gp_is_score_significant(const gp_thresholds *t, int32_t scoreMax, int32_t szSeq1, int32_t szSeq2,
+                            int32_t rowStart, int32_t colStart, int32_t nclip)
+{
+    int szOverlap0 = std::min(szSeq1, szSeq2);                              // :1894
+    int szOverlap1 = szOverlap0, szOverlap2 = szOverlap0;
+    if (rowStart + nclip == szSeq1) szOverlap1 = colStart;                  // :1896
+    if (colStart + nclip == szSeq2) szOverlap2 = rowStart;                  // :1900
+    int szOverlap = std::min(szOverlap0, std::min(szOverlap1, szOverlap2)); // :1904
+    if (szOverlap < szSeq1 * t->frac_min_overlap && szOverlap < szSeq2 * t->frac_min_overlap)
+        return 0;                                                           // :1911
+    const int MIN_ASM_EXT_LEN = 5;                                          // :1916
+    if (rowStart + nclip == szSeq1 && colStart + MIN_ASM_EXT_LEN - 1 >= szSeq2) return 0;  // :1919
+    if (colStart + nclip == szSeq2 && rowStart + MIN_ASM_EXT_LEN - 1 >= szSeq1) return 0;  // :1926
+    double scoreMinThres = szOverlap * (1 - t->fraction_loss_score);        // :1958
+    if (scoreMax < scoreMinThres) return 0;                                 // :1960
+    if (szOverlap < t->min_overlap_len_with_scaffold) return 0;             // :1972
+    if (szOverlap < t->min_overlap_len) return 1;                           // :1973
+    return 2;
+}
+
+/* ContigsCompactorAction::IsContainment, ContigsCompactor.cpp:155-159. */
+int gp_is_containment(int32_t len1, int32_t len2, const gp_result *r)
+{
+    const bool bcontained = (r->flags & GP_FLAG_CONTAINED) != 0;
+    return bcontained && ((r->row_end + r->nclip == len1 && len1 < r->col_end) ||
+                          (r->col_end + r->nclip == len2 && len2 < r->row_end));
+}
+
+/* Which branch of SetMergedStringConcat (ContigsCompactor.cpp:108-153) applies:
+ * 0: merged = s2 (:116-121)  1: merged = s1 (:122-127)
+ * 2: s1[0:len1-nclip] + s2[col_end:] (:131-139)   3: s2[0:len2-nclip] + s1[row_end:] (:141-149) */
+static int merged_case(int32_t len1, int32_t len2, const gp_result *r)
+{
+    const bool bcontained = (r->flags & GP_FLAG_CONTAINED) != 0;
+    if (bcontained && r->row_end + r->nclip == len1 && len1 < len2) return 0;
+    if (bcontained && r->col_end + r->nclip == len2 && len2 < len1) return 1;
+    if (r->row_end + r->nclip == len1) return 2;
+    return 3;
+}
+
+int32_t gp_merged_length(int32_t len1, int32_t len2, const gp_result *r)
+{
+    switch (merged_case(len1, len2, r)) {
+    case 0: return len2;
+    case 1: return len1;
+    case 2: return (len1 - r->nclip) + (len2 - r->col_end);
+    default: return (len2 - r->nclip) + (len1 - r->row_end);
+    }
+}
+
+int32_t gp_merged_concat(const char *s1, int32_t len1, const char *s2, int32_t len2,
+                         const gp_result *r, char *out)
+{
+    int32_t n = 0;
+    switch (merged_case(len1, len2, r)) {
+    case 0: memcpy(out, s2, (size_t)len2); n = len2; break;
+    case 1: memcpy(out, s1, (size_t)len1); n = len1; break;
+    case 2:
+        memcpy(out, s1, (size_t)(len1 - r->nclip)); n = len1 - r->nclip;
+        memcpy(out + n, s2 + r->col_end, (size_t)(len2 - r->col_end)); n += len2 - r->col_end;
+        break;
+    default:
+        memcpy(out, s2, (size_t)(len2 - r->nclip)); n = len2 - r->nclip;
+        memcpy(out + n, s1 + r->row_end, (size_t)(len1 - r->row_end)); n += len1 - r->row_end;
+        break;
+    }
+    out[n] = 0;
+    return n;
+}
+
+/* ContigsCompactorAction::GetOverlapSize, ContigsCompactor.h:51. */
+int32_t gp_overlap_size(int32_t len1, int32_t len2, const gp_result *r)
+{
+    return len1 + len2 - r->nclip - gp_merged_length(len1, len2, r);
+}
+
+/* GetComplement, GenSeqsUtils.cpp:24-61; FastaSequence::RevsereComplement, fastareader.cpp. */
+void gp_revcomp(const char *s, uint32_t len, char *out)
+{
+    for (uint32_t i = 0; i < len; ++i) {
+        char b = s[len - 1 - i], o;
+        if (b == 'N' || b == 'n') o = b;
+        else {
+            switch (b) {
+            case 'A': case 'a': o = 'T'; break;
+            case 'T': case 't': o = 'A'; break;
+            case 'G': case 'g': o = 'C'; break;
+            case 'C': case 'c': o = 'G'; break;
+            default: o = 'N'; break;
+            }
+        }
+        out[i] = o;
+    }
+    out[len] = 0;
+}
+
+/* 2-bit k-mer letter, SetKmerTypeForNtAt, KmerUtils.cpp:22-58: C=1, G=2, T=3, anything else 0. */
+static inline uint64_t kmer_letter(char nt)
+{
+    switch (nt) {
+    case 'c': case 'C': return 1;
+    case 'g': case 'G': return 2;
+    case 't': case 'T': return 3;
+    default: return 0;
+    }
+}
+
+/* Candidate list of the pairwise phase (MultiThreadQuickChecker::threadQuickCheck,
+ * ContigsCompactor.cpp:1068-1100, with QuickCheckerContigsMatch :1982-2095).  The reference
+ * keeps each k-mer left-aligned in a uint64 (KmerUtils.cpp:60-115); equal windows give equal
+ * values, so comparing right-aligned window codes is the same test.  Node i's k-mer set is a
+ * sorted vector instead of a std::map; the 2*(30-k+1) probes of node j are binary searches. */
+int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, uint32_t n_nodes,
+                           int32_t k, gp_pair *pairs, uint64_t cap)
+{
+    const uint32_t lenContigLen = 30;                                   // :2024
+    if (k <= 0 || k > 30 || (!nodes && n_nodes)) return GP_ERR_INVALID;
+    for (uint32_t i = 0; i < n_nodes; ++i)
+        if (node_len[i] < lenContigLen) return GP_ERR_INVALID;          // reference reads out of bounds
+    const uint64_t mask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+    // probes of every node: k-mers of its first and last 30 bases (:2026-2029)
+    const uint32_t per_side = lenContigLen - (uint32_t)k + 1;
+    std::vector<uint64_t> probes((size_t)n_nodes * 2 * per_side);
+    for (uint32_t j = 0; j < n_nodes; ++j) {
+        for (int side = 0; side < 2; ++side) {
+            const char *w = side == 0 ? nodes[j] : nodes[j] + node_len[j] - lenContigLen;
+            uint64_t v = 0;
+            for (uint32_t a = 0; a < lenContigLen; ++a) {
+                v = ((v << 2) | kmer_letter(w[a])) & mask;
+                if (a + 1 >= (uint32_t)k) probes[((size_t)j * 2 + side) * per_side + (a + 1 - k)] = v;
+            }
+        }
+    }
+    int64_t np = 0;
+    std::vector<uint64_t> codes;
+    for (uint32_t i = 0; i < n_nodes; ++i) {
+        const uint32_t len = node_len[i];
+        codes.clear();
+        uint64_t v = 0;
+        for (uint32_t a = 0; a < len; ++a) {
+            v = ((v << 2) | kmer_letter(nodes[i][a])) & mask;
+            if (a + 1 >= (uint32_t)k) codes.push_back(v);
+        }
+        std::sort(codes.begin(), codes.end());
+        for (uint32_t j = i; j < n_nodes; ++j) {                        // i <= j incl. j == i (:1008)
+            bool hit = false;
+            const uint64_t *pj = &probes[(size_t)j * 2 * per_side];
+            for (uint32_t q = 0; q < 2 * per_side && !hit; ++q)
+                hit = std::binary_search(codes.begin(), codes.end(), pj[q]);
+            if (hit) {
+                if ((uint64_t)np < cap && pairs) { pairs[np].row_seq = i; pairs[np].col_seq = j; }
+                ++np;
+            }
+        }
+    }
+    return np;
+}
+
+} // extern "C"

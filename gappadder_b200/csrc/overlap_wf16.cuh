@@ -1,0 +1,374 @@
+// overlap_wf16.cuh -- packed 16-bit overlap-DP kernel, one warp per pair (sm_100a).
+//
+// Same contract as overlap_wf32.cuh (ContigsCompactor::Evaluate before the significance test,
+// ContigsCompactor-v0.2.0/ContigsMerger/ContigsCompactor.cpp:1596-1709,:1736-1837), for pairs with
+// min(m,n) <= 4094, an alphabet of <= 8 symbols and small penalties -- i.e. everything GAPPadder
+// produces.  Two DP cells per 32-bit register, DPX packed instructions (VIADD.16x2,
+// VIMNMX.S16x2, VIADDMNMX.S16x2.RELU), a PRMT table lookup for the substitution score.
+//
+// ---- arithmetic ------------------------------------------------------------------------------
+// Potential.  Instead of H the kernel carries P = H + pot, pot(i,j) = m-i when m <= n ("row
+// potential") else n-j.  Every DP step then has a non-positive increment
+//     diag: match 0, mismatch X-1     up: G-1 (row pot) / G (col pot)     left: G / G-1
+// so P never grows along a path.  The answer has H >= 0 (cell (0,n) is scanned first and holds 0),
+// hence P >= 0 on every cell of the winning path and on every cell that can tie with it; clamping
+// P at -1 therefore changes nothing that matters: by induction the clamped recurrence computes
+// exactly max(P,-1) everywhere, so cells with P >= 0 keep their exact value, predecessor choice and
+// origin.  0 <= P <= min(m,n) for those cells, i.e. 12 bits for 4094 -- which leaves room for tags.
+//
+// Cell encoding (16 bits, signed, >= 0):   V = 8*(P+1) + 4*z + code
+//   code  origin of the cell's predecessor walk, thermometer coded by where on the border it ends,
+//         ordered along the border from bottom-left to top-right:
+//         0 = column 0 (row > 0), 1 = the corner (0,0), 3 = row 0 (column > 0).
+//   z     set on the diagonal candidate only, cleared after the max.
+// Tie rule.  The reference prefers diag, then up, then left on equal scores (:1651-1665).  Walks of
+// different cells never cross, so origins are monotone: code(left) <= code(diag) <= code(up).  With
+// the code in the low bits a packed max already resolves left-vs-diag and left-vs-up ties the way
+// the reference does (the preferred candidate has the larger or equal code, and equal codes are
+// interchangeable because only the origin survives the walk, :1834-1837).  The one remaining case,
+// diag-vs-up, is fixed by the z bonus.  max is then order independent, which lets the kernel fold
+// the `up` candidate (the only one that depends on the row above) last.
+//
+// ---- layout -----------------------------------------------------------------------------------
+// A strip is 32 lanes x 2K rows.  Lane l owns rows [2K*l, 2K*l+2K) of the strip: K "lo" rows in
+// the low halves of W[0..K) and K "hi" rows in the high halves, the hi group running one column
+// behind the lo group, so W[k] = (row k @ column j , row K+k @ column j-1) and W[k] depends on
+// W[k-1] of the same step in BOTH halves.  Only W[0] needs a fix-up (one PRMT).  Lane l runs two
+// steps behind lane l-1 and receives, per step, one word from it: the value of its last row and
+// the column's base code.  Lane 0 reads the same word from the boundary line the previous strip
+// left behind (global scratch, L2 resident, 32 columns per coalesced load).
+//
+// Host/device: the per-lane arithmetic below is __host__ __device__; tests/emulate_wf16.cu runs
+// the very same functions on the CPU, lane by lane, against the oracle.
+#pragma once
+#include "common.cuh"
+
+#if defined(__CUDACC__)
+#define GP_HD __host__ __device__ __forceinline__
+#else
+#define GP_HD inline
+#endif
+
+namespace gp {
+
+// ---- packed primitives (device: one SASS instruction each; host: emulation for the tests) -----
+GP_HD uint32_t p_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t nib = (sel >> (4 * i)) & 0xf;
+        uint32_t byte = (uint32_t)(src >> (8 * (nib & 7))) & 0xff;
+        if (nib & 8) byte = (byte & 0x80) ? 0xff : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+GP_HD uint32_t p_add2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vadd2(a, b);
+#else
+    return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16);
+#endif
+}
+GP_HD uint32_t p_max2(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(a, b);
+#else
+    int16_t al = (int16_t)a, bl = (int16_t)b, ah = (int16_t)(a >> 16), bh = (int16_t)(b >> 16);
+    return (uint16_t)(al > bl ? al : bl) | ((uint32_t)(uint16_t)(ah > bh ? ah : bh) << 16);
+#endif
+}
+// max(a + b, c, 0) per signed 16-bit half
+GP_HD uint32_t p_addmax2_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2_relu(a, b, c);
+#else
+    uint32_t s = p_add2(a, b);
+    return p_max2(p_max2(s, c), 0u);
+#endif
+}
+
+// ---- parameters -------------------------------------------------------------------------------
+constexpr uint32_t WF16_MAX_MIN_LEN = 4094;       // 8*(P+1)+7 <= 32767
+constexpr uint32_t TAG_Z2 = 0x00040004u;
+
+struct Wf16Params {
+    uint32_t tbl_lo, tbl_hi;     // PRMT table: byte 0 = diagonal increment on match, bytes 1..7 on mismatch
+    uint32_t gup_row, gleft_row; // packed up/left increments under the row potential
+    uint32_t gup_col, gleft_col; // ... under the column potential
+    int32_t max_clip;
+};
+
+inline bool wf16_params_ok(int mismatch, int indel)
+{
+    // increments must be <= 0 in the potential domain and fit a signed byte after scaling by 8
+    return mismatch <= 1 && mismatch >= -15 && indel <= 0 && indel >= -14;
+}
+
+inline bool wf16_pair_ok(uint32_t m, uint32_t n)
+{
+    return m >= 1 && n >= 1 && (m < n ? m : n) <= WF16_MAX_MIN_LEN && m <= 0xffffff && n <= 0xffffff;
+}
+
+inline Wf16Params wf16_make_params(int mismatch, int indel, int max_clip)
+{
+    Wf16Params p;
+    const uint32_t inc_match = (uint32_t)(0 * 8 + 4) & 0xff;                 // +1 - 1, z bonus
+    const uint32_t inc_mism = (uint32_t)((mismatch - 1) * 8 + 4) & 0xff;     // X - 1, z bonus
+    p.tbl_lo = inc_match | (inc_mism << 8) | (inc_mism << 16) | (inc_mism << 24);
+    p.tbl_hi = inc_mism * 0x01010101u;
+    auto pk = [](int v) { uint32_t h = (uint32_t)(v * 8) & 0xffffu; return h | (h << 16); };
+    p.gup_row = pk(indel - 1); p.gleft_row = pk(indel);
+    p.gup_col = pk(indel);     p.gleft_col = pk(indel - 1);
+    p.max_clip = max_clip;
+    return p;
+}
+
+// Geometry of one pair in the potential domain.
+struct Wf16Pair {
+    int m, n, C;
+    bool rowpot;             // pot = m - i, else pot = n - j
+    uint32_t gup, gleft;
+    GP_HD int pot(int i, int j) const { return rowpot ? m - i : n - j; }
+    // boundary values: V(i,0) for i >= 0 and V(0,j) for j >= 1
+    GP_HD uint32_t v_col0(int i) const
+    {
+        int p = pot(i, 0) + 1;
+        if (p < 0) p = 0;
+        return (uint32_t)(8 * p) + (i == 0 ? 1u : 0u);
+    }
+    GP_HD uint32_t v_row0(int j) const { return (uint32_t)(8 * (pot(0, j) + 1)) + (j == 0 ? 1u : 3u); }
+};
+
+GP_HD Wf16Pair wf16_make_pair(int m, int n, const Wf16Params& P)
+{
+    Wf16Pair g;
+    g.m = m; g.n = n; g.C = P.max_clip;
+    g.rowpot = m <= n;
+    g.gup = g.rowpot ? P.gup_row : P.gup_col;
+    g.gleft = g.rowpot ? P.gleft_row : P.gleft_col;
+    return g;
+}
+
+// code11 of a base code: the code in both nibbles of a byte (PRMT selector for a low/high byte pair)
+GP_HD uint32_t code11(uint32_t c) { return (c & 7u) * 0x11u; }
+
+// ---- per-lane state and arithmetic ------------------------------------------------------------
+template <int K>
+struct Lane16 {
+    uint32_t W[K];       // (row k @ col j | row K+k @ col j-1 << 16)
+    uint32_t Rk[K];      // selector constant: row codes in nibbles, bit 3 of the odd nibbles set
+    uint32_t cvec;       // byte 0: code11 of column j, byte 1: of column j-1 (older history above)
+    uint32_t up0_prev;   // previous step's `up` of W[0] == this step's diagonal of W[0]
+};
+
+// Start of a strip.  itop = number of table rows above this lane's first row; the lane's lo rows
+// are i = itop+1+k, its hi rows i = itop+1+K+k (1-based).  row_code(i0) returns the 4-bit code of
+// base i0 (0-based) of the row sequence, or 15 beyond its end.
+template <int K, class RowCode>
+GP_HD void lane16_begin(Lane16<K>& st, const Wf16Pair& g, int itop, RowCode row_code)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int ilo = itop + 1 + k, ihi = itop + 1 + K + k;
+        st.W[k] = g.v_col0(ilo) | (g.v_col0(ihi) << 16);
+        const uint32_t rlo = row_code(ilo - 1) & 15u, rhi = row_code(ihi - 1) & 15u;
+        st.Rk[k] = (rlo * 0x11u | 0x80u) | ((rhi * 0x11u | 0x80u) << 8);
+    }
+    st.cvec = 0;
+    st.up0_prev = g.v_col0(itop) | (g.v_col0(itop + K) << 16);
+}
+
+// After a lane's first step (lo group at column 1) the hi group has "computed" column 0; put the
+// real column-0 boundary back.
+template <int K>
+GP_HD void lane16_fix_first(Lane16<K>& st, const Wf16Pair& g, int itop)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.W[k] = (st.W[k] & 0xffffu) | (g.v_col0(itop + 1 + K + k) << 16);
+}
+
+// One step: the lo group advances to column j, the hi group to column j-1.
+// recv: bits 0-15 V(row above the lane, column j), bits 16-23 code11(column j).
+template <int K>
+GP_HD void lane16_step(Lane16<K>& st, uint32_t recv, const Wf16Params& P, uint32_t gup, uint32_t gleft)
+{
+    st.cvec = (st.cvec << 8) | ((recv >> 16) & 0xffu);
+    const uint32_t up0 = p_prmt(recv, st.W[K - 1], 0x5410u);   // (recv.lo16 , old W[K-1].lo16)
+    uint32_t diag = st.up0_prev;
+    st.up0_prev = up0;
+    uint32_t up = up0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t left = st.W[k];
+        const uint32_t inc = p_prmt(P.tbl_lo, P.tbl_hi, st.Rk[k] ^ st.cvec);
+        const uint32_t d = p_add2(diag, inc);                  // carries the z bonus
+        const uint32_t l = p_add2(left, gleft);
+        const uint32_t t = p_max2(d, l);
+        const uint32_t w = p_addmax2_relu(up, gup, t) & ~TAG_Z2;
+        diag = left;
+        up = w;
+        st.W[k] = w;
+    }
+}
+
+// Word handed to the next lane after a step: value of this lane's last row (hi half of W[K-1],
+// column j-1) and that column's code11.
+template <int K>
+GP_HD uint32_t lane16_send(const Lane16<K>& st)
+{
+    return p_prmt(st.W[K - 1], st.cvec, 0x7532u);
+}
+
+// Candidate bookkeeping for one 16-bit cell value.
+GP_HD long long wf16_cell_key(uint32_t v16, int i, int j, const Wf16Pair& g)
+{
+    const uint32_t rk = cell_rank(i, j, g.m, g.n, g.C);
+    if (rk > RANK_MAX) return (long long)0x8000000000000000ull;
+    const int H = (int)(v16 >> 3) - 1 - g.pot(i, j);
+    const uint32_t code = v16 & 3u;
+    const uint32_t origin = (code & 1u) | ((code & 2u) ? 0u : 2u);   // row0 | col0 << 1
+    return make_key(H, rk, origin);
+}
+
+// Scans the cells a lane holds after a step (lo column j, hi column j-1).
+template <int K>
+GP_HD long long lane16_scan(const Lane16<K>& st, const Wf16Pair& g, int itop, int j, long long best)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int ilo = itop + 1 + k, ihi = itop + 1 + K + k;
+        if (ilo <= g.m && j >= 1 && j <= g.n) {
+            long long key = wf16_cell_key(st.W[k] & 0xffffu, ilo, j, g);
+            best = key > best ? key : best;
+        }
+        if (ihi <= g.m && j - 1 >= 1 && j - 1 <= g.n) {
+            long long key = wf16_cell_key(st.W[k] >> 16, ihi, j - 1, g);
+            best = key > best ? key : best;
+        }
+    }
+    return best;
+}
+
+// Strip schedule: rows 1..m_fast (a multiple of 64, all above row m-C) go through non-scanning
+// strips of K = 8, 2, 1; the rest through scanning strips of K = 1 (64 rows each).
+GP_HD int wf16_fast_rows(int m, int C)
+{
+    int r = m - C - 1;
+    return r > 0 ? (r / 64) * 64 : 0;
+}
+
+#if defined(__CUDACC__)
+// ---- device side ------------------------------------------------------------------------------
+
+constexpr int WF16_THREADS = 256;
+
+// One strip of 64*K rows starting after table row `i0`.  bnd[j] (j = 1..n+1): low half V(i0, j),
+// bits 16-23 code11(column j); the low halves are replaced in place by the strip's last row.
+template <int K, bool SCAN_ALL>
+__device__ __forceinline__ long long wf16_strip(const uint32_t* __restrict__ packed, const PairDesc& pd,
+                                                const Wf16Pair& g, const Wf16Params& P, uint32_t* bnd,
+                                                int i0, bool store_bottom, long long best)
+{
+    const int lane = threadIdx.x & 31;
+    const int itop = i0 + lane * 2 * K;
+    Lane16<K> st;
+    lane16_begin<K>(st, g, itop, [&](int idx) -> uint32_t {
+        return (idx < g.m) ? load_code(packed, pd.row_off, (uint32_t)idx) : 15u;
+    });
+    uint32_t send = 0, chunk = 0;
+    const int n = g.n;
+    const int t_end = n + 1 + 62;                       // lane 31's lo group reaches column n+1
+    const int t_scan = SCAN_ALL ? 1 : (n - g.C > 1 ? n - g.C : 1);
+    uint16_t* bnd16 = reinterpret_cast<uint16_t*>(bnd);
+    for (int t = 1; t <= t_end; ++t) {
+        if (((t - 1) & 31) == 0) {
+            const int jj = t + lane;
+            if (jj <= n + 1) chunk = bnd[jj];
+        }
+        const uint32_t from_line = __shfl_sync(0xffffffffu, chunk, (t - 1) & 31);
+        uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1);
+        if (lane == 0) recv = from_line;
+        const int j = t - 2 * lane;                     // my lo column
+        if (j >= 1 && j <= n + 1) {
+            lane16_step<K>(st, recv, P, g.gup, g.gleft);
+            if (j == 1) lane16_fix_first<K>(st, g, itop);
+            send = lane16_send<K>(st);
+            if (store_bottom && lane == 31 && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
+            if (t >= t_scan) best = lane16_scan<K>(st, g, itop, j, best);
+        }
+    }
+    __syncwarp();
+    return best;
+}
+
+__global__ void __launch_bounds__(WF16_THREADS)
+overlap_wf16_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
+                    const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
+                    Wf16Params P, uint32_t* __restrict__ scratch, uint32_t scratch_stride,
+                    DevResult* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t* bnd = scratch + (size_t)warp_global * scratch_stride;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(queue, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= n_work) break;
+        const uint32_t pid = order[qi];
+        const PairDesc pd = pairs[pid];
+        const Wf16Pair g = wf16_make_pair((int)pd.m, (int)pd.n, P);
+        const int m = g.m, n = g.n;
+        // boundary line = table row 0, plus the column codes
+        for (int j = 1 + lane; j <= n + 1; j += 32) {
+            uint32_t c = (j <= n) ? load_code(packed, pd.col_off, (uint32_t)(j - 1)) : 0u;
+            bnd[j] = g.v_row0(j <= n ? j : n) | (code11(c) << 16);
+        }
+        __syncwarp();
+        long long best = make_key(0, 0u, 1u | (n == 0 ? 2u : 0u));   // cell (0,n): rank 0, H = 0
+        const int m_fast = wf16_fast_rows(m, g.C);
+        int i0 = 0;
+        while (m_fast - i0 >= 512) { best = wf16_strip<8, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 512; }
+        while (m_fast - i0 >= 128) { best = wf16_strip<2, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 128; }
+        while (m_fast - i0 >= 64)  { best = wf16_strip<1, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 64; }
+        while (i0 < m)             { best = wf16_strip<1, true>(packed, pd, g, P, bnd, i0, i0 + 64 < m, best); i0 += 64; }
+        best = warp_max_key(best);
+        if (lane == 0) store_result(out + pid, best, m, n, FLAG_KERNEL16);
+        __syncwarp();
+    }
+}
+
+inline cudaError_t wf16_configure() { return cudaSuccess; }
+
+// Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
+inline int wf16_launch(cudaStream_t stream, int sm_count, const uint32_t* packed, const PairDesc* pairs,
+                       const uint32_t* order, uint32_t n_work, unsigned int* queue, const Wf16Params& P,
+                       uint32_t max_n, void** scratch, size_t* scratch_cap, DevResult* out)
+{
+    const int blocks = sm_count * 2;
+    const uint32_t warps = (uint32_t)blocks * (WF16_THREADS / 32);
+    const uint32_t stride = (max_n + 2 + 31 + 32) & ~31u;
+    const size_t need = (size_t)warps * stride * sizeof(uint32_t);
+    if (need > *scratch_cap) {
+        if (*scratch) cudaFree(*scratch);
+        *scratch = nullptr; *scratch_cap = 0;
+        cudaError_t e = cudaMalloc(scratch, need);
+        if (e != cudaSuccess) return (int)e;
+        *scratch_cap = need;
+    }
+    overlap_wf16_kernel<<<blocks, WF16_THREADS, 0, stream>>>(packed, pairs, order, n_work, queue, P,
+                                                             (uint32_t*)*scratch, stride, out);
+    return (int)cudaGetLastError();
+}
+#endif // __CUDACC__
+
+} // namespace gp

@@ -1,0 +1,175 @@
+/* gappadder_b200.h -- C ABI of the B200-native overlap-alignment path of GAPPadder's ContigsMerger.
+ *
+ * This is the drop-in boundary for ONE path of the reference (simoncchu/GAPPadder):
+ *   ContigsCompactor::Evaluate            ContigsCompactor-v0.2.0/ContigsMerger/ContigsCompactor.cpp:1572-1873
+ * as driven by
+ *   ContigsCompactor::threadMergeContigV2 ContigsCompactor.cpp:623-693   (all-vs-all pairwise phase, call at :652)
+ *   ContigsCompactor::FormMergedSeqFromPath ContigsCompactor.cpp:1456-1515 (relax chain, call at :1491)
+ * with the candidate filter that decides which pairs are aligned
+ *   MultiThreadQuickChecker / QuickCheckerContigsMatch  ContigsCompactor.cpp:992-1100, 1982-2095
+ * and the integer/double epilogue that turns a DP result into an edge or a merged contig
+ *   IsScoreSignificant :1876-1976, ContigsCompactorAction :108-159, ContigsCompactor.h:51.
+ *
+ * The reference has no FFI for this path (it is a private C++ method behind a process boundary),
+ * so these entry points are what a binding for it has to look like: batched, plain pointers and
+ * sizes, no C++ or torch types.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every function returns GP_OK (0) or a negative gp_status; nothing throws, nothing aborts;
+ *  - the caller owns every buffer it passes; the library never frees or retains caller memory
+ *    beyond the call (device copies are the library's);
+ *  - a gp_ctx is bound to one CUDA device and owns one stream; it is thread-compatible, not
+ *    thread-safe (one host thread per context, one context per GPU);
+ *  - there is no CPU fallback: without a usable CUDA device gp_create fails.
+ *
+ * Results are bit-identical to the reference's (integer work): see tests/ and oracle/.
+ */
+#ifndef GAPPADDER_B200_H
+#define GAPPADDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GP_ABI_VERSION 1
+
+typedef enum gp_status {
+    GP_OK = 0,
+    GP_ERR_INVALID = -1,      /* null pointer, out-of-range index, bad parameter            */
+    GP_ERR_CUDA = -2,         /* a CUDA runtime call or kernel failed; see gp_last_error    */
+    GP_ERR_NO_DEVICE = -3,    /* no CUDA device / device is not sm_100                      */
+    GP_ERR_ALPHABET = -4,     /* more than 16 distinct sequence symbols in one batch        */
+    GP_ERR_RANGE = -5,        /* scores would overflow the kernels' 28-bit score field      */
+    GP_ERR_NOMEM = -6
+} gp_status;
+
+typedef struct gp_ctx gp_ctx;
+
+/* One Evaluate(s1 = rows, s2 = columns) request: indices into the batch's sequence table.
+ * Replaces the (vfs[i], vfs[j]) arguments at ContigsCompactor.cpp:652 / (&seqMerg, pSeqi) at :1491. */
+typedef struct gp_pair {
+    uint32_t row_seq;
+    uint32_t col_seq;
+} gp_pair;
+
+/* What Evaluate leaves behind before IsScoreSignificant: the best-cell scan result
+ * (ContigsCompactor.cpp:1674-1709) and where the predecessor walk from that cell ended
+ * (:1763-1837).  20 bytes. */
+typedef struct gp_result {
+    int32_t score;      /* scoreMax                                                          */
+    int32_t row_end;    /* posRowEnd                                                         */
+    int32_t col_end;    /* posColEnd                                                         */
+    int32_t nclip;      /* nclip                                                             */
+    uint32_t flags;     /* GP_FLAG_*                                                         */
+} gp_result;
+
+#define GP_FLAG_ROW0      1u  /* the walk ended with tbCur.first  == 0 (ContigsCompactor.cpp:1834) */
+#define GP_FLAG_COL0      2u  /* the walk ended with tbCur.second == 0 (:1836)                     */
+#define GP_FLAG_CONTAINED 4u  /* bcontained (:1814,:1834-1837)                                     */
+#define GP_FLAG_KERNEL16  8u  /* informational: computed by the packed 16-bit kernel               */
+
+/* DP scoring and scan parameters: the statics CM/main.cpp:250-262 sets.  match is +1
+ * (ContigsCompactor.cpp:1596).  mismatch = (int)scoreMismatch (-i1), indel = scoreIndel (-i2, must
+ * be integral), max_clip = floor(maxOverlapClipLen) (-y). */
+typedef struct gp_dp_params {
+    int32_t mismatch;
+    int32_t indel;
+    int32_t max_clip;
+} gp_dp_params;
+
+/* Thresholds of IsScoreSignificant as the doubles the reference compares with
+ * (CM/main.cpp:87-149: -s -c -x -z pass through sscanf("%f") into a float, then widen). */
+typedef struct gp_thresholds {
+    double fraction_loss_score;             /* -s  (default 0.01)    */
+    double frac_min_overlap;                /* -c  (default 0.005)   */
+    double min_overlap_len;                 /* -x  (default 100000)  */
+    double min_overlap_len_with_scaffold;   /* -z  (default 6)       */
+} gp_thresholds;
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` (one per GPU).  *out is NULL on failure. */
+int gp_create(int device, gp_ctx **out);
+void gp_destroy(gp_ctx *ctx);
+/* Message of the last error on this context (or of the last failed gp_create when ctx is NULL). */
+const char *gp_last_error(const gp_ctx *ctx);
+int gp_abi_version(void);
+/* The context's CUDA stream as a cudaStream_t (for event timing by the caller). */
+void *gp_stream(gp_ctx *ctx);
+
+/* ---- host batcher: sequence packing ---------------------------------------------------------- */
+
+/* Bytes needed for the packed form of n_seq sequences of the given lengths: 4-bit codes, eight per
+ * 32-bit word, every sequence starting on a 16-byte boundary. */
+size_t gp_packed_size(const uint32_t *seq_len, uint32_t n_seq);
+
+/* Packs ASCII sequences (as FastaReader leaves them: upper case letters, fastareader.cpp:185-229)
+ * into 4-bit codes: A,C,G,T -> 0..3, N -> 4, any other byte value -> 5.. in order of first
+ * appearance in the batch; equal bytes get equal codes, which is all Evaluate's
+ * `pSeq1->at(i-1) == pSeq2->at(j-1)` (:1641) looks at.
+ *   packed      out, gp_packed_size() bytes (pinned memory recommended)
+ *   seq_word_off out, n_seq entries: offset of each sequence in 32-bit words
+ *   n_symbols   out (optional): number of distinct codes used
+ * Returns GP_ERR_ALPHABET if the batch has more than 16 distinct byte values. */
+int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
+                      uint32_t *packed, uint32_t *seq_word_off, uint32_t *n_symbols);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* Uploads a packed sequence table to the context's GPU (replaces any previous table). */
+int gp_set_sequences(gp_ctx *ctx, const uint32_t *packed, size_t packed_bytes,
+                     const uint32_t *seq_word_off, const uint32_t *seq_len, uint32_t n_seq,
+                     uint32_t n_symbols);
+
+/* Runs Evaluate's DP + scan + walk-end for every pair against the uploaded table and copies the
+ * results to `out` (n_pairs entries, host memory).  Blocking. */
+int gp_overlap_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs,
+                     const gp_dp_params *params, gp_result *out);
+
+/* One-call form on host ASCII sequences: pack + upload + gp_overlap_pairs. */
+int gp_overlap_batch(gp_ctx *ctx, const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
+                     const gp_pair *pairs, uint64_t n_pairs,
+                     const gp_dp_params *params, gp_result *out);
+
+/* Split form used for device-resident timing: upload pairs once, launch any number of times,
+ * fetch once.  gp_launch_resident only enqueues work on gp_stream(ctx). */
+int gp_upload_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs, const gp_dp_params *params);
+int gp_launch_resident(gp_ctx *ctx);
+int gp_fetch_results(gp_ctx *ctx, gp_result *out, uint64_t n_pairs);
+/* Kernel launches enqueued by this context since creation (library kernels only). */
+uint64_t gp_kernel_launches(const gp_ctx *ctx);
+/* DP cells (sum of m*n) of the pairs currently uploaded, and how many went to each kernel. */
+int gp_pair_stats(const gp_ctx *ctx, uint64_t *cells, uint64_t *pairs16, uint64_t *pairs32);
+
+/* ---- host-side epilogue (exact double / integer restatements; no GPU involved) --------------- */
+
+/* ContigsCompactor::IsScoreSignificant (ContigsCompactor.cpp:1876-1976): 0, 1 or 2. */
+int gp_is_score_significant(const gp_thresholds *t, int32_t score, int32_t len1, int32_t len2,
+                            int32_t row_end, int32_t col_end, int32_t nclip);
+/* ContigsCompactorAction::IsContainment (:155-159). */
+int gp_is_containment(int32_t len1, int32_t len2, const gp_result *r);
+/* Length of the string SetMergedStringConcat (:108-153) builds, and the string itself
+ * (out needs len1+len2+1 bytes; NUL-terminated). */
+int32_t gp_merged_length(int32_t len1, int32_t len2, const gp_result *r);
+int32_t gp_merged_concat(const char *s1, int32_t len1, const char *s2, int32_t len2,
+                         const gp_result *r, char *out);
+/* ContigsCompactorAction::GetOverlapSize (ContigsCompactor.h:51). */
+int32_t gp_overlap_size(int32_t len1, int32_t len2, const gp_result *r);
+
+/* Candidate pairs of the pairwise phase, in the reference's -t 1 order (all i <= j including
+ * i == j, row-major): pair (i,j) is kept iff a k-mer of the first or last 30 bases of node j occurs
+ * in node i (QuickCheckerContigsMatch, ContigsCompactor.cpp:1997-2095; k-mer coding
+ * KmerUtils.cpp:22-115).  Returns the number of candidates (possibly > cap) or a negative status. */
+int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, uint32_t n_nodes,
+                           int32_t kmer_len, gp_pair *pairs, uint64_t cap);
+
+/* FastaSequence::RevsereComplement (fastareader.cpp; GetComplement GenSeqsUtils.cpp:24-61). */
+void gp_revcomp(const char *s, uint32_t len, char *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAPPADDER_B200_H */

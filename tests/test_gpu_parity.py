@@ -1,0 +1,122 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle on the same inputs.
+
+Bit-exact (integer work): (score, row_end, col_end, nclip, row0/col0/contained flags) per pair.
+"""
+import random
+
+import numpy as np
+import pytest
+
+import gappadder_b200 as g
+from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0
+from _oracle import oracle_evaluate, oracle_revcomp
+import synth_gaps
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, seqs, pairs, params=None, full=False):
+    params = params or g.GAPPADDER_DP
+    res = ctx.overlap_batch(seqs, pairs, params)
+    assert len(res) == len(pairs)
+    bad = []
+    for (a, b), r in zip(pairs, res):
+        o = oracle_evaluate(seqs[a], seqs[b], params.mismatch, params.indel, params.max_clip, full=full)
+        want = (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained)
+        got = (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]),
+               int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
+        if want != got:
+            bad.append(((a, b), len(seqs[a]), len(seqs[b]), want, got))
+    assert not bad, "first mismatches (pair, m, n, oracle, gpu): %r" % bad[:5]
+    return res
+
+
+def _rand(rng, n, alpha=b"ACGT"):
+    return bytes(rng.choice(alpha) for _ in range(n))
+
+
+def test_known_answer(ctx):
+    # the two-contig case whose reference output is NEW_CONTIG_MERGE_1 = a b
+    a = b"ACGTACGTAGCTAGCTAGCTAGCATCGATCGATCGATCAGCTAGCTAGCATCGATCAGCTACGACTAGC"
+    b = b"GATCGATCAGCTAGCTAGCATCGATCAGCTACGACTAGCTTTTGGGGCCCCAAAATTTTGGGCCCAATTGGCCAATT"
+    seqs = [a, oracle_revcomp(a), b, oracle_revcomp(b)]
+    pairs = [(i, j) for i in range(4) for j in range(i, 4)]
+    res = _check(ctx, seqs, pairs, full=True)
+    r = res[pairs.index((0, 2))]
+    assert g.merged_concat(a, b, r) == a + b[39:]
+
+
+def test_tie_heavy_small_alphabets(ctx):
+    rng = random.Random(11)
+    seqs = []
+    for _ in range(120):
+        alpha = rng.choice([b"A", b"AC", b"ACG", b"ACGT", b"ACGTN"])
+        seqs.append(_rand(rng, rng.randint(1, 90), alpha))
+    pairs = [(rng.randrange(len(seqs)), rng.randrange(len(seqs))) for _ in range(1500)]
+    _check(ctx, seqs, pairs, full=True)
+
+
+def test_empty_and_tiny(ctx):
+    seqs = [b"", b"A", b"C", b"AC", b"ACGTACGT", b"N", b"NN"]
+    pairs = [(i, j) for i in range(len(seqs)) for j in range(len(seqs))]
+    _check(ctx, seqs, pairs, full=True)
+    assert len(ctx.overlap_batch(seqs, [])) == 0
+
+
+@pytest.mark.parametrize("config,seed", [("tiny", 1), ("small", 2), ("noisy", 3)])
+def test_synthetic_gap_all_pairs(ctx, config, seed):
+    recs = synth_gaps.make_gap(seed, synth_gaps.CONFIGS[config])
+    nodes = []
+    for _, s in recs:
+        nodes += [s, oracle_revcomp(s)]
+    pairs = [(i, j) for i in range(len(nodes)) for j in range(i, len(nodes))]
+    _check(ctx, nodes, pairs)
+
+
+def test_strip_boundaries_and_clip_edges(ctx):
+    # lengths around the strip heights (32*R rows) and around max_clip
+    rng = random.Random(5)
+    base = _rand(rng, 1400)
+    seqs = []
+    for L in (49, 50, 51, 52, 255, 256, 257, 511, 512, 513, 1023, 1025):
+        st = rng.randrange(0, len(base) - L)
+        seqs.append(base[st:st + L])
+    pairs = [(i, j) for i in range(len(seqs)) for j in range(len(seqs))]
+    _check(ctx, seqs, pairs)
+
+
+@pytest.mark.parametrize("mismatch,indel,clip", [(-1, -1, 0), (-3, -2, 10), (-2, -5, 50), (0, -1, 3), (-20, -30, 7)])
+def test_other_scoring_parameters(ctx, mismatch, indel, clip):
+    rng = random.Random(100 + clip)
+    base = _rand(rng, 600)
+    seqs = []
+    for _ in range(24):
+        L = rng.randint(20, 300)
+        st = rng.randrange(0, len(base) - L)
+        s = bytearray(base[st:st + L])
+        for p in range(L):
+            if rng.random() < 0.03:
+                s[p] = rng.choice(b"ACGT")
+        seqs.append(bytes(s))
+    pairs = [(rng.randrange(24), rng.randrange(24)) for _ in range(300)]
+    _check(ctx, seqs, pairs, g.DpParams(mismatch, indel, clip))
+
+
+def test_wide_alphabet_goes_through_general_kernel(ctx):
+    rng = random.Random(9)
+    alpha = b"ACGTNRYKMSWB"
+    seqs = [_rand(rng, rng.randint(30, 200), alpha) for _ in range(20)]
+    pairs = [(i, j) for i in range(20) for j in range(20)]
+    _check(ctx, seqs, pairs)
+
+
+def test_cfg1_gap_candidates_full_size(ctx):
+    """One BASELINE cfg1 gap (40 contigs, 300-3000 bp): every candidate pair of the pairwise phase."""
+    recs = synth_gaps.make_gap(1, synth_gaps.CONFIGS["cfg1"])
+    nodes = []
+    for _, s in recs:
+        nodes += [s, g.revcomp(s)]
+    cand = g.candidate_pairs(nodes, 10)
+    pairs = [(int(p["row_seq"]), int(p["col_seq"])) for p in cand]
+    assert len(pairs) > 100
+    _check(ctx, nodes, pairs)
