@@ -17,10 +17,13 @@ build:
 build/gp_api.o: $(CSRC)/gp_api.cu $(CSRC)/common.cuh $(CSRC)/overlap_wf32.cuh $(CSRC)/overlap_wf16.cuh include/gappadder_b200.h | build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/gp_api.ptxas.log || (cat build/gp_api.ptxas.log; false)
 
+build/int_peak.o: $(CSRC)/int_peak.cu include/gappadder_b200.h | build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
 build/gp_host.o: $(CSRC)/gp_host.cpp include/gappadder_b200.h | build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 
-$(LIB): build/gp_api.o build/gp_host.o
+$(LIB): build/gp_api.o build/int_peak.o build/gp_host.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
 
 build/microbench_int: tools/microbench_int.cu | build

@@ -16,7 +16,7 @@ EXPORTS = [
     "gp_packed_size", "gp_pack_sequences", "gp_set_sequences", "gp_overlap_pairs", "gp_overlap_batch",
     "gp_upload_pairs", "gp_launch_resident", "gp_fetch_results", "gp_kernel_launches", "gp_pair_stats",
     "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
-    "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp",
+    "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
 ]
 
 
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         L.gp_candidate_pairs.restype = C.c_int64
         L.gp_revcomp.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
         L.gp_revcomp.restype = None
+        L.gp_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -210,6 +211,12 @@ class Context:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_pair_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(cells=a.value, pairs16=b.value, pairs32=c.value)
+
+    def int_peak(self):
+        """-> (ALU-pipe, dual-pipe) thread-level packed-16x2 instructions per second, measured now."""
+        a, d = C.c_double(), C.c_double()
+        self._check(self._L.gp_int_peak(self._h, C.byref(a), C.byref(d)))
+        return a.value, d.value
 
     def set_sequences(self, packed: np.ndarray, off: np.ndarray, lens: np.ndarray, n_symbols: int):
         self._check(self._L.gp_set_sequences(self._h, packed.ctypes.data, packed.nbytes, off.ctypes.data,

@@ -39,14 +39,14 @@ __device__ __forceinline__ uint32_t load_code(const uint32_t* __restrict__ packe
 //   [score:32 | (RANK_MAX - rank):30 | origin:2]  so that a plain signed max implements it.
 constexpr uint32_t RANK_MAX = 0x3fffffffu;
 
-__device__ __forceinline__ long long make_key(int score, uint32_t rank, uint32_t origin)
+__host__ __device__ __forceinline__ long long make_key(int score, uint32_t rank, uint32_t origin)
 {
     return ((long long)score << 32) | (long long)(((RANK_MAX - rank) << 2) | origin);
 }
 
 // Candidate rank of interior cell (i,j), 1<=i<=m, 1<=j<=n; returns RANK_MAX+1 if the cell is in
 // neither scan.
-__device__ __forceinline__ uint32_t cell_rank(int i, int j, int m, int n, int C)
+__host__ __device__ __forceinline__ uint32_t cell_rank(int i, int j, int m, int n, int C)
 {
     uint32_t W = (uint32_t)(m + n + 2);
     uint32_t r = RANK_MAX + 1u;
@@ -71,7 +71,7 @@ __device__ __forceinline__ long long warp_max_key(long long k)
 }
 
 // Decodes the winning key into the reference's outputs.
-__device__ __forceinline__ void store_result(DevResult* out, long long key, int m, int n, uint32_t extra_flags)
+__host__ __device__ __forceinline__ void store_result(DevResult* out, long long key, int m, int n, uint32_t extra_flags)
 {
     int score = (int)(key >> 32);
     uint32_t lo = (uint32_t)(key & 0xffffffffll);

@@ -55,7 +55,11 @@ namespace gp {
 GP_HD uint32_t p_prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
+    // prmt.b32 in its default mode: selector nibble bit 3 replicates the sign of the selected byte
+    // (__byte_perm() masks that bit away, so it cannot be used here).
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 #else
     uint64_t src = ((uint64_t)b << 32) | a;
     uint32_t r = 0;
@@ -171,16 +175,16 @@ struct Lane16 {
 };
 
 // Start of a strip.  itop = number of table rows above this lane's first row; the lane's lo rows
-// are i = itop+1+k, its hi rows i = itop+1+K+k (1-based).  row_code(i0) returns the 4-bit code of
-// base i0 (0-based) of the row sequence, or 15 beyond its end.
-template <int K, class RowCode>
-GP_HD void lane16_begin(Lane16<K>& st, const Wf16Pair& g, int itop, RowCode row_code)
+// are i = itop+1+k, its hi rows i = itop+1+K+k (1-based).  rcode[x] is the 4-bit code of the
+// base of row itop+1+x (x = 0..2K-1), or 15 beyond the end of the row sequence.
+template <int K>
+GP_HD void lane16_begin(Lane16<K>& st, const Wf16Pair& g, int itop, const uint32_t (&rcode)[2 * K])
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int ilo = itop + 1 + k, ihi = itop + 1 + K + k;
         st.W[k] = g.v_col0(ilo) | (g.v_col0(ihi) << 16);
-        const uint32_t rlo = row_code(ilo - 1) & 15u, rhi = row_code(ihi - 1) & 15u;
+        const uint32_t rlo = rcode[k] & 15u, rhi = rcode[K + k] & 15u;
         st.Rk[k] = (rlo * 0x11u | 0x80u) | ((rhi * 0x11u | 0x80u) << 8);
     }
     st.cvec = 0;
@@ -281,9 +285,12 @@ __device__ __forceinline__ long long wf16_strip(const uint32_t* __restrict__ pac
     const int lane = threadIdx.x & 31;
     const int itop = i0 + lane * 2 * K;
     Lane16<K> st;
-    lane16_begin<K>(st, g, itop, [&](int idx) -> uint32_t {
-        return (idx < g.m) ? load_code(packed, pd.row_off, (uint32_t)idx) : 15u;
-    });
+    {
+        uint32_t rcode[2 * K];
+#pragma unroll
+        for (int x = 0; x < 2 * K; ++x) rcode[x] = (itop + x < g.m) ? load_code(packed, pd.row_off, (uint32_t)(itop + x)) : 15u;
+        lane16_begin<K>(st, g, itop, rcode);
+    }
     uint32_t send = 0, chunk = 0;
     const int n = g.n;
     const int t_end = n + 1 + 62;                       // lane 31's lo group reaches column n+1

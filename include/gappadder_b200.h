@@ -144,6 +144,11 @@ uint64_t gp_kernel_launches(const gp_ctx *ctx);
 /* DP cells (sum of m*n) of the pairs currently uploaded, and how many went to each kernel. */
 int gp_pair_stats(const gp_ctx *ctx, uint64_t *cells, uint64_t *pairs16, uint64_t *pairs32);
 
+/* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):
+ * thread-level instructions per second of VIADDMNMX.S16x2 alone (ALU pipe) and of the
+ * VIMNMX.S16x2 + VIADD.16x2 dual-issue mix (both integer pipes).  bench.py's roofline denominator. */
+int gp_int_peak(gp_ctx *ctx, double *alu_inst_per_s, double *dual_inst_per_s);
+
 /* ---- host-side epilogue (exact double / integer restatements; no GPU involved) --------------- */
 
 /* ContigsCompactor::IsScoreSignificant (ContigsCompactor.cpp:1876-1976): 0, 1 or 2. */
