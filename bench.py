@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- overlap-alignment throughput of the B200 path vs the reference's CPU path.
+
+Metric (BASELINE.json): overlap-alignment GCUPS (1e9 DP cell updates / s; one Evaluate(s1,s2) call =
+len(s1)*len(s2) cells) and gaps/s, at N GPUs, next to host-CPU ContigsMerger.
+
+Workload (`config.workload`): BASELINE.json configs[0], the synthetic 200-gap ContigsMerger set
+(40 Velvet-style contigs per gap, 300-3000 bp, 8 kb locus, GAPPadder's flags -i1 -2 -i2 -2 -y 50
+-k 10): every candidate pair of the all-vs-all pairwise phase (contigs + reverse complements, k-mer
+quick check) of every gap.  configs[1] ("TERefiner contig-to-flank") has no DP in the reference
+ and is not a bench line.  One step = one pass of the hot path over the whole
+200-gap batch.  Each rank gets its own 200 gaps (seeds offset by rank): weak scaling, no collective
+on the data path.
+
+  value     GCUPS with sequences and pair lists already resident in HBM (CUDA events on the library's
+            stream around gp_launch_resident, L2 flushed between steps, max over ranks)
+  e2e       GCUPS through the public call gp_overlap_batch on HOST buffers: packing into pinned memory,
+            H2D, kernels, D2H of the results, every step (wall clock of the blocking call)
+  roofline  integer issue-rate roofline of the dominant kernel (overlap_wf16_kernel): achieved =
+            GCUPS * 6 integer ops per cell / peak = 2 lanes * measured dual-pipe packed
+            16x2 instruction rate (gp_int_peak, measured live on this GPU)
+  cpu_baseline  the reference's own Evaluate (oracle/_ref/libcm_ref.so, kind "reference") or the C
+            restatement (kind "port") on the host cores, on a bounded sample of the same pair list
+
+`--impl reference` times only that CPU path (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tools"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "overlap_alignment_gcups"
+UNIT = "GCUPS"
+OPS_PER_CELL = 6  # 1 compare/select + 3 adds + 2 max
+
+
+def build_workload(n_gaps: int, first_seed: int, config: str = "cfg1"):
+    """-> (seqs: list[bytes], pairs: structured array, cells, per-gap pair counts)"""
+    import gappadder_b200 as g
+    import synth_gaps
+    from gappadder_b200.capi import PAIR_DTYPE
+    seqs, chunks, per_gap = [], [], []
+    spec = synth_gaps.CONFIGS[config]
+    for gi in range(n_gaps):
+        recs = synth_gaps.make_gap(first_seed + gi, spec)
+        base = len(seqs)
+        nodes = []
+        for _, s in recs:                       # graph nodes [c0, c0_R, c1, c1_R, ...] (ContigsCompactor.cpp:794-799)
+            nodes.append(s)
+            nodes.append(g.revcomp(s))
+        cand = g.candidate_pairs(nodes, 10).copy()
+        cand["row_seq"] += base
+        cand["col_seq"] += base
+        seqs.extend(nodes)
+        chunks.append(cand)
+        per_gap.append(len(cand))
+    pairs = np.concatenate(chunks) if chunks else np.zeros(0, dtype=PAIR_DTYPE)
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    cells = int((lens[pairs["row_seq"]] * lens[pairs["col_seq"]]).sum()) if len(pairs) else 0
+    return seqs, pairs, cells, per_gap
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref when built, else the oracle port)
+
+def cpu_path():
+    """-> (kind, callable(s1, s2))  each call runs one Evaluate on the CPU (GIL released)."""
+    import ctypes as C
+    import _oracle
+    ref = _oracle.ref_lib()
+    if ref is not None:
+        def run(a, b, _buf=threading.local()):
+            out = (C.c_int32 * 8)()
+            ref.cmref_evaluate(a, b, 0, out)
+        return "reference", run
+    lib = _oracle.oracle_lib()
+
+    def run(a, b):
+        r = _oracle.DPResult()
+        lib.gpo_evaluate(a, len(a), b, len(b), -2, -2, 50, C.byref(r))
+    return "port", run
+
+
+def cpu_run_pairs(run, seqs, pairs, cores: int):
+    """Runs the given pairs on `cores` threads; returns elapsed seconds."""
+    it = iter(range(len(pairs)))
+    lock = threading.Lock()
+
+    def worker():
+        while True:
+            with lock:
+                k = next(it, None)
+            if k is None:
+                return
+            run(seqs[int(pairs["row_seq"][k])], seqs[int(pairs["col_seq"][k])])
+    ths = [threading.Thread(target=worker) for _ in range(cores)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0
+
+
+def cpu_sample(seqs, pairs, cores: int, budget_s: float, run):
+    """Picks a prefix of the pair list worth about budget_s seconds on `cores` threads (calibrated on a
+    small probe) and returns (sample pairs, cells)."""
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    pc = lens[pairs["row_seq"]] * lens[pairs["col_seq"]]
+    csum = np.cumsum(pc)
+    probe_n = int(np.searchsorted(csum, 3e7 * cores)) + 1          # ~0.03 Gcells per thread
+    probe_n = max(cores, min(probe_n, len(pairs)))
+    t = cpu_run_pairs(run, seqs, pairs[:probe_n], cores)
+    rate = csum[probe_n - 1] / max(t, 1e-6)
+    n = int(np.searchsorted(csum, rate * budget_s)) + 1
+    n = max(probe_n, min(n, len(pairs)))
+    return pairs[:n], int(csum[n - 1])
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, run = cpu_path()
+    cores = min(host_cores(), 64)
+    n_gaps = max(1, min(args.gaps, 8))
+    seqs, pairs, _, _ = build_workload(n_gaps, args.seed)
+    sample, cells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run_pairs(run, seqs, sample[:max(cores, len(sample) // 8)], cores)
+    times = [cpu_run_pairs(run, seqs, sample, cores) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    v = cells / t / 1e9
+    sample_desc = "first %d candidate pairs (%.3f Gcells) of the cfg1 pair list, seeds %d.., per step" % (len(sample), cells / 1e9, args.seed)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64" if kind == "reference" else "i32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args):
+    return {"workload": "cfg1: %d synthetic gaps/GPU x 40 contigs (300-3000 bp, 8 kb locus, 0.2%% subst, 50%% RC), "
+                        "all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)" % args.gaps,
+            "gaps_per_gpu": args.gaps, "first_seed": args.seed, "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": "gaps sharded by rank, no collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+
+def run_gpu(args):
+    import torch
+    import gappadder_b200 as g
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    ctx = g.Context(local_rank)                 # fails loudly without the CUDA library / a B200
+    seqs, pairs, cells, per_gap = build_workload(args.gaps, args.seed + rank * args.gaps)
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    ctx.set_sequences(packed, off, lens, nsym)
+    ctx.upload_pairs(pairs, g.GAPPADDER_DP)
+    stats = ctx.pair_stats()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # --- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.launch_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()                           # L2 flush between timed steps
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        ctx.launch_resident()
+        e1.record(stream)
+        stream.synchronize()
+    barrier()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    my_ms = float(np.mean(step_ms))
+
+    # --- end to end through the public call on host buffers ------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        ctx.overlap_batch(seqs, pairs, g.GAPPADDER_DP)
+    barrier()
+    e2e_t = []
+    res = None
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        res = ctx.overlap_batch(seqs, pairs, g.GAPPADDER_DP)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    my_e2e_ms = float(np.mean(e2e_t)) * 1e3
+    h2d = int(packed.nbytes + len(pairs) * (16 + 4))      # packed table + PairDesc + work order
+    d2h = int(len(pairs) * 20)
+    checksum = int(res["score"].astype(np.int64).sum()) if res is not None and len(res) else 0
+
+    # --- reduce over ranks ---------------------------------------------------------------------
+    tot_cells, tot_gaps, max_ms, max_e2e_ms = cells, args.gaps, my_ms, my_e2e_ms
+    if dist is not None:
+        t = torch.tensor([float(cells), float(args.gaps)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        mx = torch.tensor([my_ms, my_e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        tot_cells, tot_gaps = int(t[0].item()), int(t[1].item())
+        max_ms, max_e2e_ms = float(mx[0].item()), float(mx[1].item())
+
+    if rank == 0:
+        value = tot_cells / (max_ms * 1e-3) / 1e9
+        e2e_v = tot_cells / (max_e2e_ms * 1e-3) / 1e9
+        alu, dual = ctx.int_peak()
+        peak_lane_ops = 2.0 * dual                             # two 16-bit lanes per packed instruction
+        my_gcups = cells / (my_ms * 1e-3) / 1e9                # this GPU's kernel
+        achieved = my_gcups * 1e9 * OPS_PER_CELL
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2", "data": "synthetic", "config": workload_config(args),
+            "gaps_per_s": tot_gaps / (max_ms * 1e-3),
+            "pairs_per_step": int(len(pairs)) * world, "gcells_per_step": tot_cells / 1e9,
+            "kernel_split": {"pairs_wf16": stats["pairs16"], "pairs_wf32": stats["pairs32"]},
+            "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": max_e2e_ms, "gaps_per_s": tot_gaps / (max_e2e_ms * 1e-3), "timing": "wall clock of the blocking gp_overlap_batch call"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tintop/s",
+                         "frac": achieved / peak_lane_ops, "traffic": None,
+                         "kernel": "overlap_wf16_kernel", "ops_per_cell": OPS_PER_CELL,
+                         "peak_source": "measured live (gp_int_peak): 2 lanes x VIMNMX.S16x2+VIADD.16x2 dual-issue rate; "
+                                        "ALU pipe alone %.2f Tinst/s, both pipes %.2f Tinst/s" % (alu / 1e12, dual / 1e12)},
+            "result_checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu:
+            kind, run = cpu_path()
+            cores = min(host_cores(), 64)
+            sample, scells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+            t = cpu_run_pairs(run, seqs, sample, cores)
+            line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "first %d candidate pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--gaps", type=int, default=200, help="gaps per GPU per step (cfg1 = 200)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

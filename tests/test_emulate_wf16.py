@@ -1,0 +1,78 @@
+"""CPU: the packed 16-bit kernel's per-lane arithmetic (gappadder_b200/csrc/overlap_wf16.cuh), run
+lane by lane on the host by tests/emulate_wf16.cu, against the oracle and the golden vectors.
+Validates potential-domain clamping, the origin tags and the tie rule without a GPU."""
+import ctypes as C
+import json
+import os
+import random
+import shutil
+import subprocess
+
+import pytest
+
+import _oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CODE = bytes.maketrans(b"ACGTN", bytes([0, 1, 2, 3, 4]))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not available")
+    os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
+    so = os.path.join(ROOT, "build", "libemulate_wf16.so")
+    srcs = [os.path.join(ROOT, "tests", "emulate_wf16.cu"), os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16.cuh"),
+            os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
+                               "-o", so, srcs[0]])
+    L = C.CDLL(so)
+    L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+
+    def run(a, b, mm=-2, ind=-2, clip=50):
+        out = (C.c_int32 * 5)()
+        rc = L.wf16_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out)
+        assert rc == 0
+        f = out[4]
+        return (out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1)
+    return run
+
+
+def _want(a, b, mm=-2, ind=-2, clip=50):
+    o = _oracle.oracle_evaluate(a, b, mm, ind, clip)
+    return (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained)
+
+
+def test_golden_pairs(emu):
+    data = json.load(open(os.path.join(ROOT, "tests", "golden", "evaluate.json")))
+    for c in data["cases"]:
+        if not c["relax"]:
+            continue
+        a, b = c["s1"].encode(), c["s2"].encode()
+        got = emu(a, b)
+        assert got[:4] == (c["score"], c["row_end"], c["col_end"], c["nclip"])
+        assert got[6] == c["bcontained"]
+
+
+@pytest.mark.parametrize("seed,maxlen,iters", [(7, 200, 1500), (8, 1400, 60), (9, 700, 150)])
+def test_random_pairs(emu, seed, maxlen, iters):
+    rng = random.Random(seed)
+
+    def rnd(n, alpha):
+        return bytes(rng.choice(alpha) for _ in range(n))
+    for _ in range(iters):
+        alpha = rng.choice([b"ACGT", b"AC", b"ACGTN", b"A"])
+        m, n = rng.randint(1, maxlen), rng.randint(1, maxlen)
+        a = rnd(m, alpha)
+        if rng.random() < 0.6:
+            k = rng.randint(1, min(m, maxlen // 2))
+            b = a[-k:] + rnd(max(0, n - k), alpha)
+            if rng.random() < 0.3:
+                b = rnd(rng.randint(0, 10), alpha) + a + rnd(rng.randint(0, 10), alpha)
+        else:
+            b = rnd(n, alpha)
+        b = b or b"A"
+        clip = rng.choice([50, 50, 0, 3, 10])
+        mm, ind = rng.choice([(-2, -2), (-2, -2), (-1, -1), (-3, -2), (0, -1), (-5, -3), (1, -1), (-15, -14)])
+        assert emu(a, b, mm, ind, clip) == _want(a, b, mm, ind, clip), (len(a), len(b), clip, mm, ind)

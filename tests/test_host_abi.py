@@ -1,0 +1,100 @@
+"""CPU: the C-ABI library loads, exports every symbol include/gappadder_b200.h declares, and its
+host-side half (packing, candidate filter, significance, merged strings, reverse complement)
+matches the golden vectors / the oracle.  No compute calls that need a GPU."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gappadder_b200 as g
+from gappadder_b200 import capi
+import _oracle
+import synth_gaps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "gappadder_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    L = g.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.gp_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(g.GpError):
+        g.Context(0)
+
+
+def test_pack_layout_and_codes():
+    seqs = [b"ACGTN", b"", b"AAAAAAAAAC", b"RRYA"]
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    assert list(lens) == [5, 0, 10, 4]
+    assert all(o % 4 == 0 for o in off)           # 16-byte aligned starts
+    def code(s, i):
+        return (int(packed[off[s] + i // 8]) >> (4 * (i % 8))) & 15
+    assert [code(0, i) for i in range(5)] == [0, 1, 2, 3, 4]
+    assert [code(2, i) for i in range(10)] == [0] * 9 + [1]
+    r, y = code(3, 0), code(3, 2)
+    assert r == code(3, 1) and r >= 5 and y >= 5 and r != y and code(3, 3) == 0
+    assert nsym == 7
+    with pytest.raises(g.GpError):
+        g.pack_sequences([bytes(range(65, 65 + 20))])   # 20 distinct symbols
+
+
+def test_revcomp_golden():
+    for c in json.load(open(os.path.join(G, "revcomp.json"))):
+        assert g.revcomp(c["s"].encode()).decode() == c["rc"]
+
+
+def test_significance_golden():
+    data = json.load(open(os.path.join(G, "significant.json")))
+    t = g.gappadder_thresholds()
+    for c in data["cases"]:
+        assert g.is_score_significant(t, c["score"], c["l1"], c["l2"], c["row"], c["col"], c["nclip"]) == c["res"], c
+
+
+def test_epilogue_golden():
+    """merged string / IsContainment / GetOverlapSize from the reference's DP outputs."""
+    data = json.load(open(os.path.join(G, "evaluate.json")))
+    n = 0
+    for c in data["cases"]:
+        if c["bcontained"] < 0:
+            continue
+        a, b = c["s1"].encode(), c["s2"].encode()
+        r = dict(score=c["score"], row_end=c["row_end"], col_end=c["col_end"], nclip=c["nclip"],
+                 flags=capi.FLAG_CONTAINED if c["bcontained"] else 0)
+        assert g.merged_concat(a, b, r).decode() == c["merged"]
+        assert int(capi.is_containment(len(a), len(b), r)) == c["is_containment"]
+        assert capi.overlap_size(len(a), len(b), r) == c["overlap"]
+        n += 1
+    assert n > 300
+
+
+def test_candidate_pairs_golden_and_oracle():
+    for c in json.load(open(os.path.join(G, "quickcheck.json"))):
+        a, b = c["si"].encode(), c["sj"].encode()
+        if len(a) < 30:
+            continue
+        got = g.candidate_pairs([a, b], c["k"])
+        pairs = {(int(p["row_seq"]), int(p["col_seq"])) for p in got}
+        assert ((0, 1) in pairs) == bool(c["feasible"]), c
+    for cfg, seed in (("tiny", 1), ("small", 3), ("noisy", 2), ("cfg1", 1)):
+        recs = synth_gaps.make_gap(seed, synth_gaps.CONFIGS[cfg])
+        nodes = []
+        for _, s in recs:
+            nodes += [s, g.revcomp(s)]
+        got = [(int(p["row_seq"]), int(p["col_seq"])) for p in g.candidate_pairs(nodes, 10)]
+        want = _oracle.oracle_candidate_pairs(nodes, 10)
+        assert got == want          # same pairs, same (-t 1) order
+        assert got == sorted(got)
