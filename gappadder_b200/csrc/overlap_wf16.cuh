@@ -100,6 +100,16 @@ GP_HD uint32_t p_addmax2_relu(uint32_t a, uint32_t b, uint32_t c)
 #endif
 }
 
+// max(a + b, c) per signed 16-bit half
+GP_HD uint32_t p_addmax2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2(a, b, c);
+#else
+    return p_max2(p_add2(a, b), c);
+#endif
+}
+
 // ---- parameters -------------------------------------------------------------------------------
 constexpr uint32_t WF16_MAX_MIN_LEN = 4094;       // 8*(P+1)+7 <= 32767
 constexpr uint32_t TAG_Z2 = 0x00040004u;
@@ -172,6 +182,8 @@ struct Lane16 {
     uint32_t Rk[K];      // selector constant: row codes in nibbles, bit 3 of the odd nibbles set
     uint32_t cvec;       // byte 0: code11 of column j, byte 1: of column j-1 (older history above)
     uint32_t up0_prev;   // previous step's `up` of W[0] == this step's diagonal of W[0]
+    uint32_t negthr[K];  // candidate filter: minus the V a cell needs to matter (0x8001 = never), per half
+    uint32_t fstep[K];   // per-step drift of negthr (column potential only)
 };
 
 // Start of a strip.  itop = number of table rows above this lane's first row; the lane's lo rows
@@ -243,74 +255,233 @@ GP_HD long long wf16_cell_key(uint32_t v16, int i, int j, const Wf16Pair& g)
     return make_key(H, rk, origin);
 }
 
-// Scans the cells a lane holds after a step (lo column j, hi column j-1).
+// Exact scan of the cells a lane holds after a step (lo column j, hi column j-1); cells scoring
+// below the lane's current best are skipped before the rank arithmetic.
 template <int K>
 GP_HD long long lane16_scan(const Lane16<K>& st, const Wf16Pair& g, int itop, int j, long long best)
 {
+    const int floor_score = (int)(best >> 32);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int ilo = itop + 1 + k, ihi = itop + 1 + K + k;
         if (ilo <= g.m && j >= 1 && j <= g.n) {
-            long long key = wf16_cell_key(st.W[k] & 0xffffu, ilo, j, g);
-            best = key > best ? key : best;
+            const uint32_t v = st.W[k] & 0xffffu;
+            if ((int)(v >> 3) - 1 - g.pot(ilo, j) >= floor_score) {
+                long long key = wf16_cell_key(v, ilo, j, g);
+                best = key > best ? key : best;
+            }
         }
         if (ihi <= g.m && j - 1 >= 1 && j - 1 <= g.n) {
-            long long key = wf16_cell_key(st.W[k] >> 16, ihi, j - 1, g);
-            best = key > best ? key : best;
+            const uint32_t v = st.W[k] >> 16;
+            if ((int)(v >> 3) - 1 - g.pot(ihi, j - 1) >= floor_score) {
+                long long key = wf16_cell_key(v, ihi, j - 1, g);
+                best = key > best ? key : best;
+            }
         }
     }
     return best;
 }
 
-// Strip schedule: rows 1..m_fast (a multiple of 64, all above row m-C) go through non-scanning
-// strips of K = 8, 2, 1; the rest through scanning strips of K = 1 (64 rows each).
-GP_HD int wf16_fast_rows(int m, int C)
+// ---- candidate filter ---------------------------------------------------------------------------
+// Only cells in the last C+1 rows / columns can be the answer, and only if they score at least the
+// best score the lane has seen so far (S).  Instead of looking at every such cell the lane keeps,
+// per half, negthr = -(the V a cell of that row has when H = 1) and folds acc = max(V + negthr)
+// over its registers: one VIADDMNMX per register.  acc = 8*(H-1) + tags for the best candidate
+// cell, so "some candidate has H >= max(S,1)" is one packed compare of acc with
+// thrS = 8*(max(S,1)-1).  A lane whose compare fires runs the exact scan above on its own cells.
+// negthr does not depend on S; under the column potential it drifts by +8 per step (fstep).
+enum : int { FILTER_NONE = 0, FILTER_ROWS = 1, FILTER_ALL = 2 };
+constexpr uint32_t NEVER16 = 0x8000u;          // V + NEVER16 < 0 for every V <= 32767
+
+// Thresholds for the step whose lo column is jc (hi column jc-1).
+template <int K>
+GP_HD void lane16_set_filter(Lane16<K>& st, const Wf16Pair& g, int itop, int jc, int mode)
 {
-    int r = m - C - 1;
-    return r > 0 ? (r / 64) * 64 : 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        uint32_t nt[2], fs[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = itop + 1 + k + h * K;
+            const bool cand = i <= g.m && (mode == FILTER_ALL || (mode == FILTER_ROWS && i >= g.m - g.C));
+            const int thr = 8 * (2 + g.pot(i, jc - h));          // <= 8*(2+4094) = 32768
+            if (cand) { nt[h] = (uint32_t)(-thr) & 0xffffu; fs[h] = g.rowpot ? 0u : 8u; }
+            else { nt[h] = NEVER16; fs[h] = 0u; }
+        }
+        st.negthr[k] = nt[0] | (nt[1] << 16);
+        st.fstep[k] = fs[0] | (fs[1] << 16);
+    }
+}
+
+// Evaluates the filter on the lane's current cells and advances the thresholds to the next step.
+template <int K>
+GP_HD uint32_t lane16_filter(Lane16<K>& st)
+{
+    uint32_t acc = 0x80008000u;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        acc = p_addmax2(st.W[k], st.negthr[k], acc);
+        st.negthr[k] = p_add2(st.negthr[k], st.fstep[k]);
+    }
+    return acc;
+}
+// thrS for a best score S, both halves
+GP_HD uint32_t filter_thr(int S) { const uint32_t t = (uint32_t)(8 * ((S > 1 ? S : 1) - 1)); return t | (t << 16); }
+// true iff some half of acc is >= the same half of thr (signed)
+GP_HD bool filter_fired(uint32_t acc, uint32_t thr)
+{
+#if defined(__CUDA_ARCH__)
+    bool hi, lo;
+    (void)__vibmax_s16x2(acc, thr, &hi, &lo);
+    return hi || lo;
+#else
+    return (int16_t)acc >= (int16_t)thr || (int16_t)(acc >> 16) >= (int16_t)(thr >> 16);
+#endif
+}
+
+// ---- strip schedule -------------------------------------------------------------------------------
+// Full strips of 512 rows (K = 8), a 256-row strip (K = 4) when that keeps the last C+1 rows
+// together, and a last strip of the smallest K in {1,2,4,8} that holds the remaining rows.  A strip
+// needs the row filter (ROWSCAN) iff it reaches into the last C+1 rows.
+struct Wf16Strip { int rows; bool last; bool rowscan; };
+GP_HD Wf16Strip wf16_next_strip(int i0, int m, int C)
+{
+    const int R = m - i0;
+    Wf16Strip s;
+    if (R > 512) { s.rows = (R - 512 >= C + 1) ? 512 : 256; s.last = false; }
+    else { s.rows = R <= 64 ? 64 : R <= 128 ? 128 : R <= 256 ? 256 : 512; s.last = true; }
+    s.rowscan = i0 + s.rows >= m - C;
+    return s;
 }
 
 #if defined(__CUDACC__)
 // ---- device side ------------------------------------------------------------------------------
+// Code size matters here: 16 warps per SM run different strip variants and phases at the same
+// time, and the first version of this kernel (everything inlined, 345 KB of SASS) spent most of
+// its cycles waiting for instructions.  The cold paths (exact scan, threshold set-up) are therefore
+// out-of-line functions taking their operands by value, and each strip variant has exactly one
+// generic loop body and one steady loop body.
 
 constexpr int WF16_THREADS = 256;
 
-// One strip of 64*K rows starting after table row `i0`.  bnd[j] (j = 1..n+1): low half V(i0, j),
-// bits 16-23 code11(column j); the low halves are replaced in place by the strip's last row.
-template <int K, bool SCAN_ALL>
-__device__ __forceinline__ long long wf16_strip(const uint32_t* __restrict__ packed, const PairDesc& pd,
-                                                const Wf16Pair& g, const Wf16Params& P, uint32_t* bnd,
-                                                int i0, bool store_bottom, long long best)
+struct Wf16Warp {                       // warp-uniform state of one pair
+    const uint32_t* packed;
+    PairDesc pd;
+    Wf16Pair g;
+    uint32_t* bnd;                      // boundary line: low half V(i0, j), bits 16-23 code11(column j)
+    int S;                              // best score so far (warp wide, refreshed per strip)
+};
+
+template <int K> struct WVals { uint32_t W[K]; };
+template <int K> struct FVals { uint32_t negthr[K], fstep[K]; };
+
+template <int K>
+__device__ __noinline__ long long wf16_scan_cold(WVals<K> v, Wf16Pair g, int itop, int j, long long best)
+{
+    Lane16<K> st;
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.W[k] = v.W[k];
+    return lane16_scan<K>(st, g, itop, j, best);
+}
+
+template <int K>
+__device__ __noinline__ FVals<K> wf16_filter_cold(Wf16Pair g, int itop, int jc, int mode)
+{
+    Lane16<K> st;
+    lane16_set_filter<K>(st, g, itop, jc, mode);
+    FVals<K> f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) { f.negthr[k] = st.negthr[k]; f.fstep[k] = st.fstep[k]; }
+    return f;
+}
+
+// One strip of 64*K rows starting after table row `i0`; with store_bottom the low halves of bnd[]
+// are replaced in place by the strip's last row.
+template <int K, bool ROWSCAN>
+__device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, int i0, bool store_bottom, long long best)
 {
     const int lane = threadIdx.x & 31;
+    const Wf16Pair g = w.g;
     const int itop = i0 + lane * 2 * K;
     Lane16<K> st;
     {
         uint32_t rcode[2 * K];
 #pragma unroll
-        for (int x = 0; x < 2 * K; ++x) rcode[x] = (itop + x < g.m) ? load_code(packed, pd.row_off, (uint32_t)(itop + x)) : 15u;
+        for (int x = 0; x < 2 * K; ++x) rcode[x] = (itop + x < g.m) ? load_code(w.packed, w.pd.row_off, (uint32_t)(itop + x)) : 15u;
         lane16_begin<K>(st, g, itop, rcode);
     }
+    auto set_filter = [&](int jc, int mode) {
+        const FVals<K> f = wf16_filter_cold<K>(g, itop, jc, mode);
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.negthr[k] = f.negthr[k]; st.fstep[k] = f.fstep[k]; }
+    };
+    set_filter(1, ROWSCAN ? FILTER_ROWS : FILTER_NONE);
+    {   // start from the warp's best score: fewer false alarms than each lane's own
+        int s = (int)(best >> 32);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { int other = __shfl_xor_sync(0xffffffffu, s, o); s = other > s ? other : s; }
+        w.S = s;
+    }
+    const int S0 = w.S;
+    uint32_t thrS = filter_thr(S0);
     uint32_t send = 0, chunk = 0;
     const int n = g.n;
     const int t_end = n + 1 + 62;                       // lane 31's lo group reaches column n+1
-    const int t_scan = SCAN_ALL ? 1 : (n - g.C > 1 ? n - g.C : 1);
-    uint16_t* bnd16 = reinterpret_cast<uint16_t*>(bnd);
-    for (int t = 1; t <= t_end; ++t) {
-        if (((t - 1) & 31) == 0) {
-            const int jj = t + lane;
+    const int jswitch = n - g.C > 1 ? n - g.C : 1;      // first candidate column
+    uint32_t* const bnd = w.bnd;
+    uint16_t* const bnd16 = reinterpret_cast<uint16_t*>(bnd);
+    const bool do_store = store_bottom && lane == 31;
+
+    // exact scan of this lane's cells (divergent: only lanes whose filter fired)
+    auto slow_path = [&](int j) {
+        WVals<K> v;
+#pragma unroll
+        for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
+        best = wf16_scan_cold<K>(v, g, itop, j, best);
+        const int s = (int)(best >> 32);
+        thrS = filter_thr(s > S0 ? s : S0);
+    };
+
+    // steady blocks: every lane active, no lane in the last C+1 columns yet
+    int t_steady1 = (jswitch > 65 ? jswitch : 65);      // first step at which some lane may be in the tail
+    t_steady1 = ((t_steady1 - 1) & ~31) + 1;
+    for (int tb = 1; tb <= t_end; tb += 32) {
+        {
+            const int jj = tb + lane;
             if (jj <= n + 1) chunk = bnd[jj];
         }
-        const uint32_t from_line = __shfl_sync(0xffffffffu, chunk, (t - 1) & 31);
-        uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1);
-        if (lane == 0) recv = from_line;
-        const int j = t - 2 * lane;                     // my lo column
-        if (j >= 1 && j <= n + 1) {
-            lane16_step<K>(st, recv, P, g.gup, g.gleft);
-            if (j == 1) lane16_fix_first<K>(st, g, itop);
-            send = lane16_send<K>(st);
-            if (store_bottom && lane == 31 && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
-            if (t >= t_scan) best = lane16_scan<K>(st, g, itop, j, best);
+        if (tb >= 65 && tb < t_steady1) {
+#pragma unroll 1
+            for (int s = 0; s < 32; ++s) {
+                const uint32_t from_line = __shfl_sync(0xffffffffu, chunk, s);
+                uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1);
+                if (lane == 0) recv = from_line;
+                lane16_step<K>(st, recv, P, g.gup, g.gleft);
+                send = lane16_send<K>(st);
+                const int j = tb + s - 2 * lane;
+                if (do_store) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
+                if (ROWSCAN) {
+                    if (filter_fired(lane16_filter<K>(st), thrS)) slow_path(j);
+                }
+            }
+        } else {
+            // generic steps: lanes may be idle, first-column fix-up, switch to the column filter
+            const int s_end = t_end - tb < 31 ? t_end - tb : 31;
+#pragma unroll 1
+            for (int s = 0; s <= s_end; ++s) {
+                const uint32_t from_line = __shfl_sync(0xffffffffu, chunk, s);
+                uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1);
+                if (lane == 0) recv = from_line;
+                const int j = tb + s - 2 * lane;        // my lo column
+                if (j >= 1 && j <= n + 1) {
+                    lane16_step<K>(st, recv, P, g.gup, g.gleft);
+                    if (j == 1) lane16_fix_first<K>(st, g, itop);
+                    send = lane16_send<K>(st);
+                    if (do_store && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
+                    if (j == jswitch) set_filter(j, FILTER_ALL);
+                    if (filter_fired(lane16_filter<K>(st), thrS)) slow_path(j);
+                }
+            }
         }
     }
     __syncwarp();
@@ -325,29 +496,38 @@ overlap_wf16_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restr
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t* bnd = scratch + (size_t)warp_global * scratch_stride;
+    Wf16Warp w;
+    w.packed = packed;
+    w.bnd = scratch + (size_t)warp_global * scratch_stride;
     for (;;) {
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(queue, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= n_work) break;
         const uint32_t pid = order[qi];
-        const PairDesc pd = pairs[pid];
-        const Wf16Pair g = wf16_make_pair((int)pd.m, (int)pd.n, P);
-        const int m = g.m, n = g.n;
+        w.pd = pairs[pid];
+        w.g = wf16_make_pair((int)w.pd.m, (int)w.pd.n, P);
+        const int m = w.g.m, n = w.g.n;
         // boundary line = table row 0, plus the column codes
         for (int j = 1 + lane; j <= n + 1; j += 32) {
-            uint32_t c = (j <= n) ? load_code(packed, pd.col_off, (uint32_t)(j - 1)) : 0u;
-            bnd[j] = g.v_row0(j <= n ? j : n) | (code11(c) << 16);
+            uint32_t c = (j <= n) ? load_code(packed, w.pd.col_off, (uint32_t)(j - 1)) : 0u;
+            w.bnd[j] = w.g.v_row0(j <= n ? j : n) | (code11(c) << 16);
         }
         __syncwarp();
         long long best = make_key(0, 0u, 1u | (n == 0 ? 2u : 0u));   // cell (0,n): rank 0, H = 0
-        const int m_fast = wf16_fast_rows(m, g.C);
+        w.S = 0;
         int i0 = 0;
-        while (m_fast - i0 >= 512) { best = wf16_strip<8, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 512; }
-        while (m_fast - i0 >= 128) { best = wf16_strip<2, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 128; }
-        while (m_fast - i0 >= 64)  { best = wf16_strip<1, false>(packed, pd, g, P, bnd, i0, true, best); i0 += 64; }
-        while (i0 < m)             { best = wf16_strip<1, true>(packed, pd, g, P, bnd, i0, i0 + 64 < m, best); i0 += 64; }
+        while (i0 < m) {
+            const Wf16Strip s = wf16_next_strip(i0, m, w.g.C);
+            const bool sb = !s.last;
+            switch (s.rows) {
+            case 512: best = s.rowscan ? wf16_strip<8, true>(w, P, i0, sb, best) : wf16_strip<8, false>(w, P, i0, sb, best); break;
+            case 256: best = s.rowscan ? wf16_strip<4, true>(w, P, i0, sb, best) : wf16_strip<4, false>(w, P, i0, sb, best); break;
+            case 128: best = wf16_strip<2, true>(w, P, i0, sb, best); break;
+            default:  best = wf16_strip<1, true>(w, P, i0, sb, best); break;
+            }
+            i0 += s.rows;
+        }
         best = warp_max_key(best);
         if (lane == 0) store_result(out + pid, best, m, n, FLAG_KERNEL16);
         __syncwarp();

@@ -11,45 +11,99 @@
 
 using namespace gp;
 
+// instrumentation for tuning the candidate filter (slow-path calls, steps, threshold refreshes)
+static long g_slow_calls = 0, g_steps = 0, g_s_changes = 0;
+extern "C" void wf16_emulate_counters(long* out)
+{
+    out[0] = g_slow_calls; out[1] = g_steps; out[2] = g_s_changes;
+    g_slow_calls = g_steps = g_s_changes = 0;
+}
+
 namespace {
 
 struct HostPair {
     std::vector<uint8_t> row, col;   // 4-bit codes
 };
 
-template <int K, bool SCAN_ALL>
-long long strip_host(const HostPair& hp, const Wf16Pair& g, const Wf16Params& P, std::vector<uint32_t>& bnd,
-                     int i0, bool store_bottom, long long lane_best[32])
+struct HostWarp {
+    const HostPair* hp;
+    Wf16Pair g;
+    std::vector<uint32_t>* bnd;
+    int S;
+};
+
+template <int K, bool LAST, bool ROWSCAN>
+void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32])
 {
+    const Wf16Pair& g = w.g;
+    const HostPair& hp = *w.hp;
+    std::vector<uint32_t>& bnd = *w.bnd;
     Lane16<K> st[32];
     uint32_t send[32];
+    int mode[32];
     for (int lane = 0; lane < 32; ++lane) {
+        const int itop = i0 + lane * 2 * K;
         uint32_t rcode[2 * K];
-        for (int x = 0; x < 2 * K; ++x) { int idx = i0 + lane * 2 * K + x; rcode[x] = idx < g.m ? hp.row[idx] : 15u; }
-        lane16_begin<K>(st[lane], g, i0 + lane * 2 * K, rcode);
+        for (int x = 0; x < 2 * K; ++x) { int idx = itop + x; rcode[x] = idx < g.m ? hp.row[idx] : 15u; }
+        lane16_begin<K>(st[lane], g, itop, rcode);
+        mode[lane] = ROWSCAN ? FILTER_ROWS : FILTER_NONE;
+        lane16_set_filter<K>(st[lane], g, itop, 1, mode[lane]);
         send[lane] = 0;
     }
+    {
+        int s = -1000000000;
+        for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); s = sc > s ? sc : s; }
+        w.S = s;
+    }
+    uint32_t thrS[32];
+    for (int lane = 0; lane < 32; ++lane) thrS[lane] = filter_thr(w.S);
     const int n = g.n;
     const int t_end = n + 1 + 62;
-    const int t_scan = SCAN_ALL ? 1 : (n - g.C > 1 ? n - g.C : 1);
+    g_steps += t_end;
+    const int jswitch = n - g.C > 1 ? n - g.C : 1;
     uint16_t* bnd16 = reinterpret_cast<uint16_t*>(bnd.data());
-    for (int t = 1; t <= t_end; ++t) {
+
+    auto slow_path = [&](int lane, int j) {
+        ++g_slow_calls;
+        const int itop = i0 + lane * 2 * K;
+        lane_best[lane] = lane16_scan<K>(st[lane], g, itop, j, lane_best[lane]);
+        const int s = (int)(lane_best[lane] >> 32);
+        thrS[lane] = filter_thr(s > w.S ? s : w.S);
+    };
+    auto generic_step = [&](int t) {
         uint32_t recv[32];
-        for (int lane = 0; lane < 32; ++lane)
-            recv[lane] = lane == 0 ? (t <= n + 1 ? bnd[t] : 0u) : send[lane - 1];
+        for (int lane = 0; lane < 32; ++lane) recv[lane] = lane == 0 ? (t <= n + 1 ? bnd[t] : 0u) : send[lane - 1];
         for (int lane = 0; lane < 32; ++lane) {
-            const int itop = i0 + lane * 2 * K;
-            const int j = t - 2 * lane;
+            const int itop = i0 + lane * 2 * K, j = t - 2 * lane;
             if (j >= 1 && j <= n + 1) {
                 lane16_step<K>(st[lane], recv[lane], P, g.gup, g.gleft);
                 if (j == 1) lane16_fix_first<K>(st[lane], g, itop);
                 send[lane] = lane16_send<K>(st[lane]);
-                if (store_bottom && lane == 31 && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
-                if (t >= t_scan) lane_best[lane] = lane16_scan<K>(st[lane], g, itop, j, lane_best[lane]);
+                if (!LAST && lane == 31 && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
+                if (j == jswitch) { mode[lane] = FILTER_ALL; lane16_set_filter<K>(st[lane], g, itop, j, mode[lane]); }
+                if (filter_fired(lane16_filter<K>(st[lane]), thrS[lane])) slow_path(lane, j);
+            }
+        }
+    };
+    const int t_steady0 = 65;
+    int t_steady1 = (jswitch > 65 ? jswitch : 65);
+    t_steady1 = ((t_steady1 - 1) & ~31) + 1;
+    int t = 1;
+    for (; t <= t_end && t < t_steady0; ++t) generic_step(t);
+    for (; t < t_steady1; t += 32) {
+        for (int s = 0; s < 32; ++s) {
+            uint32_t recv[32];
+            for (int lane = 0; lane < 32; ++lane) recv[lane] = lane == 0 ? bnd[t + s] : send[lane - 1];
+            for (int lane = 0; lane < 32; ++lane) {
+                lane16_step<K>(st[lane], recv[lane], P, g.gup, g.gleft);
+                send[lane] = lane16_send<K>(st[lane]);
+                const int j = t + s - 2 * lane;
+                if (!LAST && lane == 31) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
+                if (ROWSCAN) { if (filter_fired(lane16_filter<K>(st[lane]), thrS[lane])) slow_path(lane, j); }
             }
         }
     }
-    return 0;
+    for (; t <= t_end; ++t) generic_step(t);
 }
 
 } // namespace
@@ -72,12 +126,23 @@ extern "C" int wf16_emulate(const uint8_t* row_codes, int m, const uint8_t* col_
     }
     long long lane_best[32];
     for (int l = 0; l < 32; ++l) lane_best[l] = make_key(0, 0u, 1u | (n == 0 ? 2u : 0u));
-    const int m_fast = wf16_fast_rows(m, g.C);
+    HostWarp w{&hp, g, &bnd, 0};
     int i0 = 0;
-    while (m_fast - i0 >= 512) { strip_host<8, false>(hp, g, P, bnd, i0, true, lane_best); i0 += 512; }
-    while (m_fast - i0 >= 128) { strip_host<2, false>(hp, g, P, bnd, i0, true, lane_best); i0 += 128; }
-    while (m_fast - i0 >= 64)  { strip_host<1, false>(hp, g, P, bnd, i0, true, lane_best); i0 += 64; }
-    while (i0 < m)             { strip_host<1, true>(hp, g, P, bnd, i0, i0 + 64 < m, lane_best); i0 += 64; }
+    while (i0 < m) {
+        const Wf16Strip st = wf16_next_strip(i0, m, g.C);
+        if (!st.last) {
+            if (st.rows == 512) { if (st.rowscan) strip_host<8, false, true>(w, P, i0, lane_best); else strip_host<8, false, false>(w, P, i0, lane_best); }
+            else                { if (st.rowscan) strip_host<4, false, true>(w, P, i0, lane_best); else strip_host<4, false, false>(w, P, i0, lane_best); }
+        } else {
+            switch (st.rows) {
+            case 64:  strip_host<1, true, true>(w, P, i0, lane_best); break;
+            case 128: strip_host<2, true, true>(w, P, i0, lane_best); break;
+            case 256: strip_host<4, true, true>(w, P, i0, lane_best); break;
+            default:  strip_host<8, true, true>(w, P, i0, lane_best); break;
+            }
+        }
+        i0 += st.rows;
+    }
     long long best = lane_best[0];
     for (int l = 1; l < 32; ++l) best = lane_best[l] > best ? lane_best[l] : best;
     DevResult r;

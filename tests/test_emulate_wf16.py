@@ -76,3 +76,14 @@ def test_random_pairs(emu, seed, maxlen, iters):
         clip = rng.choice([50, 50, 0, 3, 10])
         mm, ind = rng.choice([(-2, -2), (-2, -2), (-1, -1), (-3, -2), (0, -1), (-5, -3), (1, -1), (-15, -14)])
         assert emu(a, b, mm, ind, clip) == _want(a, b, mm, ind, clip), (len(a), len(b), clip, mm, ind)
+
+
+@pytest.mark.parametrize("la,ov,extra", [(2700, 2500, 150), (4094, 4000, 200), (2000, 1990, 2200)])
+def test_long_overlaps_both_potentials(emu, la, ov, extra):
+    """High-scoring suffix/prefix overlaps that end in the last rows but not the last columns (and the
+    transposed case): exercises the row filter under the drifting column potential."""
+    rng = random.Random(la)
+    a = bytes(rng.choice(b"ACGT") for _ in range(la))
+    b = a[-ov:] + bytes(rng.choice(b"ACGT") for _ in range(extra))
+    for x, y in ((a, b), (b, a)):
+        assert emu(x, y) == _want(x, y)

@@ -120,3 +120,20 @@ def test_cfg1_gap_candidates_full_size(ctx):
     pairs = [(int(p["row_seq"]), int(p["col_seq"])) for p in cand]
     assert len(pairs) > 100
     _check(ctx, nodes, pairs)
+
+
+def test_long_overlaps_both_potentials(ctx):
+    """Suffix/prefix overlaps of 1400-4000 bases ending in the last rows but not the last columns, and
+    transposed; lengths up to the 16-bit kernel's limit (min(m,n) = 4094) and just beyond it."""
+    rng = random.Random(77)
+    seqs = []
+    for la, ov, extra in [(2700, 2500, 150), (3000, 2900, 60), (4094, 4000, 200), (2000, 1990, 2200), (1500, 1400, 3000), (4200, 4100, 300)]:
+        a = _rand(rng, la)
+        seqs += [a, a[-ov:] + _rand(rng, extra)]
+    pairs = []
+    for k in range(0, len(seqs), 2):
+        pairs += [(k, k + 1), (k + 1, k), (k, k), (k + 1, k + 1)]
+    res = _check(ctx, seqs, pairs)
+    from gappadder_b200.capi import FLAG_KERNEL16
+    # 17 of the 24 pairs have min(m,n) <= 4094 and go through the 16-bit kernel, 7 through the general one
+    assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 17
