@@ -175,7 +175,7 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
 
     const uint32_t n_seq = (uint32_t)c->seq_len.size();
     const bool params16 = gp::wf16_params_ok(params->mismatch, params->indel) && c->n_symbols <= 8;
-    if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip);
+    if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip, c->n_symbols <= 4);
 
     // stage: [PairDesc n][order16 n][order32 n]
     const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);

@@ -36,7 +36,7 @@ int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t
     for (int i = 0; i < 256; ++i) code[i] = -1;
     code[(unsigned char)'A'] = 0; code[(unsigned char)'C'] = 1;
     code[(unsigned char)'G'] = 2; code[(unsigned char)'T'] = 3; code[(unsigned char)'N'] = 4;
-    int next = 5;
+    int next = 5, max_code = -1;
     size_t off = 0;
     for (uint32_t s = 0; s < n_seq; ++s) {
         const unsigned char *p = (const unsigned char *)seqs[s];
@@ -54,6 +54,7 @@ int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t
                     if (next >= 16) return GP_ERR_ALPHABET;
                     c = code[p[i]] = (int16_t)next++;
                 }
+                if (c > max_code) max_code = c;
                 word |= (uint32_t)c << (4 * k);
             }
             dst[w] = word;
@@ -61,8 +62,8 @@ int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t
         off += nw;
         if (off > 0xffffffffull) return GP_ERR_RANGE;
     }
-    // ACGT+N always count: their codes are fixed
-    if (n_symbols) *n_symbols = (uint32_t)next;
+    // highest code in use + 1: 4 for plain ACGT input, 5 with N, more with other letters
+    if (n_symbols) *n_symbols = (uint32_t)(max_code + 1);
     return GP_OK;
 }
 

@@ -115,7 +115,10 @@ constexpr uint32_t WF16_MAX_MIN_LEN = 4094;       // 8*(P+1)+7 <= 32767
 constexpr uint32_t TAG_Z2 = 0x00040004u;
 
 struct Wf16Params {
-    uint32_t tbl_lo, tbl_hi;     // PRMT table: byte 0 = diagonal increment on match, bytes 1..7 on mismatch
+    uint32_t tbl_lo, tbl_hi;     // PRMT table of diagonal increments, indexed by the selector nibble (see addsel)
+    uint32_t addsel;             // 1: <= 4 symbols, selector = row code + (4 - column code) % 4 (match at 0 and 4),
+                                 //    formed with VIADD.16x2 (FMA-side pipe); 0: <= 8 symbols, selector = row ^ column
+                                 //    (match at 0), formed with LOP3 (ALU pipe)
     uint32_t gup_row, gleft_row; // packed up/left increments under the row potential
     uint32_t gup_col, gleft_col; // ... under the column potential
     int32_t max_clip;
@@ -132,13 +135,14 @@ inline bool wf16_pair_ok(uint32_t m, uint32_t n)
     return m >= 1 && n >= 1 && (m < n ? m : n) <= WF16_MAX_MIN_LEN && m <= 0xffffff && n <= 0xffffff;
 }
 
-inline Wf16Params wf16_make_params(int mismatch, int indel, int max_clip)
+inline Wf16Params wf16_make_params(int mismatch, int indel, int max_clip, bool addsel)
 {
     Wf16Params p;
     const uint32_t inc_match = (uint32_t)(0 * 8 + 4) & 0xff;                 // +1 - 1, z bonus
     const uint32_t inc_mism = (uint32_t)((mismatch - 1) * 8 + 4) & 0xff;     // X - 1, z bonus
     p.tbl_lo = inc_match | (inc_mism << 8) | (inc_mism << 16) | (inc_mism << 24);
-    p.tbl_hi = inc_mism * 0x01010101u;
+    p.tbl_hi = (addsel ? inc_match : inc_mism) | (inc_mism << 8) | (inc_mism << 16) | (inc_mism << 24);
+    p.addsel = addsel ? 1u : 0u;
     auto pk = [](int v) { uint32_t h = (uint32_t)(v * 8) & 0xffffu; return h | (h << 16); };
     p.gup_row = pk(indel - 1); p.gleft_row = pk(indel);
     p.gup_col = pk(indel);     p.gleft_col = pk(indel - 1);
@@ -172,8 +176,9 @@ GP_HD Wf16Pair wf16_make_pair(int m, int n, const Wf16Params& P)
     return g;
 }
 
-// code11 of a base code: the code in both nibbles of a byte (PRMT selector for a low/high byte pair)
-GP_HD uint32_t code11(uint32_t c) { return (c & 7u) * 0x11u; }
+// code11 of a column base code: the selector contribution in both nibbles of a byte (PRMT selectors
+// for the low and the high byte of one 16-bit increment)
+GP_HD uint32_t code11(uint32_t c, uint32_t addsel) { return (addsel ? ((4u - c) & 3u) : (c & 7u)) * 0x11u; }
 
 // ---- per-lane state and arithmetic ------------------------------------------------------------
 template <int K>
@@ -196,7 +201,7 @@ GP_HD void lane16_begin(Lane16<K>& st, const Wf16Pair& g, int itop, const uint32
     for (int k = 0; k < K; ++k) {
         const int ilo = itop + 1 + k, ihi = itop + 1 + K + k;
         st.W[k] = g.v_col0(ilo) | (g.v_col0(ihi) << 16);
-        const uint32_t rlo = rcode[k] & 15u, rhi = rcode[K + k] & 15u;
+        const uint32_t rlo = rcode[k] & 7u, rhi = rcode[K + k] & 7u;     // rows beyond the sequence: any code
         st.Rk[k] = (rlo * 0x11u | 0x80u) | ((rhi * 0x11u | 0x80u) << 8);
     }
     st.cvec = 0;
@@ -214,10 +219,10 @@ GP_HD void lane16_fix_first(Lane16<K>& st, const Wf16Pair& g, int itop)
 
 // One step: the lo group advances to column j, the hi group to column j-1.
 // recv: bits 0-15 V(row above the lane, column j), bits 16-23 code11(column j).
-template <int K>
+template <int K, bool ADDSEL>
 GP_HD void lane16_step(Lane16<K>& st, uint32_t recv, const Wf16Params& P, uint32_t gup, uint32_t gleft)
 {
-    st.cvec = (st.cvec << 8) | ((recv >> 16) & 0xffu);
+    st.cvec = p_prmt(recv, st.cvec, 0x6542u);                  // (recv.b2, cvec.b0, cvec.b1, cvec.b2)
     const uint32_t up0 = p_prmt(recv, st.W[K - 1], 0x5410u);   // (recv.lo16 , old W[K-1].lo16)
     uint32_t diag = st.up0_prev;
     st.up0_prev = up0;
@@ -225,7 +230,7 @@ GP_HD void lane16_step(Lane16<K>& st, uint32_t recv, const Wf16Params& P, uint32
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t left = st.W[k];
-        const uint32_t inc = p_prmt(P.tbl_lo, P.tbl_hi, st.Rk[k] ^ st.cvec);
+        const uint32_t inc = p_prmt(P.tbl_lo, P.tbl_hi, ADDSEL ? p_add2(st.Rk[k], st.cvec) : (st.Rk[k] ^ st.cvec));
         const uint32_t d = p_add2(diag, inc);                  // carries the z bonus
         const uint32_t l = p_add2(left, gleft);
         const uint32_t t = p_max2(d, l);
@@ -397,7 +402,7 @@ __device__ __noinline__ FVals<K> wf16_filter_cold(Wf16Pair g, int itop, int jc, 
 
 // One strip of 64*K rows starting after table row `i0`; with store_bottom the low halves of bnd[]
 // are replaced in place by the strip's last row.
-template <int K, bool ROWSCAN>
+template <int K, bool ROWSCAN, bool ADDSEL>
 __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, int i0, bool store_bottom, long long best)
 {
     const int lane = threadIdx.x & 31;
@@ -407,7 +412,7 @@ __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, i
     {
         uint32_t rcode[2 * K];
 #pragma unroll
-        for (int x = 0; x < 2 * K; ++x) rcode[x] = (itop + x < g.m) ? load_code(w.packed, w.pd.row_off, (uint32_t)(itop + x)) : 15u;
+        for (int x = 0; x < 2 * K; ++x) rcode[x] = (itop + x < g.m) ? load_code(w.packed, w.pd.row_off, (uint32_t)(itop + x)) : 0u;
         lane16_begin<K>(st, g, itop, rcode);
     }
     auto set_filter = [&](int jc, int mode) {
@@ -431,6 +436,7 @@ __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, i
     uint32_t* const bnd = w.bnd;
     uint16_t* const bnd16 = reinterpret_cast<uint16_t*>(bnd);
     const bool do_store = store_bottom && lane == 31;
+    bool filtering = ROWSCAN;                           // per lane: any threshold armed
 
     // exact scan of this lane's cells (divergent: only lanes whose filter fired)
     auto slow_path = [&](int j) {
@@ -456,7 +462,7 @@ __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, i
                 const uint32_t from_line = __shfl_sync(0xffffffffu, chunk, s);
                 uint32_t recv = __shfl_up_sync(0xffffffffu, send, 1);
                 if (lane == 0) recv = from_line;
-                lane16_step<K>(st, recv, P, g.gup, g.gleft);
+                lane16_step<K, ADDSEL>(st, recv, P, g.gup, g.gleft);
                 send = lane16_send<K>(st);
                 const int j = tb + s - 2 * lane;
                 if (do_store) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
@@ -474,12 +480,14 @@ __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, i
                 if (lane == 0) recv = from_line;
                 const int j = tb + s - 2 * lane;        // my lo column
                 if (j >= 1 && j <= n + 1) {
-                    lane16_step<K>(st, recv, P, g.gup, g.gleft);
+                    lane16_step<K, ADDSEL>(st, recv, P, g.gup, g.gleft);
                     if (j == 1) lane16_fix_first<K>(st, g, itop);
                     send = lane16_send<K>(st);
                     if (do_store && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st.W[K - 1] >> 16);
-                    if (j == jswitch) set_filter(j, FILTER_ALL);
-                    if (filter_fired(lane16_filter<K>(st), thrS)) slow_path(j);
+                    if (j == jswitch) { set_filter(j, FILTER_ALL); filtering = true; }
+                    if (filtering) {
+                        if (filter_fired(lane16_filter<K>(st), thrS)) slow_path(j);
+                    }
                 }
             }
         }
@@ -488,6 +496,7 @@ __device__ __noinline__ long long wf16_strip(Wf16Warp& w, const Wf16Params& P, i
     return best;
 }
 
+template <bool ADDSEL>
 __global__ void __launch_bounds__(WF16_THREADS)
 overlap_wf16_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                     const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
@@ -511,7 +520,7 @@ overlap_wf16_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restr
         // boundary line = table row 0, plus the column codes
         for (int j = 1 + lane; j <= n + 1; j += 32) {
             uint32_t c = (j <= n) ? load_code(packed, w.pd.col_off, (uint32_t)(j - 1)) : 0u;
-            w.bnd[j] = w.g.v_row0(j <= n ? j : n) | (code11(c) << 16);
+            w.bnd[j] = w.g.v_row0(j <= n ? j : n) | (code11(c, ADDSEL ? 1u : 0u) << 16);
         }
         __syncwarp();
         long long best = make_key(0, 0u, 1u | (n == 0 ? 2u : 0u));   // cell (0,n): rank 0, H = 0
@@ -521,10 +530,10 @@ overlap_wf16_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restr
             const Wf16Strip s = wf16_next_strip(i0, m, w.g.C);
             const bool sb = !s.last;
             switch (s.rows) {
-            case 512: best = s.rowscan ? wf16_strip<8, true>(w, P, i0, sb, best) : wf16_strip<8, false>(w, P, i0, sb, best); break;
-            case 256: best = s.rowscan ? wf16_strip<4, true>(w, P, i0, sb, best) : wf16_strip<4, false>(w, P, i0, sb, best); break;
-            case 128: best = wf16_strip<2, true>(w, P, i0, sb, best); break;
-            default:  best = wf16_strip<1, true>(w, P, i0, sb, best); break;
+            case 512: best = s.rowscan ? wf16_strip<8, true, ADDSEL>(w, P, i0, sb, best) : wf16_strip<8, false, ADDSEL>(w, P, i0, sb, best); break;
+            case 256: best = s.rowscan ? wf16_strip<4, true, ADDSEL>(w, P, i0, sb, best) : wf16_strip<4, false, ADDSEL>(w, P, i0, sb, best); break;
+            case 128: best = wf16_strip<2, true, ADDSEL>(w, P, i0, sb, best); break;
+            default:  best = wf16_strip<1, true, ADDSEL>(w, P, i0, sb, best); break;
             }
             i0 += s.rows;
         }
@@ -552,8 +561,12 @@ inline int wf16_launch(cudaStream_t stream, int sm_count, const uint32_t* packed
         if (e != cudaSuccess) return (int)e;
         *scratch_cap = need;
     }
-    overlap_wf16_kernel<<<blocks, WF16_THREADS, 0, stream>>>(packed, pairs, order, n_work, queue, P,
-                                                             (uint32_t*)*scratch, stride, out);
+    if (P.addsel)
+        overlap_wf16_kernel<true><<<blocks, WF16_THREADS, 0, stream>>>(packed, pairs, order, n_work, queue, P,
+                                                                       (uint32_t*)*scratch, stride, out);
+    else
+        overlap_wf16_kernel<false><<<blocks, WF16_THREADS, 0, stream>>>(packed, pairs, order, n_work, queue, P,
+                                                                        (uint32_t*)*scratch, stride, out);
     return (int)cudaGetLastError();
 }
 #endif // __CUDACC__

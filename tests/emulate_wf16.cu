@@ -32,7 +32,7 @@ struct HostWarp {
     int S;
 };
 
-template <int K, bool LAST, bool ROWSCAN>
+template <int K, bool LAST, bool ROWSCAN, bool ADDSEL>
 void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32])
 {
     const Wf16Pair& g = w.g;
@@ -44,7 +44,7 @@ void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32
     for (int lane = 0; lane < 32; ++lane) {
         const int itop = i0 + lane * 2 * K;
         uint32_t rcode[2 * K];
-        for (int x = 0; x < 2 * K; ++x) { int idx = itop + x; rcode[x] = idx < g.m ? hp.row[idx] : 15u; }
+        for (int x = 0; x < 2 * K; ++x) { int idx = itop + x; rcode[x] = idx < g.m ? hp.row[idx] : 0u; }
         lane16_begin<K>(st[lane], g, itop, rcode);
         mode[lane] = ROWSCAN ? FILTER_ROWS : FILTER_NONE;
         lane16_set_filter<K>(st[lane], g, itop, 1, mode[lane]);
@@ -76,12 +76,14 @@ void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32
         for (int lane = 0; lane < 32; ++lane) {
             const int itop = i0 + lane * 2 * K, j = t - 2 * lane;
             if (j >= 1 && j <= n + 1) {
-                lane16_step<K>(st[lane], recv[lane], P, g.gup, g.gleft);
+                lane16_step<K, ADDSEL>(st[lane], recv[lane], P, g.gup, g.gleft);
                 if (j == 1) lane16_fix_first<K>(st[lane], g, itop);
                 send[lane] = lane16_send<K>(st[lane]);
                 if (!LAST && lane == 31 && j >= 2) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
                 if (j == jswitch) { mode[lane] = FILTER_ALL; lane16_set_filter<K>(st[lane], g, itop, j, mode[lane]); }
-                if (filter_fired(lane16_filter<K>(st[lane]), thrS[lane])) slow_path(lane, j);
+                if (mode[lane] != FILTER_NONE) {
+                    if (filter_fired(lane16_filter<K>(st[lane]), thrS[lane])) slow_path(lane, j);
+                }
             }
         }
     };
@@ -95,7 +97,7 @@ void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32
             uint32_t recv[32];
             for (int lane = 0; lane < 32; ++lane) recv[lane] = lane == 0 ? bnd[t + s] : send[lane - 1];
             for (int lane = 0; lane < 32; ++lane) {
-                lane16_step<K>(st[lane], recv[lane], P, g.gup, g.gleft);
+                lane16_step<K, ADDSEL>(st[lane], recv[lane], P, g.gup, g.gleft);
                 send[lane] = lane16_send<K>(st[lane]);
                 const int j = t + s - 2 * lane;
                 if (!LAST && lane == 31) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
@@ -108,13 +110,37 @@ void strip_host(HostWarp& w, const Wf16Params& P, int i0, long long lane_best[32
 
 } // namespace
 
+template <bool ADDSEL>
+static void run_pair(const HostPair& hp, const Wf16Pair& g, const Wf16Params& P, std::vector<uint32_t>& bnd, long long lane_best[32])
+{
+    const int m = g.m;
+    HostWarp w{&hp, g, &bnd, 0};
+    int i0 = 0;
+    while (i0 < m) {
+        const Wf16Strip st = wf16_next_strip(i0, m, g.C);
+        if (!st.last) {
+            if (st.rows == 512) { if (st.rowscan) strip_host<8, false, true, ADDSEL>(w, P, i0, lane_best); else strip_host<8, false, false, ADDSEL>(w, P, i0, lane_best); }
+            else                { if (st.rowscan) strip_host<4, false, true, ADDSEL>(w, P, i0, lane_best); else strip_host<4, false, false, ADDSEL>(w, P, i0, lane_best); }
+        } else {
+            switch (st.rows) {
+            case 64:  strip_host<1, true, true, ADDSEL>(w, P, i0, lane_best); break;
+            case 128: strip_host<2, true, true, ADDSEL>(w, P, i0, lane_best); break;
+            case 256: strip_host<4, true, true, ADDSEL>(w, P, i0, lane_best); break;
+            default:  strip_host<8, true, true, ADDSEL>(w, P, i0, lane_best); break;
+            }
+        }
+        i0 += st.rows;
+    }
+}
+
 // out: score, row_end, col_end, nclip, flags.  Returns 0, or -1 when the pair is outside the
-// 16-bit kernel's domain (the library would route it to the 32-bit kernel).
+// 16-bit kernel's domain (the library would route it to the 32-bit kernel).  addsel selects the
+// <= 4-symbol selector variant (codes must be 0..3).
 extern "C" int wf16_emulate(const uint8_t* row_codes, int m, const uint8_t* col_codes, int n,
-                            int mismatch, int indel, int max_clip, int32_t* out)
+                            int mismatch, int indel, int max_clip, int addsel, int32_t* out)
 {
     if (!wf16_params_ok(mismatch, indel) || !wf16_pair_ok((uint32_t)m, (uint32_t)n)) return -1;
-    const Wf16Params P = wf16_make_params(mismatch, indel, max_clip);
+    const Wf16Params P = wf16_make_params(mismatch, indel, max_clip, addsel != 0);
     const Wf16Pair g = wf16_make_pair(m, n, P);
     HostPair hp;
     hp.row.assign(row_codes, row_codes + m);
@@ -122,27 +148,11 @@ extern "C" int wf16_emulate(const uint8_t* row_codes, int m, const uint8_t* col_
     std::vector<uint32_t> bnd((size_t)n + 66, 0u);
     for (int j = 1; j <= n + 1; ++j) {
         uint32_t c = j <= n ? hp.col[j - 1] : 0u;
-        bnd[j] = g.v_row0(j <= n ? j : n) | (code11(c) << 16);
+        bnd[j] = g.v_row0(j <= n ? j : n) | (code11(c, P.addsel) << 16);
     }
     long long lane_best[32];
     for (int l = 0; l < 32; ++l) lane_best[l] = make_key(0, 0u, 1u | (n == 0 ? 2u : 0u));
-    HostWarp w{&hp, g, &bnd, 0};
-    int i0 = 0;
-    while (i0 < m) {
-        const Wf16Strip st = wf16_next_strip(i0, m, g.C);
-        if (!st.last) {
-            if (st.rows == 512) { if (st.rowscan) strip_host<8, false, true>(w, P, i0, lane_best); else strip_host<8, false, false>(w, P, i0, lane_best); }
-            else                { if (st.rowscan) strip_host<4, false, true>(w, P, i0, lane_best); else strip_host<4, false, false>(w, P, i0, lane_best); }
-        } else {
-            switch (st.rows) {
-            case 64:  strip_host<1, true, true>(w, P, i0, lane_best); break;
-            case 128: strip_host<2, true, true>(w, P, i0, lane_best); break;
-            case 256: strip_host<4, true, true>(w, P, i0, lane_best); break;
-            default:  strip_host<8, true, true>(w, P, i0, lane_best); break;
-            }
-        }
-        i0 += st.rows;
-    }
+    if (addsel) run_pair<true>(hp, g, P, bnd, lane_best); else run_pair<false>(hp, g, P, bnd, lane_best);
     long long best = lane_best[0];
     for (int l = 1; l < 32; ++l) best = lane_best[l] > best ? lane_best[l] : best;
     DevResult r;

@@ -28,14 +28,19 @@ def emu():
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
-    L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
 
     def run(a, b, mm=-2, ind=-2, clip=50):
-        out = (C.c_int32 * 5)()
-        rc = L.wf16_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out)
-        assert rc == 0
-        f = out[4]
-        return (out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1)
+        res = []
+        four = b"N" not in a and b"N" not in b
+        for addsel in ((0, 1) if four else (0,)):      # both selector variants must agree
+            out = (C.c_int32 * 5)()
+            rc = L.wf16_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, addsel, out)
+            assert rc == 0
+            f = out[4]
+            res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
+        assert len(set(res)) == 1, res
+        return res[0]
     return run
 
 
