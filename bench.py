@@ -72,6 +72,24 @@ def build_workload(n_gaps: int, first_seed: int, config: str = "cfg1"):
     return seqs, pairs, cells, per_gap
 
 
+def rank_first_seed(first_seed: int, rank: int, gaps_per_rank: int) -> int:
+    """Weak scaling: rank r works on gaps seeded first_seed + r*gaps .. first_seed + (r+1)*gaps - 1."""
+    return first_seed + rank * gaps_per_rank
+
+
+def reduce_over_ranks(dist, device, cells: int, gaps: int, my_ms: float, my_e2e_ms: float):
+    """Whole-job totals: units summed over ranks, time = max over ranks (no collective on the data path;
+    this is the only communication in the benchmark).  dist=None for a single process."""
+    if dist is None:
+        return cells, gaps, my_ms, my_e2e_ms
+    import torch
+    t = torch.tensor([float(cells), float(gaps)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    mx = torch.tensor([my_ms, my_e2e_ms], dtype=torch.float64, device=device)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return int(t[0].item()), int(t[1].item()), float(mx[0].item()), float(mx[1].item())
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -238,7 +256,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
 
     ctx = g.Context(local_rank)                 # fails loudly without the CUDA library / a B200
-    seqs, pairs, cells, per_gap = build_workload(args.gaps, args.seed + rank * args.gaps)
+    seqs, pairs, cells, per_gap = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps))
     packed, off, lens, nsym = g.pack_sequences(seqs)
     ctx.set_sequences(packed, off, lens, nsym)
     ctx.upload_pairs(pairs, g.GAPPADDER_DP)
@@ -291,14 +309,7 @@ def run_gpu(args):
     checksum = int(res["score"].astype(np.int64).sum()) if res is not None and len(res) else 0
 
     # --- reduce over ranks ---------------------------------------------------------------------
-    tot_cells, tot_gaps, max_ms, max_e2e_ms = cells, args.gaps, my_ms, my_e2e_ms
-    if dist is not None:
-        t = torch.tensor([float(cells), float(args.gaps)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        mx = torch.tensor([my_ms, my_e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        tot_cells, tot_gaps = int(t[0].item()), int(t[1].item())
-        max_ms, max_e2e_ms = float(mx[0].item()), float(mx[1].item())
+    tot_cells, tot_gaps, max_ms, max_e2e_ms = reduce_over_ranks(dist, dev, cells, args.gaps, my_ms, my_e2e_ms)
 
     if rank == 0:
         value = tot_cells / (max_ms * 1e-3) / 1e9

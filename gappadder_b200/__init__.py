@@ -8,6 +8,6 @@ creating a context fails when no sm_100 device is present.
 """
 from .capi import (  # noqa: F401
     GpError, Context, DpParams, Thresholds, Pair, Result, lib, lib_path,
-    pack_sequences, candidate_pairs, revcomp, is_score_significant, merged_concat,
+    pack_sequences, candidate_pairs, revcomp, estimate_gap_cells, partition_gaps, is_score_significant, merged_concat,
     GAPPADDER_DP, gappadder_thresholds,
 )

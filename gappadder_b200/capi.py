@@ -17,6 +17,7 @@ EXPORTS = [
     "gp_upload_pairs", "gp_launch_resident", "gp_fetch_results", "gp_kernel_launches", "gp_pair_stats",
     "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
+    "gp_estimate_gap_cells", "gp_partition_gaps",
 ]
 
 
@@ -99,6 +100,9 @@ def lib() -> C.CDLL:
         L.gp_revcomp.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p]
         L.gp_revcomp.restype = None
         L.gp_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.gp_estimate_gap_cells.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_estimate_gap_cells.restype = C.c_uint64
+        L.gp_partition_gaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -134,6 +138,21 @@ def candidate_pairs(nodes: Sequence[bytes], k: int = 10) -> np.ndarray:
     if cnt < 0:
         raise GpError(int(cnt), "gp_candidate_pairs")
     return out[:cnt]
+
+
+def estimate_gap_cells(contig_lens) -> int:
+    a = np.ascontiguousarray(contig_lens, dtype=np.uint32)
+    return int(lib().gp_estimate_gap_cells(a.ctypes.data, len(a)))
+
+
+def partition_gaps(costs, n_parts: int) -> np.ndarray:
+    """Longest-processing-time assignment of gaps to n_parts GPUs -> part index per gap."""
+    c = np.ascontiguousarray(costs, dtype=np.uint64)
+    part = np.zeros(len(c), dtype=np.int32)
+    rc = lib().gp_partition_gaps(c.ctypes.data, len(c), n_parts, part.ctypes.data)
+    if rc != 0:
+        raise GpError(rc, "gp_partition_gaps")
+    return part
 
 
 def revcomp(s: bytes) -> bytes:

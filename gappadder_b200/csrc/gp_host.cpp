@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <numeric>
 #include <vector>
 
 extern "C" {
@@ -185,19 +186,21 @@ int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, u
 {
     const uint32_t lenContigLen = 30;                                   // :2024
     if (k <= 0 || k > 30 || (!nodes && n_nodes)) return GP_ERR_INVALID;
-    for (uint32_t i = 0; i < n_nodes; ++i)
-        if (node_len[i] < lenContigLen) return GP_ERR_INVALID;          // reference reads out of bounds
+    // Nodes shorter than 30 bases make the reference read outside the string (undefined); here the
+    // two windows are clipped to the sequence.  A node shorter than k has no k-mer at all.
     const uint64_t mask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
     // probes of every node: k-mers of its first and last 30 bases (:2026-2029)
     const uint32_t per_side = lenContigLen - (uint32_t)k + 1;
     std::vector<uint64_t> probes((size_t)n_nodes * 2 * per_side);
+    std::vector<uint32_t> n_probes((size_t)n_nodes * 2, 0);
     for (uint32_t j = 0; j < n_nodes; ++j) {
+        const uint32_t wlen = node_len[j] < lenContigLen ? node_len[j] : lenContigLen;
         for (int side = 0; side < 2; ++side) {
-            const char *w = side == 0 ? nodes[j] : nodes[j] + node_len[j] - lenContigLen;
+            const char *w = side == 0 ? nodes[j] : nodes[j] + node_len[j] - wlen;
             uint64_t v = 0;
-            for (uint32_t a = 0; a < lenContigLen; ++a) {
+            for (uint32_t a = 0; a < wlen; ++a) {
                 v = ((v << 2) | kmer_letter(w[a])) & mask;
-                if (a + 1 >= (uint32_t)k) probes[((size_t)j * 2 + side) * per_side + (a + 1 - k)] = v;
+                if (a + 1 >= (uint32_t)k) probes[((size_t)j * 2 + side) * per_side + n_probes[(size_t)j * 2 + side]++] = v;
             }
         }
     }
@@ -214,9 +217,11 @@ int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, u
         std::sort(codes.begin(), codes.end());
         for (uint32_t j = i; j < n_nodes; ++j) {                        // i <= j incl. j == i (:1008)
             bool hit = false;
-            const uint64_t *pj = &probes[(size_t)j * 2 * per_side];
-            for (uint32_t q = 0; q < 2 * per_side && !hit; ++q)
-                hit = std::binary_search(codes.begin(), codes.end(), pj[q]);
+            for (int side = 0; side < 2 && !hit; ++side) {
+                const uint64_t *pj = &probes[((size_t)j * 2 + side) * per_side];
+                for (uint32_t q = 0; q < n_probes[(size_t)j * 2 + side] && !hit; ++q)
+                    hit = std::binary_search(codes.begin(), codes.end(), pj[q]);
+            }
             if (hit) {
                 if ((uint64_t)np < cap && pairs) { pairs[np].row_seq = i; pairs[np].col_seq = j; }
                 ++np;
@@ -224,6 +229,32 @@ int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, u
         }
     }
     return np;
+}
+
+uint64_t gp_estimate_gap_cells(const uint32_t *contig_len, uint32_t n_contigs)
+{
+    // nodes = contigs and their reverse complements: every contig pair appears as 4 node pairs, a
+    // contig with itself as 3:  4*sum_{a<b} la*lb + 3*sum la^2 = 2*(sum la)^2 + sum la^2
+    uint64_t sum = 0, sq = 0;
+    for (uint32_t i = 0; i < n_contigs; ++i) { sum += contig_len[i]; sq += (uint64_t)contig_len[i] * contig_len[i]; }
+    return 2 * sum * sum + sq;
+}
+
+int gp_partition_gaps(const uint64_t *cost, uint64_t n_gaps, int32_t n_parts, int32_t *part)
+{
+    if ((!cost || !part) && n_gaps) return GP_ERR_INVALID;
+    if (n_parts < 1) return GP_ERR_INVALID;
+    std::vector<uint64_t> idx(n_gaps);
+    std::iota(idx.begin(), idx.end(), (uint64_t)0);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return cost[a] > cost[b]; });
+    std::vector<uint64_t> load((size_t)n_parts, 0);
+    for (uint64_t g : idx) {
+        int best = 0;
+        for (int p = 1; p < n_parts; ++p) if (load[p] < load[best]) best = p;
+        part[g] = best;
+        load[best] += cost[g];
+    }
+    return GP_OK;
 }
 
 } // extern "C"

@@ -1,0 +1,185 @@
+// contigs_merger_main.cpp -- drop-in for GAPPadder's ContigsMerger binary
+// (ContigsCompactor-v0.2.0/ContigsMerger/main.cpp:53-231 flags, :235-289 driver):
+//
+//   ContigsMerger_b200 -s F -i1 F -i2 F -x F -y F -k I -t I -m I -o INFO IN.fa > OUT.fa
+//
+// same flags, same defaults, same stdout / INFO / ./tmp.gml bytes; the DP runs on the B200 through
+// libgappadder_b200.so.  Because one process per gap cannot amortise CUDA context creation, a batch
+// form runs any number of gaps through one context (and through several GPUs):
+//
+//   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--no-gml]
+//
+// LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
+// to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
+// OUT.fa.gml in batch mode (the reference drops ./tmp.gml in the working directory of each process).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "fasta.hpp"
+#include "gappadder_b200.h"
+#include "merger.hpp"
+
+using namespace gpm;
+
+namespace {
+
+struct Cli {
+    MergeOptions opt;
+    std::string input;
+    bool have_input = false;
+    std::string batch;
+    int gpus = 1;
+    bool write_gml = true;
+    bool stats = false;
+};
+
+float parse_float(const char* s) { float v = 0; if (s) sscanf(s, "%f", &v); return v; }   // CM/main.cpp:91-93
+int parse_int(const char* s, int dflt) { int v = dflt; if (s) sscanf(s, "%d", &v); return v; }
+
+// CheckArguments, CM/main.cpp:53-231: flags are recognised by their second (and third) character only.
+bool parse_args(int argc, char** argv, Cli& c)
+{
+    int pos = 1;
+    while (pos < argc) {
+        const char* a = argv[pos];
+        const char* val = pos + 1 < argc ? argv[pos + 1] : nullptr;
+        if (a[0] != '-') { c.input = a; c.have_input = true; ++pos; continue; }
+        if (!strcmp(a, "--batch")) { if (!val) return false; c.batch = val; pos += 2; continue; }
+        if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); pos += 2; continue; }
+        if (!strcmp(a, "--no-gml")) { c.write_gml = false; ++pos; continue; }
+        if (!strcmp(a, "--stats")) { c.stats = true; ++pos; continue; }
+        switch (a[1]) {
+        case 'V': c.opt.verbose = true; printf("Turn on Verbose\n"); ++pos; break;
+        case 'l': c.opt.line_length = parse_int(val, c.opt.line_length); pos += 2; break;
+        case 's': c.opt.max_frac_score_loss = parse_float(val); pos += 2; break;
+        case 'c': c.opt.min_frac_overlap = parse_float(val); pos += 2; break;
+        case 'x': c.opt.min_overlap_len = parse_float(val); pos += 2; break;
+        case 'y': c.opt.max_overlap_clip_len = parse_float(val); pos += 2; break;
+        case 'm': c.opt.min_support_kmer = parse_int(val, c.opt.min_support_kmer); pos += 2; break;
+        case 't': c.opt.num_threads = parse_int(val, c.opt.num_threads); pos += 2; break;
+        case 'z': c.opt.min_overlap_len_with_scaffold = parse_float(val); pos += 2; break;
+        case 'k': c.opt.quick_kmer_len = parse_int(val, c.opt.quick_kmer_len); pos += 2; break;
+        case 'i':
+            if (a[2] == '1') { c.opt.score_mismatch = parse_float(val); pos += 2; break; }
+            if (a[2] == '2') { c.opt.score_indel = parse_float(val); pos += 2; break; }
+            return false;
+        case 'o': if (val) c.opt.info_file = val; pos += 2; break;
+        case 'p':
+            if (a[2] == '1') { c.opt.max_contig_path_len = parse_int(val, -1); pos += 2; break; }
+            if (a[2] == '2') { c.opt.max_count_contig_in_path = parse_int(val, -1); pos += 2; break; }
+            return false;
+        case 'e': pos += 2; break;                         // scaffold info file: unused by CompactVer3
+        case 'u': pos += 2; break;                         // support-pairs cutoff: unused by CompactVer3
+        default: return false;
+        }
+    }
+    return true;
+}
+
+bool write_file(const std::string& path, const std::string& data)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    fwrite(data.data(), 1, data.size(), f);
+    fclose(f);
+    return true;
+}
+
+struct BatchLine { std::string in, out, info; };
+
+int run_batch(const Cli& c)
+{
+    std::vector<BatchLine> lines;
+    {
+        std::ifstream f(c.batch);
+        if (!f) { fprintf(stderr, "ContigsMerger_b200: cannot open batch list %s\n", c.batch.c_str()); return 2; }
+        std::string ln;
+        while (std::getline(f, ln)) {
+            if (ln.empty()) continue;
+            BatchLine b;
+            size_t t1 = ln.find('\t'), t2 = t1 == std::string::npos ? t1 : ln.find('\t', t1 + 1);
+            if (t2 == std::string::npos) { fprintf(stderr, "ContigsMerger_b200: bad batch line: %s\n", ln.c_str()); return 2; }
+            b.in = ln.substr(0, t1); b.out = ln.substr(t1 + 1, t2 - t1 - 1); b.info = ln.substr(t2 + 1);
+            lines.push_back(b);
+        }
+    }
+    // balance gaps over GPUs by estimated pairwise cells (contig lengths only)
+    int n_gpus = c.gpus < 1 ? 1 : c.gpus;
+    std::vector<uint64_t> cost(lines.size(), 0);
+    if (n_gpus > 1) {
+        for (size_t g = 0; g < lines.size(); ++g) {
+            std::vector<FastaRecord> recs; std::string fatal;
+            read_fasta(lines[g].in, recs, fatal);
+            std::vector<uint32_t> lens;
+            for (const FastaRecord& r : recs) lens.push_back((uint32_t)r.seq.size());
+            cost[g] = estimate_gap_cells(lens);
+        }
+    }
+    const std::vector<int> part = partition_gaps(cost, n_gpus);
+    std::vector<int> rc(n_gpus, 0);
+    std::vector<std::string> err(n_gpus);
+    std::vector<uint64_t> cells(n_gpus, 0);
+    auto worker = [&](int dev) {
+        std::vector<GapInput> in;
+        std::vector<size_t> which;
+        for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(GapInput{lines[g].in}); which.push_back(g); }
+        if (in.empty()) return;
+        gp_ctx* ctx = nullptr;
+        int r = gp_create(dev, &ctx);
+        if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
+        std::vector<GapOutput> out;
+        r = merge_gaps(ctx, c.opt, in, out, err[dev]);
+        gp_destroy(ctx);
+        if (r != GP_OK) { rc[dev] = r; return; }
+        for (size_t k = 0; k < which.size(); ++k) {
+            const BatchLine& b = lines[which[k]];
+            if (!write_file(b.out, out[k].stdout_text)) { rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + b.out; return; }
+            if (out[k].wrote_info) write_file(b.info, out[k].info_text);
+            if (c.write_gml && out[k].wrote_info) write_file(b.out + ".gml", out[k].gml_text);
+            cells[dev] += out[k].pair_cells + out[k].relax_cells;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_gpus; ++d) th.emplace_back(worker, d);
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_gpus; ++d)
+        if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: GPU %d failed (%d): %s\n", d, rc[d], err[d].c_str()); return 3; }
+    if (c.stats) {
+        uint64_t tot = 0; for (uint64_t x : cells) tot += x;
+        fprintf(stderr, "gaps %zu  DP cells %.3f G  gpus %d\n", lines.size(), tot / 1e9, n_gpus);
+    }
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char** argv)
+{
+    Cli c;
+    if (!parse_args(argc, argv, c)) { printf("Wrong input.\n"); return 1; }           // CM/main.cpp:216-220
+    if (!c.batch.empty()) return run_batch(c);
+    // single gap, exactly the reference's process: argv[repeatfileArgIndex] defaults to argv[1]
+    if (!c.have_input) { if (argc > 1) c.input = argv[1]; else { fprintf(stderr, "usage: ContigsMerger_b200 <flags> contigs.fa\n"); return 1; } }
+    gp_ctx* ctx = nullptr;
+    int rc = gp_create(0, &ctx);
+    if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s (no CPU fallback)\n", gp_last_error(nullptr)); return 3; }
+    std::vector<GapOutput> out;
+    std::string err;
+    rc = merge_gaps(ctx, c.opt, {GapInput{c.input}}, out, err);
+    gp_destroy(ctx);
+    if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s\n", err.c_str()); return 3; }   // never partial stdout
+    fwrite(out[0].stdout_text.data(), 1, out[0].stdout_text.size(), stdout);
+    if (out[0].wrote_info) {
+        if (c.write_gml) write_file("tmp.gml", out[0].gml_text);
+        if (!write_file(c.opt.info_file, out[0].info_text)) {
+            printf("Can not open file: %s\n", c.opt.info_file.c_str());                 // ContigsCompactor.cpp:1548-1552
+            return 1;
+        }
+    }
+    return out[0].exit_code;
+}

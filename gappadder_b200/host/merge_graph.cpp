@@ -1,0 +1,173 @@
+#include "merge_graph.hpp"
+
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <set>
+
+namespace gpm {
+
+bool OverlapGraph::is_neighbor(int from, int to) const
+{
+    for (const Edge& e : adj_[from]) if (e.to == to) return true;
+    return false;
+}
+
+std::vector<std::vector<int>> OverlapGraph::scc() const
+{
+    const int n = size();
+    std::vector<int> index(n, -1), low(n, -1);
+    std::vector<char> on_stack(n, 0);
+    std::vector<int> stack;
+    std::vector<std::vector<int>> done;          // in order of completion
+    int next = 1;
+    // recursive, as the reference (SCCFrom, GraphUtils.cpp:1090-1178); depth <= number of nodes
+    std::function<void(int)> visit = [&](int v) {
+        index[v] = low[v] = next++;
+        stack.push_back(v);
+        on_stack[v] = 1;
+        for (const Edge& e : adj_[v]) {
+            const int w = e.to;
+            if (index[w] < 0) { visit(w); low[v] = std::min(low[v], low[w]); }
+            else if (on_stack[w]) low[v] = std::min(low[v], index[w]);
+        }
+        if (low[v] == index[v]) {
+            std::vector<int> comp;
+            for (;;) {
+                const int w = stack.back();
+                stack.pop_back();
+                on_stack[w] = 0;
+                comp.push_back(w);
+                if (w == v) break;
+            }
+            std::sort(comp.begin(), comp.end());
+            done.push_back(comp);
+        }
+    };
+    for (int v = 0; v < n; ++v) if (index[v] < 0) visit(v);
+    std::reverse(done.begin(), done.end());      // GraphUtils.cpp:1072-1076
+    return done;
+}
+
+// FindSimplePathsTopSortStart, GraphUtils.cpp:1258-1344.
+std::vector<int> OverlapGraph::terminals(bool start, const std::vector<std::vector<int>>& sccs) const
+{
+    const int n = size();
+    std::vector<int> comp_of(n, -1), all;
+    std::set<int> cand;
+    for (size_t c = 0; c < sccs.size(); ++c)
+        for (int v : sccs[c]) { cand.insert(v); all.push_back(v); comp_of[v] = (int)c; }
+    for (int v : all) {
+        for (const Edge& e : adj_[v]) {
+            if (comp_of[e.to] != comp_of[v]) {
+                if (start) cand.erase(e.to);                 // has an incoming edge from another component
+                else { cand.erase(v); break; }               // has an outgoing edge to another component
+            }
+        }
+    }
+    for (const std::vector<int>& comp : sccs) {
+        if (comp.size() <= 1) continue;
+        bool all_in = true;
+        for (int v : comp) if (!cand.count(v)) { all_in = false; break; }
+        // keep only the first (start) / last (end) node of the component
+        for (size_t k = 0; k < comp.size(); ++k)
+            if ((start && k != 0) || (!start && comp[k] != comp.back())) cand.erase(comp[k]);
+        if (!all_in) cand.erase(start ? comp.front() : comp.back());
+    }
+    return std::vector<int>(cand.begin(), cand.end());
+}
+
+// FindSimplePathsTopSortFrom, GraphUtils.cpp:773-859: shortest-path DP over the node order, edges
+// that point backwards in the order are ignored; returns the distinct paths to the reachable ends in
+// order of first insertion.
+std::vector<std::vector<int>> OverlapGraph::paths_from(int root, const std::vector<int>& order,
+                                                       const std::vector<int>& rank, const std::vector<int>& ends) const
+{
+    const double MAX_PATH_LEN = 1.0e100;
+    const int n = (int)order.size();
+    std::vector<double> best(n, MAX_PATH_LEN);
+    std::vector<std::vector<int>> path(n);
+    const int pos_root = rank[root];
+    best[pos_root] = 0.0;
+    path[pos_root].push_back(root);
+    for (int i = pos_root; i < n; ++i) {
+        if (best[i] >= MAX_PATH_LEN) continue;
+        const int v = order[i];
+        const double cur = best[i];                          // read once, before the neighbour loop (:806)
+        for (const Edge& nb : adj_[v]) {
+            const int pos = rank[nb.to];
+            if (pos < i) continue;
+            // GetEdgeTo returns the FIRST edge to that destination (GraphUtils.cpp:147-158)
+            double len = nb.len;
+            for (const Edge& e2 : adj_[v]) if (e2.to == nb.to) { len = e2.len; break; }
+            if (cur + len < best[pos]) {
+                best[pos] = cur + len;
+                std::vector<int> p = path[i];                // copy first: pos may equal i (self edge)
+                p.push_back(nb.to);
+                path[pos] = std::move(p);
+            }
+        }
+    }
+    std::vector<std::vector<int>> out;
+    std::set<std::vector<int>> seen;
+    for (int e : ends) {
+        const int pos = rank[e];
+        if (best[pos] < MAX_PATH_LEN && seen.insert(path[pos]).second) out.push_back(path[pos]);
+    }
+    return out;
+}
+
+std::vector<std::vector<int>> OverlapGraph::find_paths(int max_per_root) const
+{
+    const std::vector<std::vector<int>> sccs = scc();
+    std::vector<int> order, rank(size(), 0);
+    for (const std::vector<int>& comp : sccs) for (int v : comp) { rank[v] = (int)order.size(); order.push_back(v); }
+    const std::vector<int> roots = terminals(true, sccs), ends = terminals(false, sccs);
+    std::set<std::vector<int>> all;
+    for (int root : roots) {
+        std::vector<std::vector<int>> found = paths_from(root, order, rank, ends);
+        // longest first; equal lengths in the order the reference's std::set<const vector*> yields,
+        // taken here as insertion order (GraphUtils.cpp:719-753).  max_per_root+1 paths are kept:
+        // the reference tests `numOut > maxNodeOccurInPath` after the insert.
+        std::stable_sort(found.begin(), found.end(),
+                         [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
+        int num_out = 0;
+        for (const std::vector<int>& p : found) {
+            all.insert(p);
+            if (++num_out > max_per_root) break;
+        }
+    }
+    return std::vector<std::vector<int>>(all.begin(), all.end());
+}
+
+std::string OverlapGraph::gml(const std::vector<std::string>& names) const
+{
+    std::string s;
+    s += "graph [\ncomment \"Automatically generated by Graphing tool\"\ndirected  1\nid  1\n";
+    s += "label \"To be more meaningful later....\n\"";
+    const int n = size();
+    for (int i = 0; i < n; ++i) {
+        s += "node [\nid " + std::to_string(i + 1) + "\nlabel \"" + names[i] + "\"\ndefaultAtrribute   1\n]\n";
+    }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (i != j && is_neighbor(i, j))
+                s += "edge [\nsource " + std::to_string(i + 1) + "\ntarget  " + std::to_string(j + 1) + "\nlabel \"\"\n]\n";
+    s += "\n]\n";
+    return s;
+}
+
+std::vector<std::vector<int>> remove_revcomp_duplicates(const std::vector<std::vector<int>>& paths)
+{
+    std::vector<std::vector<int>> kept;
+    for (size_t a = 0; a < paths.size(); ++a) {
+        std::vector<int> rc;
+        for (size_t k = paths[a].size(); k-- > 0;) rc.push_back(paths[a][k] ^ 1);
+        bool dup = false;
+        for (size_t b = 0; b < a && !dup; ++b) dup = paths[b] == rc;
+        if (!dup) kept.push_back(paths[a]);
+    }
+    return kept;     // already sorted: a subsequence of a sorted set
+}
+
+} // namespace gpm

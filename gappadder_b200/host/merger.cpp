@@ -1,0 +1,242 @@
+#include "merger.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <numeric>
+
+#include "fasta.hpp"
+#include "merge_graph.hpp"
+
+namespace gpm {
+
+namespace {
+
+struct Chain {               // one path being merged left to right (FormMergedSeqFromPath, :1456-1515)
+    int gap;
+    std::vector<int> path;
+    size_t next = 1;
+    std::string merged;
+};
+
+struct GapState {
+    std::vector<FastaRecord> contigs;
+    std::vector<std::string> node_seq, node_name;   // [c0, c0_R, c1, c1_R, ...]  (:794-799)
+    uint32_t node_base = 0;                          // index of node 0 in the batch sequence table
+    uint64_t pair_begin = 0, pair_end = 0;           // slice of the batch pair list
+    bool dead = false;                               // fatal input error, nothing more to do
+    bool arranged = false;                           // candidate pairs were generated
+    std::vector<std::vector<int>> paths;             // after RemoveDupRevCompPaths
+    std::vector<std::string> merged;                 // one per path with size > 1
+};
+
+// MultiThreadQuickChecker::runMultiThreadChecker, ContigsCompactor.cpp:992-1038: how many thread ranges
+// the reference manages to form.  Fewer than T => "Arrange error!" and an EMPTY candidate list.
+long arranged_ranges(long n_nodes, int T)
+{
+    long long total = (long long)n_nodes * n_nodes;
+    total -= n_nodes;
+    total /= 2;
+    const long avrg = (long)(total / T);
+    long ncnt = 0, ranges = 0;
+    for (long i = 0; i < n_nodes; ++i)
+        for (long j = i; j < n_nodes; ++j) {
+            ++ncnt;
+            if (ncnt == avrg) { ++ranges; ncnt = 0; }
+        }
+    return ranges;
+}
+
+} // namespace
+
+uint64_t estimate_gap_cells(const std::vector<uint32_t>& contig_len)
+{
+    return gp_estimate_gap_cells(contig_len.data(), (uint32_t)contig_len.size());
+}
+
+std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts)
+{
+    std::vector<int32_t> part(cost.size(), 0);
+    if (n_parts > 1) gp_partition_gaps(cost.data(), cost.size(), n_parts, part.data());
+    return std::vector<int>(part.begin(), part.end());
+}
+
+int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
+               std::string& error)
+{
+    const size_t G = in.size();
+    out.assign(G, GapOutput());
+    std::vector<GapState> st(G);
+
+    // ---- scoring parameters as the reference ends up with them ---------------------------------
+    gp_dp_params dp;
+    dp.mismatch = (int)opt.score_mismatch;                       // `int matchScoreStep = scoreMismatch` (:1640)
+    if (opt.score_indel != std::floor(opt.score_indel)) {
+        error = "a fractional -i2 (indel score) is outside this implementation's integer contract";
+        return GP_ERR_INVALID;
+    }
+    dp.indel = (int)opt.score_indel;
+    const bool scan_runs = opt.max_overlap_clip_len >= 0;        // `for (c = 0; c <= maxOverlapClipLen; ...)` (:1679)
+    dp.max_clip = scan_runs ? (int)std::floor(opt.max_overlap_clip_len) : 0;
+    gp_thresholds thr{opt.max_frac_score_loss, opt.min_frac_overlap, opt.min_overlap_len, opt.min_overlap_len_with_scaffold};
+    const int max_per_root = opt.max_count_contig_in_path > 0 ? opt.max_count_contig_in_path : 20;   // :33-34,:168
+
+    // ---- read inputs, build nodes, candidate pairs ----------------------------------------------
+    std::vector<const char*> seq_ptr;
+    std::vector<uint32_t> seq_len;
+    std::vector<gp_pair> pairs;
+    for (size_t g = 0; g < G; ++g) {
+        GapState& s = st[g];
+        std::string fatal;
+        if (!read_fasta(in[g].fasta_path, s.contigs, fatal)) {
+            out[g].stdout_text = "FATAL ERROR: " + fatal + "\n";          // THROW, fastareader.cpp:11-15
+            out[g].exit_code = 1;
+            s.dead = true;
+            continue;
+        }
+        const size_t nc = s.contigs.size();
+        s.node_seq.reserve(2 * nc); s.node_name.reserve(2 * nc);
+        for (const FastaRecord& r : s.contigs) {
+            s.node_seq.push_back(r.seq);
+            s.node_name.push_back(r.name);
+            std::string rc(r.seq.size(), 'N');
+            if (!r.seq.empty()) gp_revcomp(r.seq.data(), (uint32_t)r.seq.size(), &rc[0]);
+            s.node_seq.push_back(rc);
+            s.node_name.push_back(r.name + "_R");                         // :785-787
+        }
+        // QuickCheckerContigsMatch::Init on every node (:843-849): a node shorter than k is fatal there
+        bool too_short = false;
+        for (const std::string& q : s.node_seq) if ((int)q.size() < opt.quick_kmer_len) too_short = true;
+        if (too_short && !s.node_seq.empty()) {
+            out[g].stdout_text = "FATAL ERROR: k-mer length is too large.\n";   // GetKmersList, :2060-2064
+            out[g].exit_code = 1;
+            s.dead = true;
+            continue;
+        }
+    }
+    // second loop so that sequence pointers stay valid (node_seq vectors no longer grow)
+    for (size_t g = 0; g < G; ++g) {
+        GapState& s = st[g];
+        if (s.dead) continue;
+        const long N = (long)s.node_seq.size();
+        s.node_base = (uint32_t)seq_ptr.size();
+        std::vector<const char*> nodes;
+        std::vector<uint32_t> lens;
+        for (const std::string& q : s.node_seq) {
+            seq_ptr.push_back(q.data()); seq_len.push_back((uint32_t)q.size());
+            nodes.push_back(q.data()); lens.push_back((uint32_t)q.size());
+        }
+        const int T = opt.num_threads;
+        const long ranges = T > 0 ? arranged_ranges(N, T) : 0;
+        s.pair_begin = s.pair_end = pairs.size();
+        if (T <= 0 || ranges < T) {
+            out[g].stdout_text += "Arrange error! " + std::to_string(ranges) + " " + std::to_string(T) + "\n";   // :1034-1038
+            continue;
+        }
+        s.arranged = true;
+        if (!scan_runs) continue;      // no scan => every Evaluate is rejected (:1674-1722): no edges
+        const uint64_t cap = (uint64_t)N * (N + 1) / 2;
+        const size_t at = pairs.size();
+        pairs.resize(at + cap);
+        const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), (uint32_t)N, opt.quick_kmer_len, pairs.data() + at, cap);
+        if (np < 0) { error = "gp_candidate_pairs failed"; return (int)np; }
+        pairs.resize(at + (size_t)np);
+        for (size_t k = at; k < pairs.size(); ++k) { pairs[k].row_seq += s.node_base; pairs[k].col_seq += s.node_base; }
+        s.pair_end = pairs.size();
+    }
+
+    // ---- pairwise phase: one batch for all gaps (replaces runMultiThreadMergeV2, :696-721) ------
+    std::vector<gp_result> res(pairs.size());
+    if (!pairs.empty()) {
+        int rc = gp_overlap_batch(ctx, seq_ptr.data(), seq_len.data(), (uint32_t)seq_ptr.size(), pairs.data(), pairs.size(), &dp, res.data());
+        if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+    }
+
+    // ---- edges, graph, paths (threadMergeContigV2 :652-685, addEdges :724-770, :898-931) --------
+    std::vector<Chain> chains;
+    for (size_t g = 0; g < G; ++g) {
+        GapState& s = st[g];
+        if (s.dead) continue;
+        const int N = (int)s.node_seq.size();
+        OverlapGraph graph(N);
+        for (uint64_t k = s.pair_begin; k < s.pair_end; ++k) {
+            const int i = (int)(pairs[k].row_seq - s.node_base), j = (int)(pairs[k].col_seq - s.node_base);
+            const int32_t l1 = (int32_t)s.node_seq[i].size(), l2 = (int32_t)s.node_seq[j].size();
+            const gp_result& r = res[k];
+            out[g].pair_cells += (uint64_t)l1 * l2;
+            const int sig = gp_is_score_significant(&thr, r.score, l1, l2, r.row_end, r.col_end, r.nclip);
+            if (sig != 2) continue;                                        // OVERLAP_LARGER_MINLEN only (:653,:673)
+            if (gp_is_containment(l1, l2, &r)) continue;                   // :673
+            const double len = -1.0 * gp_overlap_size(l1, l2, &r);          // :675
+            if (r.row_end + r.nclip != l1) graph.add_edge(j, i, len);      // MODE_2_1: edge j -> i (:656-662,:758-763)
+            else graph.add_edge(i, j, len);                                // MODE_1_2: edge i -> j
+        }
+        out[g].n_pairs = (uint32_t)(s.pair_end - s.pair_begin);
+        out[g].gml_text = graph.gml(s.node_name);                          // :898-899
+        s.paths = remove_revcomp_duplicates(graph.find_paths(max_per_root));   // :907,:926
+        for (const std::vector<int>& p : s.paths) {
+            if (p.size() > 1) {
+                Chain c;
+                c.gap = (int)g; c.path = p; c.merged = s.node_seq[p[0]];
+                chains.push_back(std::move(c));
+            }
+        }
+    }
+
+    // ---- relax chains: step k of every chain in one batch (replaces the loop at :1463-1513) ------
+    for (;;) {
+        std::vector<size_t> active;
+        for (size_t c = 0; c < chains.size(); ++c) if (chains[c].next < chains[c].path.size()) active.push_back(c);
+        if (active.empty()) break;
+        std::vector<const char*> sp;
+        std::vector<uint32_t> sl;
+        std::vector<gp_pair> pp;
+        for (size_t c : active) {
+            const Chain& ch = chains[c];
+            const std::string& nodeseq = st[ch.gap].node_seq[ch.path[ch.next]];
+            pp.push_back(gp_pair{(uint32_t)sp.size(), (uint32_t)sp.size() + 1});
+            sp.push_back(ch.merged.data()); sl.push_back((uint32_t)ch.merged.size());
+            sp.push_back(nodeseq.data()); sl.push_back((uint32_t)nodeseq.size());
+        }
+        std::vector<gp_result> rr(pp.size());
+        int rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());
+        if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        for (size_t a = 0; a < active.size(); ++a) {
+            Chain& ch = chains[active[a]];
+            const std::string& nodeseq = st[ch.gap].node_seq[ch.path[ch.next]];
+            out[ch.gap].relax_cells += (uint64_t)ch.merged.size() * nodeseq.size();
+            out[ch.gap].n_relax += 1;
+            std::string m(ch.merged.size() + nodeseq.size() + 1, '\0');
+            const int32_t len = gp_merged_concat(ch.merged.data(), (int32_t)ch.merged.size(), nodeseq.data(),
+                                                 (int32_t)nodeseq.size(), &rr[a], &m[0]);   // ccAct.GetMerged() (:1512)
+            m.resize((size_t)len);
+            ch.merged.swap(m);
+            ++ch.next;
+        }
+    }
+    for (Chain& ch : chains) st[ch.gap].merged.push_back(std::move(ch.merged));
+
+    // ---- output (ContigsCompactor.cpp:945-971, CM/main.cpp:281-288) -------------------------------
+    for (size_t g = 0; g < G; ++g) {
+        GapState& s = st[g];
+        if (s.dead) continue;
+        std::map<std::string, std::string> name_to_path;                  // mapNewContigNameToPath
+        int next_id = 1;                                                   // static contigNumNext, one process per gap
+        size_t mi = 0;
+        for (const std::vector<int>& p : s.paths) {
+            if (p.size() <= 1) continue;
+            std::string sub;
+            for (int v : p) { sub += " "; sub += s.node_name[v]; }
+            const std::string name = "NEW_CONTIG_MERGE_" + std::to_string(next_id++);
+            append_fasta(out[g].stdout_text, name, s.merged[mi++], 60);    // printFasta(cout): DEFAULT_LINE_LENGTH
+            name_to_path.insert(std::make_pair(name, sub));
+        }
+        for (const FastaRecord& r : s.contigs) append_fasta(out[g].stdout_text, r.name, r.seq, opt.line_length);
+        for (const auto& kv : name_to_path) out[g].info_text += kv.first + "  " + kv.second + "\n";   // :1555-1560
+        out[g].wrote_info = true;
+    }
+    return GP_OK;
+}
+
+} // namespace gpm

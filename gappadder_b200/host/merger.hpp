@@ -1,0 +1,61 @@
+// merger.hpp -- ContigsMerger's per-gap pipeline (ContigsCompactor::CompactVer3,
+// ContigsCompactor.cpp:773-983) with the two Evaluate call sites (:652 pairwise phase, :1491 relax
+// chain) replaced by batched calls into the C ABI (include/gappadder_b200.h).  Any number of gaps go
+// through one GPU context together: the pairwise phase of ALL gaps is one gp_overlap_pairs call, and
+// step k of ALL merge chains is one call.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "gappadder_b200.h"
+
+namespace gpm {
+
+// The command line of CM/main.cpp:24-42,53-231 (same flags, same defaults).
+struct MergeOptions {
+    double max_frac_score_loss = 0.01;       // -s
+    double min_frac_overlap = 0.005;         // -c
+    double min_overlap_len = 100000;         // -x
+    double max_overlap_clip_len = 0;         // -y
+    double min_overlap_len_with_scaffold = 6;// -z
+    int num_threads = 6;                     // -t   (only decides the "Arrange error" case)
+    int min_support_kmer = 5;                // -m   (unused by the reference's live path)
+    int line_length = 60;                    // -l
+    int quick_kmer_len = 10;                 // -k
+    double score_mismatch = -1.0;            // -i1
+    double score_indel = -1.0;               // -i2
+    std::string info_file = "tmp.info";      // -o
+    int max_contig_path_len = -1;            // -p1 (unused by CompactVer3)
+    int max_count_contig_in_path = -1;       // -p2 (default MAX_CONTIG_IN_PATH_COUNT = 20)
+    bool verbose = false;                    // -V  (accepted, ignored: it pollutes stdout in the reference)
+};
+
+struct GapInput {
+    std::string fasta_path;
+};
+
+struct GapOutput {
+    std::string stdout_text;   // what the reference writes to stdout
+    std::string info_text;     // contents of the -o file
+    std::string gml_text;      // contents of ./tmp.gml ("" when the reference would not reach it)
+    bool wrote_info = false;   // the reference creates the -o file only when it gets that far
+    int exit_code = 0;
+    // statistics
+    uint64_t pair_cells = 0, relax_cells = 0;
+    uint32_t n_pairs = 0, n_relax = 0;
+};
+
+// Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
+// here is a GPU/library failure, never an input problem (those are reported per gap like the
+// reference does, on stdout with exit code 1).
+int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
+               std::string& error);
+
+// Estimated DP cells of one gap's pairwise phase from contig lengths alone (all node pairs i <= j):
+// used to balance gaps over GPUs before any sequence is examined.
+uint64_t estimate_gap_cells(const std::vector<uint32_t>& contig_len);
+
+// Longest-processing-time partition of gaps over `n_parts` workers; returns part index per gap.
+std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts);
+
+} // namespace gpm

@@ -171,6 +171,14 @@ int32_t gp_overlap_size(int32_t len1, int32_t len2, const gp_result *r);
 int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, uint32_t n_nodes,
                            int32_t kmer_len, gp_pair *pairs, uint64_t cap);
 
+/* Multi-GPU sharding (gaps are independent: no collective on the data path).
+ * gp_estimate_gap_cells: upper bound of one gap's pairwise-phase DP cells from its contig lengths alone
+ * (every contig and its reverse complement against every other node, i <= j), before the k-mer filter.
+ * gp_partition_gaps: longest-processing-time assignment of gaps to n_parts workers; part[g] receives
+ * the worker of gap g.  Deterministic (ties: lower gap index first, lower worker index first). */
+uint64_t gp_estimate_gap_cells(const uint32_t *contig_len, uint32_t n_contigs);
+int gp_partition_gaps(const uint64_t *cost, uint64_t n_gaps, int32_t n_parts, int32_t *part);
+
 /* FastaSequence::RevsereComplement (fastareader.cpp; GetComplement GenSeqsUtils.cpp:24-61). */
 void gp_revcomp(const char *s, uint32_t len, char *out);
 
