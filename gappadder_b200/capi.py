@@ -17,7 +17,7 @@ EXPORTS = [
     "gp_upload_pairs", "gp_launch_resident", "gp_fetch_results", "gp_kernel_launches", "gp_pair_stats",
     "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
-    "gp_estimate_gap_cells", "gp_partition_gaps",
+    "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask",
 ]
 
 
@@ -48,6 +48,7 @@ class Thresholds(C.Structure):
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
 FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16 = 1, 2, 4, 8
+KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_ALL = 1, 2, 3
 
 # GAPPadder's command line (MergeContigs.py:85): -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1
 GAPPADDER_DP = DpParams(-2, -2, 50)
@@ -103,6 +104,8 @@ def lib() -> C.CDLL:
         L.gp_estimate_gap_cells.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_estimate_gap_cells.restype = C.c_uint64
         L.gp_partition_gaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
+        L.gp_pair_split.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.gp_set_kernel_mask.argtypes = [C.c_void_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -230,6 +233,16 @@ class Context:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_pair_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(cells=a.value, pairs16=b.value, pairs32=c.value)
+
+    def pair_split(self):
+        """Pairs of the uploaded batch per kernel: table 16-bit, PRMT 16-bit, general 32-bit."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.gp_pair_split(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(table16=a.value, prmt16=b.value, wide32=c.value)
+
+    def set_kernel_mask(self, mask: int):
+        """Restricts the 16-bit kernels gp_upload_pairs may pick (tests, A/B timing); results never change."""
+        self._check(self._L.gp_set_kernel_mask(self._h, mask))
 
     def int_peak(self):
         """-> (ALU-pipe, dual-pipe) thread-level packed-16x2 instructions per second, measured now."""

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "overlap_wf32.cuh"
 #include "overlap_wf16.cuh"
+#include "overlap_wf16t.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -60,15 +61,18 @@ struct gp_ctx {
     // sequence table
     DeviceBuf d_packed;
     std::vector<uint32_t> seq_off, seq_len;
+    std::vector<uint8_t> seq_acgt;            // 1: the sequence holds codes 0..3 only (table kernel eligible)
     uint32_t n_symbols = 0;
+    uint32_t kernel_mask = GP_KERNEL_ALL;
 
     // pair work lists
-    DeviceBuf d_pairs, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16;
+    DeviceBuf d_pairs, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t;
     HostBuf h_stage;
-    uint64_t n_pairs = 0, n16 = 0, n32 = 0, cells = 0;
-    uint32_t max_n16 = 0, max_n32 = 0;
+    uint64_t n_pairs = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
+    uint32_t max_n16t = 0, max_n16 = 0, max_n32 = 0;
     gp_dp_params params{};
     gp::Wf16Params p16{};
+    gp::Wf16tParams p16t{};
 
     int fail(int code, const char* fmt, ...)
     {
@@ -113,7 +117,7 @@ int gp_create(int device, gp_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete c; return GP_ERR_CUDA;
     }
-    if ((e = gp::wf16_configure()) != cudaSuccess) {
+    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess) {
         g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
         cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA;
     }
@@ -126,7 +130,8 @@ void gp_destroy(gp_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-    c->d_packed.release(); c->d_pairs.release(); c->d_order16.release(); c->d_order32.release();
+    c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
+    c->d_scratch16t.release();
     c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
     c->h_stage.release();
     delete c;
@@ -140,8 +145,24 @@ int gp_pair_stats(const gp_ctx* c, uint64_t* cells, uint64_t* pairs16, uint64_t*
 {
     if (!c) return GP_ERR_INVALID;
     if (cells) *cells = c->cells;
-    if (pairs16) *pairs16 = c->n16;
+    if (pairs16) *pairs16 = c->n16t + c->n16;
     if (pairs32) *pairs32 = c->n32;
+    return GP_OK;
+}
+
+int gp_pair_split(const gp_ctx* c, uint64_t* table16, uint64_t* prmt16, uint64_t* wide32)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (table16) *table16 = c->n16t;
+    if (prmt16) *prmt16 = c->n16;
+    if (wide32) *wide32 = c->n32;
+    return GP_OK;
+}
+
+int gp_set_kernel_mask(gp_ctx* c, uint32_t mask)
+{
+    if (!c) return GP_ERR_INVALID;
+    c->kernel_mask = mask & GP_KERNEL_ALL;
     return GP_OK;
 }
 
@@ -157,6 +178,14 @@ int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, con
     c->seq_off.assign(seq_word_off, seq_word_off + n_seq);
     c->seq_len.assign(seq_len, seq_len + n_seq);
     c->n_symbols = n_symbols;
+    c->seq_acgt.assign(n_seq, 1);
+    if (n_symbols > 4)                            // some sequence holds N or another letter: find which
+        for (uint32_t s = 0; s < n_seq; ++s) {
+            const uint32_t* w = packed + seq_word_off[s];
+            uint32_t any = 0;
+            for (uint32_t k = 0, nw = (seq_len[s] + 7) / 8; k < nw; ++k) any |= w[k] & 0xccccccccu;
+            c->seq_acgt[s] = any ? 0 : 1;
+        }
     c->n_pairs = 0;
     GP_CUDA(c, cudaStreamSynchronize(c->stream));   // caller may reuse `packed` after return
     return GP_OK;
@@ -170,19 +199,23 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
     if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
     GP_CUDA(c, cudaSetDevice(c->device));
     c->params = *params;
-    c->n_pairs = n_pairs; c->n16 = c->n32 = 0; c->cells = 0; c->max_n16 = c->max_n32 = 0;
+    c->n_pairs = n_pairs; c->n16t = c->n16 = c->n32 = 0; c->cells = 0; c->max_n16t = c->max_n16 = c->max_n32 = 0;
     if (n_pairs == 0) return GP_OK;
 
     const uint32_t n_seq = (uint32_t)c->seq_len.size();
-    const bool params16 = gp::wf16_params_ok(params->mismatch, params->indel) && c->n_symbols <= 8;
+    const bool params_ok = gp::wf16_params_ok(params->mismatch, params->indel);
+    const bool params16 = params_ok && c->n_symbols <= 8 && (c->kernel_mask & GP_KERNEL_PRMT16);
+    const bool params16t = params_ok && (c->kernel_mask & GP_KERNEL_TABLE16);
     if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip, c->n_symbols <= 4);
+    if (params16t) c->p16t = gp::wf16t_make_params(params->mismatch, params->indel, params->max_clip);
 
-    // stage: [PairDesc n][order16 n][order32 n]
+    // stage: [PairDesc n][order16t n][order16 n][order32 n]
     const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
     const size_t ord_bytes = n_pairs * sizeof(uint32_t);
-    GP_CUDA(c, c->h_stage.reserve(desc_bytes + 2 * ord_bytes));
+    GP_CUDA(c, c->h_stage.reserve(desc_bytes + 3 * ord_bytes));
     gp::PairDesc* hd = (gp::PairDesc*)c->h_stage.p;
-    uint32_t* ho16 = (uint32_t*)((char*)c->h_stage.p + desc_bytes);
+    uint32_t* ho16t = (uint32_t*)((char*)c->h_stage.p + desc_bytes);
+    uint32_t* ho16 = ho16t + n_pairs;
     uint32_t* ho32 = ho16 + n_pairs;
     uint64_t max_total = 0;
     for (uint64_t i = 0; i < n_pairs; ++i) {
@@ -192,7 +225,8 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
         hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
         c->cells += (uint64_t)m * n;
         max_total = std::max<uint64_t>(max_total, (uint64_t)m + n);
-        if (params16 && gp::wf16_pair_ok(m, n)) { ho16[c->n16++] = (uint32_t)i; c->max_n16 = std::max(c->max_n16, n); }
+        if (params16t && gp::wf16t_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) { ho16t[c->n16t++] = (uint32_t)i; c->max_n16t = std::max(c->max_n16t, n); }
+        else if (params16 && gp::wf16_pair_ok(m, n)) { ho16[c->n16++] = (uint32_t)i; c->max_n16 = std::max(c->max_n16, n); }
         else { ho32[c->n32++] = (uint32_t)i; c->max_n32 = std::max(c->max_n32, n); }
     }
     // 28-bit score field / 30-bit rank field of the kernels
@@ -204,15 +238,18 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
         const uint64_t cx = (uint64_t)hd[x].m * hd[x].n, cy = (uint64_t)hd[y].m * hd[y].n;
         return cx != cy ? cx > cy : x < y;
     };
+    std::sort(ho16t, ho16t + c->n16t, by_cells);
     std::sort(ho16, ho16 + c->n16, by_cells);
     std::sort(ho32, ho32 + c->n32, by_cells);
 
     GP_CUDA(c, c->d_pairs.reserve(desc_bytes));
+    GP_CUDA(c, c->d_order16t.reserve(ord_bytes));
     GP_CUDA(c, c->d_order16.reserve(ord_bytes));
     GP_CUDA(c, c->d_order32.reserve(ord_bytes));
     GP_CUDA(c, c->d_results.reserve(n_pairs * sizeof(gp::DevResult)));
-    GP_CUDA(c, c->d_queue.reserve(64));
+    GP_CUDA(c, c->d_queue.reserve(128));
     GP_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hd, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->n16t) GP_CUDA(c, cudaMemcpyAsync(c->d_order16t.p, ho16t, c->n16t * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n16) GP_CUDA(c, cudaMemcpyAsync(c->d_order16.p, ho16, c->n16 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n32) GP_CUDA(c, cudaMemcpyAsync(c->d_order32.p, ho32, c->n32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -224,8 +261,15 @@ int gp_launch_resident(gp_ctx* c)
     if (!c) return GP_ERR_INVALID;
     if (c->n_pairs == 0) return GP_OK;
     GP_CUDA(c, cudaSetDevice(c->device));
-    GP_CUDA(c, cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(c->d_queue.p, 0, 128, c->stream));
     unsigned int* queue = (unsigned int*)c->d_queue.p;
+    if (c->n16t) {
+        int rc = gp::wf16t_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
+                                  (const uint32_t*)c->d_order16t.p, (uint32_t)c->n16t, queue + 16, c->p16t, c->max_n16t,
+                                  &c->d_scratch16t.p, &c->d_scratch16t.cap, (gp::DevResult*)c->d_results.p);
+        if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16t launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+    }
     if (c->n16) {
         int rc = gp::wf16_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
                                  (const uint32_t*)c->d_order16.p, (uint32_t)c->n16, queue, c->p16, c->max_n16,

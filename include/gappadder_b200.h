@@ -144,6 +144,17 @@ uint64_t gp_kernel_launches(const gp_ctx *ctx);
 /* DP cells (sum of m*n) of the pairs currently uploaded, and how many went to each kernel. */
 int gp_pair_stats(const gp_ctx *ctx, uint64_t *cells, uint64_t *pairs16, uint64_t *pairs32);
 
+/* The same split by kernel: the shared-memory-table 16-bit kernel (A/C/G/T pairs whose column sequence
+ * has <= 4094 bases), the PRMT-lookup 16-bit kernel (<= 8 symbols, min(m,n) <= 4094) and the general
+ * 32-bit kernel. */
+int gp_pair_split(const gp_ctx *ctx, uint64_t *table16, uint64_t *prmt16, uint64_t *wide32);
+/* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).
+ * Pairs no allowed kernel accepts go to the general 32-bit kernel; results never depend on the mask. */
+#define GP_KERNEL_TABLE16 1u
+#define GP_KERNEL_PRMT16  2u
+#define GP_KERNEL_ALL     3u
+int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
+
 /* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):
  * thread-level instructions per second of VIADDMNMX.S16x2 alone (ALU pipe) and of the
  * VIMNMX.S16x2 + VIADD.16x2 dual-issue mix (both integer pipes).  bench.py's roofline denominator. */

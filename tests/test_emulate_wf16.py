@@ -1,5 +1,6 @@
-"""CPU: the packed 16-bit kernel's per-lane arithmetic (gappadder_b200/csrc/overlap_wf16.cuh), run
-lane by lane on the host by tests/emulate_wf16.cu, against the oracle and the golden vectors.
+"""CPU: the packed 16-bit kernels' per-lane arithmetic (gappadder_b200/csrc/overlap_wf16.cuh and
+overlap_wf16t.cuh), run lane by lane on the host by tests/emulate_wf16.cu, against the oracle and the
+golden vectors.
 Validates potential-domain clamping, the origin tags and the tie rule without a GPU."""
 import ctypes as C
 import json
@@ -23,12 +24,13 @@ def emu():
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     so = os.path.join(ROOT, "build", "libemulate_wf16.so")
     srcs = [os.path.join(ROOT, "tests", "emulate_wf16.cu"), os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16.cuh"),
-            os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
+            os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16t.cuh"), os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
     L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.wf16t_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
 
     def run(a, b, mm=-2, ind=-2, clip=50):
         res = []
@@ -37,6 +39,11 @@ def emu():
             out = (C.c_int32 * 5)()
             rc = L.wf16_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, addsel, out)
             assert rc == 0
+            f = out[4]
+            res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
+        if four and len(b) <= 4094:                    # the table kernel's domain: A/C/G/T, column sequence <= 4094
+            out = (C.c_int32 * 5)()
+            assert L.wf16t_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out) == 0
             f = out[4]
             res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
         assert len(set(res)) == 1, res

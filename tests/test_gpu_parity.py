@@ -8,27 +8,39 @@ import numpy as np
 import pytest
 
 import gappadder_b200 as g
-from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0
+from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0, KERNEL_ALL, KERNEL_PRMT16, KERNEL_TABLE16
 from _oracle import oracle_evaluate, oracle_revcomp
 import synth_gaps
 
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, seqs, pairs, params=None, full=False):
+def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_PRMT16)):
+    """Every kernel the library can route these pairs to (default routing = table kernel first, then with the
+    table kernel masked out = PRMT kernel / general kernel) against the oracle.  Returns the default routing's results."""
     params = params or g.GAPPADDER_DP
-    res = ctx.overlap_batch(seqs, pairs, params)
-    assert len(res) == len(pairs)
-    bad = []
-    for (a, b), r in zip(pairs, res):
+    want = []
+    for a, b in pairs:
         o = oracle_evaluate(seqs[a], seqs[b], params.mismatch, params.indel, params.max_clip, full=full)
-        want = (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained)
-        got = (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]),
-               int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
-        if want != got:
-            bad.append(((a, b), len(seqs[a]), len(seqs[b]), want, got))
-    assert not bad, "first mismatches (pair, m, n, oracle, gpu): %r" % bad[:5]
-    return res
+        want.append((o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained))
+    first = None
+    try:
+        for mask in masks:
+            ctx.set_kernel_mask(mask)
+            res = ctx.overlap_batch(seqs, pairs, params)
+            assert len(res) == len(pairs)
+            bad = []
+            for (a, b), r, w in zip(pairs, res, want):
+                got = (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]),
+                       int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
+                if w != got:
+                    bad.append(((a, b), len(seqs[a]), len(seqs[b]), w, got))
+            assert not bad, "kernel mask %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, bad[:5])
+            if first is None:
+                first = res
+    finally:
+        ctx.set_kernel_mask(KERNEL_ALL)
+    return first
 
 
 def _rand(rng, n, alpha=b"ACGT"):
@@ -53,13 +65,13 @@ def test_tie_heavy_small_alphabets(ctx):
         alpha = rng.choice([b"A", b"AC", b"ACG", b"ACGT", b"ACGTN"])
         seqs.append(_rand(rng, rng.randint(1, 90), alpha))
     pairs = [(rng.randrange(len(seqs)), rng.randrange(len(seqs))) for _ in range(1500)]
-    _check(ctx, seqs, pairs, full=True)
+    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_PRMT16, 0))
 
 
 def test_empty_and_tiny(ctx):
     seqs = [b"", b"A", b"C", b"AC", b"ACGTACGT", b"N", b"NN"]
     pairs = [(i, j) for i in range(len(seqs)) for j in range(len(seqs))]
-    _check(ctx, seqs, pairs, full=True)
+    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_PRMT16, KERNEL_TABLE16, 0))
     assert len(ctx.overlap_batch(seqs, [])) == 0
 
 
@@ -135,5 +147,24 @@ def test_long_overlaps_both_potentials(ctx):
         pairs += [(k, k + 1), (k + 1, k), (k, k), (k + 1, k + 1)]
     res = _check(ctx, seqs, pairs)
     from gappadder_b200.capi import FLAG_KERNEL16
-    # 17 of the 24 pairs have min(m,n) <= 4094 and go through the 16-bit kernel, 7 through the general one
+    # 17 of the 24 pairs have min(m,n) <= 4094 and go through a 16-bit kernel, 7 through the general one
     assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 17
+
+
+def test_kernel_routing(ctx):
+    """A/C/G/T pairs with <= 4094 columns take the table kernel, pairs with N (or longer columns but short rows)
+    the PRMT kernel, the rest the general kernel; masks move pairs down that list and never change results."""
+    rng = random.Random(3)
+    seqs = [_rand(rng, 300), _rand(rng, 700), _rand(rng, 500, b"ACGTN"), _rand(rng, 4500), _rand(rng, 4300)]
+    pairs = [(0, 1), (1, 0), (0, 2), (2, 1), (0, 3), (3, 0), (3, 4)]
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    ctx.set_sequences(packed, off, lens, nsym)
+    ctx.upload_pairs(np.array(pairs, dtype=np.uint32).view(g.capi.PAIR_DTYPE).reshape(-1))
+    assert ctx.pair_split() == dict(table16=3, prmt16=3, wide32=1)       # (3,0): 4500 rows x 300 columns -> table
+    try:
+        ctx.set_kernel_mask(KERNEL_PRMT16)
+        ctx.upload_pairs(np.array(pairs, dtype=np.uint32).view(g.capi.PAIR_DTYPE).reshape(-1))
+        assert ctx.pair_split() == dict(table16=0, prmt16=6, wide32=1)
+    finally:
+        ctx.set_kernel_mask(KERNEL_ALL)
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL, KERNEL_PRMT16, 0))

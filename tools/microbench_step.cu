@@ -132,6 +132,97 @@ __global__ void __launch_bounds__(128) step_kernel(uint32_t* out, const uint32_t
     if (x == 0x12345u) out[0] = x;
 }
 
+
+// Prototype of the table kernel's steady loop: per-warp shared-memory increment table (16 column-code
+// combinations x K registers), a shared-memory ring of per-column table offsets and top-boundary values
+// (so nothing but the DP value travels through the shuffle), increments prefetched one step ahead.
+template <int K, bool ZCLEAR, bool IMM, bool SKEW3 = false>
+__global__ void __launch_bounds__(128) ring_kernel(uint32_t* out, const uint32_t* __restrict__ line, int steps, uint32_t gup_, uint32_t gleft_)
+{
+    const uint32_t gup = IMM ? 0xfff0fff0u : gup_, gleft = IMM ? 0xffe8ffe8u : gleft_;
+    extern __shared__ uint4 smem4[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int TBL4 = 16 * (K / 4) * 32;            // uint4 per warp
+    uint4* tbl = smem4 + (size_t)warp * (TBL4 + 64 + 16);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(tbl + TBL4);   // 256 words: [0,128) offsets+values, mirrored
+    uint16_t* oring = reinterpret_cast<uint16_t*>(tbl + TBL4 + 64);   // 64 halfwords
+    for (int c = 0; c < 16; ++c)
+        for (int q = 0; q < K / 4; ++q) {
+            uint4 v;
+            v.x = ((c * 7 + q * 3 + lane) & 1) ? 0x00040004u : 0xffecffecu;
+            v.y = ((c * 5 + q + lane) & 2) ? 0x00040004u : 0xffec0004u;
+            v.z = ((c + q * 3 + lane) & 1) ? 0x0004ffecu : 0xffecffecu;
+            v.w = ((c * 3 + q + lane) & 2) ? 0x00040004u : 0xffecffecu;
+            tbl[(c * (K / 4) + q) * 32 + lane] = v;
+        }
+    for (int e = lane; e < 256; e += 32) ring[e] = 0x0100u | (((line[e & 127] >> 16) & 15u) * (K / 4) * 512u) << 16;
+    __syncwarp();
+    uint32_t W[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) W[k] = 0x01000100u + lane * 8 + k * 16;
+    uint32_t up0_prev = 0x01000100u;
+    const uint32_t tbl_base = (uint32_t)__cvta_generic_to_shared(tbl) + lane * 16;
+    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t oring_base = (uint32_t)__cvta_generic_to_shared(oring);
+    uint32_t incA[K], incB[K];
+    auto load_inc = [&](uint32_t (&inc)[K], uint32_t word) {
+        const uint32_t addr = tbl_base + (word >> 16);
+#pragma unroll
+        for (int q = 0; q < K / 4; ++q)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(inc[4 * q]), "=r"(inc[4 * q + 1]), "=r"(inc[4 * q + 2]), "=r"(inc[4 * q + 3]) : "r"(addr + q * 512));
+    };
+    auto lds32 = [&](uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; };
+    uint32_t recv_next = 0;
+    auto step = [&](const uint32_t (&inc)[K], uint32_t word, int s) {
+        uint32_t recv;
+        if (SKEW3) {                       // lanes three columns apart: the value needed now left the lane above a step ago
+            recv = recv_next;
+            recv_next = __shfl_up_sync(0xffffffffu, W[K - 1], 1);
+        } else {
+            recv = __shfl_up_sync(0xffffffffu, W[K - 1], 1);
+        }
+        if (lane == 0) recv = word << 16;
+        const uint32_t up0 = prmt(recv, W[K - 1], 0x5432u);
+        uint32_t diag = up0_prev;
+        up0_prev = up0;
+        uint32_t up = up0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t left = W[k];
+            const uint32_t d = __vadd2(diag, inc[k]);
+            const uint32_t t = __viaddmax_s16x2(left, gleft, d);
+            uint32_t w = __viaddmax_s16x2_relu(up, gup, t);
+            if (ZCLEAR) w &= ZCLR;
+            diag = left;
+            up = w;
+            W[k] = w;
+        }
+        if (lane == 31) asm volatile("st.shared.u16 [%0], %1;" :: "r"(oring_base + 2 * s), "h"((uint16_t)(W[K - 1] >> 16)));
+    };
+    for (int tb = 0; tb < steps; tb += 32) {
+        uint32_t p = ring_base + (((uint32_t)(tb - 2 * lane)) & 127u) * 4u;
+        uint32_t wordA = lds32(p), wordB;
+        load_inc(incA, wordA);
+#pragma unroll 1
+        for (int s = 0; s < 32; s += 2) {
+            wordB = lds32(p + 4);
+            load_inc(incB, wordB);
+            step(incA, wordA, s);
+            wordA = lds32(p + 8);
+            load_inc(incA, wordA);
+            step(incB, wordB, s + 1);
+            p += 8;
+        }
+        // flush the bottom-row ring (coalesced) -- stands in for the boundary-line store
+        __syncwarp();
+        out[1024 + ((blockIdx.x * 4 + warp) * 64 + lane)] = oring[lane];
+    }
+    uint32_t x = up0_prev;
+#pragma unroll
+    for (int k = 0; k < K; ++k) x ^= W[k];
+    if (x == 0x12345u) out[0] = x;
+}
+
 struct Row { std::string name; int K, warps; double clk_per_regstep, tcups; float ms; };
 
 template <int K, int V>
@@ -164,6 +255,35 @@ static Row run(int warps_per_sm, uint32_t* dout, const uint32_t* dline, int sms,
     return r;
 }
 
+template <int K, bool ZCLEAR, bool IMM, bool SKEW3 = false>
+static Row run_ring(int warps_per_sm, uint32_t* dout, const uint32_t* dline, int sms, double ghz)
+{
+    const int block = 128, blocks_per_sm = warps_per_sm / 4;
+    const int grid = sms * blocks_per_sm;
+    const size_t smem = (size_t)4 * (16 * (K / 4) * 32 + 64 + 16) * sizeof(uint4);
+    auto kern = ring_kernel<K, ZCLEAR, IMM, SKEW3>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem));
+    const int steps = 1 << 15;
+    kern<<<grid, block, smem>>>(dout, dline, 1024, 0xffe8ffe8u, 0xfff0fff0u);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, block, smem>>>(dout, dline, steps, 0xffe8ffe8u, 0xfff0fff0u);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+    }
+    const double clocks = best * 1e-3 * ghz * 1e9;
+    const double regsteps_per_smsp = (double)warps_per_sm / 4 * steps * K;
+    const double cells = (double)grid * 4 * 32 * (double)steps * K * 2;
+    Row r{std::string(ZCLEAR ? "ring+table" : "ring+table no-tag-clear") + (IMM ? " imm" : " reg") + (SKEW3 ? " skew3" : ""), K, warps_per_sm, clocks / regsteps_per_smsp, cells / (best * 1e-3) / 1e12, best};
+    printf("%-26s K=%d warps/SM=%2d (occ %d blk)  %7.3f ms  %6.2f clk/reg-step/SMSP  %6.2f TCUPS\n", r.name.c_str(), K, warps_per_sm, occ, best, r.clk_per_regstep, r.tcups);
+    return r;
+}
+
 int main(int argc, char** argv)
 {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
@@ -171,7 +291,7 @@ int main(int argc, char** argv)
     int khz = 0; CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
     const double ghz = khz * 1e-6;
     printf("device %s, %d SMs, %.3f GHz nominal\n", p.name, sms, ghz);
-    uint32_t* dout; CK(cudaMalloc(&dout, 4096));
+    uint32_t* dout; CK(cudaMalloc(&dout, 4096 + 148 * 16 * 64 * 4 * 4));
     uint32_t* dline; CK(cudaMalloc(&dline, 4096));
     std::vector<uint32_t> h(1024);
     for (int i = 0; i < 1024; ++i) h[i] = 0x0100u | ((uint32_t)(rand() & 3) * 0x11u << 16);
@@ -191,6 +311,17 @@ int main(int argc, char** argv)
     rows.push_back(run<4, V_LDS_ALLSPLIT>(24, dout, dline, sms, ghz));
     rows.push_back(run<12, V_LDS>(8, dout, dline, sms, ghz));
     rows.push_back(run<12, V_LDS_SPLIT>(8, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, true, false>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, true, false>(8, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, false, false>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<4, true, false>(20, dout, dline, sms, ghz));
+    rows.push_back(run_ring<4, true, true>(24, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, true, true>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, false, true>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, true, true, true>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, true, true, true>(8, dout, dline, sms, ghz));
+    rows.push_back(run_ring<8, false, true, true>(12, dout, dline, sms, ghz));
+    rows.push_back(run_ring<4, true, true, true>(24, dout, dline, sms, ghz));
     if (argc > 1) {
         FILE* f = fopen(argv[1], "w");
         if (f) {
