@@ -31,6 +31,7 @@
 // Host/device: the per-lane arithmetic is __host__ __device__; tests/emulate_wf16.cu runs it on
 // the CPU against the oracle.
 #pragma once
+#include <type_traits>
 #include "overlap_wf16.cuh"
 
 namespace gp {
@@ -159,11 +160,11 @@ GP_HD uint32_t lane16t_max(const Lane16t<K>& st)
 // lane's best cell, compared with thrS = 8*(max(S,1)-1) as in overlap_wf16.cuh.
 GP_HD uint32_t wf16t_nthr(const Wf16Pair& g, int j)
 {
-    const uint32_t lo = (uint32_t)(-8 * (g.n - j + 2)) & 0xffffu;          // >= -8*(4094+1) = -32760
-    const uint32_t hi = (uint32_t)(-8 * (g.n - j + 3)) & 0xffffu;          // column j-1, j >= 1: >= -32768
+    const uint32_t lo = (uint32_t)(-8 * (g.n - j + 2)) & 0xffffu;          // 1 <= j: >= -8*(4094+1) = -32760
+    const uint32_t hi = (uint32_t)(-8 * (g.n - j + 3)) & 0xffffu;          // column j-1: >= -32768; other j wrap mod 2^16
     return lo | (hi << 16);
 }
-constexpr uint32_t WF16T_NEVER = 0x80008000u;
+constexpr uint32_t WF16T_UNARMED = 0x7fff7fffu;   // threshold no acc reaches (acc <= 8*n + 7 < 32767)
 constexpr uint32_t WF16T_NSTEP = 0x00080008u;
 
 #if defined(__CUDACC__)
@@ -279,7 +280,6 @@ __device__ __noinline__ long long wf16t_strip(Wf16tWarp& w, const Wf16tParams& P
         S0 = s;
     }
     uint32_t thrS = filter_thr(S0);
-    uint32_t nthr = WF16T_NEVER, nstep = 0u;
     const int jswitch = n - g.C > 1 ? n - g.C : 1;                        // first candidate column
     const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
     const int jarm = rowlane ? 1 : jswitch;
@@ -297,6 +297,48 @@ __device__ __noinline__ long long wf16t_strip(Wf16tWarp& w, const Wf16tParams& P
     };
     __syncwarp();
 
+    // One block of up to 32 steps, two steps per iteration; the table words of a step are fetched one
+    // step ahead and the ring word two steps ahead.  EDGE: some lane is outside columns 1..n+1 (range
+    // test per lane, first-column fix-up).  FILT: some lane may hold scan candidates (filter).
+    auto run_block = [&](auto edge_c, auto filt_c, int tb, int cnt) {
+        constexpr bool EDGE = decltype(edge_c)::value, FILT = decltype(filt_c)::value;
+        uint32_t p = ring_base + (((uint32_t)(tb - D * lane)) & (WF16T_RING - 1)) * 4u;
+        uint32_t optr = oring_base;
+        int j = tb - D * lane;                                            // my lo column
+        uint32_t nthr = FILT ? wf16t_nthr(g, j) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
+        uint32_t incA[K], incB[K];
+        uint32_t wordA = lds32(p), wordB = lds32(p + 4);
+        lds_inc<K>(incA, my_tab + (wordA >> 16));
+        auto step = [&](const uint32_t (&inc)[K], uint32_t word, uint32_t oaddr, int jj) {
+            uint32_t recv = recv_next;
+            recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
+            if (lane == 0) recv = word << 16;
+            if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
+                lane16t_step<K>(st, recv, inc, gup, gleft);
+                if (EDGE && jj == 1) lane16t_fix_first<K>(st, g);
+                if (do_store) sts32(oaddr, st.W[K - 1]);
+                if (FILT) {
+                    const uint32_t acc = p_add2(lane16t_max<K>(st), nthr);
+                    if (filter_fired(acc, jj >= jarm ? thrS : WF16T_UNARMED)) slow_path(jj);
+                }
+            }
+            if (FILT) nthr = p_add2(nthr, WF16T_NSTEP);
+        };
+#pragma unroll 1
+        for (int s = 0; s < cnt; s += 2) {
+            lds_inc<K>(incB, my_tab + (wordB >> 16));
+            const uint32_t wordA2 = lds32(p + 8);
+            step(incA, wordA, optr, j);
+            lds_inc<K>(incA, my_tab + (wordA2 >> 16));
+            const uint32_t wordB2 = lds32(p + 12);
+            step(incB, wordB, optr + 4, j + 1);
+            wordA = wordA2; wordB = wordB2;
+            p += 8; optr += 8; j += 2;
+        }
+    };
+    using std::true_type;
+    using std::false_type;
+
     for (int tb = 1; tb <= t_end; tb += 32) {
         // the next block's boundary words (L2 latency hidden behind this block)
         uint32_t next_line = 0;
@@ -304,61 +346,9 @@ __device__ __noinline__ long long wf16t_strip(Wf16tWarp& w, const Wf16tParams& P
         if (have_next) { const int jj = tb + 32 + lane; next_line = bnd[jj <= n + 1 ? jj : n + 1]; }
         const bool edge = tb < 31 * D + 1 || tb + 31 > n + 1;             // some lane outside columns 1..n+1
         const bool filt = rowscan || tb + 31 >= jswitch;                  // some lane may hold candidates
-        uint32_t p = ring_base + (((uint32_t)(tb - D * lane)) & (WF16T_RING - 1)) * 4u;
-        uint32_t optr = oring_base;
-        uint32_t incA[K], incB[K];
-        uint32_t wordA = lds32(p), wordB = lds32(p + 4);
-        lds_inc<K>(incA, my_tab + (wordA >> 16));
-        int cnt = 32;
-
-        if (!edge && !filt) {
-            // ---- steady block: no branches, two steps per iteration, loads one and two steps ahead ----
-            auto step = [&](const uint32_t (&inc)[K], uint32_t word, uint32_t oaddr) {
-                uint32_t recv = recv_next;
-                recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
-                if (lane == 0) recv = word << 16;
-                lane16t_step<K>(st, recv, inc, gup, gleft);
-                if (do_store) sts32(oaddr, st.W[K - 1]);
-            };
-#pragma unroll 1
-            for (int s = 0; s < 32; s += 2) {
-                lds_inc<K>(incB, my_tab + (wordB >> 16));
-                const uint32_t wordA2 = lds32(p + 8);
-                step(incA, wordA, optr);
-                lds_inc<K>(incA, my_tab + (wordA2 >> 16));
-                const uint32_t wordB2 = lds32(p + 12);
-                step(incB, wordB, optr + 4);
-                wordA = wordA2; wordB = wordB2;
-                p += 8; optr += 8;
-            }
-        } else {
-            // ---- checked block ------------------------------------------------------------------------------
-            cnt = t_end - tb + 1 < 32 ? t_end - tb + 1 : 32;
-            int j = tb - D * lane;                                        // my lo column
-#pragma unroll 1
-            for (int s = 0; s < cnt; ++s) {
-                lds_inc<K>(incB, my_tab + (wordB >> 16));
-                const uint32_t wordB2 = lds32(p + 8);
-                uint32_t recv = recv_next;
-                recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
-                if (lane == 0) recv = wordA << 16;
-                if (!edge || (j >= 1 && j <= n + 1)) {
-                    lane16t_step<K>(st, recv, incA, gup, gleft);
-                    if (edge && j == 1) lane16t_fix_first<K>(st, g);
-                    if (do_store) sts32(optr, st.W[K - 1]);
-                    if (filt) {
-                        if (j == jarm) { nthr = wf16t_nthr(g, j); nstep = WF16T_NSTEP; }
-                        const uint32_t acc = p_add2(lane16t_max<K>(st), nthr);
-                        nthr = p_add2(nthr, nstep);
-                        if (filter_fired(acc, thrS)) slow_path(j);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < K; ++k) incA[k] = incB[k];
-                wordA = wordB; wordB = wordB2;
-                p += 4; optr += 4; ++j;
-            }
-        }
+        const int cnt = t_end - tb + 1 < 32 ? ((t_end - tb + 2) & ~1) : 32;   // steps past t_end find every lane out of range
+        if (!edge) { if (!filt) run_block(false_type(), false_type(), tb, cnt); else run_block(false_type(), true_type(), tb, cnt); }
+        else       { if (!filt) run_block(true_type(), false_type(), tb, cnt);  else run_block(true_type(), true_type(), tb, cnt); }
         __syncwarp();
         if (store_bottom) {                                               // bottom row of the columns lane 31 finished
             const int c = tb + lane - (31 * D + 1);

@@ -184,8 +184,8 @@ void strip_host_t(const HostPair& hp, const Wf16Pair& g, const Wf16tParams& P, s
     }
     int S0 = -1000000000;
     for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); S0 = sc > S0 ? sc : S0; }
-    uint32_t thrS[32], nthr[32], nstep[32];
-    for (int lane = 0; lane < 32; ++lane) { thrS[lane] = filter_thr(S0); nthr[lane] = WF16T_NEVER; nstep[lane] = 0; }
+    uint32_t thrS[32];
+    for (int lane = 0; lane < 32; ++lane) thrS[lane] = filter_thr(S0);
     const int jswitch = n - g.C > 1 ? n - g.C : 1;
     constexpr int D = WF16T_SKEW;
     const int t_end = n + 1 + 31 * D;
@@ -195,7 +195,7 @@ void strip_host_t(const HostPair& hp, const Wf16Pair& g, const Wf16tParams& P, s
     std::vector<uint32_t> top(bnd.begin(), bnd.end());      // the ring holds values read before they are overwritten
     for (int tb = 1; tb <= t_end; tb += 32) {
         const bool filt = rowscan || tb + 31 >= jswitch;
-        const int cnt = t_end - tb + 1 < 32 ? t_end - tb + 1 : 32;
+        const int cnt = t_end - tb + 1 < 32 ? ((t_end - tb + 2) & ~1) : 32;
         for (int s = 0; s < cnt; ++s) {
             const int t = tb + s;
             uint32_t recv[32];
@@ -212,10 +212,8 @@ void strip_host_t(const HostPair& hp, const Wf16Pair& g, const Wf16tParams& P, s
                 if (store_bottom && lane == 31 && j >= 2 && j - 1 <= n) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
                 if (filt) {
                     const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
-                    if (j == (rowlane ? 1 : jswitch)) { nthr[lane] = wf16t_nthr(g, j); nstep[lane] = WF16T_NSTEP; }
-                    const uint32_t acc = p_add2(lane16t_max<K>(st[lane]), nthr[lane]);
-                    nthr[lane] = p_add2(nthr[lane], nstep[lane]);
-                    if (filter_fired(acc, thrS[lane])) {
+                    const uint32_t acc = p_add2(lane16t_max<K>(st[lane]), wf16t_nthr(g, j));
+                    if (filter_fired(acc, j >= (rowlane ? 1 : jswitch) ? thrS[lane] : WF16T_UNARMED)) {
                         ++g_slow_calls;
                         Lane16<K> tmp;
                         for (int k = 0; k < K; ++k) tmp.W[k] = st[lane].W[k];
