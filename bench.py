@@ -16,7 +16,7 @@ on the data path.
             stream around gp_launch_resident, L2 flushed between steps, max over ranks)
   e2e       GCUPS through the public call gp_overlap_batch on HOST buffers: packing into pinned memory,
             H2D, kernels, D2H of the results, every step (wall clock of the blocking call)
-  roofline  integer issue-rate roofline of the dominant kernel (overlap_wf16_kernel): achieved =
+  roofline  integer issue-rate roofline of the dominant kernel (overlap_wf16t_kernel): achieved =
             GCUPS * 6 integer ops per cell / peak = 2 lanes * measured dual-pipe packed
             16x2 instruction rate (gp_int_peak, measured live on this GPU)
   cpu_baseline  the reference's own Evaluate (oracle/_ref/libcm_ref.so, kind "reference") or the C
@@ -261,6 +261,7 @@ def run_gpu(args):
     ctx.set_sequences(packed, off, lens, nsym)
     ctx.upload_pairs(pairs, g.GAPPADDER_DP)
     stats = ctx.pair_stats()
+    split = ctx.pair_split()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -304,6 +305,7 @@ def run_gpu(args):
         e2e_t.append(time.perf_counter() - t0)
     barrier()
     my_e2e_ms = float(np.mean(e2e_t)) * 1e3
+    breakdown = ctx.last_timing()
     h2d = int(packed.nbytes + len(pairs) * (16 + 4))      # packed table + PairDesc + work order
     d2h = int(len(pairs) * 20)
     checksum = int(res["score"].astype(np.int64).sum()) if res is not None and len(res) else 0
@@ -324,14 +326,15 @@ def run_gpu(args):
             "dtype": "s16x2", "data": "synthetic", "config": workload_config(args),
             "gaps_per_s": tot_gaps / (max_ms * 1e-3),
             "pairs_per_step": int(len(pairs)) * world, "gcells_per_step": tot_cells / 1e9,
-            "kernel_split": {"pairs_wf16": stats["pairs16"], "pairs_wf32": stats["pairs32"]},
+            "kernel_split": {"pairs_table16": split["table16"], "pairs_prmt16": split["prmt16"], "pairs_wide32": split["wide32"]},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": max_e2e_ms, "gaps_per_s": tot_gaps / (max_e2e_ms * 1e-3), "timing": "wall clock of the blocking gp_overlap_batch call"},
+                    "ms_per_step": max_e2e_ms, "gaps_per_s": tot_gaps / (max_e2e_ms * 1e-3), "timing": "wall clock of the blocking gp_overlap_batch call",
+                    "last_call_breakdown_ms": {k: round(v, 3) for k, v in breakdown.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tintop/s",
                          "frac": achieved / peak_lane_ops, "traffic": None,
-                         "kernel": "overlap_wf16_kernel", "ops_per_cell": OPS_PER_CELL,
+                         "kernel": "overlap_wf16t_kernel" if split["table16"] >= split["prmt16"] else "overlap_wf16_kernel", "ops_per_cell": OPS_PER_CELL,
                          "peak_source": "measured live (gp_int_peak): 2 lanes x VIMNMX.S16x2+VIADD.16x2 dual-issue rate; "
                                         "ALU pipe alone %.2f Tinst/s, both pipes %.2f Tinst/s" % (alu / 1e12, dual / 1e12)},
             "result_checksum": checksum,

@@ -17,7 +17,7 @@ EXPORTS = [
     "gp_upload_pairs", "gp_launch_resident", "gp_fetch_results", "gp_kernel_launches", "gp_pair_stats",
     "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
-    "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask",
+    "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
 ]
 
 
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         L.gp_partition_gaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
         L.gp_pair_split.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gp_set_kernel_mask.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         _lib = L
     return _lib
 
@@ -243,6 +244,12 @@ class Context:
     def set_kernel_mask(self, mask: int):
         """Restricts the 16-bit kernels gp_upload_pairs may pick (tests, A/B timing); results never change."""
         self._check(self._L.gp_set_kernel_mask(self._h, mask))
+
+    def last_timing(self):
+        """Host wall-clock breakdown (ms) of the last overlap_batch: pack, prepare pairs, device, total."""
+        a = (C.c_double * 4)()
+        self._check(self._L.gp_last_timing(self._h, a, 4))
+        return dict(pack_ms=a[0], prepare_ms=a[1], device_ms=a[2], total_ms=a[3])
 
     def int_peak(self):
         """-> (ALU-pipe, dual-pipe) thread-level packed-16x2 instructions per second, measured now."""

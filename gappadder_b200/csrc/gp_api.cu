@@ -8,6 +8,7 @@
 #include "overlap_wf16t.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -67,7 +68,9 @@ struct gp_ctx {
 
     // pair work lists
     DeviceBuf d_pairs, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t;
-    HostBuf h_stage;
+    HostBuf h_stage, h_pack, h_results;
+    std::vector<uint32_t> pack_off;
+    double timing[GP_TIMING_SLOTS] = {0};       // milliseconds of the last gp_overlap_batch, see gp_last_timing
     uint64_t n_pairs = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
     uint32_t max_n16t = 0, max_n16 = 0, max_n32 = 0;
     gp_dp_params params{};
@@ -133,7 +136,7 @@ void gp_destroy(gp_ctx* c)
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
     c->d_scratch16t.release();
     c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
-    c->h_stage.release();
+    c->h_stage.release(); c->h_pack.release(); c->h_results.release();
     delete c;
 }
 
@@ -166,10 +169,9 @@ int gp_set_kernel_mask(gp_ctx* c, uint32_t mask)
     return GP_OK;
 }
 
-int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, const uint32_t* seq_word_off,
-                     const uint32_t* seq_len, uint32_t n_seq, uint32_t n_symbols)
+static int set_sequences_async(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, const uint32_t* seq_word_off,
+                               const uint32_t* seq_len, uint32_t n_seq, uint32_t n_symbols)
 {
-    if (!c) return GP_ERR_INVALID;
     if ((!packed || !seq_word_off || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequence table");
     if (n_symbols > 16) return c->fail(GP_ERR_ALPHABET, "more than 16 symbols");
     GP_CUDA(c, cudaSetDevice(c->device));
@@ -187,13 +189,21 @@ int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, con
             c->seq_acgt[s] = any ? 0 : 1;
         }
     c->n_pairs = 0;
+    return GP_OK;
+}
+
+int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, const uint32_t* seq_word_off,
+                     const uint32_t* seq_len, uint32_t n_seq, uint32_t n_symbols)
+{
+    if (!c) return GP_ERR_INVALID;
+    int rc = set_sequences_async(c, packed, packed_bytes, seq_word_off, seq_len, n_seq, n_symbols);
+    if (rc != GP_OK) return rc;
     GP_CUDA(c, cudaStreamSynchronize(c->stream));   // caller may reuse `packed` after return
     return GP_OK;
 }
 
-int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
 {
-    if (!c) return GP_ERR_INVALID;
     if (!params || (!pairs && n_pairs)) return c->fail(GP_ERR_INVALID, "null pairs/params");
     if (params->max_clip < 0) return c->fail(GP_ERR_INVALID, "max_clip must be >= 0");
     if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
@@ -233,14 +243,23 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
     const uint64_t amax = (uint64_t)std::max(std::max(std::abs(params->mismatch), std::abs(params->indel)), 1);
     if (amax * max_total >= (1ull << 26) || (uint64_t)(params->max_clip + 1) * (max_total + 2) >= (1ull << 30))
         return c->fail(GP_ERR_RANGE, "sequence lengths / penalties / max_clip exceed the kernels' score or rank range");
-    // longest first: the tail of the queue is then made of short pairs (load balance)
-    auto by_cells = [&](uint32_t x, uint32_t y) {
-        const uint64_t cx = (uint64_t)hd[x].m * hd[x].n, cy = (uint64_t)hd[y].m * hd[y].n;
-        return cx != cy ? cx > cy : x < y;
+    // longest first: the tail of the queue is then made of short pairs (load balance).  The order only has
+    // to be roughly by size, so it is a counting sort on 2048 size classes of equal width.
+    auto by_cells = [&](uint32_t* ord, uint64_t cnt) {
+        if (cnt < 2) return;
+        uint64_t mx = 0;
+        for (uint64_t k = 0; k < cnt; ++k) mx = std::max<uint64_t>(mx, (uint64_t)hd[ord[k]].m * hd[ord[k]].n);
+        constexpr uint32_t B = 2048;
+        const uint64_t width = mx / B + 1;
+        std::vector<uint32_t> start(B + 1, 0), tmp(ord, ord + cnt);
+        for (uint64_t k = 0; k < cnt; ++k) ++start[B - 1 - (uint32_t)(((uint64_t)hd[tmp[k]].m * hd[tmp[k]].n) / width)];
+        uint32_t run = 0;
+        for (uint32_t b = 0; b <= B; ++b) { const uint32_t v = start[b]; start[b] = run; run += v; }
+        for (uint64_t k = 0; k < cnt; ++k) ord[start[B - 1 - (uint32_t)(((uint64_t)hd[tmp[k]].m * hd[tmp[k]].n) / width)]++] = tmp[k];
     };
-    std::sort(ho16t, ho16t + c->n16t, by_cells);
-    std::sort(ho16, ho16 + c->n16, by_cells);
-    std::sort(ho32, ho32 + c->n32, by_cells);
+    by_cells(ho16t, c->n16t);
+    by_cells(ho16, c->n16);
+    by_cells(ho32, c->n32);
 
     GP_CUDA(c, c->d_pairs.reserve(desc_bytes));
     GP_CUDA(c, c->d_order16t.reserve(ord_bytes));
@@ -252,6 +271,14 @@ int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_
     if (c->n16t) GP_CUDA(c, cudaMemcpyAsync(c->d_order16t.p, ho16t, c->n16t * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n16) GP_CUDA(c, cudaMemcpyAsync(c->d_order16.p, ho16, c->n16 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n32) GP_CUDA(c, cudaMemcpyAsync(c->d_order32.p, ho32, c->n32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    return GP_OK;       // h_stage is the context's own pinned memory: no need to wait for the copies here
+}
+
+int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+{
+    if (!c) return GP_ERR_INVALID;
+    int rc = upload_pairs_async(c, pairs, n_pairs, params);
+    if (rc != GP_OK) return rc;
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
     return GP_OK;
 }
@@ -306,12 +333,27 @@ int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n_pairs)
     return GP_OK;
 }
 
+// Launch + copy the results into the context's pinned buffer + one synchronisation + memcpy to `out`.
+static int run_and_fetch(gp_ctx* c, gp_result* out, uint64_t n_pairs)
+{
+    int rc = gp_launch_resident(c);
+    if (rc != GP_OK) return rc;
+    if (n_pairs == 0) return GP_OK;
+    if (!out) return c->fail(GP_ERR_INVALID, "null output");
+    const size_t bytes = n_pairs * sizeof(gp_result);
+    GP_CUDA(c, c->h_results.reserve(bytes));
+    GP_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, c->h_results.p, bytes);
+    return GP_OK;
+}
+
 int gp_overlap_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params, gp_result* out)
 {
-    int rc = gp_upload_pairs(c, pairs, n_pairs, params);
+    if (!c) return GP_ERR_INVALID;
+    int rc = upload_pairs_async(c, pairs, n_pairs, params);
     if (rc != GP_OK) return rc;
-    if ((rc = gp_launch_resident(c)) != GP_OK) return rc;
-    return gp_fetch_results(c, out, n_pairs);
+    return run_and_fetch(c, out, n_pairs);
 }
 
 int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len, uint32_t n_seq,
@@ -319,20 +361,39 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
 {
     if (!c) return GP_ERR_INVALID;
     if ((!seqs || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequences");
+    using clk = std::chrono::steady_clock;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
+    // pack into the context's pinned staging buffer (kept across calls), then everything is enqueued
+    // on the stream without waiting: H2D of the table, pair descriptors and work orders (built on the
+    // host while the table is in flight), kernels, D2H of the results; one synchronisation at the end.
     const size_t bytes = gp_packed_size(seq_len, n_seq);
-    std::vector<uint32_t> off(n_seq);
-    HostBuf pinned;
-    {
-        cudaError_t e = pinned.reserve(bytes ? bytes : 16);
-        if (e != cudaSuccess) return c->fail(GP_ERR_CUDA, "cudaMallocHost failed: %s", cudaGetErrorString(e));
-    }
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, c->h_pack.reserve(bytes ? bytes : 16));
+    c->pack_off.resize(n_seq);
     uint32_t nsym = 0;
-    int rc = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)pinned.p, off.data(), &nsym);
-    if (rc != GP_OK) { pinned.release(); return c->fail(rc, rc == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed"); }
-    rc = gp_set_sequences(c, (const uint32_t*)pinned.p, bytes, off.data(), seq_len, n_seq, nsym);
-    pinned.release();
+    int rc = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)c->h_pack.p, c->pack_off.data(), &nsym);
+    if (rc != GP_OK) return c->fail(rc, rc == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed");
+    const auto t1 = clk::now();
+    rc = set_sequences_async(c, (const uint32_t*)c->h_pack.p, bytes, c->pack_off.data(), seq_len, n_seq, nsym);
     if (rc != GP_OK) return rc;
-    return gp_overlap_pairs(c, pairs, n_pairs, params, out);
+    rc = upload_pairs_async(c, pairs, n_pairs, params);
+    if (rc != GP_OK) return rc;
+    const auto t2 = clk::now();
+    rc = run_and_fetch(c, out, n_pairs);
+    const auto t3 = clk::now();
+    c->timing[0] = ms(t0, t1);      // pack
+    c->timing[1] = ms(t1, t2);      // table upload enqueue + pair classification, ordering, upload enqueue
+    c->timing[2] = ms(t2, t3);      // copies + kernels + result copy, until the stream is idle
+    c->timing[3] = ms(t0, t3);
+    return rc;
+}
+
+int gp_last_timing(const gp_ctx* c, double* out_ms, int n)
+{
+    if (!c || !out_ms || n < 0) return GP_ERR_INVALID;
+    for (int i = 0; i < n && i < GP_TIMING_SLOTS; ++i) out_ms[i] = c->timing[i];
+    return GP_OK;
 }
 
 } // extern "C"

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 extern "C" {
@@ -28,40 +29,105 @@ size_t gp_packed_size(const uint32_t *seq_len, uint32_t n_seq)
     return words * sizeof(uint32_t);
 }
 
+namespace {
+
+// Packs sequences [s0, s1) with a fixed byte -> code table.  Returns the first sequence index that
+// holds a byte the table does not know (code 0xff), or s1 when all went through.  max_code is updated.
+uint32_t pack_range(const char *const *seqs, const uint32_t *seq_len, const size_t *word_off, uint32_t s0, uint32_t s1,
+                    const uint8_t *code, uint32_t *packed, int *max_code)
+{
+    uint32_t mx = (uint32_t)(*max_code + 1);             // highest code seen + 1
+    for (uint32_t s = s0; s < s1; ++s) {
+        const unsigned char *p = (const unsigned char *)seqs[s];
+        const uint32_t len = seq_len[s];
+        const size_t nw = words_for(len);
+        uint32_t *dst = packed + word_off[s];
+        const uint32_t full = len / 8;
+        uint32_t top = 0;                                // max code + 1 of this sequence; >= 0x100 with an unknown byte
+        for (uint32_t w = 0; w < full; ++w) {
+            const unsigned char *q = p + (size_t)w * 8;
+            uint32_t word = 0;
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t c = code[q[k]];
+                top = std::max(top, c + 1);
+                word |= (c & 15u) << (4 * k);
+            }
+            dst[w] = word;
+        }
+        uint32_t word = 0;
+        for (uint32_t i = full * 8, k = 0; i < len; ++i, ++k) {
+            const uint32_t c = code[p[i]];
+            top = std::max(top, c + 1);
+            word |= (c & 15u) << (4 * k);
+        }
+        for (size_t w = full; w < nw; ++w) { dst[w] = word; word = 0; }
+        if (top > 16) { *max_code = (int)mx - 1; return s; }   // unknown byte (0xff): caller assigns a code and redoes s
+        mx = std::max(mx, top);
+    }
+    *max_code = (int)mx - 1;
+    return s1;
+}
+
+} // namespace
+
 int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
                       uint32_t *packed, uint32_t *seq_word_off, uint32_t *n_symbols)
 {
     if ((!seqs || !seq_len || !packed || !seq_word_off) && n_seq) return GP_ERR_INVALID;
+    std::vector<size_t> off(n_seq);
+    size_t total = 0, bases = 0;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        if (!seqs[s] && seq_len[s]) return GP_ERR_INVALID;
+        off[s] = total;
+        seq_word_off[s] = (uint32_t)total;
+        total += words_for(seq_len[s]);
+        bases += seq_len[s];
+        if (total > 0xffffffffull) return GP_ERR_RANGE;
+    }
     // byte -> code.  Equality of codes == equality of bytes (ContigsCompactor.cpp:1641).
-    int16_t code[256];
-    for (int i = 0; i < 256; ++i) code[i] = -1;
+    uint8_t code[256];
+    memset(code, 0xff, sizeof code);
     code[(unsigned char)'A'] = 0; code[(unsigned char)'C'] = 1;
     code[(unsigned char)'G'] = 2; code[(unsigned char)'T'] = 3; code[(unsigned char)'N'] = 4;
     int next = 5, max_code = -1;
-    size_t off = 0;
-    for (uint32_t s = 0; s < n_seq; ++s) {
-        const unsigned char *p = (const unsigned char *)seqs[s];
-        const uint32_t len = seq_len[s];
-        if (!p && len) return GP_ERR_INVALID;
-        const size_t nw = words_for(len);
-        seq_word_off[s] = (uint32_t)off;
-        uint32_t *dst = packed + off;
-        uint32_t i = 0;
-        for (size_t w = 0; w < nw; ++w) {
-            uint32_t word = 0;
-            for (int k = 0; k < 8 && i < len; ++k, ++i) {
-                int c = code[p[i]];
-                if (c < 0) {
-                    if (next >= 16) return GP_ERR_ALPHABET;
-                    c = code[p[i]] = (int16_t)next++;
-                }
-                if (c > max_code) max_code = c;
-                word |= (uint32_t)c << (4 * k);
-            }
-            dst[w] = word;
+
+    // Large batches of plain A/C/G/T/N input: several host threads, each on a contiguous range of
+    // sequences.  A byte outside the table is rare (GAPPadder's contigs never have one); it sends the
+    // whole batch through the sequential loop below, which assigns codes in order of first appearance.
+    const unsigned hw = std::thread::hardware_concurrency();
+    const uint32_t T = bases < (4u << 20) ? 1u : std::min<uint32_t>(hw ? hw : 1u, 8u);
+    bool done = false;
+    if (T > 1) {
+        std::vector<std::thread> th;
+        std::vector<uint32_t> stop(T);
+        std::vector<int> mx(T, -1);
+        std::vector<uint32_t> cut(T + 1, n_seq);
+        cut[0] = 0;
+        for (uint32_t t = 1, s = 0; t < T; ++t) {      // equal shares of the packed words
+            const size_t want = total * t / T;
+            while (s < n_seq && off[s] < want) ++s;
+            cut[t] = s;
         }
-        off += nw;
-        if (off > 0xffffffffull) return GP_ERR_RANGE;
+        for (uint32_t t = 0; t < T; ++t)
+            th.emplace_back([&, t] { stop[t] = pack_range(seqs, seq_len, off.data(), cut[t], cut[t + 1], code, packed, &mx[t]); });
+        for (auto &x : th) x.join();
+        done = true;
+        for (uint32_t t = 0; t < T; ++t) { done = done && stop[t] == cut[t + 1]; max_code = std::max(max_code, mx[t]); }
+        if (!done) max_code = -1;
+    }
+    if (!done) {
+        uint32_t s = 0;
+        while (s < n_seq) {
+            s = pack_range(seqs, seq_len, off.data(), s, n_seq, code, packed, &max_code);
+            if (s == n_seq) break;
+            // sequence s holds unknown bytes: give each a code (order of first appearance) and pack it again
+            const unsigned char *p = (const unsigned char *)seqs[s];
+            for (uint32_t i = 0; i < seq_len[s]; ++i)
+                if (code[p[i]] == 0xff) {
+                    if (next >= 16) return GP_ERR_ALPHABET;
+                    code[p[i]] = (uint8_t)next++;
+                }
+        }
     }
     // highest code in use + 1: 4 for plain ACGT input, 5 with N, more with other letters
     if (n_symbols) *n_symbols = (uint32_t)(max_code + 1);

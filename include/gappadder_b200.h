@@ -134,6 +134,12 @@ int gp_overlap_batch(gp_ctx *ctx, const char *const *seqs, const uint32_t *seq_l
                      const gp_pair *pairs, uint64_t n_pairs,
                      const gp_dp_params *params, gp_result *out);
 
+/* Host-side wall-clock breakdown of the last gp_overlap_batch on this context, milliseconds:
+ * [0] packing into pinned memory, [1] classifying and ordering the pairs (table upload in flight),
+ * [2] from the first kernel launch until the results are on the host, [3] the whole call. */
+#define GP_TIMING_SLOTS 4
+int gp_last_timing(const gp_ctx *ctx, double *out_ms, int n);
+
 /* Split form used for device-resident timing: upload pairs once, launch any number of times,
  * fetch once.  gp_launch_resident only enqueues work on gp_stream(ctx). */
 int gp_upload_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs, const gp_dp_params *params);
