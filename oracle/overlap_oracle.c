@@ -9,7 +9,7 @@
  * load this file's shared object.  The product (libgappadder_b200.so, the gp_* host code) never
  * links, loads or calls it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function below against
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function below against
  * oracle/_ref/libcm_ref.so (the reference's own Evaluate compiled from /root/reference by
  * oracle/build_ref.sh) on seeded random pairs, and tests/golden/ holds vectors generated from
  * that library (tests/golden/make_golden.py) for machines where the reference is absent.
