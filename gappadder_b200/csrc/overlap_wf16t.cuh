@@ -204,6 +204,40 @@ __device__ __forceinline__ void lds_inc(uint32_t (&inc)[K], uint32_t addr)
     }
 }
 
+// Exact scan of the cells a lane holds after a step (lo column j, hi column j-1), out of line.  A cell can
+// only change `best` if it scores at least the lane's best score (and at least 1: the initial best is
+// cell (0,n) with H = 0 and rank 0), i.e. V >= 8*(max(S,1) + n - j' + 1) under the column potential; that
+// one compare per cell comes first, the rank arithmetic only runs for the cells that pass.
+template <int K>
+__device__ __noinline__ long long wf16t_scan_cold(WVals<K> v, int m, int n, int C, int itop, int j, long long best)
+{
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int jh = j - half;
+        if (jh < 1 || jh > n) continue;
+        int S = (int)(best >> 32);
+        int thrV = 8 * ((S > 1 ? S : 1) + n - jh + 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int vv = half ? (int)(v.W[k] >> 16) : (int)(v.W[k] & 0xffffu);
+            if (vv >= thrV) {
+                const int i = itop + 1 + k + half * K;
+                const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, C) : RANK_MAX + 1u;
+                if (rk <= RANK_MAX) {
+                    const uint32_t code = (uint32_t)vv & 3u;
+                    const long long key = make_key((vv >> 3) - 1 - (n - jh), rk, (code & 1u) | ((code & 2u) ? 0u : 2u));
+                    if (key > best) {
+                        best = key;
+                        S = (int)(best >> 32);
+                        thrV = 8 * ((S > 1 ? S : 1) + n - jh + 1);
+                    }
+                }
+            }
+        }
+    }
+    return best;
+}
+
 // One strip of 64*K rows starting after table row `i0`.  rowscan: the strip reaches into the last
 // C+1 rows.  With store_bottom the low halves of bnd[] are replaced in place by the strip's last row.
 //
@@ -291,7 +325,7 @@ __device__ __noinline__ long long wf16t_strip(Wf16tWarp& w, const Wf16tParams& P
         WVals<K> v;
 #pragma unroll
         for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
-        best = wf16_scan_cold<K>(v, g, itop, j, best);
+        best = wf16t_scan_cold<K>(v, m, n, g.C, itop, j, best);
         const int s = (int)(best >> 32);
         thrS = filter_thr(s > S0 ? s : S0);
     };
