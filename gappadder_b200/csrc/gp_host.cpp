@@ -243,22 +243,27 @@ static inline uint64_t kmer_letter(char nt)
 }
 
 /* Candidate list of the pairwise phase (MultiThreadQuickChecker::threadQuickCheck,
- * ContigsCompactor.cpp:1068-1100, with QuickCheckerContigsMatch :1982-2095).  The reference
- * keeps each k-mer left-aligned in a uint64 (KmerUtils.cpp:60-115); equal windows give equal
- * values, so comparing right-aligned window codes is the same test.  Node i's k-mer set is a
- * sorted vector instead of a std::map; the 2*(30-k+1) probes of node j are binary searches. */
+ * ContigsCompactor.cpp:1068-1100, with QuickCheckerContigsMatch :1982-2095): pair (i,j), i <= j, is a
+ * candidate iff a k-mer of the first or last 30 bases of node j occurs anywhere in node i.  The
+ * reference keeps every k-mer of node i in a std::map and probes it with node j's window k-mers,
+ * N(N+1)/2 times; here the test is inverted: the window k-mers of ALL nodes go into one open-addressing
+ * table (k-mer -> list of owner nodes j), every node i is scanned once against it and sets hit(i,j) for
+ * the owners j >= i of each k-mer it holds.  Same predicate, O(total bases) instead of
+ * O(N^2 * 42 * log L).  The reference keeps each k-mer left-aligned in a uint64 (KmerUtils.cpp:60-115);
+ * equal windows give equal values, so comparing right-aligned window codes is the same test. */
 int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, uint32_t n_nodes,
                            int32_t k, gp_pair *pairs, uint64_t cap)
 {
     const uint32_t lenContigLen = 30;                                   // :2024
     if (k <= 0 || k > 30 || (!nodes && n_nodes)) return GP_ERR_INVALID;
+    if (n_nodes == 0) return 0;
     // Nodes shorter than 30 bases make the reference read outside the string (undefined); here the
     // two windows are clipped to the sequence.  A node shorter than k has no k-mer at all.
-    const uint64_t mask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-    // probes of every node: k-mers of its first and last 30 bases (:2026-2029)
-    const uint32_t per_side = lenContigLen - (uint32_t)k + 1;
-    std::vector<uint64_t> probes((size_t)n_nodes * 2 * per_side);
-    std::vector<uint32_t> n_probes((size_t)n_nodes * 2, 0);
+    const uint64_t mask = (1ull << (2 * k)) - 1;                        // k <= 30
+    // (k-mer, owner) of every window k-mer (:2026-2029), sorted so equal k-mers are adjacent
+    struct Probe { uint64_t kmer; uint32_t owner; };
+    std::vector<Probe> probes;
+    probes.reserve((size_t)n_nodes * 2 * (lenContigLen - (uint32_t)k + 1));
     for (uint32_t j = 0; j < n_nodes; ++j) {
         const uint32_t wlen = node_len[j] < lenContigLen ? node_len[j] : lenContigLen;
         for (int side = 0; side < 2; ++side) {
@@ -266,33 +271,52 @@ int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, u
             uint64_t v = 0;
             for (uint32_t a = 0; a < wlen; ++a) {
                 v = ((v << 2) | kmer_letter(w[a])) & mask;
-                if (a + 1 >= (uint32_t)k) probes[((size_t)j * 2 + side) * per_side + n_probes[(size_t)j * 2 + side]++] = v;
+                if (a + 1 >= (uint32_t)k) probes.push_back(Probe{v, j});
             }
         }
     }
+    std::sort(probes.begin(), probes.end(), [](const Probe &a, const Probe &b) { return a.kmer != b.kmer ? a.kmer < b.kmer : a.owner < b.owner; });
+    // open-addressing table: slot -> [first, last) range of `probes` with that k-mer
+    size_t n_unique = 0;
+    for (size_t q = 0; q < probes.size(); ++q) if (q == 0 || probes[q].kmer != probes[q - 1].kmer) ++n_unique;
+    size_t tcap = 16;
+    while (tcap < 2 * n_unique + 2) tcap <<= 1;
+    struct Slot { uint64_t kmer; uint32_t first, last; };
+    std::vector<Slot> table(tcap, Slot{0, 0, 0});                       // first == last: empty
+    auto slot_of = [&](uint64_t v) { return (size_t)((v * 0x9E3779B97F4A7C15ull) >> 20) & (tcap - 1); };
+    for (size_t q = 0; q < probes.size();) {
+        size_t e = q + 1;
+        while (e < probes.size() && probes[e].kmer == probes[q].kmer) ++e;
+        size_t h = slot_of(probes[q].kmer);
+        while (table[h].first != table[h].last) h = (h + 1) & (tcap - 1);
+        table[h] = Slot{probes[q].kmer, (uint32_t)q, (uint32_t)e};
+        q = e;
+    }
+    // hit(i, j): one byte per pair, row i reused for every node
+    std::vector<uint8_t> hit(n_nodes);
     int64_t np = 0;
-    std::vector<uint64_t> codes;
     for (uint32_t i = 0; i < n_nodes; ++i) {
+        std::fill(hit.begin() + i, hit.end(), 0);
+        const char *s = nodes[i];
         const uint32_t len = node_len[i];
-        codes.clear();
         uint64_t v = 0;
         for (uint32_t a = 0; a < len; ++a) {
-            v = ((v << 2) | kmer_letter(nodes[i][a])) & mask;
-            if (a + 1 >= (uint32_t)k) codes.push_back(v);
-        }
-        std::sort(codes.begin(), codes.end());
-        for (uint32_t j = i; j < n_nodes; ++j) {                        // i <= j incl. j == i (:1008)
-            bool hit = false;
-            for (int side = 0; side < 2 && !hit; ++side) {
-                const uint64_t *pj = &probes[((size_t)j * 2 + side) * per_side];
-                for (uint32_t q = 0; q < n_probes[(size_t)j * 2 + side] && !hit; ++q)
-                    hit = std::binary_search(codes.begin(), codes.end(), pj[q]);
+            v = ((v << 2) | kmer_letter(s[a])) & mask;
+            if (a + 1 < (uint32_t)k) continue;
+            size_t h = slot_of(v);
+            while (table[h].first != table[h].last) {
+                if (table[h].kmer == v) {
+                    for (uint32_t q = table[h].first; q < table[h].last; ++q) hit[probes[q].owner] = 1;   // owners < i are never read
+                    break;
+                }
+                h = (h + 1) & (tcap - 1);
             }
-            if (hit) {
+        }
+        for (uint32_t j = i; j < n_nodes; ++j)                          // i <= j incl. j == i (:1008), row-major like -t 1
+            if (hit[j]) {
                 if ((uint64_t)np < cap && pairs) { pairs[np].row_seq = i; pairs[np].col_seq = j; }
                 ++np;
             }
-        }
     }
     return np;
 }

@@ -12,6 +12,7 @@
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
 // OUT.fa.gml in batch mode (the reference drops ./tmp.gml in the working directory of each process).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -123,7 +124,9 @@ int run_batch(const Cli& c)
     const std::vector<int> part = partition_gaps(cost, n_gpus);
     std::vector<int> rc(n_gpus, 0);
     std::vector<std::string> err(n_gpus);
-    std::vector<uint64_t> cells(n_gpus, 0);
+    std::vector<uint64_t> cells(n_gpus, 0), pcells(n_gpus, 0);
+    std::vector<MergeTimings> tim(n_gpus);
+    std::vector<double> wall(n_gpus, 0);
     auto worker = [&](int dev) {
         std::vector<GapInput> in;
         std::vector<size_t> which;
@@ -133,7 +136,9 @@ int run_batch(const Cli& c)
         int r = gp_create(dev, &ctx);
         if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
         std::vector<GapOutput> out;
-        r = merge_gaps(ctx, c.opt, in, out, err[dev]);
+        const auto w0 = std::chrono::steady_clock::now();
+        r = merge_gaps(ctx, c.opt, in, out, err[dev], &tim[dev]);
+        wall[dev] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
         gp_destroy(ctx);
         if (r != GP_OK) { rc[dev] = r; return; }
         for (size_t k = 0; k < which.size(); ++k) {
@@ -142,6 +147,7 @@ int run_batch(const Cli& c)
             if (out[k].wrote_info) write_file(b.info, out[k].info_text);
             if (c.write_gml && out[k].wrote_info) write_file(b.out + ".gml", out[k].gml_text);
             cells[dev] += out[k].pair_cells + out[k].relax_cells;
+            pcells[dev] += out[k].pair_cells;
         }
     };
     std::vector<std::thread> th;
@@ -150,8 +156,13 @@ int run_batch(const Cli& c)
     for (int d = 0; d < n_gpus; ++d)
         if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: GPU %d failed (%d): %s\n", d, rc[d], err[d].c_str()); return 3; }
     if (c.stats) {
-        uint64_t tot = 0; for (uint64_t x : cells) tot += x;
-        fprintf(stderr, "gaps %zu  DP cells %.3f G  gpus %d\n", lines.size(), tot / 1e9, n_gpus);
+        // one JSON line per run: cells and the slowest GPU's phase times (merge_gaps only, context creation excluded)
+        uint64_t tot = 0, ptot = 0; for (uint64_t x : cells) tot += x; for (uint64_t x : pcells) ptot += x;
+        int slow = 0; for (int d = 1; d < n_gpus; ++d) if (wall[d] > wall[slow]) slow = d;
+        const MergeTimings& t = tim[slow];
+        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"merge_ms\": %.3f, "
+                        "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f}\n",
+                lines.size(), n_gpus, tot / 1e9, ptot / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms);
     }
     return 0;
 }

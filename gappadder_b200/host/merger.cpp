@@ -1,10 +1,13 @@
 #include "merger.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <thread>
 
 #include "fasta.hpp"
 #include "merge_graph.hpp"
@@ -27,6 +30,8 @@ struct GapState {
     uint64_t pair_begin = 0, pair_end = 0;           // slice of the batch pair list
     bool dead = false;                               // fatal input error, nothing more to do
     bool arranged = false;                           // candidate pairs were generated
+    std::vector<gp_pair> cand;                       // ... with node indices local to the gap
+    int cand_rc = 0;
     std::vector<std::vector<int>> paths;             // after RemoveDupRevCompPaths
     std::vector<std::string> merged;                 // one per path with size > 1
 };
@@ -48,6 +53,19 @@ long arranged_ranges(long n_nodes, int T)
     return ranges;
 }
 
+// Runs fn(g) for g in [0, G) on up to `threads` host threads (gaps are independent).
+template <class F>
+void for_each_gap(size_t G, unsigned threads, F fn)
+{
+    if (threads <= 1 || G < 2) { for (size_t g = 0; g < G; ++g) fn(g); return; }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    const unsigned T = (unsigned)std::min<size_t>(threads, G);
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&] { for (size_t g = next.fetch_add(1); g < G; g = next.fetch_add(1)) fn(g); });
+    for (auto& x : th) x.join();
+}
+
 } // namespace
 
 uint64_t estimate_gap_cells(const std::vector<uint32_t>& contig_len)
@@ -63,8 +81,15 @@ std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts)
 }
 
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error)
+               std::string& error, MergeTimings* timings)
 {
+    using clk = std::chrono::steady_clock;
+    auto t_prev = clk::now();
+    auto lap = [&](double MergeTimings::*slot) {
+        const auto now = clk::now();
+        if (timings) timings->*slot += std::chrono::duration<double, std::milli>(now - t_prev).count();
+        t_prev = now;
+    };
     const size_t G = in.size();
     out.assign(G, GapOutput());
     std::vector<GapState> st(G);
@@ -86,14 +111,15 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     std::vector<const char*> seq_ptr;
     std::vector<uint32_t> seq_len;
     std::vector<gp_pair> pairs;
-    for (size_t g = 0; g < G; ++g) {
+    const unsigned host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    for_each_gap(G, host_threads, [&](size_t g) {
         GapState& s = st[g];
         std::string fatal;
         if (!read_fasta(in[g].fasta_path, s.contigs, fatal)) {
             out[g].stdout_text = "FATAL ERROR: " + fatal + "\n";          // THROW, fastareader.cpp:11-15
             out[g].exit_code = 1;
             s.dead = true;
-            continue;
+            return;
         }
         const size_t nc = s.contigs.size();
         s.node_seq.reserve(2 * nc); s.node_name.reserve(2 * nc);
@@ -112,40 +138,41 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             out[g].stdout_text = "FATAL ERROR: k-mer length is too large.\n";   // GetKmersList, :2060-2064
             out[g].exit_code = 1;
             s.dead = true;
-            continue;
+            return;
         }
-    }
-    // second loop so that sequence pointers stay valid (node_seq vectors no longer grow)
+        // candidate pairs of this gap (the quick check), or the reference's "Arrange error!" line
+        const long N = (long)s.node_seq.size();
+        const int T = opt.num_threads;
+        const long ranges = T > 0 ? arranged_ranges(N, T) : 0;
+        if (T <= 0 || ranges < T) {
+            out[g].stdout_text += "Arrange error! " + std::to_string(ranges) + " " + std::to_string(T) + "\n";   // :1034-1038
+            return;
+        }
+        s.arranged = true;
+        if (!scan_runs) return;        // no scan => every Evaluate is rejected (:1674-1722): no edges
+        std::vector<const char*> nodes;
+        std::vector<uint32_t> lens;
+        for (const std::string& q : s.node_seq) { nodes.push_back(q.data()); lens.push_back((uint32_t)q.size()); }
+        const uint64_t cap = (uint64_t)N * (N + 1) / 2;
+        s.cand.resize(cap);
+        const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), (uint32_t)N, opt.quick_kmer_len, s.cand.data(), cap);
+        if (np < 0) { s.cand_rc = (int)np; s.cand.clear(); return; }
+        s.cand.resize((size_t)np);
+    });
+    // serial: one sequence table and one pair list for the batch (node_seq vectors no longer grow)
     for (size_t g = 0; g < G; ++g) {
         GapState& s = st[g];
         if (s.dead) continue;
-        const long N = (long)s.node_seq.size();
+        if (s.cand_rc != 0) { error = "gp_candidate_pairs failed"; return s.cand_rc; }
         s.node_base = (uint32_t)seq_ptr.size();
-        std::vector<const char*> nodes;
-        std::vector<uint32_t> lens;
-        for (const std::string& q : s.node_seq) {
-            seq_ptr.push_back(q.data()); seq_len.push_back((uint32_t)q.size());
-            nodes.push_back(q.data()); lens.push_back((uint32_t)q.size());
-        }
-        const int T = opt.num_threads;
-        const long ranges = T > 0 ? arranged_ranges(N, T) : 0;
-        s.pair_begin = s.pair_end = pairs.size();
-        if (T <= 0 || ranges < T) {
-            out[g].stdout_text += "Arrange error! " + std::to_string(ranges) + " " + std::to_string(T) + "\n";   // :1034-1038
-            continue;
-        }
-        s.arranged = true;
-        if (!scan_runs) continue;      // no scan => every Evaluate is rejected (:1674-1722): no edges
-        const uint64_t cap = (uint64_t)N * (N + 1) / 2;
-        const size_t at = pairs.size();
-        pairs.resize(at + cap);
-        const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), (uint32_t)N, opt.quick_kmer_len, pairs.data() + at, cap);
-        if (np < 0) { error = "gp_candidate_pairs failed"; return (int)np; }
-        pairs.resize(at + (size_t)np);
-        for (size_t k = at; k < pairs.size(); ++k) { pairs[k].row_seq += s.node_base; pairs[k].col_seq += s.node_base; }
+        for (const std::string& q : s.node_seq) { seq_ptr.push_back(q.data()); seq_len.push_back((uint32_t)q.size()); }
+        s.pair_begin = pairs.size();
+        for (const gp_pair& c : s.cand) pairs.push_back(gp_pair{c.row_seq + s.node_base, c.col_seq + s.node_base});
         s.pair_end = pairs.size();
+        std::vector<gp_pair>().swap(s.cand);
     }
 
+    lap(&MergeTimings::read_ms);
     // ---- pairwise phase: one batch for all gaps (replaces runMultiThreadMergeV2, :696-721) ------
     std::vector<gp_result> res(pairs.size());
     if (!pairs.empty()) {
@@ -153,11 +180,13 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
     }
 
+    lap(&MergeTimings::pairwise_ms);
     // ---- edges, graph, paths (threadMergeContigV2 :652-685, addEdges :724-770, :898-931) --------
     std::vector<Chain> chains;
-    for (size_t g = 0; g < G; ++g) {
+    std::vector<std::vector<Chain>> gap_chains(G);
+    for_each_gap(G, host_threads, [&](size_t g) {
         GapState& s = st[g];
-        if (s.dead) continue;
+        if (s.dead) return;
         const int N = (int)s.node_seq.size();
         OverlapGraph graph(N);
         for (uint64_t k = s.pair_begin; k < s.pair_end; ++k) {
@@ -179,16 +208,19 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             if (p.size() > 1) {
                 Chain c;
                 c.gap = (int)g; c.path = p; c.merged = s.node_seq[p[0]];
-                chains.push_back(std::move(c));
+                gap_chains[g].push_back(std::move(c));
             }
         }
-    }
+    });
+    for (size_t g = 0; g < G; ++g) for (Chain& c : gap_chains[g]) chains.push_back(std::move(c));
 
+    lap(&MergeTimings::graph_ms);
     // ---- relax chains: step k of every chain in one batch (replaces the loop at :1463-1513) ------
     for (;;) {
         std::vector<size_t> active;
         for (size_t c = 0; c < chains.size(); ++c) if (chains[c].next < chains[c].path.size()) active.push_back(c);
         if (active.empty()) break;
+        if (timings) ++timings->relax_steps;
         std::vector<const char*> sp;
         std::vector<uint32_t> sl;
         std::vector<gp_pair> pp;
@@ -216,11 +248,12 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         }
     }
     for (Chain& ch : chains) st[ch.gap].merged.push_back(std::move(ch.merged));
+    lap(&MergeTimings::relax_ms);
 
     // ---- output (ContigsCompactor.cpp:945-971, CM/main.cpp:281-288) -------------------------------
-    for (size_t g = 0; g < G; ++g) {
+    for_each_gap(G, host_threads, [&](size_t g) {
         GapState& s = st[g];
-        if (s.dead) continue;
+        if (s.dead) return;
         std::map<std::string, std::string> name_to_path;                  // mapNewContigNameToPath
         int next_id = 1;                                                   // static contigNumNext, one process per gap
         size_t mi = 0;
@@ -235,7 +268,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         for (const FastaRecord& r : s.contigs) append_fasta(out[g].stdout_text, r.name, r.seq, opt.line_length);
         for (const auto& kv : name_to_path) out[g].info_text += kv.first + "  " + kv.second + "\n";   // :1555-1560
         out[g].wrote_info = true;
-    }
+    });
+    lap(&MergeTimings::output_ms);
     return GP_OK;
 }
 

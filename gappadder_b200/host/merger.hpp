@@ -45,11 +45,21 @@ struct GapOutput {
     uint32_t n_pairs = 0, n_relax = 0;
 };
 
+// Wall-clock phases of one merge_gaps call, milliseconds (filled when the pointer is given).
+struct MergeTimings {
+    double read_ms = 0;        // FASTA parsing, reverse complements, candidate pairs (quick check)
+    double pairwise_ms = 0;    // gp_overlap_batch of the pairwise phase (pack + H2D + kernels + D2H)
+    double graph_ms = 0;       // edges, overlap graph, GML text, path search
+    double relax_ms = 0;       // all relax-chain steps (one gp_overlap_batch per step)
+    double output_ms = 0;      // output text
+    uint32_t relax_steps = 0;
+};
+
 // Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
 // here is a GPU/library failure, never an input problem (those are reported per gap like the
 // reference does, on stdout with exit code 1).
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error);
+               std::string& error, MergeTimings* timings = nullptr);
 
 // Estimated DP cells of one gap's pairwise phase from contig lengths alone (all node pairs i <= j):
 // used to balance gaps over GPUs before any sequence is examined.
