@@ -18,6 +18,7 @@ EXPORTS = [
     "gp_is_score_significant", "gp_is_containment", "gp_merged_length", "gp_merged_concat",
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
+    "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
 ]
 
 
@@ -48,7 +49,7 @@ class Thresholds(C.Structure):
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
 FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16 = 1, 2, 4, 8
-KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_ALL = 1, 2, 3
+KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_ALL = 1, 2, 4, 7
 
 # GAPPadder's command line (MergeContigs.py:85): -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1
 GAPPADDER_DP = DpParams(-2, -2, 50)
@@ -106,6 +107,9 @@ def lib() -> C.CDLL:
         L.gp_partition_gaps.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_void_p]
         L.gp_pair_split.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gp_set_kernel_mask.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_cert_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.gp_set_cert_system.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.gp_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
         _lib = L
     return _lib
@@ -240,6 +244,23 @@ class Context:
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_pair_split(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return dict(table16=a.value, prmt16=b.value, wide32=c.value)
+
+    def cert_stats(self):
+        """Certificate kernel: pairs routed to it, and of the last fetched run the second passes and exact retries."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._L.gp_cert_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(cert16=a.value, second_passes=b.value, exact_retries=c.value)
+
+    def kernel_times(self):
+        """Device milliseconds of the last launch and host-routed DP cells per kernel: cert16, table16, prmt16, wide32."""
+        ms, cells = (C.c_double * 4)(), (C.c_uint64 * 4)()
+        self._check(self._L.gp_kernel_times(self._h, ms, cells))
+        names = ("cert16", "table16", "prmt16", "wide32")
+        return {k: dict(ms=ms[i], cells=int(cells[i])) for i, k in enumerate(names)}
+
+    def set_cert_system(self, system: int):
+        """Tests: 0 probe decides (default), 1 start with system U (column 0), 2 with system L (row 0)."""
+        self._check(self._L.gp_set_cert_system(self._h, system))
 
     def set_kernel_mask(self, mask: int):
         """Restricts the 16-bit kernels gp_upload_pairs may pick (tests, A/B timing); results never change."""

@@ -6,6 +6,7 @@
 #include "overlap_wf32.cuh"
 #include "overlap_wf16.cuh"
 #include "overlap_wf16t.cuh"
+#include "overlap_wf16c.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -67,12 +68,18 @@ struct gp_ctx {
     uint32_t kernel_mask = GP_KERNEL_ALL;
 
     // pair work lists
-    DeviceBuf d_pairs, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t;
-    HostBuf h_stage, h_pack, h_results;
+    DeviceBuf d_pairs, d_order16c, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t, d_scratch16c;
+    HostBuf h_stage, h_pack, h_results, h_queue;   // h_queue: [0,32) initial d_queue image, [32,64) counters read back
     std::vector<uint32_t> pack_off;
     double timing[GP_TIMING_SLOTS] = {0};       // milliseconds of the last gp_overlap_batch, see gp_last_timing
-    uint64_t n_pairs = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
-    uint32_t max_n16t = 0, max_n16 = 0, max_n32 = 0;
+    uint64_t n_pairs = 0, n16c = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
+    uint32_t max_n16c = 0, max_n16c_small = 0, max_n16t = 0, max_n16 = 0, max_n32 = 0;
+    uint32_t cert_system = 0;                   // 0: probe decides, 1: start with system U, 2: with system L (tests)
+    uint64_t second_passes = 0, exact_retries = 0;   // of the last fetched run
+    uint64_t cells16c = 0, cells16t = 0, cells16 = 0, cells32 = 0;     // host-routed DP cells per kernel
+    cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // kernel boundaries of the last launch
+    bool kev_valid = false;
+    gp::Wf16cParams p16c{};
     gp_dp_params params{};
     gp::Wf16Params p16{};
     gp::Wf16tParams p16t{};
@@ -120,7 +127,9 @@ int gp_create(int device, gp_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete c; return GP_ERR_CUDA;
     }
-    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess) {
+    for (auto& ev : c->kev)
+        if ((e = cudaEventCreate(&ev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA; }
+    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess) {
         g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
         cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA;
     }
@@ -133,8 +142,9 @@ void gp_destroy(gp_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
-    c->d_scratch16t.release();
+    c->d_scratch16t.release(); c->d_scratch16c.release(); c->d_order16c.release(); c->h_queue.release();
     c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
     c->h_stage.release(); c->h_pack.release(); c->h_results.release();
     delete c;
@@ -148,7 +158,7 @@ int gp_pair_stats(const gp_ctx* c, uint64_t* cells, uint64_t* pairs16, uint64_t*
 {
     if (!c) return GP_ERR_INVALID;
     if (cells) *cells = c->cells;
-    if (pairs16) *pairs16 = c->n16t + c->n16;
+    if (pairs16) *pairs16 = c->n16c + c->n16t + c->n16;
     if (pairs32) *pairs32 = c->n32;
     return GP_OK;
 }
@@ -156,9 +166,44 @@ int gp_pair_stats(const gp_ctx* c, uint64_t* cells, uint64_t* pairs16, uint64_t*
 int gp_pair_split(const gp_ctx* c, uint64_t* table16, uint64_t* prmt16, uint64_t* wide32)
 {
     if (!c) return GP_ERR_INVALID;
-    if (table16) *table16 = c->n16t;
+    if (table16) *table16 = c->n16t;      // routed by the host; the certificate kernel's retries come on top
     if (prmt16) *prmt16 = c->n16;
     if (wide32) *wide32 = c->n32;
+    return GP_OK;
+}
+
+int gp_cert_stats(const gp_ctx* c, uint64_t* cert16, uint64_t* second_passes, uint64_t* exact_retries)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (cert16) *cert16 = c->n16c;
+    if (second_passes) *second_passes = c->second_passes;
+    if (exact_retries) *exact_retries = c->exact_retries;
+    return GP_OK;
+}
+
+int gp_kernel_times(gp_ctx* c, double* ms, uint64_t* cells)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (cells) { cells[0] = c->cells16c; cells[1] = c->cells16t; cells[2] = c->cells16; cells[3] = c->cells32; }
+    if (ms) {
+        for (int k = 0; k < 4; ++k) ms[k] = 0.0;
+        if (c->kev_valid) {
+            GP_CUDA(c, cudaSetDevice(c->device));
+            GP_CUDA(c, cudaEventSynchronize(c->kev[4]));
+            for (int k = 0; k < 4; ++k) {
+                float t = 0.f;
+                GP_CUDA(c, cudaEventElapsedTime(&t, c->kev[k], c->kev[k + 1]));
+                ms[k] = t;
+            }
+        }
+    }
+    return GP_OK;
+}
+
+int gp_set_cert_system(gp_ctx* c, uint32_t system)
+{
+    if (!c || system > 2) return GP_ERR_INVALID;
+    c->cert_system = system;
     return GP_OK;
 }
 
@@ -209,22 +254,27 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
     if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
     GP_CUDA(c, cudaSetDevice(c->device));
     c->params = *params;
-    c->n_pairs = n_pairs; c->n16t = c->n16 = c->n32 = 0; c->cells = 0; c->max_n16t = c->max_n16 = c->max_n32 = 0;
+    c->n_pairs = n_pairs; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
+    c->max_n16c = c->max_n16c_small = c->max_n16t = c->max_n16 = c->max_n32 = 0;
+    c->cells16c = c->cells16t = c->cells16 = c->cells32 = 0; c->kev_valid = false;
     if (n_pairs == 0) return GP_OK;
 
     const uint32_t n_seq = (uint32_t)c->seq_len.size();
     const bool params_ok = gp::wf16_params_ok(params->mismatch, params->indel);
     const bool params16 = params_ok && c->n_symbols <= 8 && (c->kernel_mask & GP_KERNEL_PRMT16);
     const bool params16t = params_ok && (c->kernel_mask & GP_KERNEL_TABLE16);
+    const bool params16c = params_ok && (c->kernel_mask & GP_KERNEL_CERT16);
     if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip, c->n_symbols <= 4);
-    if (params16t) c->p16t = gp::wf16t_make_params(params->mismatch, params->indel, params->max_clip);
+    if (params16t || params16c) c->p16t = gp::wf16t_make_params(params->mismatch, params->indel, params->max_clip);
+    if (params16c) c->p16c = gp::wf16c_make_params(params->mismatch, params->indel, params->max_clip);
 
-    // stage: [PairDesc n][order16t n][order16 n][order32 n]
+    // stage: [PairDesc n][order16c n][order16t n][order16 n][order32 n]
     const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
     const size_t ord_bytes = n_pairs * sizeof(uint32_t);
-    GP_CUDA(c, c->h_stage.reserve(desc_bytes + 3 * ord_bytes));
+    GP_CUDA(c, c->h_stage.reserve(desc_bytes + 4 * ord_bytes));
     gp::PairDesc* hd = (gp::PairDesc*)c->h_stage.p;
-    uint32_t* ho16t = (uint32_t*)((char*)c->h_stage.p + desc_bytes);
+    uint32_t* ho16c = (uint32_t*)((char*)c->h_stage.p + desc_bytes);
+    uint32_t* ho16t = ho16c + n_pairs;
     uint32_t* ho16 = ho16t + n_pairs;
     uint32_t* ho32 = ho16 + n_pairs;
     uint64_t max_total = 0;
@@ -235,9 +285,15 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
         hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
         c->cells += (uint64_t)m * n;
         max_total = std::max<uint64_t>(max_total, (uint64_t)m + n);
-        if (params16t && gp::wf16t_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) { ho16t[c->n16t++] = (uint32_t)i; c->max_n16t = std::max(c->max_n16t, n); }
-        else if (params16 && gp::wf16_pair_ok(m, n)) { ho16[c->n16++] = (uint32_t)i; c->max_n16 = std::max(c->max_n16, n); }
-        else { ho32[c->n32++] = (uint32_t)i; c->max_n32 = std::max(c->max_n32, n); }
+        // certificate kernel: everything A/C/G/T except a sequence against itself (its walk ends in the corner
+        // (0,0), which no certificate covers: straight to an exact kernel)
+        if (params16c && a != b && gp::wf16c_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) {
+            ho16c[c->n16c++] = (uint32_t)i; c->max_n16c = std::max(c->max_n16c, n); c->cells16c += (uint64_t)m * n;
+            if (n <= gp::WF16T_MAX_N) c->max_n16c_small = std::max(c->max_n16c_small, n);
+        }
+        else if (params16t && gp::wf16t_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) { ho16t[c->n16t++] = (uint32_t)i; c->max_n16t = std::max(c->max_n16t, n); c->cells16t += (uint64_t)m * n; }
+        else if (params16 && gp::wf16_pair_ok(m, n)) { ho16[c->n16++] = (uint32_t)i; c->max_n16 = std::max(c->max_n16, n); c->cells16 += (uint64_t)m * n; }
+        else { ho32[c->n32++] = (uint32_t)i; c->max_n32 = std::max(c->max_n32, n); c->cells32 += (uint64_t)m * n; }
     }
     // 28-bit score field / 30-bit rank field of the kernels
     const uint64_t amax = (uint64_t)std::max(std::max(std::abs(params->mismatch), std::abs(params->indel)), 1);
@@ -257,17 +313,27 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
         for (uint32_t b = 0; b <= B; ++b) { const uint32_t v = start[b]; start[b] = run; run += v; }
         for (uint64_t k = 0; k < cnt; ++k) ord[start[B - 1 - (uint32_t)(((uint64_t)hd[tmp[k]].m * hd[tmp[k]].n) / width)]++] = tmp[k];
     };
+    by_cells(ho16c, c->n16c);
     by_cells(ho16t, c->n16t);
     by_cells(ho16, c->n16);
     by_cells(ho32, c->n32);
 
     GP_CUDA(c, c->d_pairs.reserve(desc_bytes));
+    GP_CUDA(c, c->d_order16c.reserve(ord_bytes));
     GP_CUDA(c, c->d_order16t.reserve(ord_bytes));
     GP_CUDA(c, c->d_order16.reserve(ord_bytes));
     GP_CUDA(c, c->d_order32.reserve(ord_bytes));
     GP_CUDA(c, c->d_results.reserve(n_pairs * sizeof(gp::DevResult)));
     GP_CUDA(c, c->d_queue.reserve(128));
+    GP_CUDA(c, c->h_queue.reserve(256));
+    {   // initial image of the queue block: work-queue heads 0, fill counts of the exact kernels' lists
+        uint32_t* q = (uint32_t*)c->h_queue.p;
+        memset(q, 0, 128);
+        q[4] = (uint32_t)c->n16t;
+        q[12] = (uint32_t)c->n32;
+    }
     GP_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hd, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->n16c) GP_CUDA(c, cudaMemcpyAsync(c->d_order16c.p, ho16c, c->n16c * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n16t) GP_CUDA(c, cudaMemcpyAsync(c->d_order16t.p, ho16t, c->n16t * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n16) GP_CUDA(c, cudaMemcpyAsync(c->d_order16.p, ho16, c->n16 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n32) GP_CUDA(c, cudaMemcpyAsync(c->d_order32.p, ho32, c->n32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -288,15 +354,33 @@ int gp_launch_resident(gp_ctx* c)
     if (!c) return GP_ERR_INVALID;
     if (c->n_pairs == 0) return GP_OK;
     GP_CUDA(c, cudaSetDevice(c->device));
-    GP_CUDA(c, cudaMemsetAsync(c->d_queue.p, 0, 128, c->stream));
+    // queue block (32 words): [0] wf16 head, [8] wf32 head, [16] wf16t head, [24] wf16c head,
+    // [4] fill count of the wf16t work list, [12] of the wf32 work list (the certificate kernel appends its
+    // retries to both), [20] second passes, [21] exact retries
+    GP_CUDA(c, cudaMemcpyAsync(c->d_queue.p, c->h_queue.p, 128, cudaMemcpyHostToDevice, c->stream));
     unsigned int* queue = (unsigned int*)c->d_queue.p;
-    if (c->n16t) {
+    const bool cert = c->n16c != 0;
+    GP_CUDA(c, cudaEventRecord(c->kev[0], c->stream));
+    if (cert) {
+        int rc = gp::wf16c_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
+                                  (const uint32_t*)c->d_order16c.p, (uint32_t)c->n16c, queue + 24, c->p16c, c->max_n16c,
+                                  &c->d_scratch16c.p, &c->d_scratch16c.cap,
+                                  (uint32_t*)c->d_order16t.p, queue + 4, (uint32_t*)c->d_order32.p, queue + 12,
+                                  queue + 20, c->cert_system, (gp::DevResult*)c->d_results.p);
+        if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16c launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        c->launches += 1;
+    }
+    GP_CUDA(c, cudaEventRecord(c->kev[1], c->stream));
+    const bool big_retries = cert && c->max_n16c > gp::WF16T_MAX_N;      // retries the table kernel cannot take
+    if (c->n16t || cert) {
         int rc = gp::wf16t_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
-                                  (const uint32_t*)c->d_order16t.p, (uint32_t)c->n16t, queue + 16, c->p16t, c->max_n16t,
-                                  &c->d_scratch16t.p, &c->d_scratch16t.cap, (gp::DevResult*)c->d_results.p);
+                                  (const uint32_t*)c->d_order16t.p, (uint32_t)c->n16t, queue + 16, c->p16t,
+                                  std::max(c->max_n16t, c->max_n16c_small),
+                                  &c->d_scratch16t.p, &c->d_scratch16t.cap, (gp::DevResult*)c->d_results.p, cert ? queue + 4 : nullptr);
         if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16t launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
     }
+    GP_CUDA(c, cudaEventRecord(c->kev[2], c->stream));
     if (c->n16) {
         int rc = gp::wf16_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
                                  (const uint32_t*)c->d_order16.p, (uint32_t)c->n16, queue, c->p16, c->max_n16,
@@ -304,19 +388,22 @@ int gp_launch_resident(gp_ctx* c)
         if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16 launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
     }
-    if (c->n32) {
+    GP_CUDA(c, cudaEventRecord(c->kev[3], c->stream));
+    if (c->n32 || big_retries) {
         constexpr int R = 8, THREADS = 128;
         const int blocks = c->sm_count * 8;
         const uint32_t warps = (uint32_t)blocks * (THREADS / 32);
-        const uint32_t stride = (c->max_n32 + 1 + 31) & ~31u;
+        const uint32_t stride = (std::max(c->max_n32, big_retries ? c->max_n16c : 0u) + 1 + 31) & ~31u;
         GP_CUDA(c, c->d_scratch32.reserve((size_t)warps * stride * sizeof(int32_t)));
         gp::overlap_wf32_kernel<R><<<blocks, THREADS, 0, c->stream>>>(
             (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p, (const uint32_t*)c->d_order32.p,
             (uint32_t)c->n32, queue + 8, c->params.mismatch, c->params.indel, c->params.max_clip,
-            (int32_t*)c->d_scratch32.p, stride, (gp::DevResult*)c->d_results.p);
+            (int32_t*)c->d_scratch32.p, stride, (gp::DevResult*)c->d_results.p, big_retries ? queue + 12 : nullptr);
         GP_CUDA(c, cudaGetLastError());
         c->launches += 1;
     }
+    GP_CUDA(c, cudaEventRecord(c->kev[4], c->stream));
+    c->kev_valid = true;
     return GP_OK;
 }
 
@@ -329,7 +416,10 @@ int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n_pairs)
     GP_CUDA(c, cudaSetDevice(c->device));
     static_assert(sizeof(gp_result) == sizeof(gp::DevResult), "result layouts must match");
     GP_CUDA(c, cudaMemcpyAsync(out, c->d_results.p, n_pairs * sizeof(gp_result), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync((uint32_t*)c->h_queue.p + 32, c->d_queue.p, 128, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->second_passes = ((const uint32_t*)c->h_queue.p)[32 + 20];
+    c->exact_retries = ((const uint32_t*)c->h_queue.p)[32 + 21];
     return GP_OK;
 }
 
@@ -343,7 +433,10 @@ static int run_and_fetch(gp_ctx* c, gp_result* out, uint64_t n_pairs)
     const size_t bytes = n_pairs * sizeof(gp_result);
     GP_CUDA(c, c->h_results.reserve(bytes));
     GP_CUDA(c, cudaMemcpyAsync(c->h_results.p, c->d_results.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync((uint32_t*)c->h_queue.p + 32, c->d_queue.p, 128, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->second_passes = ((const uint32_t*)c->h_queue.p)[32 + 20];
+    c->exact_retries = ((const uint32_t*)c->h_queue.p)[32 + 21];
     memcpy(out, c->h_results.p, bytes);
     return GP_OK;
 }

@@ -1,0 +1,578 @@
+// overlap_wf16c.cuh -- packed 16-bit overlap-DP kernel with origin CERTIFICATES instead of tie tags
+// ("certificate kernel", sm_100a).  The hot kernel for what GAPPadder produces: A/C/G/T sequences whose
+// column sequence has at most 16382 bases.  Same contract as the other overlap kernels
+// (ContigsCompactor::Evaluate before the significance test,
+// ContigsCompactor-v0.2.0/ContigsMerger/ContigsCompactor.cpp:1596-1709,:1736-1837).
+//
+// Why.  The table kernel (overlap_wf16t.cuh) spends one of its three ALU-pipe instructions per cell
+// pair on the z tag that makes a packed max reproduce the reference's diag > up > left tie rule
+// (:1651-1665).  The tie rule never changes a score, only WHICH optimal predecessor walk the
+// reference follows, and the walk is used for exactly one thing: whether it ends in row 0 or in
+// column 0 (:1834-1837).  This kernel drops the tag (two ALU-pipe instructions per cell pair) and
+// proves the walk's end instead:
+//
+//   V = 2*(P+1) + b,   P = H + (n - j) clamped at -1 (as in overlap_wf16.cuh),   b = one origin bit.
+//
+//   A packed max over candidates with equal P takes the larger b, so b(cell) = OR of b over ALL
+//   optimal predecessor walks into the cell, whatever the tie rule.
+//     system U:  b = 1 on row 0 (corner included), 0 on column 0.   b(best) = 0  <=>  every optimal
+//                walk into the best cell ends in column 0 below the corner, so the reference's walk
+//                does:  tbCur.second == 0, tbCur.first > 0.
+//     system L:  b = 1 on column 0 (corner included), 0 on row 0.   b(best) = 0  <=>  every optimal
+//                walk ends in row 0 right of the corner: tbCur.first == 0, tbCur.second > 0.
+//   Scores, and therefore the best cell (score, posRowEnd, posColEnd, nclip), are exact in either system.
+//
+// Per pair: a 16-base probe predicts the system (the first bases of the column sequence occur in the row
+// sequence -> the walk will end in column 0 -> U; the first bases of the row sequence occur in the column
+// sequence -> L).  If the certificate fails (b = 1) the other system is run on the sub-table that ends
+// at the best cell (rows 1..posRowEnd, columns 1..posColEnd: usually a sliver, because a wrong guess
+// means the best cell sits in the opposite corner) and reports that one cell's bit.  If that fails too
+// (walks through the corner (0,0), e.g. a sequence against itself, or a genuine tie between a row-0 and
+// a column-0 walk) the pair is appended to a retry list and recomputed by an exact kernel
+// (overlap_wf16t.cuh or overlap_wf32.cuh) launched behind this one.  Results are therefore always
+// the reference's; the certificates only decide which kernel produces them.
+//
+// The wavefront machinery is the table kernel's: one warp per pair, strips of 64*K rows, lane l owns 2K
+// consecutive rows (K lo rows in the low halves, K hi rows one column behind in the high halves),
+// per-warp shared-memory increment table (16 column-symbol combinations x K words per lane), a ring of
+// per-column data, lanes 3 columns apart with the shuffle issued one step ahead, 32-step blocks
+// instantiated for {edge, filter} flags, candidate filter under the column potential.
+//
+// Host/device: the per-lane arithmetic is __host__ __device__; tests/emulate_wf16.cu runs it on the CPU
+// against the oracle.
+#pragma once
+#include <type_traits>
+#include "overlap_wf16t.cuh"
+
+namespace gp {
+
+constexpr uint32_t WF16C_MAX_N = 16382;           // 2*(n+1)+1 <= 32767
+constexpr int WF16C_THREADS = 128;                // 4 warps per CTA
+constexpr int WF16C_CTAS_PER_SM = 3;              // 12 warps per SM: 3 x (4 x 17.1 KB) of shared memory
+constexpr int WF16C_RING = 128;
+constexpr int WF16C_SKEW = 3;
+constexpr int WF16C_TAB_WORDS = 16 * 8 * 32;
+constexpr int WF16C_WARP_WORDS = WF16C_TAB_WORDS + 2 * WF16C_RING + 32;
+constexpr size_t WF16C_SMEM_BYTES = (size_t)(WF16C_THREADS / 32) * WF16C_WARP_WORDS * sizeof(uint32_t);
+constexpr int WF16C_PROBE = 16;                   // bases of the orientation probe (two packed words)
+
+inline bool wf16c_pair_ok(uint32_t m, uint32_t n) { return m >= 1 && n >= 1 && n <= WF16C_MAX_N && m <= 0xffffff; }
+
+struct Wf16cParams {
+    uint32_t inc_mism;              // 16-bit diagonal increment of a mismatch, 2*(X-1) (a match adds 0)
+    uint32_t gup, gleft;            // packed up / left increments under the column potential
+    int32_t max_clip;
+    int32_t std_scores;             // mismatch == -2 && indel == -2: the kernel with immediate operands
+};
+
+inline Wf16cParams wf16c_make_params(int mismatch, int indel, int max_clip)
+{
+    Wf16cParams p;
+    p.inc_mism = (uint32_t)((mismatch - 1) * 2) & 0xffffu;
+    auto pk = [](int v) { uint32_t h = (uint32_t)(v * 2) & 0xffffu; return h | (h << 16); };
+    p.gup = pk(indel);
+    p.gleft = pk(indel - 1);
+    p.max_clip = max_clip;
+    p.std_scores = (mismatch == -2 && indel == -2) ? 1 : 0;
+    return p;
+}
+
+// One DP pass: the sub-table rows 1..m, columns 1..n of a pair in one certificate system.
+//   scan mode: the reference's best-cell scan (C = max_clip) over the whole table of the pair;
+//   cell mode: only cell (m, n) is reported (its score must be s_cell).
+struct Wf16cPass {
+    int m, n, C;
+    uint32_t brow, bcol;            // origin bit on row 0 (j >= 1) / on column 0 (i >= 1); the corner has 1
+    bool cell;
+    int s_cell;
+    uint32_t gup, gleft;
+    GP_HD uint32_t v_col0(int i) const { return (uint32_t)(2 * (n + 1)) + (i == 0 ? 1u : bcol); }
+    GP_HD uint32_t v_row0(int j) const { return (uint32_t)(2 * (n - j + 1)) + (j == 0 ? 1u : brow); }
+};
+
+GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, bool sysL, bool cell, int s_cell)
+{
+    Wf16cPass g;
+    g.m = m; g.n = n; g.C = cell ? 0 : P.max_clip;
+    g.brow = sysL ? 0u : 1u;
+    g.bcol = sysL ? 1u : 0u;
+    g.cell = cell; g.s_cell = s_cell;
+    g.gup = P.gup; g.gleft = P.gleft;
+    return g;
+}
+
+// Boundary-line word of column j (1..n+1): V(0,j) in the low half, the symbol combination
+// c_j + 4*c_{j-1} (c_0 = c_{n+1} = 0) above it.
+GP_HD uint32_t wf16c_line_word(const Wf16cPass& g, int j, uint32_t cj, uint32_t cjm1)
+{
+    return g.v_row0(j <= g.n ? j : g.n) | (((cj & 3u) | ((cjm1 & 3u) << 2)) << 16);
+}
+
+GP_HD uint32_t wf16c_table_word(uint32_t row_lo, uint32_t row_hi, uint32_t ca, uint32_t cb, const Wf16cParams& P)
+{
+    return (row_lo == ca ? 0u : P.inc_mism) | ((row_hi == cb ? 0u : P.inc_mism) << 16);
+}
+
+template <int K>
+struct Lane16c {
+    uint32_t W[K];       // (row k @ col j | row K+k @ col j-1 << 16)
+    uint32_t up0_prev;   // previous step's `up` of W[0] == this step's diagonal of W[0]
+};
+
+template <int K>
+GP_HD void lane16c_begin(Lane16c<K>& st, const Wf16cPass& g, int itop)
+{
+    const uint32_t c0 = g.v_col0(1);                       // the same for every row >= 1
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.W[k] = c0 | (c0 << 16);
+    st.up0_prev = g.v_col0(itop) | (c0 << 16);
+}
+
+// After a lane's first step the hi group has "computed" column 0: put the boundary back.
+template <int K>
+GP_HD void lane16c_fix_first(Lane16c<K>& st, const Wf16cPass& g)
+{
+    const uint32_t c0 = g.v_col0(1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.W[k] = (st.W[k] & 0xffffu) | (c0 << 16);
+}
+
+// One step: VIADD.16x2 + 2 x VIADDMNMX.S16x2 per register, nothing else.
+template <int K>
+GP_HD void lane16c_step(Lane16c<K>& st, uint32_t recv, const uint32_t (&inc)[K], uint32_t gup, uint32_t gleft)
+{
+    const uint32_t up0 = p_prmt(recv, st.W[K - 1], 0x5432u);   // (recv.hi16 , old W[K-1].lo16)
+    uint32_t diag = st.up0_prev;
+    st.up0_prev = up0;
+    uint32_t up = up0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t left = st.W[k];
+        const uint32_t d = p_add2(diag, inc[k]);
+        const uint32_t t = p_addmax2(left, gleft, d);
+        const uint32_t w = p_addmax2_relu(up, gup, t);
+        diag = left;
+        up = w;
+        st.W[k] = w;
+    }
+}
+
+template <int K>
+GP_HD uint32_t lane16c_max(const Lane16c<K>& st)
+{
+    uint32_t a = st.W[0];
+    if (K == 2) a = p_max2(a, st.W[1]);
+    if (K >= 4) a = p_max3_2(p_max2(a, st.W[1]), st.W[2], st.W[3]);
+    if (K == 8) a = p_max3_2(p_max3_2(a, st.W[4], st.W[5]), st.W[6], st.W[7]);
+    return a;
+}
+
+// Candidate filter under the column potential.  nthr = -(the V a cell has when H = 1) for the lo column
+// j (low half) and the hi column j-1 (high half): acc = max(V) + nthr = 2*(H-1) + b of the lane's best
+// cell, compared with thrS = 2*(max(S,1)-1).
+GP_HD uint32_t wf16c_nthr(const Wf16cPass& g, int j)
+{
+    const uint32_t lo = (uint32_t)(-2 * (g.n - j + 2)) & 0xffffu;          // 1 <= j: >= -2*(16382+1)
+    const uint32_t hi = (uint32_t)(-2 * (g.n - j + 3)) & 0xffffu;          // column j-1 >= 0: >= -32768; other j wrap mod 2^16
+    return lo | (hi << 16);
+}
+constexpr uint32_t WF16C_UNARMED = 0x7fff7fffu;   // threshold no acc reaches (acc <= 2*n + 1 < 32767)
+constexpr uint32_t WF16C_NSTEP = 0x00020002u;
+GP_HD uint32_t wf16c_filter_thr(int S) { const uint32_t t = (uint32_t)(2 * ((S > 1 ? S : 1) - 1)); return t | (t << 16); }
+
+// Exact scan of the cells a lane holds after a step (lo column j, hi column j-1).  Scan mode: a cell can
+// only change `best` if it scores at least the lane's best score (and at least 1: the initial best is
+// cell (0,n) with H = 0 and rank 0); that one compare per cell comes first, the rank arithmetic only runs
+// for the cells that pass.  Cell mode: only cell (m, n) counts.  The key's origin field holds b.
+template <int K>
+GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int j, long long best)
+{
+    const int m = g.m, n = g.n;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int jh = j - half;
+        if (jh < 1 || jh > n) continue;
+        if (g.cell) {
+            if (jh != n) continue;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = itop + 1 + k + half * K;
+                if (i == m) {
+                    const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
+                    const long long key = make_key((vv >> 1) - 1, 0u, (uint32_t)vv & 1u);
+                    best = key > best ? key : best;
+                }
+            }
+            continue;
+        }
+        int S = (int)(best >> 32);
+        int thrV = 2 * ((S > 1 ? S : 1) + n - jh + 1);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
+            if (vv >= thrV) {
+                const int i = itop + 1 + k + half * K;
+                const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, g.C) : RANK_MAX + 1u;
+                if (rk <= RANK_MAX) {
+                    const long long key = make_key((vv >> 1) - 1 - (n - jh), rk, (uint32_t)vv & 1u);
+                    if (key > best) {
+                        best = key;
+                        S = (int)(best >> 32);
+                        thrV = 2 * ((S > 1 ? S : 1) + n - jh + 1);
+                    }
+                }
+            }
+        }
+    }
+    return best;
+}
+
+// Initial `best` of a pass.  Scan mode: cell (0,n), the first cell the reference scans (rank 0, H = 0);
+// its walk ends where it starts, in row 0, so its b is the row-0 bit (1 for the corner).  Cell mode: a
+// sentinel just below the expected score.
+GP_HD long long wf16c_initial_best(const Wf16cPass& g)
+{
+    if (g.cell) return make_key(g.s_cell - 1, RANK_MAX, 0u);
+    return make_key(0, 0u, g.n == 0 ? 1u : g.brow);
+}
+
+// What a finished pass proves.  Returns the origin flags (FLAG_ROW0 | FLAG_COL0) when the pass certifies
+// them, 0 when it does not.  `key` is the pass's warp-wide best.
+GP_HD uint32_t wf16c_certified_origin(const Wf16cPass& g, long long key)
+{
+    const uint32_t lo = (uint32_t)(key & 0xffffffffll);
+    if (!g.cell && (int)(key >> 32) == 0 && (RANK_MAX - (lo >> 2)) == 0u)     // the best cell is (0,n) itself
+        return FLAG_ROW0 | (g.n == 0 ? FLAG_COL0 : 0u);
+    if (g.cell && (int)(key >> 32) != g.s_cell) return 0u;                      // cannot happen; be safe
+    if (lo & 1u) return 0u;
+    return g.brow ? FLAG_COL0 : FLAG_ROW0;      // system U proves column 0, system L proves row 0
+}
+
+#if defined(__CUDACC__)
+// ---- device side ------------------------------------------------------------------------------
+
+struct Wf16cWarp {                      // warp-uniform state of one pass
+    const uint32_t* packed;
+    PairDesc pd;
+    Wf16cPass g;
+    uint32_t* bnd;                      // boundary line in global scratch (see wf16c_line_word)
+    uint32_t* smem;                     // this warp's WF16C_WARP_WORDS words of shared memory
+};
+
+template <int K> struct CVals { uint32_t W[K]; };
+
+template <int K>
+__device__ __noinline__ long long wf16c_scan_cold(CVals<K> v, Wf16cPass g, int itop, int j, long long best)
+{
+    return lane16c_scan<K>(v.W, g, itop, j, best);
+}
+
+// One strip of 64*K rows starting after table row `i0` (see wf16t_strip for the block structure).
+template <int K, bool STD>
+__device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P, int i0, bool rowscan, bool store_bottom, long long best)
+{
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t LANE_BYTES = K >= 4 ? 16u : 4u * K;         // bytes a lane owns per table row
+    constexpr uint32_t COMBO_BYTES = K * 128u;                      // table bytes per combination
+    constexpr int D = WF16C_SKEW;
+    const int lane = threadIdx.x & 31;
+    const Wf16cPass g = w.g;
+    const int n = g.n, m = g.m;
+    const int itop = i0 + lane * 2 * K;
+    const uint32_t gup = STD ? 0xfffcfffcu : g.gup, gleft = STD ? 0xfffafffau : g.gleft;
+    uint32_t* const bnd = w.bnd;
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(w.smem);
+    const uint32_t ring_base = tab_base + WF16C_TAB_WORDS * 4;
+    const uint32_t oring_base = ring_base + 2 * WF16C_RING * 4;
+    const uint32_t my_tab = tab_base + lane * LANE_BYTES;
+
+    // ---- increment table of this lane's rows ---------------------------------------------------
+    {
+        uint32_t rc[2 * K];
+#pragma unroll
+        for (int x = 0; x < 2 * K; ++x) rc[x] = (itop + x < m) ? load_code(w.packed, w.pd.row_off, (uint32_t)(itop + x)) : 0u;
+#pragma unroll 1
+        for (uint32_t combo = 0; combo < 16; ++combo) {
+            const uint32_t ca = combo & 3u, cb = combo >> 2;
+            uint32_t wd[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) wd[k] = wf16c_table_word(rc[k], rc[K + k], ca, cb, P);
+            const uint32_t a = my_tab + combo * COMBO_BYTES;
+            if constexpr (K >= 4) {
+#pragma unroll
+                for (int q = 0; q < K / 4; ++q)
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a + q * 512), "r"(wd[4 * q]), "r"(wd[4 * q + 1]),
+                                 "r"(wd[4 * q + 2]), "r"(wd[4 * q + 3]) : "memory");
+            } else if constexpr (K == 2) {
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(wd[0]), "r"(wd[1]) : "memory");
+            } else {
+                sts32(a, wd[0]);
+            }
+        }
+    }
+    // ---- ring: every slot valid (offset 0), then columns 1..32 ------------------------------------
+    auto ring_word = [&](uint32_t line) {      // boundary-line word -> (table offset << 16 | value)
+        return (line & 0xffffu) | (((line >> 16) & 15u) * COMBO_BYTES) << 16;
+    };
+    auto ring_put = [&](int jj, uint32_t line) {
+        const uint32_t v = ring_word(line);
+        sts32(ring_base + 4 * (jj & (WF16C_RING - 1)), v);
+        sts32(ring_base + 4 * ((jj & (WF16C_RING - 1)) + WF16C_RING), v);
+    };
+    for (int e = lane; e < 2 * WF16C_RING; e += 32) sts32(ring_base + 4 * e, 0u);
+    __syncwarp();
+    { const int jj = 1 + lane; ring_put(jj, bnd[jj <= n + 1 ? jj : n + 1]); }
+    Lane16c<K> st;
+    lane16c_begin<K>(st, g, itop);
+
+    // ---- candidate filter state --------------------------------------------------------------------
+    int S0;
+    {   // start from the warp's best score
+        int s = (int)(best >> 32);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { int other = __shfl_xor_sync(FULL, s, o); s = other > s ? other : s; }
+        S0 = s;
+    }
+    uint32_t thrS = wf16c_filter_thr(S0);
+    const int jswitch = n - g.C > 1 ? n - g.C : 1;                        // first candidate column
+    const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
+    const int jarm = rowlane ? 1 : jswitch;
+    const int t_end = n + 1 + 31 * D;                                     // lane 31's lo group reaches column n+1
+    const bool do_store = store_bottom && lane == 31;
+    uint32_t recv_next = 0;                                               // shuffle issued one step ahead
+
+    auto slow_path = [&](int j) {                                         // exact scan of this lane's cells
+        CVals<K> v;
+#pragma unroll
+        for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
+        best = wf16c_scan_cold<K>(v, g, itop, j, best);
+        const int s = (int)(best >> 32);
+        thrS = wf16c_filter_thr(s > S0 ? s : S0);
+    };
+    __syncwarp();
+
+    auto run_block = [&](auto edge_c, auto filt_c, int tb, int cnt) {
+        constexpr bool EDGE = decltype(edge_c)::value, FILT = decltype(filt_c)::value;
+        uint32_t p = ring_base + (((uint32_t)(tb - D * lane)) & (WF16C_RING - 1)) * 4u;
+        uint32_t optr = oring_base;
+        int j = tb - D * lane;                                            // my lo column
+        uint32_t nthr = FILT ? wf16c_nthr(g, j) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
+        uint32_t incA[K], incB[K];
+        uint32_t wordA = lds32(p), wordB = lds32(p + 4);
+        lds_inc<K>(incA, my_tab + (wordA >> 16));
+        auto step = [&](const uint32_t (&inc)[K], uint32_t word, uint32_t oaddr, int jj) {
+            uint32_t recv = recv_next;
+            recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
+            if (lane == 0) recv = word << 16;
+            if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
+                lane16c_step<K>(st, recv, inc, gup, gleft);
+                if (EDGE && jj == 1) lane16c_fix_first<K>(st, g);
+                if (do_store) sts32(oaddr, st.W[K - 1]);
+                if (FILT) {
+                    const uint32_t acc = p_add2(lane16c_max<K>(st), nthr);
+                    if (filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED)) slow_path(jj);
+                }
+            }
+            if (FILT) nthr = p_add2(nthr, WF16C_NSTEP);
+        };
+#pragma unroll 1
+        for (int s = 0; s < cnt; s += 2) {
+            lds_inc<K>(incB, my_tab + (wordB >> 16));
+            const uint32_t wordA2 = lds32(p + 8);
+            step(incA, wordA, optr, j);
+            lds_inc<K>(incA, my_tab + (wordA2 >> 16));
+            const uint32_t wordB2 = lds32(p + 12);
+            step(incB, wordB, optr + 4, j + 1);
+            wordA = wordA2; wordB = wordB2;
+            p += 8; optr += 8; j += 2;
+        }
+    };
+    using std::true_type;
+    using std::false_type;
+
+    for (int tb = 1; tb <= t_end; tb += 32) {
+        // the next block's boundary words (L2 latency hidden behind this block)
+        uint32_t next_line = 0;
+        const bool have_next = tb + 32 <= t_end;
+        if (have_next) { const int jj = tb + 32 + lane; next_line = bnd[jj <= n + 1 ? jj : n + 1]; }
+        const bool edge = tb < 31 * D + 1 || tb + 31 > n + 1;             // some lane outside columns 1..n+1
+        const bool filt = rowscan || tb + 31 >= jswitch;                  // some lane may hold candidates
+        const int cnt = t_end - tb + 1 < 32 ? ((t_end - tb + 2) & ~1) : 32;   // steps past t_end find every lane out of range
+        if (!edge) { if (!filt) run_block(false_type(), false_type(), tb, cnt); else run_block(false_type(), true_type(), tb, cnt); }
+        else       { if (!filt) run_block(true_type(), false_type(), tb, cnt);  else run_block(true_type(), true_type(), tb, cnt); }
+        __syncwarp();
+        if (store_bottom) {                                               // bottom row of the columns lane 31 finished
+            const int c = tb + lane - (31 * D + 1);
+            const uint32_t v = lds32(oring_base + 4 * lane);
+            if (c >= 1 && c <= n && lane < cnt) reinterpret_cast<uint16_t*>(bnd)[2 * c] = (uint16_t)(v >> 16);
+        }
+        if (have_next) ring_put(tb + 32 + lane, next_line);
+        if (filt) {                                                       // share the best score across the warp
+            int s = (int)(best >> 32);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { int other = __shfl_xor_sync(FULL, s, o); s = other > s ? other : s; }
+            S0 = s > S0 ? s : S0;
+            thrS = wf16c_filter_thr(S0);
+        }
+        __syncwarp();
+    }
+    return best;
+}
+
+// One pass (all strips of the sub-table); returns the warp-wide best key.
+template <bool STD>
+__device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P)
+{
+    const int lane = threadIdx.x & 31;
+    const int m = w.g.m, n = w.g.n;
+    // boundary line = table row 0 plus the column symbol combinations
+    for (int j = 1 + lane; j <= n + 1; j += 32) {
+        const uint32_t cj = (j <= n) ? load_code(w.packed, w.pd.col_off, (uint32_t)(j - 1)) : 0u;
+        const uint32_t cp = (j >= 2) ? load_code(w.packed, w.pd.col_off, (uint32_t)(j - 2)) : 0u;
+        w.bnd[j] = wf16c_line_word(w.g, j, cj, cp);
+    }
+    __syncwarp();
+    long long best = wf16c_initial_best(w.g);
+    int i0 = 0;
+    while (i0 < m) {
+        const Wf16Strip s = wf16_next_strip(i0, m, w.g.C);
+        const bool sb = !s.last;
+        const bool rs = s.rowscan && !w.g.cell;
+        switch (s.rows) {
+        case 512: best = wf16c_strip<8, STD>(w, P, i0, rs, sb, best); break;
+        case 256: best = wf16c_strip<4, STD>(w, P, i0, rs, sb, best); break;
+        case 128: best = wf16c_strip<2, STD>(w, P, i0, rs, sb, best); break;
+        default:  best = wf16c_strip<1, STD>(w, P, i0, rs, sb, best); break;
+        }
+        i0 += s.rows;
+    }
+    return warp_max_key(best);
+}
+
+// Does the 16-base word pair (plo, phi) occur in the sequence at word offset `off` with `len` bases?
+// Warp-wide; every lane returns the same answer.
+__device__ __forceinline__ bool wf16c_probe_hit(const uint32_t* __restrict__ packed, uint32_t off, uint32_t len, uint32_t plo, uint32_t phi)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t nw = (len + 7u) >> 3;
+    bool hit = false;
+    for (uint32_t q0 = 0; q0 < nw; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        const uint32_t w0 = q < nw ? __ldg(packed + off + q) : 0u;
+        const uint32_t w1 = q + 1 < nw ? __ldg(packed + off + q + 1) : 0u;
+        const uint32_t w2 = q + 2 < nw ? __ldg(packed + off + q + 2) : 0u;
+#pragma unroll
+        for (uint32_t s = 0; s < 8; ++s) {
+            const uint32_t lo = __funnelshift_r(w0, w1, 4 * s), hi = __funnelshift_r(w1, w2, 4 * s);
+            hit |= (lo == plo) && (hi == phi) && (8u * q + s + WF16C_PROBE <= len);
+        }
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    return false;
+}
+
+// Orientation probe: true -> start with system L (the walk is expected to end in row 0).
+__device__ __forceinline__ bool wf16c_predict_sysL(const uint32_t* __restrict__ packed, const PairDesc& pd)
+{
+    if (pd.m < (uint32_t)WF16C_PROBE || pd.n < (uint32_t)WF16C_PROBE) return false;
+    // the first bases of the column sequence occur in the row sequence: the overlap starts in column 0
+    if (wf16c_probe_hit(packed, pd.row_off, pd.m, __ldg(packed + pd.col_off), __ldg(packed + pd.col_off + 1))) return false;
+    // the first bases of the row sequence occur in the column sequence: it starts in row 0
+    return wf16c_probe_hit(packed, pd.col_off, pd.n, __ldg(packed + pd.row_off), __ldg(packed + pd.row_off + 1));
+}
+
+// counters[0] second passes run, counters[1] pairs handed to an exact kernel.
+// retry16t / retry32: work lists of the exact kernels behind this one (pairs with n <= WF16T_MAX_N go to
+// the table kernel); *retry16t_n / *retry32_n are their fill counts (the host may have pre-filled them).
+template <bool STD>
+__global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
+overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
+                     const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
+                     Wf16cParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride,
+                     uint32_t* __restrict__ retry16t, unsigned int* __restrict__ retry16t_n,
+                     uint32_t* __restrict__ retry32, unsigned int* __restrict__ retry32_n,
+                     unsigned int* __restrict__ counters, uint32_t force_sys, DevResult* __restrict__ out)
+{
+    extern __shared__ uint32_t wf16c_smem[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    Wf16cWarp w;
+    w.packed = packed;
+    w.bnd = scratch + (size_t)warp_global * scratch_stride;
+    w.smem = wf16c_smem + (threadIdx.x >> 5) * WF16C_WARP_WORDS;
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(queue, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= n_work) break;
+        const uint32_t pid = order[qi];
+        w.pd = pairs[pid];
+        const int m = (int)w.pd.m, n = (int)w.pd.n;
+        const bool sysL = force_sys == 1u ? false : force_sys == 2u ? true : wf16c_predict_sysL(packed, w.pd);
+        w.g = wf16c_make_pass(m, n, P, sysL, false, 0);
+        const long long key = wf16c_pass<STD>(w, P);
+        uint32_t origin = wf16c_certified_origin(w.g, key);
+        DevResult r;
+        store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
+        if (origin == 0u) {
+            // the other system on the sub-table that ends at the best cell, that cell only
+            __syncwarp();
+            if (lane == 0) atomicAdd(counters, 1u);
+            w.g = wf16c_make_pass(r.row_end, r.col_end, P, !sysL, true, r.score);
+            const long long key2 = wf16c_pass<STD>(w, P);
+            origin = wf16c_certified_origin(w.g, key2);
+        }
+        if (lane == 0) {
+            if (origin != 0u) {
+                store_result(out + pid, (key & ~3ll) | (long long)origin, m, n, FLAG_KERNEL16);
+            } else {
+                out[pid] = r;                                                // overwritten by the exact kernel
+                atomicAdd(counters + 1, 1u);
+                if ((uint32_t)n <= WF16T_MAX_N) retry16t[atomicAdd(retry16t_n, 1u)] = pid;
+                else retry32[atomicAdd(retry32_n, 1u)] = pid;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+inline cudaError_t wf16c_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(overlap_wf16c_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(overlap_wf16c_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(overlap_wf16c_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+// Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
+inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packed, const PairDesc* pairs,
+                        const uint32_t* order, uint32_t n_work, unsigned int* queue, const Wf16cParams& P,
+                        uint32_t max_n, void** scratch, size_t* scratch_cap,
+                        uint32_t* retry16t, unsigned int* retry16t_n, uint32_t* retry32, unsigned int* retry32_n,
+                        unsigned int* counters, uint32_t force_sys, DevResult* out)
+{
+    const int blocks = sm_count * WF16C_CTAS_PER_SM;
+    const uint32_t warps = (uint32_t)blocks * (WF16C_THREADS / 32);
+    const uint32_t stride = (max_n + 2 + 31 + 32) & ~31u;
+    const size_t need = (size_t)warps * stride * sizeof(uint32_t);
+    if (need > *scratch_cap) {
+        if (*scratch) cudaFree(*scratch);
+        *scratch = nullptr; *scratch_cap = 0;
+        cudaError_t e = cudaMalloc(scratch, need);
+        if (e != cudaSuccess) return (int)e;
+        *scratch_cap = need;
+    }
+    if (P.std_scores)
+        overlap_wf16c_kernel<true><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(
+            packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, counters, force_sys, out);
+    else
+        overlap_wf16c_kernel<false><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(
+            packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, counters, force_sys, out);
+    return (int)cudaGetLastError();
+}
+#endif // __CUDACC__
+
+} // namespace gp

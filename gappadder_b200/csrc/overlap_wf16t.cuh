@@ -408,9 +408,10 @@ __global__ void __launch_bounds__(WF16T_THREADS, WF16T_CTAS_PER_SM)
 overlap_wf16t_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                      const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
                      Wf16tParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride,
-                     DevResult* __restrict__ out)
+                     DevResult* __restrict__ out, const unsigned int* __restrict__ n_work_dev)
 {
     extern __shared__ uint32_t wf16t_smem[];
+    if (n_work_dev) n_work = *n_work_dev;             // work list filled on the device (overlap_wf16c.cuh's retries)
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Wf16tWarp w;
@@ -467,7 +468,8 @@ inline cudaError_t wf16t_configure()
 // Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
 inline int wf16t_launch(cudaStream_t stream, int sm_count, const uint32_t* packed, const PairDesc* pairs,
                         const uint32_t* order, uint32_t n_work, unsigned int* queue, const Wf16tParams& P,
-                        uint32_t max_n, void** scratch, size_t* scratch_cap, DevResult* out)
+                        uint32_t max_n, void** scratch, size_t* scratch_cap, DevResult* out,
+                        const unsigned int* n_work_dev = nullptr)
 {
     const int blocks = sm_count * WF16T_CTAS_PER_SM;
     const uint32_t warps = (uint32_t)blocks * (WF16T_THREADS / 32);
@@ -482,10 +484,10 @@ inline int wf16t_launch(cudaStream_t stream, int sm_count, const uint32_t* packe
     }
     if (P.std_scores)
         overlap_wf16t_kernel<true><<<blocks, WF16T_THREADS, WF16T_SMEM_BYTES, stream>>>(packed, pairs, order, n_work, queue, P,
-                                                                                         (uint32_t*)*scratch, stride, out);
+                                                                                         (uint32_t*)*scratch, stride, out, n_work_dev);
     else
         overlap_wf16t_kernel<false><<<blocks, WF16T_THREADS, WF16T_SMEM_BYTES, stream>>>(packed, pairs, order, n_work, queue, P,
-                                                                                          (uint32_t*)*scratch, stride, out);
+                                                                                          (uint32_t*)*scratch, stride, out, n_work_dev);
     return (int)cudaGetLastError();
 }
 #endif // __CUDACC__

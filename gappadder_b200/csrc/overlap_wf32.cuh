@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(128)
 overlap_wf32_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                     const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
                     int mismatch, int indel, int max_clip,
-                    int32_t* __restrict__ scratch, uint32_t scratch_stride, DevResult* __restrict__ out)
+                    int32_t* __restrict__ scratch, uint32_t scratch_stride, DevResult* __restrict__ out,
+                    const unsigned int* __restrict__ n_work_dev)
 {
+    if (n_work_dev) n_work = *n_work_dev;             // work list filled on the device (overlap_wf16c.cuh's retries)
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int32_t* bnd = scratch + (size_t)warp_global * scratch_stride;

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 1
+#define GP_ABI_VERSION 2
 
 typedef enum gp_status {
     GP_OK = 0,
@@ -150,15 +150,32 @@ uint64_t gp_kernel_launches(const gp_ctx *ctx);
 /* DP cells (sum of m*n) of the pairs currently uploaded, and how many went to each kernel. */
 int gp_pair_stats(const gp_ctx *ctx, uint64_t *cells, uint64_t *pairs16, uint64_t *pairs32);
 
-/* The same split by kernel: the shared-memory-table 16-bit kernel (A/C/G/T pairs whose column sequence
- * has <= 4094 bases), the PRMT-lookup 16-bit kernel (<= 8 symbols, min(m,n) <= 4094) and the general
- * 32-bit kernel. */
+/* The same split by kernel, as routed by the host: the shared-memory-table 16-bit kernel with tie tags
+ * (A/C/G/T pairs whose column sequence has <= 4094 bases), the PRMT-lookup 16-bit kernel (<= 8 symbols,
+ * min(m,n) <= 4094) and the general 32-bit kernel.  Pairs routed to the certificate kernel (below) are not
+ * in these three counts. */
 int gp_pair_split(const gp_ctx *ctx, uint64_t *table16, uint64_t *prmt16, uint64_t *wide32);
+/* The certificate kernel (the default for A/C/G/T pairs whose column sequence has <= 16382 bases, a
+ * sequence against itself excepted): same DP without tie tags; it proves where the reference's
+ * predecessor walk ends instead of following it, and hands the pairs it cannot prove to the exact
+ * kernels above on the device.  cert16: pairs of the uploaded batch routed to it; second_passes: pairs of
+ * the last fetched run that needed the second (small) pass; exact_retries: pairs of that run recomputed
+ * by an exact kernel.  Results never depend on which kernel produced them. */
+int gp_cert_stats(const gp_ctx *ctx, uint64_t *cert16, uint64_t *second_passes, uint64_t *exact_retries);
+/* Per-kernel device time (CUDA events on the context's stream) of the last gp_launch_resident /
+ * gp_overlap_* call, milliseconds, and the DP cells the host routed to each kernel:
+ * [0] certificate kernel, [1] table kernel (its certificate retries included in the time, not in the cells),
+ * [2] PRMT kernel, [3] general kernel (likewise).  Waits for that launch to finish.  ms and cells hold 4 entries. */
+int gp_kernel_times(gp_ctx *ctx, double *ms, uint64_t *cells);
+/* Testing: which certificate system the kernel tries first (0: a 16-base probe decides, the default;
+ * 1: "walk ends in column 0"; 2: "walk ends in row 0"). */
+int gp_set_cert_system(gp_ctx *ctx, uint32_t system);
 /* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).
  * Pairs no allowed kernel accepts go to the general 32-bit kernel; results never depend on the mask. */
 #define GP_KERNEL_TABLE16 1u
 #define GP_KERNEL_PRMT16  2u
-#define GP_KERNEL_ALL     3u
+#define GP_KERNEL_CERT16  4u
+#define GP_KERNEL_ALL     7u
 int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
 
 /* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):

@@ -5,7 +5,7 @@
 // the strip schedule and the key bookkeeping), 32 lanes in lock step with the warp shuffles
 // replaced by array reads.  `-m "not gpu"` tests compare it with the oracle, so the arithmetic
 // (potential, clamping, tags, tie rule) is validated on a machine without a GPU.
-#include "../gappadder_b200/csrc/overlap_wf16t.cuh"
+#include "../gappadder_b200/csrc/overlap_wf16c.cuh"
 #include <cstring>
 #include <vector>
 
@@ -265,4 +265,128 @@ extern "C" int wf16t_emulate(const uint8_t* row_codes, int m, const uint8_t* col
     store_result(&r, best, m, n, FLAG_KERNEL16);
     out[0] = r.score; out[1] = r.row_end; out[2] = r.col_end; out[3] = r.nclip; out[4] = (int32_t)r.flags;
     return 0;
+}
+
+// ---- certificate kernel (overlap_wf16c.cuh) -------------------------------------------------------------
+// Same block structure as wf16c_strip; the pass logic (scan pass in one system, cell pass in the other on
+// the sub-table that ends at the best cell) is the kernel's, with the starting system given by the caller.
+namespace {
+
+template <int K>
+void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, std::vector<uint32_t>& bnd, int i0, bool rowscan,
+                  bool store_bottom, long long lane_best[32])
+{
+    const int n = g.n, m = g.m;
+    Lane16c<K> st[32];
+    std::vector<uint32_t> tab((size_t)32 * 16 * K);
+    for (int lane = 0; lane < 32; ++lane) {
+        const int itop = i0 + lane * 2 * K;
+        uint32_t rc[2 * K];
+        for (int x = 0; x < 2 * K; ++x) rc[x] = itop + x < m ? hp.row[itop + x] : 0u;
+        for (uint32_t combo = 0; combo < 16; ++combo)
+            for (int k = 0; k < K; ++k) tab[((size_t)lane * 16 + combo) * K + k] = wf16c_table_word(rc[k], rc[K + k], combo & 3u, combo >> 2, P);
+        lane16c_begin<K>(st[lane], g, itop);
+    }
+    int S0 = -1000000000;
+    for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); S0 = sc > S0 ? sc : S0; }
+    uint32_t thrS[32];
+    for (int lane = 0; lane < 32; ++lane) thrS[lane] = wf16c_filter_thr(S0);
+    const int jswitch = n - g.C > 1 ? n - g.C : 1;
+    constexpr int D = WF16C_SKEW;
+    const int t_end = n + 1 + 31 * D;
+    uint16_t* bnd16 = reinterpret_cast<uint16_t*>(bnd.data());
+    uint32_t sent1[32], sent2[32];
+    for (int lane = 0; lane < 32; ++lane) sent1[lane] = sent2[lane] = st[lane].W[K - 1];
+    std::vector<uint32_t> top(bnd.begin(), bnd.end());
+    for (int tb = 1; tb <= t_end; tb += 32) {
+        const bool filt = rowscan || tb + 31 >= jswitch;
+        const int cnt = t_end - tb + 1 < 32 ? ((t_end - tb + 2) & ~1) : 32;
+        for (int s = 0; s < cnt; ++s) {
+            const int t = tb + s;
+            uint32_t recv[32];
+            for (int lane = 0; lane < 32; ++lane) recv[lane] = lane == 0 ? (top[t <= n + 1 ? t : n + 1] << 16) : sent2[lane - 1];
+            for (int lane = 0; lane < 32; ++lane) { sent2[lane] = sent1[lane]; }
+            for (int lane = 0; lane < 32; ++lane) {
+                const int itop = i0 + lane * 2 * K, j = t - D * lane;
+                if (j < 1 || j > n + 1) { sent1[lane] = st[lane].W[K - 1]; continue; }
+                const uint32_t combo = (top[j] >> 16) & 15u;
+                uint32_t inc[K];
+                for (int k = 0; k < K; ++k) inc[k] = tab[((size_t)lane * 16 + combo) * K + k];
+                lane16c_step<K>(st[lane], recv[lane], inc, g.gup, g.gleft);
+                if (j == 1) lane16c_fix_first<K>(st[lane], g);
+                if (store_bottom && lane == 31 && j >= 2 && j - 1 <= n) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
+                if (filt) {
+                    const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
+                    const uint32_t acc = p_add2(lane16c_max<K>(st[lane]), wf16c_nthr(g, j));
+                    if (filter_fired(acc, j >= (rowlane ? 1 : jswitch) ? thrS[lane] : WF16C_UNARMED)) {
+                        ++g_slow_calls;
+                        lane_best[lane] = lane16c_scan<K>(st[lane].W, g, itop, j, lane_best[lane]);
+                        const int sc = (int)(lane_best[lane] >> 32);
+                        thrS[lane] = wf16c_filter_thr(sc > S0 ? sc : S0);
+                    }
+                }
+                sent1[lane] = st[lane].W[K - 1];
+            }
+        }
+        g_steps += cnt;
+        if (filt) {
+            for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); S0 = sc > S0 ? sc : S0; }
+            for (int lane = 0; lane < 32; ++lane) thrS[lane] = wf16c_filter_thr(S0);
+        }
+    }
+}
+
+long long pass_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P)
+{
+    const int m = g.m, n = g.n;
+    std::vector<uint32_t> bnd((size_t)n + 66, 0u);
+    for (int j = 1; j <= n + 1; ++j) bnd[j] = wf16c_line_word(g, j, j <= n ? hp.col[j - 1] : 0u, j >= 2 ? hp.col[j - 2] : 0u);
+    long long lane_best[32];
+    for (int l = 0; l < 32; ++l) lane_best[l] = wf16c_initial_best(g);
+    int i0 = 0;
+    while (i0 < m) {
+        const Wf16Strip s = wf16_next_strip(i0, m, g.C);
+        const bool rs = s.rowscan && !g.cell;
+        switch (s.rows) {
+        case 512: strip_host_c<8>(hp, g, P, bnd, i0, rs, !s.last, lane_best); break;
+        case 256: strip_host_c<4>(hp, g, P, bnd, i0, rs, !s.last, lane_best); break;
+        case 128: strip_host_c<2>(hp, g, P, bnd, i0, rs, !s.last, lane_best); break;
+        default:  strip_host_c<1>(hp, g, P, bnd, i0, rs, !s.last, lane_best); break;
+        }
+        i0 += s.rows;
+    }
+    long long best = lane_best[0];
+    for (int l = 1; l < 32; ++l) best = lane_best[l] > best ? lane_best[l] : best;
+    return best;
+}
+
+} // namespace
+
+// out: score, row_end, col_end, nclip, flags.  Returns 0 when the first pass certified the origin, 1 when
+// the second pass did, 2 when neither did (origin flags in out[4] are then 0: the library recomputes the
+// pair with an exact kernel), -1 outside the kernel's domain.  first_sys: 0 = U, 1 = L.
+extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col_codes, int n,
+                             int mismatch, int indel, int max_clip, int first_sys, int32_t* out)
+{
+    if (!wf16_params_ok(mismatch, indel) || !wf16c_pair_ok((uint32_t)m, (uint32_t)n)) return -1;
+    const Wf16cParams P = wf16c_make_params(mismatch, indel, max_clip);
+    HostPair hp;
+    hp.row.assign(row_codes, row_codes + m);
+    hp.col.assign(col_codes, col_codes + n);
+    const bool sysL = first_sys != 0;
+    Wf16cPass g = wf16c_make_pass(m, n, P, sysL, false, 0);
+    const long long key = pass_host_c(hp, g, P);
+    uint32_t origin = wf16c_certified_origin(g, key);
+    DevResult r;
+    store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);
+    int status = 0;
+    if (origin == 0u) {
+        status = 1;
+        g = wf16c_make_pass(r.row_end, r.col_end, P, !sysL, true, r.score);
+        origin = wf16c_certified_origin(g, pass_host_c(hp, g, P));
+        if (origin == 0u) status = 2;
+    }
+    store_result(&r, (key & ~3ll) | (long long)origin, m, n, FLAG_KERNEL16);
+    out[0] = r.score; out[1] = r.row_end; out[2] = r.col_end; out[3] = r.nclip; out[4] = (int32_t)r.flags;
+    return status;
 }

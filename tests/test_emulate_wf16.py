@@ -24,13 +24,16 @@ def emu():
     os.makedirs(os.path.join(ROOT, "build"), exist_ok=True)
     so = os.path.join(ROOT, "build", "libemulate_wf16.so")
     srcs = [os.path.join(ROOT, "tests", "emulate_wf16.cu"), os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16.cuh"),
-            os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16t.cuh"), os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
+            os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16t.cuh"), os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16c.cuh"),
+            os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
     L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.wf16t_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    L.wf16c_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+    cert_status = [0, 0, 0]          # certificate kernel: certified by the first pass / by the second / handed to an exact kernel
 
     def run(a, b, mm=-2, ind=-2, clip=50):
         res = []
@@ -46,8 +49,22 @@ def emu():
             assert L.wf16t_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out) == 0
             f = out[4]
             res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
+        if four and len(b) <= 16382:                   # the certificate kernel's domain; both starting systems
+            for first_sys in (0, 1):
+                out = (C.c_int32 * 5)()
+                st = L.wf16c_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, first_sys, out)
+                assert st in (0, 1, 2)
+                cert_status[st] += 1
+                f = out[4]
+                tup = (out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1)
+                if st == 2:                            # not certified: score, ends and clip are still exact
+                    assert tup[:4] == res[0][:4], (tup, res[0])
+                else:
+                    res.append(tup)
         assert len(set(res)) == 1, res
         return res[0]
+    run.cert_status = cert_status
+    run.cert = L.wf16c_emulate
     return run
 
 
@@ -99,3 +116,35 @@ def test_long_overlaps_both_potentials(emu, la, ov, extra):
     b = a[-ov:] + bytes(rng.choice(b"ACGT") for _ in range(extra))
     for x, y in ((a, b), (b, a)):
         assert emu(x, y) == _want(x, y)
+
+
+def test_certificate_kernel_resolves_overlaps_and_long_columns(emu):
+    """Certificate kernel: plain suffix/prefix overlaps are certified (first pass when the starting system fits,
+    second pass otherwise), a sequence against itself never is, and columns beyond the tagged kernels' 4094
+    limit stay in 16 bits."""
+    rng = random.Random(5)
+    a = bytes(rng.choice(b"ACGT") for _ in range(900))
+    b = a[-400:] + bytes(rng.choice(b"ACGT") for _ in range(700))
+    tr = bytes.maketrans(b"ACGT", bytes([0, 1, 2, 3]))
+
+    def cert(x, y, first_sys):
+        out = (C.c_int32 * 5)()
+        st = emu.cert(x.translate(tr), len(x), y.translate(tr), len(y), -2, -2, 50, first_sys, out)
+        f = out[4]
+        return st, (out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1)
+    # a's suffix = b's prefix: the walk ends in column 0 -> system U (0) certifies at once, L needs the second pass
+    assert cert(a, b, 0) == (0, _want(a, b))
+    assert cert(a, b, 1) == (1, _want(a, b))
+    # transposed: the walk ends in row 0
+    assert cert(b, a, 1) == (0, _want(b, a))
+    assert cert(b, a, 0) == (1, _want(b, a))
+    # a sequence against itself: the walk ends in the corner, no certificate
+    assert cert(a, a, 0)[0] == 2 and cert(a, a, 1)[0] == 2
+    assert cert(a, a, 0)[1][:4] == _want(a, a)[:4]
+    # long columns
+    c = bytes(rng.choice(b"ACGT") for _ in range(5200))
+    d = c[-3000:] + bytes(rng.choice(b"ACGT") for _ in range(3100))
+    for x, y in ((c, d), (d, c)):
+        w = _want(x, y)
+        got = [cert(x, y, fs) for fs in (0, 1)]
+        assert sorted(st for st, _ in got) == [0, 1] and all(t == w for _, t in got)

@@ -8,16 +8,19 @@ import numpy as np
 import pytest
 
 import gappadder_b200 as g
-from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0, KERNEL_ALL, KERNEL_PRMT16, KERNEL_TABLE16
+from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0, KERNEL_ALL, KERNEL_CERT16, KERNEL_PRMT16, KERNEL_TABLE16
+
+KERNEL_TAGGED = KERNEL_TABLE16 | KERNEL_PRMT16      # everything but the certificate kernel
 from _oracle import oracle_evaluate, oracle_revcomp
 import synth_gaps
 
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_PRMT16)):
-    """Every kernel the library can route these pairs to (default routing = table kernel first, then with the
-    table kernel masked out = PRMT kernel / general kernel) against the oracle.  Returns the default routing's results."""
+def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_TAGGED, KERNEL_PRMT16)):
+    """Every kernel the library can route these pairs to (default routing = certificate kernel first -- run with
+    the probe and with either starting system forced --, then the table kernel, then the PRMT kernel / general
+    kernel) against the oracle.  Returns the default routing's results."""
     params = params or g.GAPPADDER_DP
     want = []
     for a, b in pairs:
@@ -25,8 +28,12 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         want.append((o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained))
     first = None
     try:
+        runs = []
         for mask in masks:
+            runs += [(mask, 0), (mask, 1), (mask, 2)] if mask & KERNEL_CERT16 else [(mask, 0)]
+        for mask, system in runs:
             ctx.set_kernel_mask(mask)
+            ctx.set_cert_system(system)
             res = ctx.overlap_batch(seqs, pairs, params)
             assert len(res) == len(pairs)
             bad = []
@@ -35,11 +42,12 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
                        int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
                 if w != got:
                     bad.append(((a, b), len(seqs[a]), len(seqs[b]), w, got))
-            assert not bad, "kernel mask %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, bad[:5])
+            assert not bad, "kernel mask %d system %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, system, bad[:5])
             if first is None:
                 first = res
     finally:
         ctx.set_kernel_mask(KERNEL_ALL)
+        ctx.set_cert_system(0)
     return first
 
 
@@ -65,13 +73,13 @@ def test_tie_heavy_small_alphabets(ctx):
         alpha = rng.choice([b"A", b"AC", b"ACG", b"ACGT", b"ACGTN"])
         seqs.append(_rand(rng, rng.randint(1, 90), alpha))
     pairs = [(rng.randrange(len(seqs)), rng.randrange(len(seqs))) for _ in range(1500)]
-    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_PRMT16, 0))
+    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_TAGGED, KERNEL_PRMT16, 0))
 
 
 def test_empty_and_tiny(ctx):
     seqs = [b"", b"A", b"C", b"AC", b"ACGTACGT", b"N", b"NN"]
     pairs = [(i, j) for i in range(len(seqs)) for j in range(len(seqs))]
-    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_PRMT16, KERNEL_TABLE16, 0))
+    _check(ctx, seqs, pairs, full=True, masks=(KERNEL_ALL, KERNEL_CERT16, KERNEL_TAGGED, KERNEL_PRMT16, KERNEL_TABLE16, 0))
     assert len(ctx.overlap_batch(seqs, [])) == 0
 
 
@@ -132,6 +140,12 @@ def test_cfg1_gap_candidates_full_size(ctx):
     pairs = [(int(p["row_seq"]), int(p["col_seq"])) for p in cand]
     assert len(pairs) > 100
     _check(ctx, nodes, pairs)
+    # certificate kernel bookkeeping on realistic pairs: a sequence against itself is routed to an exact kernel by
+    # the host; of the rest few need the second pass and hardly any the exact kernel
+    ctx.overlap_batch(nodes, pairs)
+    st = ctx.cert_stats()
+    assert st["cert16"] == len(pairs) - sum(1 for a, b in pairs if a == b)
+    assert st["second_passes"] <= 0.3 * st["cert16"] and st["exact_retries"] <= 0.02 * st["cert16"], st
 
 
 def test_long_overlaps_both_potentials(ctx):
@@ -147,24 +161,50 @@ def test_long_overlaps_both_potentials(ctx):
         pairs += [(k, k + 1), (k + 1, k), (k, k), (k + 1, k + 1)]
     res = _check(ctx, seqs, pairs)
     from gappadder_b200.capi import FLAG_KERNEL16
-    # 17 of the 24 pairs have min(m,n) <= 4094 and go through a 16-bit kernel, 7 through the general one
-    assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 17
+    # the 12 overlap pairs go through the certificate kernel (columns <= 16382), 7 of the 12 self pairs through the
+    # table kernel (<= 4094 columns), the other 5 through the general one
+    assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 19
+    ctx.overlap_batch(seqs, pairs)
+    assert ctx.cert_stats() == dict(cert16=12, second_passes=0, exact_retries=0)
 
 
 def test_kernel_routing(ctx):
-    """A/C/G/T pairs with <= 4094 columns take the table kernel, pairs with N (or longer columns but short rows)
-    the PRMT kernel, the rest the general kernel; masks move pairs down that list and never change results."""
+    """A/C/G/T pairs with <= 16382 columns take the certificate kernel; without it those with <= 4094 columns take
+    the table kernel, pairs with N (or longer columns but short rows) the PRMT kernel, the rest the general kernel;
+    masks move pairs down that list and never change results."""
     rng = random.Random(3)
     seqs = [_rand(rng, 300), _rand(rng, 700), _rand(rng, 500, b"ACGTN"), _rand(rng, 4500), _rand(rng, 4300)]
     pairs = [(0, 1), (1, 0), (0, 2), (2, 1), (0, 3), (3, 0), (3, 4)]
     packed, off, lens, nsym = g.pack_sequences(seqs)
     ctx.set_sequences(packed, off, lens, nsym)
     ctx.upload_pairs(np.array(pairs, dtype=np.uint32).view(g.capi.PAIR_DTYPE).reshape(-1))
-    assert ctx.pair_split() == dict(table16=3, prmt16=3, wide32=1)       # (3,0): 4500 rows x 300 columns -> table
+    assert ctx.pair_split() == dict(table16=0, prmt16=2, wide32=0) and ctx.cert_stats()["cert16"] == 5
     try:
+        ctx.set_kernel_mask(KERNEL_TAGGED)
+        ctx.upload_pairs(np.array(pairs, dtype=np.uint32).view(g.capi.PAIR_DTYPE).reshape(-1))
+        assert ctx.pair_split() == dict(table16=3, prmt16=3, wide32=1)   # (3,0): 4500 rows x 300 columns -> table
+        assert ctx.cert_stats()["cert16"] == 0
         ctx.set_kernel_mask(KERNEL_PRMT16)
         ctx.upload_pairs(np.array(pairs, dtype=np.uint32).view(g.capi.PAIR_DTYPE).reshape(-1))
         assert ctx.pair_split() == dict(table16=0, prmt16=6, wide32=1)
     finally:
         ctx.set_kernel_mask(KERNEL_ALL)
-    _check(ctx, seqs, pairs, masks=(KERNEL_ALL, KERNEL_PRMT16, 0))
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL, KERNEL_TAGGED, KERNEL_PRMT16, 0))
+
+
+def test_certificate_kernel_long_columns_and_fallbacks(ctx):
+    """Certificate kernel beyond the tagged kernels' range (columns up to 16382), pairs whose walks end in the
+    corner (identical sequences under different indices: second pass, then an exact kernel -- the general one when
+    the column sequence is too long for the table kernel), and junk pairs whose best cell sits in a corner."""
+    rng = random.Random(21)
+    a = _rand(rng, 9000)
+    b = a[-5000:] + _rand(rng, 6000)          # 11000 columns
+    c = _rand(rng, 16382)
+    d = c[:700]
+    e = _rand(rng, 5000)
+    seqs = [a, b, c, d, e, bytes(e), a[:3000], bytes(a[:3000])]
+    pairs = [(0, 1), (1, 0), (3, 2), (2, 3), (0, 2), (4, 5), (5, 4), (6, 7), (3, 4), (4, 3), (1, 2)]
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
+    ctx.overlap_batch(seqs, pairs)
+    st = ctx.cert_stats()
+    assert st["cert16"] == len(pairs) and st["exact_retries"] >= 3, st      # (4,5), (5,4), (6,7) end in the corner
