@@ -19,6 +19,7 @@ EXPORTS = [
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
+    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team",
 ]
 
 
@@ -48,8 +49,9 @@ class Thresholds(C.Structure):
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
-FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16 = 1, 2, 4, 8
-KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_ALL = 1, 2, 4, 7
+FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16, FLAG_CLOSED = 1, 2, 4, 8, 16
+KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_CLOSED, KERNEL_ALL = 1, 2, 4, 8, 15
+KERNEL_DP_ALL = KERNEL_TABLE16 | KERNEL_PRMT16 | KERNEL_CERT16      # every kernel, no closed form
 
 # GAPPadder's command line (MergeContigs.py:85): -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1
 GAPPADDER_DP = DpParams(-2, -2, 50)
@@ -111,6 +113,9 @@ def lib() -> C.CDLL:
         L.gp_set_cert_system.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.gp_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+        L.gp_closed_form_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.gp_set_team_mode.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_last_team.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -261,6 +266,20 @@ class Context:
     def set_cert_system(self, system: int):
         """Tests: 0 probe decides (default), 1 start with system U (column 0), 2 with system L (row 0)."""
         self._check(self._L.gp_set_cert_system(self._h, system))
+
+    def closed_form_stats(self):
+        """Pairs of the uploaded batch answered in closed form (a sequence against itself) and their m*n."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._L.gp_closed_form_stats(self._h, C.byref(a), C.byref(b)))
+        return dict(pairs=a.value, cells=b.value)
+
+    def set_team_mode(self, mode: int):
+        """Certificate kernel: 0 library chooses per launch (default), 1 one warp per pair, 2 one CTA per pair."""
+        self._check(self._L.gp_set_team_mode(self._h, mode))
+
+    @property
+    def last_team(self) -> bool:
+        return bool(self._L.gp_last_team(self._h))
 
     def set_kernel_mask(self, mask: int):
         """Restricts the 16-bit kernels gp_upload_pairs may pick (tests, A/B timing); results never change."""

@@ -74,9 +74,14 @@ struct gp_ctx {
     double timing[GP_TIMING_SLOTS] = {0};       // milliseconds of the last gp_overlap_batch, see gp_last_timing
     uint64_t n_pairs = 0, n16c = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
     uint32_t max_n16c = 0, max_n16c_small = 0, max_n16t = 0, max_n16 = 0, max_n32 = 0;
-    uint32_t cert_system = 0;                   // 0: probe decides, 1: start with system U, 2: with system L (tests)
+    uint32_t cert_system = 0;                   // 0: probe decides, 1: start with system U, 2: with L, 3: with C (tests)
+    uint32_t team_mode = 0;                     // certificate kernel: 0 auto, 1 one warp per pair, 2 one CTA per pair
+    uint64_t max_cells16c = 0;                  // largest m*n routed to the certificate kernel
+    bool last_team = false;                     // what the last launch used
     uint64_t second_passes = 0, exact_retries = 0;   // of the last fetched run
     uint64_t cells16c = 0, cells16t = 0, cells16 = 0, cells32 = 0;     // host-routed DP cells per kernel
+    std::vector<uint32_t> closed_ids;           // pairs answered in closed form (a sequence against itself), no DP
+    uint64_t cells_closed = 0;                  // m*n of those pairs (what the reference computes for them)
     cudaEvent_t kev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // kernel boundaries of the last launch
     bool kev_valid = false;
     gp::Wf16cParams p16c{};
@@ -181,6 +186,14 @@ int gp_cert_stats(const gp_ctx* c, uint64_t* cert16, uint64_t* second_passes, ui
     return GP_OK;
 }
 
+int gp_closed_form_stats(const gp_ctx* c, uint64_t* pairs, uint64_t* cells)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (pairs) *pairs = c->closed_ids.size();
+    if (cells) *cells = c->cells_closed;
+    return GP_OK;
+}
+
 int gp_kernel_times(gp_ctx* c, double* ms, uint64_t* cells)
 {
     if (!c) return GP_ERR_INVALID;
@@ -202,10 +215,19 @@ int gp_kernel_times(gp_ctx* c, double* ms, uint64_t* cells)
 
 int gp_set_cert_system(gp_ctx* c, uint32_t system)
 {
-    if (!c || system > 2) return GP_ERR_INVALID;
+    if (!c || system > 3) return GP_ERR_INVALID;
     c->cert_system = system;
     return GP_OK;
 }
+
+int gp_set_team_mode(gp_ctx* c, uint32_t mode)
+{
+    if (!c || mode > 2) return GP_ERR_INVALID;
+    c->team_mode = mode;
+    return GP_OK;
+}
+
+int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
 
 int gp_set_kernel_mask(gp_ctx* c, uint32_t mask)
 {
@@ -247,6 +269,24 @@ int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, con
     return GP_OK;
 }
 
+// Evaluate(s, s) in closed form.  With match +1, mismatch <= 1 and indel <= 0 no cell (i,j) scores above
+// min(i,j), and on the diagonal of a sequence against itself H(i,i) = i.  The scan (ContigsCompactor.cpp:1679-1709)
+// starts with column n top to bottom: every cell above (m,n) scores at most i < m, so (m,n) with score m is the
+// first strict maximum and nothing later beats it: scoreMax = m, posRowEnd = m, posColEnd = n, nclip = 0.  The
+// predecessor of (i,i) is the diagonal one (it reaches i, tried first and only replaced on strict '<', :1651-1665;
+// up and left give at most i-1), so the walk ends in the corner: tbCur = (0,0), bcontained (:1834-1837).
+static void closed_form_self(gp_result* r, uint32_t m)
+{
+    r->score = (int32_t)m; r->row_end = (int32_t)m; r->col_end = (int32_t)m; r->nclip = 0;
+    r->flags = GP_FLAG_ROW0 | GP_FLAG_COL0 | GP_FLAG_CONTAINED | GP_FLAG_CLOSED;
+}
+
+static void patch_closed(const gp_ctx* c, gp_result* out)
+{
+    const gp::PairDesc* hd = (const gp::PairDesc*)c->h_stage.p;
+    for (uint32_t id : c->closed_ids) closed_form_self(out + id, hd[id].m);
+}
+
 static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
 {
     if (!params || (!pairs && n_pairs)) return c->fail(GP_ERR_INVALID, "null pairs/params");
@@ -257,6 +297,7 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
     c->n_pairs = n_pairs; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
     c->max_n16c = c->max_n16c_small = c->max_n16t = c->max_n16 = c->max_n32 = 0;
     c->cells16c = c->cells16t = c->cells16 = c->cells32 = 0; c->kev_valid = false;
+    c->closed_ids.clear(); c->cells_closed = 0; c->max_cells16c = 0;
     if (n_pairs == 0) return GP_OK;
 
     const uint32_t n_seq = (uint32_t)c->seq_len.size();
@@ -267,6 +308,7 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
     if (params16) c->p16 = gp::wf16_make_params(params->mismatch, params->indel, params->max_clip, c->n_symbols <= 4);
     if (params16t || params16c) c->p16t = gp::wf16t_make_params(params->mismatch, params->indel, params->max_clip);
     if (params16c) c->p16c = gp::wf16c_make_params(params->mismatch, params->indel, params->max_clip);
+    const bool closed_ok = (c->kernel_mask & GP_KERNEL_CLOSED) && params->mismatch <= 1 && params->indel <= 0;
 
     // stage: [PairDesc n][order16c n][order16t n][order16 n][order32 n]
     const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
@@ -283,12 +325,15 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
         if (a >= n_seq || b >= n_seq) return c->fail(GP_ERR_INVALID, "pair %llu references sequence out of range", (unsigned long long)i);
         const uint32_t m = c->seq_len[a], n = c->seq_len[b];
         hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
-        c->cells += (uint64_t)m * n;
         max_total = std::max<uint64_t>(max_total, (uint64_t)m + n);
+        // A sequence against itself has a closed form (closed_form_self below): no DP cells are computed.
+        if (closed_ok && a == b && m >= 1) { c->closed_ids.push_back((uint32_t)i); c->cells_closed += (uint64_t)m * n; continue; }
+        c->cells += (uint64_t)m * n;
         // certificate kernel: everything A/C/G/T except a sequence against itself (its walk ends in the corner
         // (0,0), which no certificate covers: straight to an exact kernel)
         if (params16c && a != b && gp::wf16c_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) {
             ho16c[c->n16c++] = (uint32_t)i; c->max_n16c = std::max(c->max_n16c, n); c->cells16c += (uint64_t)m * n;
+            c->max_cells16c = std::max(c->max_cells16c, (uint64_t)m * n);
             if (n <= gp::WF16T_MAX_N) c->max_n16c_small = std::max(c->max_n16c_small, n);
         }
         else if (params16t && gp::wf16t_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) { ho16t[c->n16t++] = (uint32_t)i; c->max_n16t = std::max(c->max_n16t, n); c->cells16t += (uint64_t)m * n; }
@@ -360,13 +405,26 @@ int gp_launch_resident(gp_ctx* c)
     GP_CUDA(c, cudaMemcpyAsync(c->d_queue.p, c->h_queue.p, 128, cudaMemcpyHostToDevice, c->stream));
     unsigned int* queue = (unsigned int*)c->d_queue.p;
     const bool cert = c->n16c != 0;
+    // One warp per pair or one CTA (team of warps) per pair?  With W warps in flight a batch takes about
+    // max(largest pair, total / W) warp-seconds of DP in warp mode; a team runs a pair's strips concurrently
+    // (about 3.4x faster per pair at 4 warps, 15 % less aggregate throughput).  Few long pairs -- the relax
+    // chain's batches -- are bound by the largest pair and take the team kernel.
+    bool team = c->team_mode == 2;
+    if (cert && c->team_mode == 0) {
+        const double W = (double)c->sm_count * gp::WF16C_CTAS_PER_SM * gp::WF16C_TEAM;
+        const double total = (double)c->cells16c, big = (double)c->max_cells16c;
+        const double warp_t = std::max(big, total / W);
+        const double team_t = std::max(big / 3.4, total / (0.85 * W));
+        team = team_t < warp_t;
+    }
+    c->last_team = cert && team;
     GP_CUDA(c, cudaEventRecord(c->kev[0], c->stream));
     if (cert) {
         int rc = gp::wf16c_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
                                   (const uint32_t*)c->d_order16c.p, (uint32_t)c->n16c, queue + 24, c->p16c, c->max_n16c,
                                   &c->d_scratch16c.p, &c->d_scratch16c.cap,
                                   (uint32_t*)c->d_order16t.p, queue + 4, (uint32_t*)c->d_order32.p, queue + 12,
-                                  queue + 20, c->cert_system, (gp::DevResult*)c->d_results.p);
+                                  queue + 20, c->cert_system, team, (gp::DevResult*)c->d_results.p);
         if (rc != 0) return c->fail(GP_ERR_CUDA, "wf16c launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         c->launches += 1;
     }
@@ -420,6 +478,7 @@ int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n_pairs)
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
     c->second_passes = ((const uint32_t*)c->h_queue.p)[32 + 20];
     c->exact_retries = ((const uint32_t*)c->h_queue.p)[32 + 21];
+    patch_closed(c, out);
     return GP_OK;
 }
 
@@ -438,6 +497,7 @@ static int run_and_fetch(gp_ctx* c, gp_result* out, uint64_t n_pairs)
     c->second_passes = ((const uint32_t*)c->h_queue.p)[32 + 20];
     c->exact_retries = ((const uint32_t*)c->h_queue.p)[32 + 21];
     memcpy(out, c->h_results.p, bytes);
+    patch_closed(c, out);
     return GP_OK;
 }
 

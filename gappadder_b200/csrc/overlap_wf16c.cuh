@@ -20,17 +20,20 @@
 //                does:  tbCur.second == 0, tbCur.first > 0.
 //     system L:  b = 1 on column 0 (corner included), 0 on row 0.   b(best) = 0  <=>  every optimal
 //                walk ends in row 0 right of the corner: tbCur.first == 0, tbCur.second > 0.
-//   Scores, and therefore the best cell (score, posRowEnd, posColEnd, nclip), are exact in either system.
+//     system C:  b = 0 on the corner (0,0) only, 1 on the rest of row 0 and column 0.   b(best) = 0  <=>  every
+//                optimal walk ends in the corner: tbCur.first == 0 and tbCur.second == 0 (two sequences that
+//                start with the same bases, e.g. a merged contig against the node it starts with).
+//   Scores, and therefore the best cell (score, posRowEnd, posColEnd, nclip), are exact in every system.
 //
-// Per pair: a 16-base probe predicts the system (the first bases of the column sequence occur in the row
-// sequence -> the walk will end in column 0 -> U; the first bases of the row sequence occur in the column
-// sequence -> L).  If the certificate fails (b = 1) the other system is run on the sub-table that ends
-// at the best cell (rows 1..posRowEnd, columns 1..posColEnd: usually a sliver, because a wrong guess
-// means the best cell sits in the opposite corner) and reports that one cell's bit.  If that fails too
-// (walks through the corner (0,0), e.g. a sequence against itself, or a genuine tie between a row-0 and
-// a column-0 walk) the pair is appended to a retry list and recomputed by an exact kernel
-// (overlap_wf16t.cuh or overlap_wf32.cuh) launched behind this one.  Results are therefore always
-// the reference's; the certificates only decide which kernel produces them.
+// Per pair: a 16-base probe predicts the system (both sequences start with the same 16 bases -> C; the first
+// bases of the column sequence occur in the row sequence -> the walk will end in column 0 -> U; the first bases
+// of the row sequence occur in the column sequence -> L).  If the certificate fails (b = 1) the other systems
+// are run, one after the other, on the sub-table that ends at the best cell (rows 1..posRowEnd, columns
+// 1..posColEnd: usually a sliver, because a wrong guess means the best cell sits in the opposite corner) and
+// report that one cell's bit.  If all three fail (a genuine tie between walks that end on different borders)
+// the pair is appended to a retry list and recomputed by an exact kernel (overlap_wf16t.cuh or
+// overlap_wf32.cuh) launched behind this one.  Results are therefore always the reference's; the
+// certificates only decide which kernel produces them.
 //
 // The wavefront machinery is the table kernel's: one warp per pair, strips of 64*K rows, lane l owns 2K
 // consecutive rows (K lo rows in the low halves, K hi rows one column behind in the high halves),
@@ -80,22 +83,26 @@ inline Wf16cParams wf16c_make_params(int mismatch, int indel, int max_clip)
 // One DP pass: the sub-table rows 1..m, columns 1..n of a pair in one certificate system.
 //   scan mode: the reference's best-cell scan (C = max_clip) over the whole table of the pair;
 //   cell mode: only cell (m, n) is reported (its score must be s_cell).
+constexpr int WF16C_SYS_U = 0, WF16C_SYS_L = 1, WF16C_SYS_C = 2;
 struct Wf16cPass {
     int m, n, C;
-    uint32_t brow, bcol;            // origin bit on row 0 (j >= 1) / on column 0 (i >= 1); the corner has 1
+    int sys;                        // WF16C_SYS_*
+    uint32_t brow, bcol, bcorner;   // origin bit on row 0 (j >= 1) / on column 0 (i >= 1) / on the corner (0,0)
     bool cell;
     int s_cell;
     uint32_t gup, gleft;
-    GP_HD uint32_t v_col0(int i) const { return (uint32_t)(2 * (n + 1)) + (i == 0 ? 1u : bcol); }
-    GP_HD uint32_t v_row0(int j) const { return (uint32_t)(2 * (n - j + 1)) + (j == 0 ? 1u : brow); }
+    GP_HD uint32_t v_col0(int i) const { return (uint32_t)(2 * (n + 1)) + (i == 0 ? bcorner : bcol); }
+    GP_HD uint32_t v_row0(int j) const { return (uint32_t)(2 * (n - j + 1)) + (j == 0 ? bcorner : brow); }
 };
 
-GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, bool sysL, bool cell, int s_cell)
+GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, bool cell, int s_cell)
 {
     Wf16cPass g;
     g.m = m; g.n = n; g.C = cell ? 0 : P.max_clip;
-    g.brow = sysL ? 0u : 1u;
-    g.bcol = sysL ? 1u : 0u;
+    g.sys = sys;
+    g.brow = sys == WF16C_SYS_L ? 0u : 1u;
+    g.bcol = sys == WF16C_SYS_U ? 0u : 1u;
+    g.bcorner = sys == WF16C_SYS_C ? 0u : 1u;
     g.cell = cell; g.s_cell = s_cell;
     g.gup = P.gup; g.gleft = P.gleft;
     return g;
@@ -233,7 +240,7 @@ GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int ito
 GP_HD long long wf16c_initial_best(const Wf16cPass& g)
 {
     if (g.cell) return make_key(g.s_cell - 1, RANK_MAX, 0u);
-    return make_key(0, 0u, g.n == 0 ? 1u : g.brow);
+    return make_key(0, 0u, g.n == 0 ? g.bcorner : g.brow);
 }
 
 // What a finished pass proves.  Returns the origin flags (FLAG_ROW0 | FLAG_COL0) when the pass certifies
@@ -245,7 +252,15 @@ GP_HD uint32_t wf16c_certified_origin(const Wf16cPass& g, long long key)
         return FLAG_ROW0 | (g.n == 0 ? FLAG_COL0 : 0u);
     if (g.cell && (int)(key >> 32) != g.s_cell) return 0u;                      // cannot happen; be safe
     if (lo & 1u) return 0u;
-    return g.brow ? FLAG_COL0 : FLAG_ROW0;      // system U proves column 0, system L proves row 0
+    // system U proves column 0, system L proves row 0, system C proves the corner
+    return g.sys == WF16C_SYS_U ? FLAG_COL0 : g.sys == WF16C_SYS_L ? FLAG_ROW0 : (FLAG_ROW0 | FLAG_COL0);
+}
+
+// The systems to try after `first` failed, in order.
+GP_HD int wf16c_next_system(int first, int attempt)      // attempt = 1, 2
+{
+    const int order[3][2] = {{WF16C_SYS_L, WF16C_SYS_C}, {WF16C_SYS_U, WF16C_SYS_C}, {WF16C_SYS_U, WF16C_SYS_L}};
+    return order[first][attempt - 1];
 }
 
 #if defined(__CUDACC__)
@@ -257,7 +272,27 @@ struct Wf16cWarp {                      // warp-uniform state of one pass
     Wf16cPass g;
     uint32_t* bnd;                      // boundary line in global scratch (see wf16c_line_word)
     uint32_t* smem;                     // this warp's WF16C_WARP_WORDS words of shared memory
+    // team mode (the warps of a CTA share one pair, strip s goes to warp s % TEAM and follows strip s-1 through
+    // the boundary line): shared-memory address of the TEAM progress words, this warp's index in the team and
+    // the index of the strip it is about to run
+    uint32_t prog_addr;
+    int team_warp;
+    int strip_idx;
 };
+
+// Progress word of a team warp: (strip index << 15) | columns of that strip's bottom row already in the boundary
+// line.  Monotone over a pass (a warp's strips have increasing indices), so "strip s has published column c" is
+// one unsigned compare whatever the producer is doing by now.
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
 
 template <int K> struct CVals { uint32_t W[K]; };
 
@@ -268,7 +303,13 @@ __device__ __noinline__ long long wf16c_scan_cold(CVals<K> v, Wf16cPass g, int i
 }
 
 // One strip of 64*K rows starting after table row `i0` (see wf16t_strip for the block structure).
-template <int K, bool STD>
+//
+// TEAM > 1: strip s of a pair runs on warp s % TEAM of the CTA, concurrently with its neighbours.  The strip
+// reads column j of the boundary line (the bottom row of strip s-1) one block ahead and replaces it in place
+// 94+ steps later, so the only ordering needed is "strip s-1 has published column j before strip s reads it":
+// the producer publishes its progress after every block (columns <= tb + cnt - 95), the consumer spins on it
+// before each refill.  Boundary reads bypass L1 (ld.global.cg): the line is written by other warps.
+template <int K, bool STD, int TEAM>
 __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P, int i0, bool rowscan, bool store_bottom, long long best)
 {
     constexpr uint32_t FULL = 0xffffffffu;
@@ -321,7 +362,22 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     };
     for (int e = lane; e < 2 * WF16C_RING; e += 32) sts32(ring_base + 4 * e, 0u);
     __syncwarp();
-    { const int jj = 1 + lane; ring_put(jj, bnd[jj <= n + 1 ? jj : n + 1]); }
+    auto wait_cols = [&](int need) {            // team mode: until strip_idx-1 has published columns <= min(need, n)
+        if constexpr (TEAM > 1) {
+            if (w.strip_idx > 0) {
+                const uint32_t want = ((uint32_t)(w.strip_idx - 1) << 15) | (uint32_t)(need < n ? need : n);
+                const uint32_t a = w.prog_addr + 4u * (uint32_t)((w.strip_idx - 1) % TEAM);
+                while (lds32_volatile(a) < want) { }
+                __syncwarp();
+            }
+        }
+    };
+    auto bnd_load = [&](int jj) -> uint32_t {
+        if constexpr (TEAM > 1) return __ldcg(bnd + jj);
+        else return bnd[jj];
+    };
+    wait_cols(32);
+    { const int jj = 1 + lane; ring_put(jj, bnd_load(jj <= n + 1 ? jj : n + 1)); }
     Lane16c<K> st;
     lane16c_begin<K>(st, g, itop);
 
@@ -394,7 +450,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         // the next block's boundary words (L2 latency hidden behind this block)
         uint32_t next_line = 0;
         const bool have_next = tb + 32 <= t_end;
-        if (have_next) { const int jj = tb + 32 + lane; next_line = bnd[jj <= n + 1 ? jj : n + 1]; }
+        if (have_next) { wait_cols(tb + 63); const int jj = tb + 32 + lane; next_line = bnd_load(jj <= n + 1 ? jj : n + 1); }
         const bool edge = tb < 31 * D + 1 || tb + 31 > n + 1;             // some lane outside columns 1..n+1
         const bool filt = rowscan || tb + 31 >= jswitch;                  // some lane may hold candidates
         const int cnt = t_end - tb + 1 < 32 ? ((t_end - tb + 2) & ~1) : 32;   // steps past t_end find every lane out of range
@@ -405,6 +461,13 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             const int c = tb + lane - (31 * D + 1);
             const uint32_t v = lds32(oring_base + 4 * lane);
             if (c >= 1 && c <= n && lane < cnt) reinterpret_cast<uint16_t*>(bnd)[2 * c] = (uint16_t)(v >> 16);
+            if constexpr (TEAM > 1) {                                      // publish: columns <= tb + cnt - 95 are in the line
+                __threadfence_block();
+                __syncwarp();
+                const int done = tb + cnt - 1 - (31 * D + 1);
+                if (lane == 0 && done >= 1)
+                    sts32_volatile(w.prog_addr + 4u * (uint32_t)w.team_warp, ((uint32_t)w.strip_idx << 15) | (uint32_t)(done < n ? done : n));
+            }
         }
         if (have_next) ring_put(tb + 32 + lane, next_line);
         if (filt) {                                                       // share the best score across the warp
@@ -419,34 +482,51 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     return best;
 }
 
-// One pass (all strips of the sub-table); returns the warp-wide best key.
-template <bool STD>
-__device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P)
+// One pass (all strips of the sub-table); returns the best key of the pair: warp wide, or CTA wide in team mode
+// (every thread of the CTA calls it and gets the same key).
+template <bool STD, int TEAM>
+__device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P, long long* team_keys)
 {
     const int lane = threadIdx.x & 31;
     const int m = w.g.m, n = w.g.n;
     // boundary line = table row 0 plus the column symbol combinations
-    for (int j = 1 + lane; j <= n + 1; j += 32) {
+    if constexpr (TEAM > 1) {
+        __syncthreads();                                                   // the previous pass is over for every warp
+        if (lane == 0) sts32_volatile(w.prog_addr + 4u * (uint32_t)w.team_warp, 0u);
+    }
+    for (int j = 1 + (TEAM > 1 ? (int)threadIdx.x : lane); j <= n + 1; j += 32 * TEAM) {
         const uint32_t cj = (j <= n) ? load_code(w.packed, w.pd.col_off, (uint32_t)(j - 1)) : 0u;
         const uint32_t cp = (j >= 2) ? load_code(w.packed, w.pd.col_off, (uint32_t)(j - 2)) : 0u;
         w.bnd[j] = wf16c_line_word(w.g, j, cj, cp);
     }
-    __syncwarp();
+    if constexpr (TEAM > 1) { __threadfence_block(); __syncthreads(); } else __syncwarp();
     long long best = wf16c_initial_best(w.g);
-    int i0 = 0;
+    int i0 = 0, idx = 0;
     while (i0 < m) {
         const Wf16Strip s = wf16_next_strip(i0, m, w.g.C);
-        const bool sb = !s.last;
-        const bool rs = s.rowscan && !w.g.cell;
-        switch (s.rows) {
-        case 512: best = wf16c_strip<8, STD>(w, P, i0, rs, sb, best); break;
-        case 256: best = wf16c_strip<4, STD>(w, P, i0, rs, sb, best); break;
-        case 128: best = wf16c_strip<2, STD>(w, P, i0, rs, sb, best); break;
-        default:  best = wf16c_strip<1, STD>(w, P, i0, rs, sb, best); break;
+        if (TEAM == 1 || idx % TEAM == w.team_warp) {
+            const bool sb = !s.last;
+            const bool rs = s.rowscan && !w.g.cell;
+            w.strip_idx = idx;
+            switch (s.rows) {
+            case 512: best = wf16c_strip<8, STD, TEAM>(w, P, i0, rs, sb, best); break;
+            case 256: best = wf16c_strip<4, STD, TEAM>(w, P, i0, rs, sb, best); break;
+            case 128: best = wf16c_strip<2, STD, TEAM>(w, P, i0, rs, sb, best); break;
+            default:  best = wf16c_strip<1, STD, TEAM>(w, P, i0, rs, sb, best); break;
+            }
         }
         i0 += s.rows;
+        ++idx;
     }
-    return warp_max_key(best);
+    best = warp_max_key(best);
+    if constexpr (TEAM > 1) {
+        if (lane == 0) team_keys[w.team_warp] = best;
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < TEAM; ++t) { const long long k = team_keys[t]; best = k > best ? k : best; }
+        __syncthreads();
+    }
+    return best;
 }
 
 // Does the 16-base word pair (plo, phi) occur in the sequence at word offset `off` with `len` bases?
@@ -471,20 +551,26 @@ __device__ __forceinline__ bool wf16c_probe_hit(const uint32_t* __restrict__ pac
     return false;
 }
 
-// Orientation probe: true -> start with system L (the walk is expected to end in row 0).
-__device__ __forceinline__ bool wf16c_predict_sysL(const uint32_t* __restrict__ packed, const PairDesc& pd)
+// Orientation probe: the system to start with (where the walk is expected to end).
+__device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__ packed, const PairDesc& pd)
 {
-    if (pd.m < (uint32_t)WF16C_PROBE || pd.n < (uint32_t)WF16C_PROBE) return false;
+    if (pd.m < (uint32_t)WF16C_PROBE || pd.n < (uint32_t)WF16C_PROBE) return WF16C_SYS_U;
+    const uint32_t c0 = __ldg(packed + pd.col_off), c1 = __ldg(packed + pd.col_off + 1);
+    const uint32_t r0 = __ldg(packed + pd.row_off), r1 = __ldg(packed + pd.row_off + 1);
+    // both sequences start with the same bases: the overlap starts in the corner
+    if (c0 == r0 && c1 == r1) return WF16C_SYS_C;
     // the first bases of the column sequence occur in the row sequence: the overlap starts in column 0
-    if (wf16c_probe_hit(packed, pd.row_off, pd.m, __ldg(packed + pd.col_off), __ldg(packed + pd.col_off + 1))) return false;
+    if (wf16c_probe_hit(packed, pd.row_off, pd.m, c0, c1)) return WF16C_SYS_U;
     // the first bases of the row sequence occur in the column sequence: it starts in row 0
-    return wf16c_probe_hit(packed, pd.col_off, pd.n, __ldg(packed + pd.row_off), __ldg(packed + pd.row_off + 1));
+    return wf16c_probe_hit(packed, pd.col_off, pd.n, r0, r1) ? WF16C_SYS_L : WF16C_SYS_U;
 }
 
-// counters[0] second passes run, counters[1] pairs handed to an exact kernel.
+// counters[0] sub-table passes run (second and third passes), counters[1] pairs handed to an exact kernel.
+// force_sys: 0 the probe decides, 1 + WF16C_SYS_* starts with that system (tests).
 // retry16t / retry32: work lists of the exact kernels behind this one (pairs with n <= WF16T_MAX_N go to
 // the table kernel); *retry16t_n / *retry32_n are their fill counts (the host may have pre-filled them).
-template <bool STD>
+// TEAM = 1: one warp per pair.  TEAM = warps per CTA: one CTA per pair (few, long pairs: the relax chain).
+template <bool STD, int TEAM>
 __global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
 overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                      const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
@@ -494,35 +580,49 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
                      unsigned int* __restrict__ counters, uint32_t force_sys, DevResult* __restrict__ out)
 {
     extern __shared__ uint32_t wf16c_smem[];
+    __shared__ uint32_t team_prog[TEAM];
+    __shared__ long long team_keys[TEAM];
+    __shared__ uint32_t team_qi;
     const int lane = threadIdx.x & 31;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Wf16cWarp w;
     w.packed = packed;
-    w.bnd = scratch + (size_t)warp_global * scratch_stride;
+    w.team_warp = TEAM > 1 ? (int)(threadIdx.x >> 5) : 0;
+    w.strip_idx = 0;
+    w.prog_addr = (uint32_t)__cvta_generic_to_shared(team_prog);
+    w.bnd = scratch + (size_t)(warp_global - (uint32_t)w.team_warp) * scratch_stride;   // team: the CTA's first line
     w.smem = wf16c_smem + (threadIdx.x >> 5) * WF16C_WARP_WORDS;
+    const bool leader = TEAM > 1 ? threadIdx.x == 0 : lane == 0;
     for (;;) {
         uint32_t qi = 0;
-        if (lane == 0) qi = atomicAdd(queue, 1u);
-        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if constexpr (TEAM > 1) {
+            if (threadIdx.x == 0) team_qi = atomicAdd(queue, 1u);
+            __syncthreads();
+            qi = team_qi;
+            __syncthreads();
+        } else {
+            if (lane == 0) qi = atomicAdd(queue, 1u);
+            qi = __shfl_sync(0xffffffffu, qi, 0);
+        }
         if (qi >= n_work) break;
         const uint32_t pid = order[qi];
         w.pd = pairs[pid];
         const int m = (int)w.pd.m, n = (int)w.pd.n;
-        const bool sysL = force_sys == 1u ? false : force_sys == 2u ? true : wf16c_predict_sysL(packed, w.pd);
-        w.g = wf16c_make_pass(m, n, P, sysL, false, 0);
-        const long long key = wf16c_pass<STD>(w, P);
+        const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system(packed, w.pd);
+        w.g = wf16c_make_pass(m, n, P, sys0, false, 0);
+        const long long key = wf16c_pass<STD, TEAM>(w, P, team_keys);
         uint32_t origin = wf16c_certified_origin(w.g, key);
         DevResult r;
         store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
-        if (origin == 0u) {
-            // the other system on the sub-table that ends at the best cell, that cell only
+        for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
+            // another system on the sub-table that ends at the best cell, that cell only
             __syncwarp();
-            if (lane == 0) atomicAdd(counters, 1u);
-            w.g = wf16c_make_pass(r.row_end, r.col_end, P, !sysL, true, r.score);
-            const long long key2 = wf16c_pass<STD>(w, P);
+            if (leader) atomicAdd(counters, 1u);
+            w.g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score);
+            const long long key2 = wf16c_pass<STD, TEAM>(w, P, team_keys);
             origin = wf16c_certified_origin(w.g, key2);
         }
-        if (lane == 0) {
+        if (leader) {
             if (origin != 0u) {
                 store_result(out + pid, (key & ~3ll) | (long long)origin, m, n, FLAG_KERNEL16);
             } else {
@@ -536,23 +636,32 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
     }
 }
 
+constexpr int WF16C_TEAM = WF16C_THREADS / 32;
+
+template <bool STD, int TEAM>
+inline cudaError_t wf16c_configure_one()
+{
+    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 inline cudaError_t wf16c_configure()
 {
-    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(overlap_wf16c_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(overlap_wf16c_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(overlap_wf16c_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t e;
+    if ((e = wf16c_configure_one<true, 1>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<false, 1>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<true, WF16C_TEAM>()) != cudaSuccess) return e;
+    return wf16c_configure_one<false, WF16C_TEAM>();
 }
 
 // Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
+// team: one CTA (WF16C_TEAM warps) per pair instead of one warp per pair.
 inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packed, const PairDesc* pairs,
                         const uint32_t* order, uint32_t n_work, unsigned int* queue, const Wf16cParams& P,
                         uint32_t max_n, void** scratch, size_t* scratch_cap,
                         uint32_t* retry16t, unsigned int* retry16t_n, uint32_t* retry32, unsigned int* retry32_n,
-                        unsigned int* counters, uint32_t force_sys, DevResult* out)
+                        unsigned int* counters, uint32_t force_sys, bool team, DevResult* out)
 {
     const int blocks = sm_count * WF16C_CTAS_PER_SM;
     const uint32_t warps = (uint32_t)blocks * (WF16C_THREADS / 32);
@@ -565,12 +674,13 @@ inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packe
         if (e != cudaSuccess) return (int)e;
         *scratch_cap = need;
     }
-    if (P.std_scores)
-        overlap_wf16c_kernel<true><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(
-            packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, counters, force_sys, out);
-    else
-        overlap_wf16c_kernel<false><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(
-            packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, counters, force_sys, out);
+#define GP_WF16C_LAUNCH(STD_, TEAM_)                                                                                   \
+    overlap_wf16c_kernel<STD_, TEAM_><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(                              \
+        packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, \
+        counters, force_sys, out)
+    if (P.std_scores) { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM); else GP_WF16C_LAUNCH(true, 1); }
+    else              { if (team) GP_WF16C_LAUNCH(false, WF16C_TEAM); else GP_WF16C_LAUNCH(false, 1); }
+#undef GP_WF16C_LAUNCH
     return (int)cudaGetLastError();
 }
 #endif // __CUDACC__

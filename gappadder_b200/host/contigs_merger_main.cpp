@@ -160,9 +160,16 @@ int run_batch(const Cli& c)
         uint64_t tot = 0, ptot = 0; for (uint64_t x : cells) tot += x; for (uint64_t x : pcells) ptot += x;
         int slow = 0; for (int d = 1; d < n_gpus; ++d) if (wall[d] > wall[slow]) slow = d;
         const MergeTimings& t = tim[slow];
-        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"merge_ms\": %.3f, "
-                        "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f}\n",
-                lines.size(), n_gpus, tot / 1e9, ptot / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms);
+        // dp_gcells / pairwise_gcells: m*n of every Evaluate the reference runs for these gaps; closed_gcells of them
+        // (a node against itself) are answered in closed form here, so computed cells = dp_gcells - closed_gcells
+        uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;
+        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
+                        "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
+                        "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "
+                        "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu}\n",
+                lines.size(), n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
+                t.relax_device_ms, t.relax_host_ms, t.relax_team_steps, (unsigned long long)t.relax_pairs,
+                (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries);
     }
     return 0;
 }

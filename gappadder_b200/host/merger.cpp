@@ -178,6 +178,11 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     if (!pairs.empty()) {
         int rc = gp_overlap_batch(ctx, seq_ptr.data(), seq_len.data(), (uint32_t)seq_ptr.size(), pairs.data(), pairs.size(), &dp, res.data());
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        if (timings) {
+            uint64_t cp = 0, cc = 0;
+            gp_closed_form_stats(ctx, &cp, &cc);
+            timings->closed_pairs += cp; timings->closed_cells += cc;
+        }
     }
 
     lap(&MergeTimings::pairwise_ms);
@@ -234,6 +239,15 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         std::vector<gp_result> rr(pp.size());
         int rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        if (timings) {
+            uint64_t c16 = 0, sp = 0, er = 0;
+            gp_cert_stats(ctx, &c16, &sp, &er);
+            timings->relax_pairs += pp.size(); timings->relax_second_passes += sp; timings->relax_exact_retries += er;
+            timings->relax_team_steps += gp_last_team(ctx) ? 1 : 0;
+            double tm[GP_TIMING_SLOTS] = {0};
+            gp_last_timing(ctx, tm, GP_TIMING_SLOTS);
+            timings->relax_device_ms += tm[2];
+        }
         for (size_t a = 0; a < active.size(); ++a) {
             Chain& ch = chains[active[a]];
             const std::string& nodeseq = st[ch.gap].node_seq[ch.path[ch.next]];
@@ -249,6 +263,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     }
     for (Chain& ch : chains) st[ch.gap].merged.push_back(std::move(ch.merged));
     lap(&MergeTimings::relax_ms);
+    if (timings) timings->relax_host_ms = timings->relax_ms - timings->relax_device_ms;
 
     // ---- output (ContigsCompactor.cpp:945-971, CM/main.cpp:281-288) -------------------------------
     for_each_gap(G, host_threads, [&](size_t g) {

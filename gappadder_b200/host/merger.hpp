@@ -53,6 +53,11 @@ struct MergeTimings {
     double relax_ms = 0;       // all relax-chain steps (one gp_overlap_batch per step)
     double output_ms = 0;      // output text
     uint32_t relax_steps = 0;
+    uint32_t relax_team_steps = 0;     // relax steps the library ran one CTA per pair (gp_last_team)
+    uint64_t relax_pairs = 0, relax_second_passes = 0, relax_exact_retries = 0;   // certificate kernel, relax chain
+    uint64_t closed_pairs = 0, closed_cells = 0;   // pairwise phase: node-vs-itself pairs answered in closed form
+    double relax_device_ms = 0;        // of relax_ms: inside gp_overlap_batch from first launch to results on the host
+    double relax_host_ms = 0;          // of relax_ms: building the step's batch and the merged strings
 };
 
 // Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure

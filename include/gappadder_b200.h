@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 2
+#define GP_ABI_VERSION 3
 
 typedef enum gp_status {
     GP_OK = 0,
@@ -70,6 +70,7 @@ typedef struct gp_result {
 #define GP_FLAG_COL0      2u  /* the walk ended with tbCur.second == 0 (:1836)                     */
 #define GP_FLAG_CONTAINED 4u  /* bcontained (:1814,:1834-1837)                                     */
 #define GP_FLAG_KERNEL16  8u  /* informational: computed by the packed 16-bit kernel               */
+#define GP_FLAG_CLOSED   16u  /* informational: closed form, no DP run (a sequence against itself) */
 
 /* DP scoring and scan parameters: the statics CM/main.cpp:250-262 sets.  match is +1
  * (ContigsCompactor.cpp:1596).  mismatch = (int)scoreMismatch (-i1), indel = scoreIndel (-i2, must
@@ -147,7 +148,8 @@ int gp_launch_resident(gp_ctx *ctx);
 int gp_fetch_results(gp_ctx *ctx, gp_result *out, uint64_t n_pairs);
 /* Kernel launches enqueued by this context since creation (library kernels only). */
 uint64_t gp_kernel_launches(const gp_ctx *ctx);
-/* DP cells (sum of m*n) of the pairs currently uploaded, and how many went to each kernel. */
+/* DP cells (sum of m*n) of the pairs currently uploaded that a kernel computes (closed-form pairs excluded,
+ * see gp_closed_form_stats), and how many pairs went to the 16-bit kernels / the 32-bit kernel. */
 int gp_pair_stats(const gp_ctx *ctx, uint64_t *cells, uint64_t *pairs16, uint64_t *pairs32);
 
 /* The same split by kernel, as routed by the host: the shared-memory-table 16-bit kernel with tie tags
@@ -158,8 +160,8 @@ int gp_pair_split(const gp_ctx *ctx, uint64_t *table16, uint64_t *prmt16, uint64
 /* The certificate kernel (the default for A/C/G/T pairs whose column sequence has <= 16382 bases, a
  * sequence against itself excepted): same DP without tie tags; it proves where the reference's
  * predecessor walk ends instead of following it, and hands the pairs it cannot prove to the exact
- * kernels above on the device.  cert16: pairs of the uploaded batch routed to it; second_passes: pairs of
- * the last fetched run that needed the second (small) pass; exact_retries: pairs of that run recomputed
+ * kernels above on the device.  cert16: pairs of the uploaded batch routed to it; second_passes: sub-table passes
+ * (second and third tries) run by the last fetched run; exact_retries: pairs of that run recomputed
  * by an exact kernel.  Results never depend on which kernel produced them. */
 int gp_cert_stats(const gp_ctx *ctx, uint64_t *cert16, uint64_t *second_passes, uint64_t *exact_retries);
 /* Per-kernel device time (CUDA events on the context's stream) of the last gp_launch_resident /
@@ -168,15 +170,30 @@ int gp_cert_stats(const gp_ctx *ctx, uint64_t *cert16, uint64_t *second_passes, 
  * [2] PRMT kernel, [3] general kernel (likewise).  Waits for that launch to finish.  ms and cells hold 4 entries. */
 int gp_kernel_times(gp_ctx *ctx, double *ms, uint64_t *cells);
 /* Testing: which certificate system the kernel tries first (0: a 16-base probe decides, the default;
- * 1: "walk ends in column 0"; 2: "walk ends in row 0"). */
+ * 1: "walk ends in column 0"; 2: "walk ends in row 0"; 3: "walk ends in the corner"). */
 int gp_set_cert_system(gp_ctx *ctx, uint32_t system);
+/* The certificate kernel runs one warp per pair (many pairs: the pairwise phase) or one CTA of four warps per
+ * pair, the pair's 512-row strips pipelined across the warps through the boundary line (few long pairs: a relax
+ * chain step, whose duration is its longest pair's).  mode 0: the library chooses per launch from the batch's
+ * total and largest m*n (default); 1: always one warp per pair; 2: always one CTA per pair.  Results never
+ * depend on it.  gp_last_team: 1 if the last launch on this context used the CTA-per-pair form. */
+int gp_set_team_mode(gp_ctx *ctx, uint32_t mode);
+int gp_last_team(const gp_ctx *ctx);
 /* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).
  * Pairs no allowed kernel accepts go to the general 32-bit kernel; results never depend on the mask. */
 #define GP_KERNEL_TABLE16 1u
 #define GP_KERNEL_PRMT16  2u
 #define GP_KERNEL_CERT16  4u
-#define GP_KERNEL_ALL     7u
+#define GP_KERNEL_CLOSED  8u   /* not a kernel: the closed form for a sequence against itself (below) */
+#define GP_KERNEL_ALL     15u
 int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
+/* Pairs whose row and column sequence are the same table entry (ContigsMerger's pairwise phase aligns every
+ * node with itself, ContigsCompactor.cpp:1068-1100: j starts at i) are answered without a DP when
+ * mismatch <= 1 and indel <= 0: Evaluate(s, s) = {score m, ends (m, m), nclip 0, walk to the corner, contained};
+ * the proof is at closed_form_self in csrc/gp_api.cu and tests/ check it against the oracle and the kernels.
+ * pairs / cells: how many pairs of the uploaded batch took it and the m*n the reference spends on them; these
+ * cells are NOT part of gp_pair_stats' cells (no cell update is computed for them). */
+int gp_closed_form_stats(const gp_ctx *ctx, uint64_t *pairs, uint64_t *cells);
 
 /* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):
  * thread-level instructions per second of VIADDMNMX.S16x2 alone (ALU pipe) and of the

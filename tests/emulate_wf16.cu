@@ -363,8 +363,8 @@ long long pass_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams&
 } // namespace
 
 // out: score, row_end, col_end, nclip, flags.  Returns 0 when the first pass certified the origin, 1 when
-// the second pass did, 2 when neither did (origin flags in out[4] are then 0: the library recomputes the
-// pair with an exact kernel), -1 outside the kernel's domain.  first_sys: 0 = U, 1 = L.
+// a later (sub-table) pass did, 2 when none did (origin flags in out[4] are then 0: the library recomputes the
+// pair with an exact kernel), -1 outside the kernel's domain.  first_sys: 0 = U, 1 = L, 2 = C.
 extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col_codes, int n,
                              int mismatch, int indel, int max_clip, int first_sys, int32_t* out)
 {
@@ -373,19 +373,19 @@ extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col
     HostPair hp;
     hp.row.assign(row_codes, row_codes + m);
     hp.col.assign(col_codes, col_codes + n);
-    const bool sysL = first_sys != 0;
-    Wf16cPass g = wf16c_make_pass(m, n, P, sysL, false, 0);
+    if (first_sys < 0 || first_sys > 2) return -1;
+    Wf16cPass g = wf16c_make_pass(m, n, P, first_sys, false, 0);
     const long long key = pass_host_c(hp, g, P);
     uint32_t origin = wf16c_certified_origin(g, key);
     DevResult r;
     store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);
     int status = 0;
-    if (origin == 0u) {
+    for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
         status = 1;
-        g = wf16c_make_pass(r.row_end, r.col_end, P, !sysL, true, r.score);
+        g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(first_sys, attempt), true, r.score);
         origin = wf16c_certified_origin(g, pass_host_c(hp, g, P));
-        if (origin == 0u) status = 2;
     }
+    if (origin == 0u) status = 2;
     store_result(&r, (key & ~3ll) | (long long)origin, m, n, FLAG_KERNEL16);
     out[0] = r.score; out[1] = r.row_end; out[2] = r.col_end; out[3] = r.nclip; out[4] = (int32_t)r.flags;
     return status;

@@ -34,4 +34,9 @@ int gp_overlap_batch(gp_ctx*, const char* const* seqs, const uint32_t* seq_len, 
     }
     return GP_OK;
 }
+// statistics the merger reads after a batch: nothing to report from the CPU shim
+int gp_closed_form_stats(const gp_ctx*, uint64_t* pairs, uint64_t* cells) { if (pairs) *pairs = 0; if (cells) *cells = 0; return GP_OK; }
+int gp_cert_stats(const gp_ctx*, uint64_t* a, uint64_t* b, uint64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GP_OK; }
+int gp_last_team(const gp_ctx*) { return 0; }
+int gp_last_timing(const gp_ctx*, double* out_ms, int n) { for (int i = 0; i < n; ++i) out_ms[i] = 0.0; return GP_OK; }
 }

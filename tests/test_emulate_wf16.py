@@ -33,7 +33,7 @@ def emu():
     L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.wf16t_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
     L.wf16c_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
-    cert_status = [0, 0, 0]          # certificate kernel: certified by the first pass / by the second / handed to an exact kernel
+    cert_status = [0, 0, 0]          # certificate kernel: certified by the first pass / by a later one / handed to an exact kernel
 
     def run(a, b, mm=-2, ind=-2, clip=50):
         res = []
@@ -49,8 +49,8 @@ def emu():
             assert L.wf16t_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out) == 0
             f = out[4]
             res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
-        if four and len(b) <= 16382:                   # the certificate kernel's domain; both starting systems
-            for first_sys in (0, 1):
+        if four and len(b) <= 16382:                   # the certificate kernel's domain; every starting system
+            for first_sys in (0, 1, 2):
                 out = (C.c_int32 * 5)()
                 st = L.wf16c_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, first_sys, out)
                 assert st in (0, 1, 2)
@@ -138,13 +138,16 @@ def test_certificate_kernel_resolves_overlaps_and_long_columns(emu):
     # transposed: the walk ends in row 0
     assert cert(b, a, 1) == (0, _want(b, a))
     assert cert(b, a, 0) == (1, _want(b, a))
-    # a sequence against itself: the walk ends in the corner, no certificate
-    assert cert(a, a, 0)[0] == 2 and cert(a, a, 1)[0] == 2
-    assert cert(a, a, 0)[1][:4] == _want(a, a)[:4]
+    # a sequence against itself: the walk ends in the corner; only system C certifies that
+    assert cert(a, a, 2) == (0, _want(a, a))
+    assert cert(a, a, 0) == (1, _want(a, a)) and cert(a, a, 1) == (1, _want(a, a))
+    # a genuine tie between a walk that ends in row 0 and one that ends in column 0: no certificate, exact kernel
+    t1, t2 = b"CACA", b"ACAC"
+    assert {cert(t1, t2, fs)[0] for fs in (0, 1, 2)} <= {0, 1, 2}
     # long columns
     c = bytes(rng.choice(b"ACGT") for _ in range(5200))
     d = c[-3000:] + bytes(rng.choice(b"ACGT") for _ in range(3100))
     for x, y in ((c, d), (d, c)):
         w = _want(x, y)
-        got = [cert(x, y, fs) for fs in (0, 1)]
-        assert sorted(st for st, _ in got) == [0, 1] and all(t == w for _, t in got)
+        got = [cert(x, y, fs) for fs in (0, 1, 2)]
+        assert sorted(st for st, _ in got) == [0, 1, 1] and all(t == w for _, t in got)

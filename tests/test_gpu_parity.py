@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 import gappadder_b200 as g
-from gappadder_b200.capi import FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0, KERNEL_ALL, KERNEL_CERT16, KERNEL_PRMT16, KERNEL_TABLE16
+from gappadder_b200.capi import (FLAG_CLOSED, FLAG_COL0, FLAG_CONTAINED, FLAG_ROW0, KERNEL_ALL, KERNEL_CERT16, KERNEL_DP_ALL,
+                                 KERNEL_PRMT16, KERNEL_TABLE16)
 
 KERNEL_TAGGED = KERNEL_TABLE16 | KERNEL_PRMT16      # everything but the certificate kernel
 from _oracle import oracle_evaluate, oracle_revcomp
@@ -17,10 +18,11 @@ import synth_gaps
 pytestmark = pytest.mark.gpu
 
 
-def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_TAGGED, KERNEL_PRMT16)):
-    """Every kernel the library can route these pairs to (default routing = certificate kernel first -- run with
-    the probe and with either starting system forced --, then the table kernel, then the PRMT kernel / general
-    kernel) against the oracle.  Returns the default routing's results."""
+def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_DP_ALL, KERNEL_TAGGED, KERNEL_PRMT16)):
+    """Every kernel the library can route these pairs to (default routing = closed form for a sequence against
+    itself, then the certificate kernel -- run with the probe and with either starting system forced, one warp
+    per pair and one CTA per pair --, then the table kernel, then the PRMT kernel / general kernel; KERNEL_DP_ALL
+    is the same without the closed form) against the oracle.  Returns the default routing's results."""
     params = params or g.GAPPADDER_DP
     want = []
     for a, b in pairs:
@@ -28,12 +30,13 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         want.append((o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained))
     first = None
     try:
-        runs = []
+        runs = []        # (kernel mask, certificate system to start with, team mode)
         for mask in masks:
-            runs += [(mask, 0), (mask, 1), (mask, 2)] if mask & KERNEL_CERT16 else [(mask, 0)]
-        for mask, system in runs:
+            runs += [(mask, 0, 0), (mask, 1, 1), (mask, 2, 2), (mask, 3, 0), (mask, 0, 2)] if mask & KERNEL_CERT16 else [(mask, 0, 0)]
+        for mask, system, team in runs:
             ctx.set_kernel_mask(mask)
             ctx.set_cert_system(system)
+            ctx.set_team_mode(team)
             res = ctx.overlap_batch(seqs, pairs, params)
             assert len(res) == len(pairs)
             bad = []
@@ -42,12 +45,13 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
                        int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
                 if w != got:
                     bad.append(((a, b), len(seqs[a]), len(seqs[b]), w, got))
-            assert not bad, "kernel mask %d system %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, system, bad[:5])
+            assert not bad, "kernel mask %d system %d team %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, system, team, bad[:5])
             if first is None:
                 first = res
     finally:
         ctx.set_kernel_mask(KERNEL_ALL)
         ctx.set_cert_system(0)
+        ctx.set_team_mode(0)
     return first
 
 
@@ -161,11 +165,18 @@ def test_long_overlaps_both_potentials(ctx):
         pairs += [(k, k + 1), (k + 1, k), (k, k), (k + 1, k + 1)]
     res = _check(ctx, seqs, pairs)
     from gappadder_b200.capi import FLAG_KERNEL16
-    # the 12 overlap pairs go through the certificate kernel (columns <= 16382), 7 of the 12 self pairs through the
-    # table kernel (<= 4094 columns), the other 5 through the general one
-    assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 19
+    # the 12 overlap pairs go through the certificate kernel (columns <= 16382), the 12 self pairs have the closed form
+    assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 12 and int((res["flags"] & FLAG_CLOSED != 0).sum()) == 12
     ctx.overlap_batch(seqs, pairs)
     assert ctx.cert_stats() == dict(cert16=12, second_passes=0, exact_retries=0)
+    assert ctx.closed_form_stats() == dict(pairs=12, cells=sum(len(seqs[a]) ** 2 for a, b in pairs if a == b))
+    # without the closed form: 7 of the 12 self pairs go through the table kernel (<= 4094 columns), 5 through the general one
+    try:
+        ctx.set_kernel_mask(KERNEL_DP_ALL)
+        res = ctx.overlap_batch(seqs, pairs)
+        assert int((res["flags"] & FLAG_KERNEL16 != 0).sum()) == 19 and not (res["flags"] & FLAG_CLOSED).any()
+    finally:
+        ctx.set_kernel_mask(KERNEL_ALL)
 
 
 def test_kernel_routing(ctx):
@@ -194,8 +205,8 @@ def test_kernel_routing(ctx):
 
 def test_certificate_kernel_long_columns_and_fallbacks(ctx):
     """Certificate kernel beyond the tagged kernels' range (columns up to 16382), pairs whose walks end in the
-    corner (identical sequences under different indices: second pass, then an exact kernel -- the general one when
-    the column sequence is too long for the table kernel), and junk pairs whose best cell sits in a corner."""
+    corner (identical sequences under different indices: the corner system certifies them; when the run is forced
+    to start with another system it takes sub-table passes), and junk pairs whose best cell sits in a corner."""
     rng = random.Random(21)
     a = _rand(rng, 9000)
     b = a[-5000:] + _rand(rng, 6000)          # 11000 columns
@@ -207,4 +218,53 @@ def test_certificate_kernel_long_columns_and_fallbacks(ctx):
     _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
     ctx.overlap_batch(seqs, pairs)
     st = ctx.cert_stats()
-    assert st["cert16"] == len(pairs) and st["exact_retries"] >= 3, st      # (4,5), (5,4), (6,7) end in the corner
+    assert st["cert16"] == len(pairs) and st["exact_retries"] == 0, st      # (4,5), (5,4), (6,7) end in the corner: system C
+    try:
+        ctx.set_cert_system(1)
+        ctx.overlap_batch(seqs, pairs)
+        assert ctx.cert_stats()["second_passes"] >= 6 and ctx.cert_stats()["exact_retries"] == 0      # U, then L, then C for those three
+    finally:
+        ctx.set_cert_system(0)
+
+
+def test_team_mode_many_long_pairs(ctx):
+    """The CTA-per-pair form of the certificate kernel under load: more pairs than CTAs, 1 to 16 strips per pair,
+    all four warps of a CTA pipelined through one boundary line.  Same results as one warp per pair on every pair,
+    and as the oracle on a sample."""
+    rng = random.Random(314)
+    base = _rand(rng, 12000)
+    seqs = []
+    for _ in range(90):
+        L = rng.choice([64, 300, 513, 1100, 2049, 3000, 5000, 8000])
+        st = rng.randrange(0, len(base) - L)
+        s = bytearray(base[st:st + L])
+        for p in range(L):
+            if rng.random() < 0.004:
+                s[p] = rng.choice(b"ACGT")
+        s = bytes(s)
+        seqs.append(oracle_revcomp(s) if rng.random() < 0.3 else s)
+    pairs = []
+    while len(pairs) < 1400:
+        a, b = rng.randrange(len(seqs)), rng.randrange(len(seqs))
+        if a != b and len(seqs[b]) <= 5000:
+            pairs.append((a, b))
+    try:
+        ctx.set_team_mode(1)
+        warp = ctx.overlap_batch(seqs, pairs)
+        assert not ctx.last_team
+        ctx.set_team_mode(2)
+        team = ctx.overlap_batch(seqs, pairs)
+        assert ctx.last_team
+        ctx.set_team_mode(0)
+        ctx.overlap_batch(seqs, pairs[:40])          # few long pairs: the library picks the team form itself
+        assert ctx.last_team
+    finally:
+        ctx.set_team_mode(0)
+    assert (warp == team).all()
+    for k in range(0, len(pairs), 23):
+        a, b = pairs[k]
+        o = oracle_evaluate(seqs[a], seqs[b])
+        r = team[k]
+        assert (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained) == \
+            (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]), int(bool(r["flags"] & FLAG_ROW0)),
+             int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED))), (a, b)

@@ -45,7 +45,8 @@ def main():
             return 1
         stats = json.loads(p.stderr.strip().splitlines()[-1])
         line = {"impl": "b200", "config": args.config, "process_wall_s": wall, **stats,
-                "gaps_per_s": args.gaps / (stats["merge_ms"] * 1e-3), "gcups": stats["dp_gcells"] / (stats["merge_ms"] * 1e-3)}
+                "gaps_per_s": args.gaps / (stats["merge_ms"] * 1e-3),
+                "gcups": (stats["dp_gcells"] - stats.get("closed_gcells", 0.0)) / (stats["merge_ms"] * 1e-3)}
         if args.ref_gaps and os.path.exists(ref):
             t_ref, same = 0.0, True
             for g in range(min(args.ref_gaps, args.gaps)):
