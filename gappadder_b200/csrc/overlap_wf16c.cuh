@@ -51,11 +51,12 @@ namespace gp {
 
 constexpr uint32_t WF16C_MAX_N = 16382;           // 2*(n+1)+1 <= 32767
 constexpr int WF16C_THREADS = 128;                // 4 warps per CTA
-constexpr int WF16C_CTAS_PER_SM = 3;              // 12 warps per SM: 3 x (4 x 17.1 KB) of shared memory
+constexpr int WF16C_CTAS_PER_SM = 3;              // 12 warps per SM: 3 x (4 x 17.6 KB) of shared memory
 constexpr int WF16C_RING = 128;
 constexpr int WF16C_SKEW = 3;
 constexpr int WF16C_TAB_WORDS = 16 * 8 * 32;
-constexpr int WF16C_WARP_WORDS = WF16C_TAB_WORDS + 2 * WF16C_RING + 32;
+constexpr int WF16C_ORING = WF16C_RING + 32;        // bottom-row ring: addressed like the input ring, a block never wraps
+constexpr int WF16C_WARP_WORDS = WF16C_TAB_WORDS + 2 * WF16C_RING + WF16C_ORING;
 constexpr size_t WF16C_SMEM_BYTES = (size_t)(WF16C_THREADS / 32) * WF16C_WARP_WORDS * sizeof(uint32_t);
 constexpr int WF16C_PROBE = 16;                   // bases of the orientation probe (two packed words)
 
@@ -144,24 +145,37 @@ GP_HD void lane16c_fix_first(Lane16c<K>& st, const Wf16cPass& g)
     for (int k = 0; k < K; ++k) st.W[k] = (st.W[k] & 0xffffu) | (c0 << 16);
 }
 
-// One step: VIADD.16x2 + 2 x VIADDMNMX.S16x2 per register, nothing else.
+// One step: VIADD.16x2 + 2 x VIADDMNMX.S16x2 per register, nothing else.  Two phases so that the kernel can
+// reload the increment registers between them (the diagonal adds are the only readers of `inc`):
+//   lane16c_diag   d[k] = diagonal + increment, from the values before the step;
+//   lane16c_chain  the left and up candidates and the maxima, the `up` chain through the K registers.
 template <int K>
-GP_HD void lane16c_step(Lane16c<K>& st, uint32_t recv, const uint32_t (&inc)[K], uint32_t gup, uint32_t gleft)
+GP_HD void lane16c_diag(const Lane16c<K>& st, const uint32_t (&inc)[K], uint32_t (&d)[K])
+{
+    d[0] = p_add2(st.up0_prev, inc[0]);
+#pragma unroll
+    for (int k = 1; k < K; ++k) d[k] = p_add2(st.W[k - 1], inc[k]);
+}
+template <int K>
+GP_HD void lane16c_chain(Lane16c<K>& st, uint32_t recv, const uint32_t (&d)[K], uint32_t gup, uint32_t gleft)
 {
     const uint32_t up0 = p_prmt(recv, st.W[K - 1], 0x5432u);   // (recv.hi16 , old W[K-1].lo16)
-    uint32_t diag = st.up0_prev;
     st.up0_prev = up0;
     uint32_t up = up0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const uint32_t left = st.W[k];
-        const uint32_t d = p_add2(diag, inc[k]);
-        const uint32_t t = p_addmax2(left, gleft, d);
+        const uint32_t t = p_addmax2(st.W[k], gleft, d[k]);
         const uint32_t w = p_addmax2_relu(up, gup, t);
-        diag = left;
         up = w;
         st.W[k] = w;
     }
+}
+template <int K>
+GP_HD void lane16c_step(Lane16c<K>& st, uint32_t recv, const uint32_t (&inc)[K], uint32_t gup, uint32_t gleft)
+{
+    uint32_t d[K];
+    lane16c_diag<K>(st, inc, d);
+    lane16c_chain<K>(st, recv, d, gup, gleft);
 }
 
 template <int K>
@@ -189,18 +203,31 @@ GP_HD uint32_t wf16c_filter_thr(int S) { const uint32_t t = (uint32_t)(2 * ((S >
 
 // Exact scan of the cells a lane holds after a step (lo column j, hi column j-1).  Scan mode: a cell can
 // only change `best` if it scores at least the lane's best score (and at least 1: the initial best is
-// cell (0,n) with H = 0 and rank 0); that one compare per cell comes first, the rank arithmetic only runs
-// for the cells that pass.  Cell mode: only cell (m, n) counts.  The key's origin field holds b.
-template <int K>
-GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int j, long long best)
+// cell (0,n) with H = 0 and rank 0).  That test comes first and is PACKED: one signed compare per register
+// (two cells) against the threshold of both columns; the rank arithmetic only runs for the cells that pass
+// (one or two per call as a rule).  The result is an order-independent maximum over keys, so the order in
+// which cells are visited does not matter.  Cell mode: only cell (m, n) counts.  The key's origin field holds b.
+GP_HD void p_ge2(uint32_t a, uint32_t b, bool& hi, bool& lo)      // per half: a >= b (signed); one VIMNMX.S16x2 with predicates
 {
-    const int m = g.m, n = g.n;
+#if defined(__CUDA_ARCH__)
+    (void)__vibmax_s16x2(a, b, &hi, &lo);
+#else
+    lo = (int16_t)a >= (int16_t)b;
+    hi = (int16_t)(a >> 16) >= (int16_t)(b >> 16);
+#endif
+}
+GP_HD uint32_t wf16c_scan_thr(int S, int n, int j)          // V of a cell with H = max(S,1): column j | column j-1
+{
+    const int lo = 2 * ((S > 1 ? S : 1) + n - j + 1), hi = lo + 2;
+    return (uint32_t)(lo < 0x7fff ? lo : 0x7fff) | ((uint32_t)(hi < 0x7fff ? hi : 0x7fff) << 16);
+}
+template <int K>
+GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, bool cell, int itop, int j, int s_floor, long long best)
+{
+    if (cell) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int jh = j - half;
-        if (jh < 1 || jh > n) continue;
-        if (g.cell) {
-            if (jh != n) continue;
+        for (int half = 0; half < 2; ++half) {
+            if (j - half != n) continue;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int i = itop + 1 + k + half * K;
@@ -210,28 +237,42 @@ GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int ito
                     best = key > best ? key : best;
                 }
             }
-            continue;
         }
-        int S = (int)(best >> 32);
-        int thrV = 2 * ((S > 1 ? S : 1) + n - jh + 1);
+        return best;
+    }
+    // s_floor: a score some candidate of the pair is already known to reach (the warp's shared best); cells
+    // below it cannot win, cells that equal it can (by rank).
+    const bool vlo = (uint32_t)(j - 1) < (uint32_t)n, vhi = (uint32_t)(j - 2) < (uint32_t)n;   // columns inside the table
+    auto thr_of = [&](long long b) { const int s = (int)(b >> 32); return wf16c_scan_thr(s > s_floor ? s : s_floor, n, j); };
+    uint32_t thr2 = thr_of(best);
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k) {
+        bool hit[2];
+        p_ge2(W[k], thr2, hit[1], hit[0]);
+        hit[0] = hit[0] && vlo; hit[1] = hit[1] && vhi;
+        if (!(hit[0] || hit[1])) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if (!hit[half]) continue;
+            const int jh = j - half;
             const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
-            if (vv >= thrV) {
-                const int i = itop + 1 + k + half * K;
-                const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, g.C) : RANK_MAX + 1u;
-                if (rk <= RANK_MAX) {
-                    const long long key = make_key((vv >> 1) - 1 - (n - jh), rk, (uint32_t)vv & 1u);
-                    if (key > best) {
-                        best = key;
-                        S = (int)(best >> 32);
-                        thrV = 2 * ((S > 1 ? S : 1) + n - jh + 1);
-                    }
+            const int i = itop + 1 + k + half * K;
+            const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, C) : RANK_MAX + 1u;
+            if (rk <= RANK_MAX) {
+                const long long key = make_key((vv >> 1) - 1 - (n - jh), rk, (uint32_t)vv & 1u);
+                if (key > best) {
+                    best = key;
+                    thr2 = thr_of(best);
                 }
             }
         }
     }
     return best;
+}
+template <int K>
+GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int j, long long best)
+{
+    return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, best);
 }
 
 // Initial `best` of a pass.  Scan mode: cell (0,n), the first cell the reference scans (rank 0, H = 0);
@@ -296,10 +337,11 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
 
 template <int K> struct CVals { uint32_t W[K]; };
 
+// Scalars only: a struct by value would travel through the stack on every call.
 template <int K>
-__device__ __noinline__ long long wf16c_scan_cold(CVals<K> v, Wf16cPass g, int itop, int j, long long best)
+__device__ __noinline__ long long wf16c_scan_cold(CVals<K> v, int m, int n, int C_or_cell, int itop, int j, int s_floor, long long best)
 {
-    return lane16c_scan<K>(v.W, g, itop, j, best);
+    return lane16c_scan_mn<K>(v.W, m, n, C_or_cell < 0 ? 0 : C_or_cell, C_or_cell < 0, itop, j, s_floor, best);
 }
 
 // One strip of 64*K rows starting after table row `i0` (see wf16t_strip for the block structure).
@@ -325,6 +367,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(w.smem);
     const uint32_t ring_base = tab_base + WF16C_TAB_WORDS * 4;
     const uint32_t oring_base = ring_base + 2 * WF16C_RING * 4;
+    constexpr uint32_t OR_OFF = 2 * WF16C_RING * 4;                // bottom-row ring slot of the input-ring slot at the same index
     const uint32_t my_tab = tab_base + lane * LANE_BYTES;
 
     // ---- increment table of this lane's rows ---------------------------------------------------
@@ -401,27 +444,33 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         CVals<K> v;
 #pragma unroll
         for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
-        best = wf16c_scan_cold<K>(v, g, itop, j, best);
+        best = wf16c_scan_cold<K>(v, m, n, g.cell ? -1 : g.C, itop, j, S0, best);
         const int s = (int)(best >> 32);
         thrS = wf16c_filter_thr(s > S0 ? s : S0);
     };
     __syncwarp();
 
+    // One register set of increments: a step adds them to the diagonals first, the loads of the NEXT step's
+    // increments go out right behind those adds and come back under the max chain.  The ring pointer is the
+    // only moving address: the bottom-row ring is addressed relative to it, the loop ends on it.
     auto run_block = [&](auto edge_c, auto filt_c, int tb, int cnt) {
         constexpr bool EDGE = decltype(edge_c)::value, FILT = decltype(filt_c)::value;
         uint32_t p = ring_base + (((uint32_t)(tb - D * lane)) & (WF16C_RING - 1)) * 4u;
-        uint32_t optr = oring_base;
+        const uint32_t p_end = p + 4u * (uint32_t)cnt;
         int j = tb - D * lane;                                            // my lo column
         uint32_t nthr = FILT ? wf16c_nthr(g, j) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
-        uint32_t incA[K], incB[K];
-        uint32_t wordA = lds32(p), wordB = lds32(p + 4);
-        lds_inc<K>(incA, my_tab + (wordA >> 16));
-        auto step = [&](const uint32_t (&inc)[K], uint32_t word, uint32_t oaddr, int jj) {
+        uint32_t inc[K];
+        uint32_t w0 = lds32(p), w1 = lds32(p + 4);
+        lds_inc<K>(inc, my_tab + (w0 >> 16));
+        auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj) {
+            uint32_t d[K];
+            lane16c_diag<K>(st, inc, d);
+            lds_inc<K>(inc, my_tab + (next_word >> 16));
             uint32_t recv = recv_next;
             recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             if (lane == 0) recv = word << 16;
             if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
-                lane16c_step<K>(st, recv, inc, gup, gleft);
+                lane16c_chain<K>(st, recv, d, gup, gleft);
                 if (EDGE && jj == 1) lane16c_fix_first<K>(st, g);
                 if (do_store) sts32(oaddr, st.W[K - 1]);
                 if (FILT) {
@@ -432,16 +481,14 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             if (FILT) nthr = p_add2(nthr, WF16C_NSTEP);
         };
 #pragma unroll 1
-        for (int s = 0; s < cnt; s += 2) {
-            lds_inc<K>(incB, my_tab + (wordB >> 16));
-            const uint32_t wordA2 = lds32(p + 8);
-            step(incA, wordA, optr, j);
-            lds_inc<K>(incA, my_tab + (wordA2 >> 16));
-            const uint32_t wordB2 = lds32(p + 12);
-            step(incB, wordB, optr + 4, j + 1);
-            wordA = wordA2; wordB = wordB2;
-            p += 8; optr += 8; j += 2;
-        }
+        do {
+            const uint32_t w2 = lds32(p + 8);
+            step(w0, w1, p + OR_OFF, j);
+            const uint32_t w3 = lds32(p + 12);
+            step(w1, w2, p + OR_OFF + 4, j + 1);
+            w0 = w2; w1 = w3;
+            p += 8; j += 2;
+        } while (p != p_end);
     };
     using std::true_type;
     using std::false_type;
@@ -459,7 +506,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         __syncwarp();
         if (store_bottom) {                                               // bottom row of the columns lane 31 finished
             const int c = tb + lane - (31 * D + 1);
-            const uint32_t v = lds32(oring_base + 4 * lane);
+            const uint32_t v = lds32(oring_base + 4 * ((((uint32_t)(tb - 31 * D)) & (WF16C_RING - 1)) + lane));
             if (c >= 1 && c <= n && lane < cnt) reinterpret_cast<uint16_t*>(bnd)[2 * c] = (uint16_t)(v >> 16);
             if constexpr (TEAM > 1) {                                      // publish: columns <= tb + cnt - 95 are in the line
                 __threadfence_block();
