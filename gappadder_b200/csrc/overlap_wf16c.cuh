@@ -275,6 +275,44 @@ GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int ito
     return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, best);
 }
 
+// Deferred exact scans.  Along an alignment path inside the candidate zone a lane's best cell gains a point at
+// every column, so resolving every fired step costs one exact scan per column although only the last one can
+// win.  A fired step is instead kept as a snapshot of the lane's registers together with its SCORE: the exact
+// maximum of H over the step's candidate cells.  A later step whose score is strictly higher replaces it unseen
+// (every cell of the old step loses to the new step's best cell, whatever the ranks); an equal or lower score
+// resolves the old snapshot first.  Whatever is pending at the end of the strip is resolved then.  Results are
+// the same maxima over the same keys.
+//   A step is deferrable when both its columns are inside the table and on the same side of the first candidate
+//   column (jswitch): then the candidate cells are whole rows, rows 1..m when both columns are candidate columns,
+//   rows m-C..m otherwise, and the score is a maximum over the lane's registers masked to those rows.
+//   score form: a = 2*(H-1) + 1 (the filter's accumulator with the origin bit forced).
+constexpr int WF16C_NO_SNAP = -(1 << 30);
+GP_HD int wf16c_score_of(int a) { return (a >> 1) + 1; }      // H of a step score
+GP_HD bool wf16c_deferrable(int n, int C, bool cell, int j)
+{
+    const int jswitch = n - C > 1 ? n - C : 1;
+    return !cell && j >= 2 && j <= n && j != jswitch;
+}
+// Exact score of a deferrable step; WF16C_NO_SNAP when the lane holds no candidate cell in it.
+template <int K>
+GP_HD int wf16c_exact_step_score(const uint32_t (&W)[K], int m, int n, int C, int itop, int j)
+{
+    const int jswitch = n - C > 1 ? n - C : 1;
+    const int rlo = j - 1 >= jswitch ? 1 : m - C;              // candidate rows rlo..m
+    int vlo = -1, vhi = -1;                                     // V >= 0 for every real cell
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int il = itop + 1 + k, ih = il + K;
+        const int a = (int)(W[k] & 0xffffu), b = (int)(W[k] >> 16);
+        if (il >= rlo && il <= m) vlo = a > vlo ? a : vlo;
+        if (ih >= rlo && ih <= m) vhi = b > vhi ? b : vhi;
+    }
+    int best = WF16C_NO_SNAP;
+    if (vlo >= 0) best = vlo - 2 * (n - j + 2);                 // V + nthr of column j
+    if (vhi >= 0) { const int h = vhi - 2 * (n - j + 3); best = h > best ? h : best; }
+    return best == WF16C_NO_SNAP ? best : (best | 1);
+}
+
 // Initial `best` of a pass.  Scan mode: cell (0,n), the first cell the reference scans (rank 0, H = 0);
 // its walk ends where it starts, in row 0, so its b is the row-0 bit (1 for the corner).  Cell mode: a
 // sentinel just below the expected score.
@@ -337,11 +375,44 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
 
 template <int K> struct CVals { uint32_t W[K]; };
 
-// Scalars only: a struct by value would travel through the stack on every call.
+// The cold side of a fired step (scalars only: a struct by value would travel through the stack on every call).
+// `slot` is the lane's pending step in local memory (so that the steady loops carry no extra live registers):
+// K registers, the lo column, the score.  Returns the lane's best key; slot[K+1] holds the pending score after.
 template <int K>
-__device__ __noinline__ long long wf16c_scan_cold(CVals<K> v, int m, int n, int C_or_cell, int itop, int j, int s_floor, long long best)
+__device__ __noinline__ long long wf16c_fire_cold(CVals<K> v, uint32_t* slot, int m, int n, int C_or_cell, int itop, int j,
+                                                  int s_floor, long long best)
 {
-    return lane16c_scan_mn<K>(v.W, m, n, C_or_cell < 0 ? 0 : C_or_cell, C_or_cell < 0, itop, j, s_floor, best);
+    const bool cell = C_or_cell < 0;
+    const int C = cell ? 0 : C_or_cell;
+    CVals<K> x = v;
+    int js = j;
+    bool scan = true;
+    if (wf16c_deferrable(n, C, cell, j)) {
+        const int a = wf16c_exact_step_score<K>(v.W, m, n, C, itop, j);
+        if (a == WF16C_NO_SNAP || wf16c_score_of(a) < (s_floor > 1 ? s_floor : 1)) return best;   // no candidate can matter
+        const int old = (int)slot[K + 1];
+        scan = old != WF16C_NO_SNAP && a <= old && wf16c_score_of(old) >= s_floor;
+        if (scan) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) x.W[k] = slot[k];
+            js = (int)slot[K];
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) slot[k] = v.W[k];
+        slot[K] = (uint32_t)j;
+        slot[K + 1] = (uint32_t)a;
+    }
+    if (scan) best = lane16c_scan_mn<K>(x.W, m, n, C, cell, itop, js, s_floor, best);
+    return best;
+}
+// The pending step at the end of a strip.
+template <int K>
+__device__ __noinline__ long long wf16c_flush_cold(const uint32_t* slot, int m, int n, int C, int itop, int s_floor, long long best)
+{
+    CVals<K> x;
+#pragma unroll
+    for (int k = 0; k < K; ++k) x.W[k] = slot[k];
+    return lane16c_scan_mn<K>(x.W, m, n, C, false, itop, (int)slot[K], s_floor, best);
 }
 
 // One strip of 64*K rows starting after table row `i0` (see wf16t_strip for the block structure).
@@ -425,13 +496,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     lane16c_begin<K>(st, g, itop);
 
     // ---- candidate filter state --------------------------------------------------------------------
-    int S0;
-    {   // start from the warp's best score
-        int s = (int)(best >> 32);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { int other = __shfl_xor_sync(FULL, s, o); s = other > s ? other : s; }
-        S0 = s;
-    }
+    int S0 = __reduce_max_sync(FULL, (int)(best >> 32));                   // the warp's best score so far
     uint32_t thrS = wf16c_filter_thr(S0);
     const int jswitch = n - g.C > 1 ? n - g.C : 1;                        // first candidate column
     const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
@@ -440,13 +505,24 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     const bool do_store = store_bottom && lane == 31;
     uint32_t recv_next = 0;                                               // shuffle issued one step ahead
 
-    auto slow_path = [&](int j) {                                         // exact scan of this lane's cells
+    // deferred exact scan (see wf16c_exact_step_score): the pending step's score here, its registers in local memory
+    uint32_t snap_slot[K + 2];
+    int snapA = WF16C_NO_SNAP;
+    snap_slot[K + 1] = (uint32_t)WF16C_NO_SNAP;
+    auto fire_path = [&](int jj) {                                        // this lane fired at lo column jj
         CVals<K> v;
 #pragma unroll
         for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
-        best = wf16c_scan_cold<K>(v, m, n, g.cell ? -1 : g.C, itop, j, S0, best);
-        const int s = (int)(best >> 32);
-        thrS = wf16c_filter_thr(s > S0 ? s : S0);
+        best = wf16c_fire_cold<K>(v, snap_slot, m, n, g.cell ? -1 : g.C, itop, jj, S0, best);
+        snapA = (int)snap_slot[K + 1];
+    };
+    // After any lane's fire the whole warp learns the new best score at once (one REDUX): without it the
+    // lanes below an alignment path, whose cells all gain a point per column, fire at every column of the
+    // candidate zone until the next block end although another lane already holds a better cell.
+    auto share_floor = [&]() {
+        const int mine = (int)(best >> 32), pend = snapA != WF16C_NO_SNAP ? wf16c_score_of(snapA) : mine;
+        S0 = __reduce_max_sync(FULL, mine > pend ? mine : pend);
+        thrS = wf16c_filter_thr(S0);
     };
     __syncwarp();
 
@@ -456,7 +532,8 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     auto run_block = [&](auto edge_c, auto filt_c, int tb, int cnt) {
         constexpr bool EDGE = decltype(edge_c)::value, FILT = decltype(filt_c)::value;
         uint32_t p = ring_base + (((uint32_t)(tb - D * lane)) & (WF16C_RING - 1)) * 4u;
-        const uint32_t p_end = p + 4u * (uint32_t)cnt;
+        uint32_t p_end = p + 4u * (uint32_t)cnt;
+        asm volatile("" : "+r"(p_end));                              // opaque: kept in a register, not recomputed every iteration
         int j = tb - D * lane;                                            // my lo column
         uint32_t nthr = FILT ? wf16c_nthr(g, j) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
         uint32_t inc[K];
@@ -469,16 +546,24 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             uint32_t recv = recv_next;
             recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             if (lane == 0) recv = word << 16;
+            bool fire = false;
+            uint32_t acc = 0u;
             if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
                 lane16c_chain<K>(st, recv, d, gup, gleft);
                 if (EDGE && jj == 1) lane16c_fix_first<K>(st, g);
                 if (do_store) sts32(oaddr, st.W[K - 1]);
                 if (FILT) {
-                    const uint32_t acc = p_add2(lane16c_max<K>(st), nthr);
-                    if (filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED)) slow_path(jj);
+                    acc = p_add2(lane16c_max<K>(st), nthr);
+                    fire = filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
                 }
             }
-            if (FILT) nthr = p_add2(nthr, WF16C_NSTEP);
+            if (FILT) {
+                if (__any_sync(FULL, fire)) {                             // warp-uniform: every lane runs every step
+                    if (fire) fire_path(jj);
+                    share_floor();
+                }
+                nthr = p_add2(nthr, WF16C_NSTEP);
+            }
         };
 #pragma unroll 1
         do {
@@ -517,15 +602,11 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             }
         }
         if (have_next) ring_put(tb + 32 + lane, next_line);
-        if (filt) {                                                       // share the best score across the warp
-            int s = (int)(best >> 32);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { int other = __shfl_xor_sync(FULL, s, o); s = other > s ? other : s; }
-            S0 = s > S0 ? s : S0;
-            thrS = wf16c_filter_thr(S0);
-        }
         __syncwarp();
     }
+    if (snapA != WF16C_NO_SNAP && wf16c_score_of(snapA) >= S0)
+        best = wf16c_flush_cold<K>(snap_slot, m, n, g.C, itop, S0, best);
+    __syncwarp();
     return best;
 }
 

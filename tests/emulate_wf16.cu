@@ -292,6 +292,14 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
     uint32_t thrS[32];
     for (int lane = 0; lane < 32; ++lane) thrS[lane] = wf16c_filter_thr(S0);
     const int jswitch = n - g.C > 1 ? n - g.C : 1;
+    // deferred exact scans, as wf16c_fire_cold / wf16c_flush_cold do them: the pending step of every lane
+    uint32_t snapW[32][K];
+    int snapj[32], snapA[32];
+    for (int lane = 0; lane < 32; ++lane) { snapj[lane] = 0; snapA[lane] = WF16C_NO_SNAP; }
+    auto scan_pending = [&](int lane) {
+        ++g_slow_calls;
+        lane_best[lane] = lane16c_scan_mn<K>(snapW[lane], g.m, g.n, g.C, false, i0 + lane * 2 * K, snapj[lane], S0, lane_best[lane]);
+    };
     constexpr int D = WF16C_SKEW;
     const int t_end = n + 1 + 31 * D;
     uint16_t* bnd16 = reinterpret_cast<uint16_t*>(bnd.data());
@@ -306,6 +314,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
             uint32_t recv[32];
             for (int lane = 0; lane < 32; ++lane) recv[lane] = lane == 0 ? (top[t <= n + 1 ? t : n + 1] << 16) : sent2[lane - 1];
             for (int lane = 0; lane < 32; ++lane) { sent2[lane] = sent1[lane]; }
+            bool any_fired = false;
             for (int lane = 0; lane < 32; ++lane) {
                 const int itop = i0 + lane * 2 * K, j = t - D * lane;
                 if (j < 1 || j > n + 1) { sent1[lane] = st[lane].W[K - 1]; continue; }
@@ -319,21 +328,37 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
                     const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
                     const uint32_t acc = p_add2(lane16c_max<K>(st[lane]), wf16c_nthr(g, j));
                     if (filter_fired(acc, j >= (rowlane ? 1 : jswitch) ? thrS[lane] : WF16C_UNARMED)) {
-                        ++g_slow_calls;
-                        lane_best[lane] = lane16c_scan<K>(st[lane].W, g, itop, j, lane_best[lane]);
-                        const int sc = (int)(lane_best[lane] >> 32);
-                        thrS[lane] = wf16c_filter_thr(sc > S0 ? sc : S0);
+                        any_fired = true;
+                        if (wf16c_deferrable(n, g.C, g.cell, j)) {                      // wf16c_fire_cold
+                            const int a = wf16c_exact_step_score<K>(st[lane].W, m, n, g.C, itop, j);
+                            if (!(a == WF16C_NO_SNAP || wf16c_score_of(a) < (S0 > 1 ? S0 : 1))) {
+                                if (snapA[lane] != WF16C_NO_SNAP && a <= snapA[lane] && wf16c_score_of(snapA[lane]) >= S0) scan_pending(lane);
+                                for (int k = 0; k < K; ++k) snapW[lane][k] = st[lane].W[k];
+                                snapj[lane] = j; snapA[lane] = a;
+                            }
+                        } else {
+                            ++g_slow_calls;
+                            lane_best[lane] = lane16c_scan_mn<K>(st[lane].W, g.m, g.n, g.C, g.cell, itop, j, S0, lane_best[lane]);
+                        }
                     }
                 }
                 sent1[lane] = st[lane].W[K - 1];
             }
+            if (any_fired) {                     // the kernel's share_floor(): one REDUX after a step in which a lane fired
+                int s0 = -1000000000;
+                for (int lane = 0; lane < 32; ++lane) {
+                    int sc = (int)(lane_best[lane] >> 32);
+                    if (snapA[lane] != WF16C_NO_SNAP && wf16c_score_of(snapA[lane]) > sc) sc = wf16c_score_of(snapA[lane]);
+                    s0 = sc > s0 ? sc : s0;
+                }
+                S0 = s0;
+                for (int lane = 0; lane < 32; ++lane) thrS[lane] = wf16c_filter_thr(S0);
+            }
         }
         g_steps += cnt;
-        if (filt) {
-            for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); S0 = sc > S0 ? sc : S0; }
-            for (int lane = 0; lane < 32; ++lane) thrS[lane] = wf16c_filter_thr(S0);
-        }
     }
+    for (int lane = 0; lane < 32; ++lane)        // end of the strip: wf16c_flush_cold
+        if (snapA[lane] != WF16C_NO_SNAP && wf16c_score_of(snapA[lane]) >= S0) scan_pending(lane);
 }
 
 long long pass_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P)

@@ -27,7 +27,7 @@ def emu():
             os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16t.cuh"), os.path.join(ROOT, "gappadder_b200", "csrc", "overlap_wf16c.cuh"),
             os.path.join(ROOT, "gappadder_b200", "csrc", "common.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC", "-shared",
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-shared",
                                "-o", so, srcs[0]])
     L = C.CDLL(so)
     L.wf16_emulate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
