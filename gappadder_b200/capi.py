@@ -199,6 +199,27 @@ def overlap_size(len1: int, len2: int, r) -> int:
     return int(lib().gp_overlap_size(len1, len2, C.byref(res)))
 
 
+class HostBatch:
+    """Host-side arguments of gp_overlap_batch in the C ABI's own shape: `const char* const*` sequence pointers
+    (the bytes objects stay referenced here), lengths, gp_pair array, and the gp_result array the call fills.
+    Building it is Python marshalling, not part of the library."""
+
+    def __init__(self, seqs: Sequence[bytes], pairs):
+        self.seqs = list(seqs)
+        self.arr, self.lens = _seq_arrays(self.seqs)
+        self.n_seq = len(self.seqs)
+        p = np.zeros(len(pairs), dtype=PAIR_DTYPE)
+        if len(pairs):
+            pa = np.asarray(pairs)
+            if pa.dtype == PAIR_DTYPE:
+                p = np.ascontiguousarray(pa)
+            else:
+                p["row_seq"] = pa[:, 0]
+                p["col_seq"] = pa[:, 1]
+        self.pairs = p
+        self.out = np.zeros(len(p), dtype=RESULT_DTYPE)
+
+
 class Context:
     """One gp_ctx (one GPU, one stream)."""
 
@@ -322,16 +343,13 @@ class Context:
 
     def overlap_batch(self, seqs: Sequence[bytes], pairs, params: DpParams = GAPPADDER_DP) -> np.ndarray:
         """The call a user makes: host ASCII sequences + (row, col) index pairs -> results."""
-        arr, lens = _seq_arrays(seqs)
-        p = np.zeros(len(pairs), dtype=PAIR_DTYPE)
-        if len(pairs):
-            pa = np.asarray(pairs)
-            if pa.dtype == PAIR_DTYPE:
-                p = np.ascontiguousarray(pa)
-            else:
-                p["row_seq"] = pa[:, 0]
-                p["col_seq"] = pa[:, 1]
-        out = np.zeros(len(p), dtype=RESULT_DTYPE)
-        self._check(self._L.gp_overlap_batch(self._h, arr, lens.ctypes.data, len(seqs), p.ctypes.data, len(p),
-                                             C.byref(params), out.ctypes.data))
+        return self.overlap_host_batch(HostBatch(seqs, pairs), params)
+
+    def overlap_host_batch(self, batch: "HostBatch", params: DpParams = GAPPADDER_DP) -> np.ndarray:
+        """gp_overlap_batch on host buffers that already have the C ABI's shape (what a C++ caller holds: an
+        array of sequence pointers, their lengths, the pair list).  Everything device-side -- packing into
+        pinned memory, the copies in both directions, the kernels -- happens inside the call."""
+        out = batch.out
+        self._check(self._L.gp_overlap_batch(self._h, batch.arr, batch.lens.ctypes.data, batch.n_seq, batch.pairs.ctypes.data,
+                                             len(batch.pairs), C.byref(params), out.ctypes.data))
         return out

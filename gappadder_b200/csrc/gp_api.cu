@@ -15,6 +15,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -523,20 +524,50 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     const size_t bytes = gp_packed_size(seq_len, n_seq);
     GP_CUDA(c, cudaSetDevice(c->device));
     GP_CUDA(c, c->h_pack.reserve(bytes ? bytes : 16));
+    if (bytes / sizeof(uint32_t) > 0xffffffffull) return c->fail(GP_ERR_RANGE, "packed table exceeds 2^32 words");
+    // The bases are packed on helper threads while this thread classifies, orders and enqueues the pairs: that
+    // only needs the lengths and the table offsets, which follow from the lengths (the layout of
+    // gp_pack_sequences), plus the assumption that everything is A/C/G/T -- checked after the join; input with N
+    // or other letters classifies again (its routing differs).
     c->pack_off.resize(n_seq);
+    {
+        size_t w = 0;
+        for (uint32_t s = 0; s < n_seq; ++s) { c->pack_off[s] = (uint32_t)w; w += gp_packed_size(seq_len + s, 1) / sizeof(uint32_t); }
+    }
+    c->seq_off.assign(c->pack_off.begin(), c->pack_off.end());
+    c->seq_len.assign(seq_len, seq_len + n_seq);
+    c->n_symbols = 4;
+    c->seq_acgt.assign(n_seq, 1);
     uint32_t nsym = 0;
-    int rc = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)c->h_pack.p, c->pack_off.data(), &nsym);
-    if (rc != GP_OK) return c->fail(rc, rc == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed");
+    int rc_pack = GP_OK;
+    std::vector<uint32_t> off_check(n_seq);
+    std::thread packer([&] { rc_pack = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)c->h_pack.p, off_check.data(), &nsym); });
+    int rc = upload_pairs_async(c, pairs, n_pairs, params);
+    const auto t_cls = clk::now();
+    packer.join();
     const auto t1 = clk::now();
-    rc = set_sequences_async(c, (const uint32_t*)c->h_pack.p, bytes, c->pack_off.data(), seq_len, n_seq, nsym);
-    if (rc != GP_OK) return rc;
-    rc = upload_pairs_async(c, pairs, n_pairs, params);
-    if (rc != GP_OK) return rc;
+    if (rc_pack != GP_OK || rc != GP_OK || off_check != c->pack_off) {
+        cudaStreamSynchronize(c->stream);
+        c->n_pairs = 0;
+        if (rc_pack != GP_OK) return c->fail(rc_pack, rc_pack == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed");
+        if (rc != GP_OK) return rc;
+        return c->fail(GP_ERR_INVALID, "internal: table layout mismatch");
+    }
+    GP_CUDA(c, c->d_packed.reserve(bytes ? bytes : 16));
+    if (bytes) GP_CUDA(c, cudaMemcpyAsync(c->d_packed.p, c->h_pack.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (nsym > 4) {                               // N or other letters somewhere: exact per-sequence flags, classify again
+        GP_CUDA(c, cudaStreamSynchronize(c->stream));            // the staging buffer of the first classification is in flight
+        rc = set_sequences_async(c, (const uint32_t*)c->h_pack.p, 0, c->pack_off.data(), seq_len, n_seq, nsym);
+        if (rc != GP_OK) return rc;
+        rc = upload_pairs_async(c, pairs, n_pairs, params);
+        if (rc != GP_OK) return rc;
+    }
+    (void)t_cls;
     const auto t2 = clk::now();
     rc = run_and_fetch(c, out, n_pairs);
     const auto t3 = clk::now();
-    c->timing[0] = ms(t0, t1);      // pack
-    c->timing[1] = ms(t1, t2);      // table upload enqueue + pair classification, ordering, upload enqueue
+    c->timing[0] = ms(t0, t1);      // pack (helper threads) with pair classification, ordering and upload enqueue beside it
+    c->timing[1] = ms(t1, t2);      // table upload enqueue (and a second classification for input with N or other letters)
     c->timing[2] = ms(t2, t3);      // copies + kernels + result copy, until the stream is idle
     c->timing[3] = ms(t0, t3);
     return rc;

@@ -299,6 +299,13 @@ GP_HD int wf16c_exact_step_score(const uint32_t (&W)[K], int m, int n, int C, in
 {
     const int jswitch = n - C > 1 ? n - C : 1;
     const int rlo = j - 1 >= jswitch ? 1 : m - C;              // candidate rows rlo..m
+    if (itop + 1 >= rlo && itop + 2 * K <= m) {                 // every row of the lane is one: a packed maximum
+        uint32_t mx = W[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) mx = p_max2(mx, W[k]);
+        const int lo = (int)(mx & 0xffffu) - 2 * (n - j + 2), hi = (int)(mx >> 16) - 2 * (n - j + 3);
+        return (lo > hi ? lo : hi) | 1;
+    }
     int vlo = -1, vhi = -1;                                     // V >= 0 for every real cell
 #pragma unroll
     for (int k = 0; k < K; ++k) {
