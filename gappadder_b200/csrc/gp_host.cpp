@@ -29,7 +29,32 @@ size_t gp_packed_size(const uint32_t *seq_len, uint32_t n_seq)
     return words * sizeof(uint32_t);
 }
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
 namespace {
+
+#if defined(__x86_64__)
+// 16 bases -> two packed words, for the bytes A C G T N (codes 0..4: their low nibbles 1 3 7 4 E are distinct, so
+// one PSHUFB looks the code up and a second one checks that the byte really is that letter).  Returns false when
+// some byte is another character (the caller takes the table-driven path); *has_n is set when an N went through.
+__attribute__((target("ssse3"))) inline bool pack16_ssse3(const unsigned char *q, uint32_t *dst, bool *has_n)
+{
+    const __m128i code_of = _mm_setr_epi8(-1, 0, -1, 1, 3, -1, -1, 2, -1, -1, -1, -1, -1, -1, 4, -1);
+    const __m128i byte_of = _mm_setr_epi8(0, 'A', 0, 'C', 'T', 0, 0, 'G', 0, 0, 0, 0, 0, 0, 'N', 0);
+    const __m128i v = _mm_loadu_si128((const __m128i *)q);
+    const __m128i nib = _mm_and_si128(v, _mm_set1_epi8(0x0f));
+    const __m128i codes = _mm_shuffle_epi8(code_of, nib);
+    const __m128i expect = _mm_shuffle_epi8(byte_of, nib);
+    if (_mm_movemask_epi8(_mm_cmpeq_epi8(expect, v)) != 0xffff) return false;
+    if (_mm_movemask_epi8(_mm_cmpeq_epi8(codes, _mm_set1_epi8(4)))) *has_n = true;
+    const __m128i pairs = _mm_maddubs_epi16(codes, _mm_set1_epi16(0x1001));        // c0 + 16*c1 per 16-bit lane
+    const __m128i bytes = _mm_packus_epi16(pairs, pairs);
+    _mm_storel_epi64((__m128i *)dst, bytes);
+    return true;
+}
+#endif
 
 // Packs sequences [s0, s1) with a fixed byte -> code table.  Returns the first sequence index that
 // holds a byte the table does not know (code 0xff), or s1 when all went through.  max_code is updated.
@@ -37,6 +62,9 @@ uint32_t pack_range(const char *const *seqs, const uint32_t *seq_len, const size
                     const uint8_t *code, uint32_t *packed, int *max_code)
 {
     uint32_t mx = (uint32_t)(*max_code + 1);             // highest code seen + 1
+#if defined(__x86_64__)
+    const bool simd = __builtin_cpu_supports("ssse3");
+#endif
     for (uint32_t s = s0; s < s1; ++s) {
         const unsigned char *p = (const unsigned char *)seqs[s];
         const uint32_t len = seq_len[s];
@@ -44,7 +72,17 @@ uint32_t pack_range(const char *const *seqs, const uint32_t *seq_len, const size
         uint32_t *dst = packed + word_off[s];
         const uint32_t full = len / 8;
         uint32_t top = 0;                                // max code + 1 of this sequence; >= 0x100 with an unknown byte
-        for (uint32_t w = 0; w < full; ++w) {
+        uint32_t w0 = 0;
+#if defined(__x86_64__)
+        // plain A/C/G/T/N stretches 16 bases at a time (the table below must still be the initial one for them)
+        if (simd && code[(unsigned char)'A'] == 0 && code[(unsigned char)'C'] == 1 && code[(unsigned char)'G'] == 2 &&
+            code[(unsigned char)'T'] == 3 && code[(unsigned char)'N'] == 4) {
+            bool has_n = false;
+            while (w0 + 2 <= full && pack16_ssse3(p + (size_t)w0 * 8, dst + w0, &has_n)) w0 += 2;
+            if (w0) top = has_n ? 5 : 4;
+        }
+#endif
+        for (uint32_t w = w0; w < full; ++w) {
             const unsigned char *q = p + (size_t)w * 8;
             uint32_t word = 0;
             for (int k = 0; k < 8; ++k) {
@@ -95,7 +133,7 @@ int gp_pack_sequences(const char *const *seqs, const uint32_t *seq_len, uint32_t
     // sequences.  A byte outside the table is rare (GAPPadder's contigs never have one); it sends the
     // whole batch through the sequential loop below, which assigns codes in order of first appearance.
     const unsigned hw = std::thread::hardware_concurrency();
-    const uint32_t T = bases < (4u << 20) ? 1u : std::min<uint32_t>(hw ? hw : 1u, 8u);
+    const uint32_t T = bases < (4u << 20) ? 1u : std::min<uint32_t>(hw ? hw : 1u, 16u);
     bool done = false;
     if (T > 1) {
         std::vector<std::thread> th;

@@ -98,3 +98,41 @@ def test_candidate_pairs_golden_and_oracle():
         want = _oracle.oracle_candidate_pairs(nodes, 10)
         assert got == want          # same pairs, same (-t 1) order
         assert got == sorted(got)
+
+
+def _reference_pack(seqs):
+    """Plain restatement of gp_pack_sequences' layout: 4-bit codes (A C G T N = 0..4, other bytes in order of first
+    appearance), eight per word, every sequence padded to a multiple of 4 words and at least one block."""
+    code = {ord("A"): 0, ord("C"): 1, ord("G"): 2, ord("T"): 3, ord("N"): 4}
+    words, offs = [], []
+    for s in seqs:
+        offs.append(len(words))
+        nw = ((len(s) + 7) // 8 + 3) & ~3
+        w = [0] * (nw or 4)
+        for i, ch in enumerate(s):
+            if ch not in code:
+                code[ch] = len(code)
+            w[i // 8] |= (code[ch] & 15) << (4 * (i % 8))
+        words += w
+    return np.array(words, dtype=np.uint32), offs
+
+
+def test_pack_matches_reference_layout_all_lengths_and_alphabets():
+    """The packer's vector path (16 bases at a time) and its table path must agree with the plain layout for every
+    length around the 8/16-base boundaries, with N, with other letters, and on the threaded large-batch path."""
+    import random
+    rnd = random.Random(5)
+    for _ in range(150):
+        alph = rnd.choice([b"ACGT", b"ACGTN", b"ACGTNRY", b"AC"])
+        seqs = [bytes(rnd.choice(alph) for _ in range(rnd.choice([0, 1, 7, 8, 15, 16, 17, 31, 32, 33, 100, 257])))
+                for _ in range(rnd.randint(1, 6))]
+        packed, off, lens, nsym = g.pack_sequences(seqs)
+        want, woff = _reference_pack(seqs)
+        assert list(off) == woff
+        assert np.array_equal(packed, want)
+        assert (nsym <= 4) == all(ch in b"ACGT" for s in seqs for ch in s)
+    seqs = [bytes(rnd.choice(b"ACGT") for _ in range(3000)) for _ in range(1500)]      # > 4 Mbases: several threads
+    seqs[777] = seqs[777][:100] + b"N" + seqs[777][101:]
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    want, woff = _reference_pack(seqs)
+    assert np.array_equal(packed, want) and nsym == 5
