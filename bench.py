@@ -195,6 +195,36 @@ def cpu_sample(seqs, pairs, cores: int, budget_s: float, run):
     return pairs[:n], int(csum[n - 1])
 
 
+def parity_sample(seqs, pairs, res, cores: int, n: int = 48):
+    """Checker (part of the cpu_baseline leg): n pairs spread over this run's pair list, the timed end-to-end
+    step's results against the oracle's Evaluate, field by field."""
+    import _oracle
+    idx = np.unique(np.linspace(0, len(pairs) - 1, num=min(n, len(pairs)), dtype=np.int64)) if len(pairs) else []
+    bad, lock, it = [], threading.Lock(), iter(list(idx))
+
+    def worker():
+        while True:
+            with lock:
+                k = next(it, None)
+            if k is None:
+                return
+            a, b = seqs[int(pairs["row_seq"][k])], seqs[int(pairs["col_seq"][k])]
+            o = _oracle.oracle_evaluate(a, b, -2, -2, 50)
+            r = res[k]
+            want = (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), int(o.bcontained))
+            f = int(r["flags"])
+            got = (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]), f & 1, (f >> 1) & 1, (f >> 2) & 1)
+            if got != want:
+                with lock:
+                    bad.append(int(k))
+    ths = [threading.Thread(target=worker) for _ in range(max(1, min(cores, len(idx))))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return {"pairs": int(len(idx)), "mismatches": len(bad), "first_bad": bad[:4], "against": "oracle/overlap_oracle.c gpo_evaluate"}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -209,14 +239,14 @@ def run_reference(args):
     kind, run = cpu_path()
     cores = min(host_cores(), 64)
     n_gaps = max(1, min(args.gaps, 8))
-    seqs, pairs, _, _ = build_workload(n_gaps, args.seed)
+    seqs, pairs, _, _ = build_workload(n_gaps, args.seed, args.config)
     sample, cells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
     for _ in range(min(args.warmup, 1)):
         cpu_run_pairs(run, seqs, sample[:max(cores, len(sample) // 8)], cores)
     times = [cpu_run_pairs(run, seqs, sample, cores) for _ in range(args.steps)]
     t = float(np.mean(times))
     v = cells / t / 1e9
-    sample_desc = "first %d candidate pairs (%.3f Gcells) of the cfg1 pair list, seeds %d.., per step" % (len(sample), cells / 1e9, args.seed)
+    sample_desc = "first %d candidate pairs (%.3f Gcells) of the %s pair list, seeds %d.., per step" % (len(sample), cells / 1e9, args.config, args.seed)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -229,9 +259,16 @@ def run_reference(args):
     return 0
 
 
+WORKLOADS = {
+    "cfg1": "cfg1: %d synthetic gaps/GPU x 40 contigs (300-3000 bp, 8 kb locus, 0.2%% subst, 50%% RC)",
+    "cfg3": "cfg3 (BASELINE configs[2]/[3] shape): %d synthetic gaps/GPU x 10-80 contigs, six k-mer sets (300-3000 bp, 8 kb locus)",
+    "cfg5": "cfg5 (BASELINE configs[4], long-contig stress): %d synthetic gaps/GPU x 200 contigs x 10 kb on a 40 kb repeat-rich locus",
+}
+
+
 def workload_config(args):
-    return {"workload": "cfg1: %d synthetic gaps/GPU x 40 contigs (300-3000 bp, 8 kb locus, 0.2%% subst, 50%% RC), "
-                        "all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)" % args.gaps,
+    return {"workload": WORKLOADS[args.config] % args.gaps +
+                        ", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)",
             "gaps_per_gpu": args.gaps, "first_seed": args.seed, "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": "gaps sharded by rank, no collective"}
 
@@ -256,7 +293,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
 
     ctx = g.Context(local_rank)                 # fails loudly without the CUDA library / a B200
-    seqs, pairs, cells, per_gap = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps))
+    seqs, pairs, cells, per_gap = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps), args.config)
     packed, off, lens, nsym = g.pack_sequences(seqs)
     ctx.set_sequences(packed, off, lens, nsym)
     ctx.set_kernel_mask(args.kernel_mask)
@@ -372,6 +409,7 @@ def run_gpu(args):
             t = cpu_run_pairs(run, seqs, sample, cores)
             line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "first %d candidate pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
+            line["parity_sample"] = parity_sample(seqs, pairs, res, cores)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
@@ -388,6 +426,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gaps", type=int, default=200, help="gaps per GPU per step (cfg1 = 200)")
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS), help="workload shape (tools/synth_gaps.py); the bench line is cfg1")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-mask", type=int, default=15, help="A/B: what the library may use (1 table, 2 PRMT, 4 certificate kernel, 8 closed form for s-vs-s)")
