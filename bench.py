@@ -225,6 +225,25 @@ def parity_sample(seqs, pairs, res, cores: int, n: int = 48):
     return {"pairs": int(len(idx)), "mismatches": len(bad), "first_bad": bad[:4], "against": "oracle/overlap_oracle.c gpo_evaluate"}
 
 
+def dropin_line(args):
+    """Whole-gap throughput beside the bench line (not part of any timed region above): the drop-in binary
+    build/ContigsMerger_b200 --batch on the same gaps as FASTA files -- read, quick check, pairwise phase, graph,
+    relax chains, output -- timed by tools/dropin_bench.py.  gaps_per_s here is whole gaps merged per second."""
+    tool = os.path.join(ROOT, "tools", "dropin_bench.py")
+    binary = os.path.join(ROOT, "build", "ContigsMerger_b200")
+    if not os.path.exists(binary):
+        return {"unavailable": "build/ContigsMerger_b200 not built"}
+    try:
+        p = subprocess.run([sys.executable, tool, "--gaps", str(args.gaps), "--seed", str(args.seed), "--ref-gaps", "0"],
+                           capture_output=True, text=True, timeout=300)
+        d = json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception as e:                                   # the bench line must not depend on it
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+    keep = ("gaps", "gpus", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
+            "relax_steps", "output_ms", "gaps_per_s", "gcups", "error")
+    return {k: d[k] for k in keep if k in d}
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -410,6 +429,8 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "first %d candidate pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
             line["parity_sample"] = parity_sample(seqs, pairs, res, cores)
+        if world == 1 and not args.no_dropin and args.config == "cfg1":
+            line["dropin"] = dropin_line(args)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
@@ -429,6 +450,7 @@ def main():
     ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS), help="workload shape (tools/synth_gaps.py); the bench line is cfg1")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the whole-ContigsMerger (drop-in binary) timing beside the bench line")
     ap.add_argument("--kernel-mask", type=int, default=15, help="A/B: what the library may use (1 table, 2 PRMT, 4 certificate kernel, 8 closed form for s-vs-s)")
     args = ap.parse_args()
     if args.impl == "reference":

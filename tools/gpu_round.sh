@@ -19,9 +19,9 @@ if [ -z "$SKIP_REF" ]; then
 fi
 if [ -z "$SKIP_NCU" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-      --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $out/${tag}_ncu_launches.log 2>&1
+      --log-file $out/${tag}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-dropin > $out/${tag}_ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-overlap_wf16c} -s 1 -c 1 \
-      -o $out/${tag}_wf16 -f python bench.py --steps 1 --warmup 1 --no-cpu ${NCU_BENCH_ARGS} > $out/${tag}_ncu_full.log 2>&1
+      -o $out/${tag}_wf16 -f python bench.py --steps 1 --warmup 1 --no-cpu --no-dropin ${NCU_BENCH_ARGS} > $out/${tag}_ncu_full.log 2>&1
   tail -3 $out/${tag}_ncu_full.log
 fi
 ls -la $out
