@@ -19,7 +19,7 @@ EXPORTS = [
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
-    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team",
+    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout",
 ]
 
 
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         L.gp_closed_form_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.gp_set_team_mode.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_last_team.argtypes = [C.c_void_p]
+        L.gp_set_cert_layout.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_last_layout.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -293,6 +295,14 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_closed_form_stats(self._h, C.byref(a), C.byref(b)))
         return dict(pairs=a.value, cells=b.value)
+
+    def set_cert_layout(self, mode: int):
+        """Certificate kernel: 0 free-moves layout whenever a launch allows it (default), 1 always the column potential."""
+        self._check(self._L.gp_set_cert_layout(self._h, mode))
+
+    @property
+    def last_layout(self) -> int:
+        return int(self._L.gp_last_layout(self._h))
 
     def set_team_mode(self, mode: int):
         """Certificate kernel: 0 library chooses per launch (default), 1 one warp per pair, 2 one CTA per pair."""

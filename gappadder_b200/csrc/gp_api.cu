@@ -79,6 +79,8 @@ struct gp_ctx {
     uint32_t team_mode = 0;                     // certificate kernel: 0 auto, 1 one warp per pair, 2 one CTA per pair
     uint64_t max_cells16c = 0;                  // largest m*n routed to the certificate kernel
     bool last_team = false;                     // what the last launch used
+    uint32_t cert_layout = 0;                   // certificate kernel: 0 free-moves layout when the launch allows it, 1 never
+    bool last_pot2 = false;
     uint64_t second_passes = 0, exact_retries = 0;   // of the last fetched run
     uint64_t cells16c = 0, cells16t = 0, cells16 = 0, cells32 = 0;     // host-routed DP cells per kernel
     std::vector<uint32_t> closed_ids;           // pairs answered in closed form (a sequence against itself), no DP
@@ -229,6 +231,15 @@ int gp_set_team_mode(gp_ctx* c, uint32_t mode)
 }
 
 int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
+
+int gp_set_cert_layout(gp_ctx* c, uint32_t mode)
+{
+    if (!c || mode > 1) return GP_ERR_INVALID;
+    c->cert_layout = mode;
+    return GP_OK;
+}
+
+int gp_last_layout(const gp_ctx* c) { return c && c->last_pot2 ? 1 : 0; }
 
 int gp_set_kernel_mask(gp_ctx* c, uint32_t mask)
 {
@@ -419,6 +430,8 @@ int gp_launch_resident(gp_ctx* c)
         team = team_t < warp_t;
     }
     c->last_team = cert && team;
+    c->p16c.pot2 = (cert && c->cert_layout == 0 && c->p16c.std_scores && c->max_n16c <= gp::WF16C_POT2_MAX_N) ? 1 : 0;
+    c->last_pot2 = c->p16c.pot2 != 0;
     GP_CUDA(c, cudaEventRecord(c->kev[0], c->stream));
     if (cert) {
         int rc = gp::wf16c_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,

@@ -59,6 +59,11 @@ constexpr int WF16C_ORING = WF16C_RING + 32;        // bottom-row ring: addresse
 constexpr int WF16C_WARP_WORDS = WF16C_TAB_WORDS + 2 * WF16C_RING + WF16C_ORING;
 constexpr size_t WF16C_SMEM_BYTES = (size_t)(WF16C_THREADS / 32) * WF16C_WARP_WORDS * sizeof(uint32_t);
 constexpr int WF16C_PROBE = 16;                   // bases of the orientation probe (two packed words)
+// Second value layout ("free moves"): V = 2*Q + b with Q = H + 2*i_rel + 2*j + n + 1 (i_rel: row inside the strip).
+// Under it the up and left moves (-2 each) add nothing and the diagonal adds 2*(s+4), so a cell is ONE 3-input
+// max after the diagonal add.  Only for the standard scores (-2, -2) and columns short enough for 15 bits:
+// Q <= n + 2*512 + 2*n + n + 1.
+constexpr uint32_t WF16C_POT2_MAX_N = 3800;         // 2*(4n + 1025) + 1 + 10 <= 32767
 
 inline bool wf16c_pair_ok(uint32_t m, uint32_t n) { return m >= 1 && n >= 1 && n <= WF16C_MAX_N && m <= 0xffffff; }
 
@@ -67,6 +72,8 @@ struct Wf16cParams {
     uint32_t gup, gleft;            // packed up / left increments under the column potential
     int32_t max_clip;
     int32_t std_scores;             // mismatch == -2 && indel == -2: the kernel with immediate operands
+    int32_t pot2;                   // free-moves layout (set per launch: std scores and every n <= WF16C_POT2_MAX_N)
+    uint32_t inc2_match, inc2_mism; // its diagonal increments, 2*(s - 2*indel)
 };
 
 inline Wf16cParams wf16c_make_params(int mismatch, int indel, int max_clip)
@@ -78,6 +85,9 @@ inline Wf16cParams wf16c_make_params(int mismatch, int indel, int max_clip)
     p.gleft = pk(indel - 1);
     p.max_clip = max_clip;
     p.std_scores = (mismatch == -2 && indel == -2) ? 1 : 0;
+    p.pot2 = 0;
+    p.inc2_match = (uint32_t)(2 * (1 - 2 * indel)) & 0xffffu;
+    p.inc2_mism = (uint32_t)(2 * (mismatch - 2 * indel)) & 0xffffu;
     return p;
 }
 
@@ -92,8 +102,12 @@ struct Wf16cPass {
     bool cell;
     int s_cell;
     uint32_t gup, gleft;
-    GP_HD uint32_t v_col0(int i) const { return (uint32_t)(2 * (n + 1)) + (i == 0 ? bcorner : bcol); }
-    GP_HD uint32_t v_row0(int j) const { return (uint32_t)(2 * (n - j + 1)) + (j == 0 ? bcorner : brow); }
+    bool pot2;                      // free-moves layout (see WF16C_POT2_MAX_N); rows are then strip-relative (irel)
+    // V of a cell with score H and origin bit 0 / H of a cell value
+    GP_HD int v_of(int H, int irel, int j) const { return pot2 ? 2 * (H + 2 * irel + 2 * j + n + 1) : 2 * (H + n - j + 1); }
+    GP_HD int h_of(int vv, int irel, int j) const { return pot2 ? (vv >> 1) - (2 * irel + 2 * j + n + 1) : (vv >> 1) - 1 - (n - j); }
+    GP_HD uint32_t v_col0(int i, int irel) const { return (uint32_t)v_of(0, irel, 0) + (i == 0 ? bcorner : bcol); }
+    GP_HD uint32_t v_row0(int j) const { return (uint32_t)v_of(0, 0, j) + (j == 0 ? bcorner : brow); }
 };
 
 GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, bool cell, int s_cell)
@@ -106,6 +120,7 @@ GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, boo
     g.bcorner = sys == WF16C_SYS_C ? 0u : 1u;
     g.cell = cell; g.s_cell = s_cell;
     g.gup = P.gup; g.gleft = P.gleft;
+    g.pot2 = P.pot2 != 0;
     return g;
 }
 
@@ -118,7 +133,8 @@ GP_HD uint32_t wf16c_line_word(const Wf16cPass& g, int j, uint32_t cj, uint32_t 
 
 GP_HD uint32_t wf16c_table_word(uint32_t row_lo, uint32_t row_hi, uint32_t ca, uint32_t cb, const Wf16cParams& P)
 {
-    return (row_lo == ca ? 0u : P.inc_mism) | ((row_hi == cb ? 0u : P.inc_mism) << 16);
+    const uint32_t mt = P.pot2 ? P.inc2_match : 0u, mm = P.pot2 ? P.inc2_mism : P.inc_mism;
+    return (row_lo == ca ? mt : mm) | ((row_hi == cb ? mt : mm) << 16);
 }
 
 template <int K>
@@ -127,22 +143,22 @@ struct Lane16c {
     uint32_t up0_prev;   // previous step's `up` of W[0] == this step's diagonal of W[0]
 };
 
+// irel_top: the lane's first row minus one, relative to the strip (itop - i0).
 template <int K>
-GP_HD void lane16c_begin(Lane16c<K>& st, const Wf16cPass& g, int itop)
+GP_HD void lane16c_begin(Lane16c<K>& st, const Wf16cPass& g, int itop, int irel_top)
 {
-    const uint32_t c0 = g.v_col0(1);                       // the same for every row >= 1
 #pragma unroll
-    for (int k = 0; k < K; ++k) st.W[k] = c0 | (c0 << 16);
-    st.up0_prev = g.v_col0(itop) | (c0 << 16);
+    for (int k = 0; k < K; ++k)                            // column 0 of rows itop+1+k (lo) and itop+1+K+k (hi)
+        st.W[k] = g.v_col0(itop + 1 + k, irel_top + 1 + k) | (g.v_col0(itop + 1 + K + k, irel_top + 1 + K + k) << 16);
+    st.up0_prev = g.v_col0(itop, irel_top) | (g.v_col0(itop + K, irel_top + K) << 16);
 }
 
 // After a lane's first step the hi group has "computed" column 0: put the boundary back.
 template <int K>
-GP_HD void lane16c_fix_first(Lane16c<K>& st, const Wf16cPass& g)
+GP_HD void lane16c_fix_first(Lane16c<K>& st, const Wf16cPass& g, int itop, int irel_top)
 {
-    const uint32_t c0 = g.v_col0(1);
 #pragma unroll
-    for (int k = 0; k < K; ++k) st.W[k] = (st.W[k] & 0xffffu) | (c0 << 16);
+    for (int k = 0; k < K; ++k) st.W[k] = (st.W[k] & 0xffffu) | (g.v_col0(itop + 1 + K + k, irel_top + 1 + K + k) << 16);
 }
 
 // One step: VIADD.16x2 + 2 x VIADDMNMX.S16x2 per register, nothing else.  Two phases so that the kernel can
@@ -156,7 +172,15 @@ GP_HD void lane16c_diag(const Lane16c<K>& st, const uint32_t (&inc)[K], uint32_t
 #pragma unroll
     for (int k = 1; k < K; ++k) d[k] = p_add2(st.W[k - 1], inc[k]);
 }
-template <int K>
+GP_HD uint32_t p_max3_relu2(uint32_t a, uint32_t b, uint32_t c)           // max(a, b, c, 0) per signed 16-bit half
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s16x2_relu(a, b, c);
+#else
+    return p_max2(p_max2(p_max2(a, b), c), 0u);
+#endif
+}
+template <int K, bool POT2 = false>
 GP_HD void lane16c_chain(Lane16c<K>& st, uint32_t recv, const uint32_t (&d)[K], uint32_t gup, uint32_t gleft)
 {
     const uint32_t up0 = p_prmt(recv, st.W[K - 1], 0x5432u);   // (recv.hi16 , old W[K-1].lo16)
@@ -164,18 +188,24 @@ GP_HD void lane16c_chain(Lane16c<K>& st, uint32_t recv, const uint32_t (&d)[K], 
     uint32_t up = up0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const uint32_t t = p_addmax2(st.W[k], gleft, d[k]);
-        const uint32_t w = p_addmax2_relu(up, gup, t);
+        uint32_t w;
+        if (POT2) {
+            w = p_max3_relu2(st.W[k], up, d[k]);                // left and up moves are free under this layout
+        } else {
+            const uint32_t t = p_addmax2(st.W[k], gleft, d[k]);
+            w = p_addmax2_relu(up, gup, t);
+        }
         up = w;
         st.W[k] = w;
     }
 }
 template <int K>
-GP_HD void lane16c_step(Lane16c<K>& st, uint32_t recv, const uint32_t (&inc)[K], uint32_t gup, uint32_t gleft)
+GP_HD void lane16c_step(Lane16c<K>& st, uint32_t recv, const uint32_t (&inc)[K], uint32_t gup, uint32_t gleft, bool pot2 = false)
 {
     uint32_t d[K];
     lane16c_diag<K>(st, inc, d);
-    lane16c_chain<K>(st, recv, d, gup, gleft);
+    if (pot2) lane16c_chain<K, true>(st, recv, d, gup, gleft);
+    else lane16c_chain<K, false>(st, recv, d, gup, gleft);
 }
 
 template <int K>
@@ -187,18 +217,29 @@ GP_HD uint32_t lane16c_max(const Lane16c<K>& st)
     if (K == 8) a = p_max3_2(p_max3_2(a, st.W[4], st.W[5]), st.W[6], st.W[7]);
     return a;
 }
-
-// Candidate filter under the column potential.  nthr = -(the V a cell has when H = 1) for the lo column
-// j (low half) and the hi column j-1 (high half): acc = max(V) + nthr = 2*(H-1) + b of the lane's best
-// cell, compared with thrS = 2*(max(S,1)-1).
-GP_HD uint32_t wf16c_nthr(const Wf16cPass& g, int j)
+// Free-moves layout: row k of either group sits 2*k higher than row 0, i.e. 4*k in V.
+template <int K>
+GP_HD uint32_t lane16c_max_pot2(const Lane16c<K>& st)
 {
-    const uint32_t lo = (uint32_t)(-2 * (g.n - j + 2)) & 0xffffu;          // 1 <= j: >= -2*(16382+1)
-    const uint32_t hi = (uint32_t)(-2 * (g.n - j + 3)) & 0xffffu;          // column j-1 >= 0: >= -32768; other j wrap mod 2^16
+    uint32_t a = st.W[0];
+#pragma unroll
+    for (int k = 1; k < K; ++k) a = p_addmax2(st.W[k], (uint32_t)((-4 * k) & 0xffff) * 0x00010001u, a);
+    return a;
+}
+
+// Candidate filter.  nthr = -(the V a cell has when H = 1) for the lane's first lo row at column j (low half)
+// and its first hi row at column j-1 (high half): acc = max(V) + nthr = 2*(H-1) + b of the lane's best
+// cell, compared with thrS = 2*(max(S,1)-1).
+template <int K>
+GP_HD uint32_t wf16c_nthr(const Wf16cPass& g, int j, int irel_top)
+{
+    const uint32_t lo = (uint32_t)(-g.v_of(1, irel_top + 1, j)) & 0xffffu;          // other j wrap mod 2^16
+    const uint32_t hi = (uint32_t)(-g.v_of(1, irel_top + 1 + K, j - 1)) & 0xffffu;
     return lo | (hi << 16);
 }
 constexpr uint32_t WF16C_UNARMED = 0x7fff7fffu;   // threshold no acc reaches (acc <= 2*n + 1 < 32767)
-constexpr uint32_t WF16C_NSTEP = 0x00020002u;
+constexpr uint32_t WF16C_NSTEP = 0x00020002u;          // nthr of the next column
+constexpr uint32_t WF16C_NSTEP_POT2 = 0xfffcfffcu;
 GP_HD uint32_t wf16c_filter_thr(int S) { const uint32_t t = (uint32_t)(2 * ((S > 1 ? S : 1) - 1)); return t | (t << 16); }
 
 // Exact scan of the cells a lane holds after a step (lo column j, hi column j-1).  Scan mode: a cell can
@@ -216,26 +257,29 @@ GP_HD void p_ge2(uint32_t a, uint32_t b, bool& hi, bool& lo)      // per half: a
     hi = (int16_t)(a >> 16) >= (int16_t)(b >> 16);
 #endif
 }
-GP_HD uint32_t wf16c_scan_thr(int S, int n, int j)          // V of a cell with H = max(S,1): column j | column j-1
+// Layout arithmetic without the pass structure (the cold functions take scalars): pot2 < 0 is the column-potential
+// layout, otherwise pot2 = irel_top, the lane's first row minus one relative to its strip (free-moves layout).
+GP_HD int wf16c_v_of(int H, int n, int pot2, int rk, int j) { return pot2 >= 0 ? 2 * (H + 2 * (pot2 + rk) + 2 * j + n + 1) : 2 * (H + n - j + 1); }
+GP_HD int wf16c_h_of(int vv, int n, int pot2, int rk, int j) { return pot2 >= 0 ? (vv >> 1) - (2 * (pot2 + rk) + 2 * j + n + 1) : (vv >> 1) - 1 - (n - j); }
+// V of a cell with H = max(S,1) in register k: lo row (column j) | hi row (column j-1)
+GP_HD uint32_t wf16c_scan_thr(int S, int n, int pot2, int K, int k, int j)
 {
-    const int lo = 2 * ((S > 1 ? S : 1) + n - j + 1), hi = lo + 2;
+    const int s1 = S > 1 ? S : 1;
+    const int lo = wf16c_v_of(s1, n, pot2, 1 + k, j), hi = wf16c_v_of(s1, n, pot2, 1 + K + k, j - 1);
     return (uint32_t)(lo < 0x7fff ? lo : 0x7fff) | ((uint32_t)(hi < 0x7fff ? hi : 0x7fff) << 16);
 }
-template <int K>
-GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, bool cell, int itop, int j, int s_floor, long long best)
+// The exact scan takes K at run time and loops: it is cold code, and four unrolled copies of it (one per strip
+// height) made up a third of the kernel's instructions -- enough to push the kernel out of the instruction cache.
+GP_HD long long lane16c_scan_rt(const uint32_t* W, int K, int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best)
 {
     if (cell) {
-#pragma unroll
         for (int half = 0; half < 2; ++half) {
             if (j - half != n) continue;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int i = itop + 1 + k + half * K;
-                if (i == m) {
-                    const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
-                    const long long key = make_key((vv >> 1) - 1, 0u, (uint32_t)vv & 1u);
-                    best = key > best ? key : best;
-                }
+            const int k = m - itop - 1 - half * K;                 // the register that holds row m, if this lane does
+            if (k >= 0 && k < K) {
+                const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
+                const long long key = make_key(wf16c_h_of(vv, n, pot2, 1 + k + half * K, n), 0u, (uint32_t)vv & 1u);
+                best = key > best ? key : best;
             }
         }
         return best;
@@ -243,26 +287,32 @@ GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, boo
     // s_floor: a score some candidate of the pair is already known to reach (the warp's shared best); cells
     // below it cannot win, cells that equal it can (by rank).
     const bool vlo = (uint32_t)(j - 1) < (uint32_t)n, vhi = (uint32_t)(j - 2) < (uint32_t)n;   // columns inside the table
-    auto thr_of = [&](long long b) { const int s = (int)(b >> 32); return wf16c_scan_thr(s > s_floor ? s : s_floor, n, j); };
-    uint32_t thr2 = thr_of(best);
-#pragma unroll
+    int sthr = (int)(best >> 32);
+    sthr = sthr > s_floor ? sthr : s_floor;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int k = 0; k < K; ++k) {
         bool hit[2];
-        p_ge2(W[k], thr2, hit[1], hit[0]);
+        const uint32_t w = W[k];
+        p_ge2(w, wf16c_scan_thr(sthr, n, pot2, K, k, j), hit[1], hit[0]);
         hit[0] = hit[0] && vlo; hit[1] = hit[1] && vhi;
         if (!(hit[0] || hit[1])) continue;
-#pragma unroll
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
         for (int half = 0; half < 2; ++half) {
             if (!hit[half]) continue;
             const int jh = j - half;
-            const int vv = half ? (int)(W[k] >> 16) : (int)(W[k] & 0xffffu);
+            const int vv = half ? (int)(w >> 16) : (int)(w & 0xffffu);
             const int i = itop + 1 + k + half * K;
             const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, C) : RANK_MAX + 1u;
             if (rk <= RANK_MAX) {
-                const long long key = make_key((vv >> 1) - 1 - (n - jh), rk, (uint32_t)vv & 1u);
+                const long long key = make_key(wf16c_h_of(vv, n, pot2, 1 + k + half * K, jh), rk, (uint32_t)vv & 1u);
                 if (key > best) {
                     best = key;
-                    thr2 = thr_of(best);
+                    const int sb = (int)(best >> 32);
+                    sthr = sb > sthr ? sb : sthr;
                 }
             }
         }
@@ -270,9 +320,14 @@ GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, boo
     return best;
 }
 template <int K>
-GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int j, long long best)
+GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best)
 {
-    return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, best);
+    return lane16c_scan_rt(W, K, m, n, C, cell, itop, j, s_floor, pot2, best);
+}
+template <int K>
+GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int irel_top, int j, long long best)
+{
+    return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, g.pot2 ? irel_top : -1, best);
 }
 
 // Deferred exact scans.  Along an alignment path inside the candidate zone a lane's best cell gains a point at
@@ -294,30 +349,28 @@ GP_HD bool wf16c_deferrable(int n, int C, bool cell, int j)
     return !cell && j >= 2 && j <= n && j != jswitch;
 }
 // Exact score of a deferrable step; WF16C_NO_SNAP when the lane holds no candidate cell in it.
-template <int K>
-GP_HD int wf16c_exact_step_score(const uint32_t (&W)[K], int m, int n, int C, int itop, int j)
+GP_HD int wf16c_exact_step_score_rt(const uint32_t* W, int K, int m, int n, int C, int itop, int j, int pot2)
 {
     const int jswitch = n - C > 1 ? n - C : 1;
     const int rlo = j - 1 >= jswitch ? 1 : m - C;              // candidate rows rlo..m
-    if (itop + 1 >= rlo && itop + 2 * K <= m) {                 // every row of the lane is one: a packed maximum
-        uint32_t mx = W[0];
-#pragma unroll
-        for (int k = 1; k < K; ++k) mx = p_max2(mx, W[k]);
-        const int lo = (int)(mx & 0xffffu) - 2 * (n - j + 2), hi = (int)(mx >> 16) - 2 * (n - j + 3);
-        return (lo > hi ? lo : hi) | 1;
-    }
-    int vlo = -1, vhi = -1;                                     // V >= 0 for every real cell
-#pragma unroll
+    int best = WF16C_NO_SNAP;                                   // 2*(H-1) + b of the best candidate cell
+    const int v1lo = wf16c_v_of(1, n, pot2, 1, j), v1hi = wf16c_v_of(1, n, pot2, 1 + K, j - 1);
+    const int per_row = pot2 >= 0 ? 4 : 0;                      // free-moves layout: row k sits 4*k higher in V
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int k = 0; k < K; ++k) {
         const int il = itop + 1 + k, ih = il + K;
         const int a = (int)(W[k] & 0xffffu), b = (int)(W[k] >> 16);
-        if (il >= rlo && il <= m) vlo = a > vlo ? a : vlo;
-        if (ih >= rlo && ih <= m) vhi = b > vhi ? b : vhi;
+        if (il >= rlo && il <= m) { const int h = a - v1lo - per_row * k; best = h > best ? h : best; }
+        if (ih >= rlo && ih <= m) { const int h = b - v1hi - per_row * k; best = h > best ? h : best; }
     }
-    int best = WF16C_NO_SNAP;
-    if (vlo >= 0) best = vlo - 2 * (n - j + 2);                 // V + nthr of column j
-    if (vhi >= 0) { const int h = vhi - 2 * (n - j + 3); best = h > best ? h : best; }
     return best == WF16C_NO_SNAP ? best : (best | 1);
+}
+template <int K>
+GP_HD int wf16c_exact_step_score(const uint32_t (&W)[K], int m, int n, int C, int itop, int j, int pot2)
+{
+    return wf16c_exact_step_score_rt(W, K, m, n, C, itop, j, pot2);
 }
 
 // Initial `best` of a pass.  Scan mode: cell (0,n), the first cell the reference scans (rank 0, H = 0);
@@ -382,44 +435,30 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
 
 template <int K> struct CVals { uint32_t W[K]; };
 
-// The cold side of a fired step (scalars only: a struct by value would travel through the stack on every call).
-// `slot` is the lane's pending step in local memory (so that the steady loops carry no extra live registers):
-// K registers, the lo column, the score.  Returns the lane's best key; slot[K+1] holds the pending score after.
-template <int K>
-__device__ __noinline__ long long wf16c_fire_cold(CVals<K> v, uint32_t* slot, int m, int n, int C_or_cell, int itop, int j,
-                                                  int s_floor, long long best)
+// The cold side of the candidate bookkeeping: ONE function for every strip height (K at run time; scalars and
+// pointers only).  `cur` holds the lane's K registers of the fired step, `slot` the lane's pending step (K registers,
+// the lo column, the score), both in local memory so that the steady loops carry no extra live registers.
+//   flush == 0: the lane fired at lo column j.  A deferrable step becomes the pending step (the old pending step is
+//               scanned first when it ties or beats the new one and can still win); any other step is scanned now.
+//   flush != 0: end of the strip, the pending step is scanned.
+// Returns the lane's best key; slot[K+1] holds the pending score afterwards.
+__device__ __noinline__ long long wf16c_cold(const uint32_t* cur, uint32_t* slot, int K, int flush, int m, int n, int C_or_cell,
+                                             int itop, int j, int s_floor, int pot2, long long best)
 {
     const bool cell = C_or_cell < 0;
     const int C = cell ? 0 : C_or_cell;
-    CVals<K> x = v;
-    int js = j;
-    bool scan = true;
-    if (wf16c_deferrable(n, C, cell, j)) {
-        const int a = wf16c_exact_step_score<K>(v.W, m, n, C, itop, j);
-        if (a == WF16C_NO_SNAP || wf16c_score_of(a) < (s_floor > 1 ? s_floor : 1)) return best;   // no candidate can matter
-        const int old = (int)slot[K + 1];
-        scan = old != WF16C_NO_SNAP && a <= old && wf16c_score_of(old) >= s_floor;
-        if (scan) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) x.W[k] = slot[k];
-            js = (int)slot[K];
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) slot[k] = v.W[k];
-        slot[K] = (uint32_t)j;
-        slot[K + 1] = (uint32_t)a;
-    }
-    if (scan) best = lane16c_scan_mn<K>(x.W, m, n, C, cell, itop, js, s_floor, best);
+    if (flush) return lane16c_scan_rt(slot, K, m, n, C, false, itop, (int)slot[K], s_floor, pot2, best);
+    if (!wf16c_deferrable(n, C, cell, j)) return lane16c_scan_rt(cur, K, m, n, C, cell, itop, j, s_floor, pot2, best);
+    const int a = wf16c_exact_step_score_rt(cur, K, m, n, C, itop, j, pot2);
+    if (a == WF16C_NO_SNAP || wf16c_score_of(a) < (s_floor > 1 ? s_floor : 1)) return best;   // no candidate can matter
+    const int old = (int)slot[K + 1];
+    if (old != WF16C_NO_SNAP && a <= old && wf16c_score_of(old) >= s_floor)
+        best = lane16c_scan_rt(slot, K, m, n, C, false, itop, (int)slot[K], s_floor, pot2, best);
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) slot[k] = cur[k];
+    slot[K] = (uint32_t)j;
+    slot[K + 1] = (uint32_t)a;
     return best;
-}
-// The pending step at the end of a strip.
-template <int K>
-__device__ __noinline__ long long wf16c_flush_cold(const uint32_t* slot, int m, int n, int C, int itop, int s_floor, long long best)
-{
-    CVals<K> x;
-#pragma unroll
-    for (int k = 0; k < K; ++k) x.W[k] = slot[k];
-    return lane16c_scan_mn<K>(x.W, m, n, C, false, itop, (int)slot[K], s_floor, best);
 }
 
 // One strip of 64*K rows starting after table row `i0` (see wf16t_strip for the block structure).
@@ -429,7 +468,7 @@ __device__ __noinline__ long long wf16c_flush_cold(const uint32_t* slot, int m, 
 // 94+ steps later, so the only ordering needed is "strip s-1 has published column j before strip s reads it":
 // the producer publishes its progress after every block (columns <= tb + cnt - 95), the consumer spins on it
 // before each refill.  Boundary reads bypass L1 (ld.global.cg): the line is written by other warps.
-template <int K, bool STD, int TEAM>
+template <int K, bool STD, int TEAM, bool POT2>
 __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P, int i0, bool rowscan, bool store_bottom, long long best)
 {
     constexpr uint32_t FULL = 0xffffffffu;
@@ -439,7 +478,8 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     const int lane = threadIdx.x & 31;
     const Wf16cPass g = w.g;
     const int n = g.n, m = g.m;
-    const int itop = i0 + lane * 2 * K;
+    const int itop = i0 + lane * 2 * K, irel_top = lane * 2 * K;
+    const int pot2 = POT2 ? irel_top : -1;                             // layout argument of the cold functions
     const uint32_t gup = STD ? 0xfffcfffcu : g.gup, gleft = STD ? 0xfffafffau : g.gleft;
     uint32_t* const bnd = w.bnd;
     const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(w.smem);
@@ -500,7 +540,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     wait_cols(32);
     { const int jj = 1 + lane; ring_put(jj, bnd_load(jj <= n + 1 ? jj : n + 1)); }
     Lane16c<K> st;
-    lane16c_begin<K>(st, g, itop);
+    lane16c_begin<K>(st, g, itop, irel_top);
 
     // ---- candidate filter state --------------------------------------------------------------------
     int S0 = __reduce_max_sync(FULL, (int)(best >> 32));                   // the warp's best score so far
@@ -516,11 +556,11 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     uint32_t snap_slot[K + 2];
     int snapA = WF16C_NO_SNAP;
     snap_slot[K + 1] = (uint32_t)WF16C_NO_SNAP;
+    uint32_t cur_w[K];                                                    // the fired step's registers, for the cold function
     auto fire_path = [&](int jj) {                                        // this lane fired at lo column jj
-        CVals<K> v;
 #pragma unroll
-        for (int k = 0; k < K; ++k) v.W[k] = st.W[k];
-        best = wf16c_fire_cold<K>(v, snap_slot, m, n, g.cell ? -1 : g.C, itop, jj, S0, best);
+        for (int k = 0; k < K; ++k) cur_w[k] = st.W[k];
+        best = wf16c_cold(cur_w, snap_slot, K, 0, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
         snapA = (int)snap_slot[K + 1];
     };
     // After any lane's fire the whole warp learns the new best score at once (one REDUX): without it the
@@ -542,25 +582,29 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         uint32_t p_end = p + 4u * (uint32_t)cnt;
         asm volatile("" : "+r"(p_end));                              // opaque: kept in a register, not recomputed every iteration
         int j = tb - D * lane;                                            // my lo column
-        uint32_t nthr = FILT ? wf16c_nthr(g, j) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
+        uint32_t nthr = FILT ? wf16c_nthr<K>(g, j, irel_top) : 0u;                     // follows j (mod 2^16 outside 1..n+1)
         uint32_t inc[K];
         uint32_t w0 = lds32(p), w1 = lds32(p + 4);
         lds_inc<K>(inc, my_tab + (w0 >> 16));
         auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj) {
+            // Where the shuffle goes out is a scheduling matter (its result is needed a step from now): first thing
+            // under the free-moves layout, whose short max chain hides less latency (ptxas otherwise parks the copy
+            // of the loop-carried value right behind it: 7 % of the kernel waiting), behind the loads otherwise.
+            uint32_t recv = recv_next;
+            if (POT2) recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             uint32_t d[K];
             lane16c_diag<K>(st, inc, d);
             lds_inc<K>(inc, my_tab + (next_word >> 16));
-            uint32_t recv = recv_next;
-            recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
+            if (!POT2) recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             if (lane == 0) recv = word << 16;
             bool fire = false;
             uint32_t acc = 0u;
             if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
-                lane16c_chain<K>(st, recv, d, gup, gleft);
-                if (EDGE && jj == 1) lane16c_fix_first<K>(st, g);
+                lane16c_chain<K, POT2>(st, recv, d, gup, gleft);
+                if (EDGE && jj == 1) lane16c_fix_first<K>(st, g, itop, irel_top);
                 if (do_store) sts32(oaddr, st.W[K - 1]);
                 if (FILT) {
-                    acc = p_add2(lane16c_max<K>(st), nthr);
+                    acc = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr);
                     fire = filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
                 }
             }
@@ -569,7 +613,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
                     if (fire) fire_path(jj);
                     share_floor();
                 }
-                nthr = p_add2(nthr, WF16C_NSTEP);
+                nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
             }
         };
 #pragma unroll 1
@@ -599,7 +643,10 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         if (store_bottom) {                                               // bottom row of the columns lane 31 finished
             const int c = tb + lane - (31 * D + 1);
             const uint32_t v = lds32(oring_base + 4 * ((((uint32_t)(tb - 31 * D)) & (WF16C_RING - 1)) + lane));
-            if (c >= 1 && c <= n && lane < cnt) reinterpret_cast<uint16_t*>(bnd)[2 * c] = (uint16_t)(v >> 16);
+            // free-moves layout: the bottom row becomes row 0 of the next strip, 64*K rows lower in the row potential
+            int vb = (int)(v >> 16);
+            if (POT2) { vb -= 4 * 64 * K; vb = vb > 0 ? vb : 0; }
+            if (c >= 1 && c <= n && lane < cnt) reinterpret_cast<uint16_t*>(bnd)[2 * c] = (uint16_t)vb;
             if constexpr (TEAM > 1) {                                      // publish: columns <= tb + cnt - 95 are in the line
                 __threadfence_block();
                 __syncwarp();
@@ -612,14 +659,14 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         __syncwarp();
     }
     if (snapA != WF16C_NO_SNAP && wf16c_score_of(snapA) >= S0)
-        best = wf16c_flush_cold<K>(snap_slot, m, n, g.C, itop, S0, best);
+        best = wf16c_cold(snap_slot, snap_slot, K, 1, m, n, g.C, itop, 0, S0, pot2, best);
     __syncwarp();
     return best;
 }
 
 // One pass (all strips of the sub-table); returns the best key of the pair: warp wide, or CTA wide in team mode
 // (every thread of the CTA calls it and gets the same key).
-template <bool STD, int TEAM>
+template <bool STD, int TEAM, bool POT2>
 __device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P, long long* team_keys)
 {
     const int lane = threadIdx.x & 31;
@@ -644,10 +691,10 @@ __device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P,
             const bool rs = s.rowscan && !w.g.cell;
             w.strip_idx = idx;
             switch (s.rows) {
-            case 512: best = wf16c_strip<8, STD, TEAM>(w, P, i0, rs, sb, best); break;
-            case 256: best = wf16c_strip<4, STD, TEAM>(w, P, i0, rs, sb, best); break;
-            case 128: best = wf16c_strip<2, STD, TEAM>(w, P, i0, rs, sb, best); break;
-            default:  best = wf16c_strip<1, STD, TEAM>(w, P, i0, rs, sb, best); break;
+            case 512: best = wf16c_strip<8, STD, TEAM, POT2>(w, P, i0, rs, sb, best); break;
+            case 256: best = wf16c_strip<4, STD, TEAM, POT2>(w, P, i0, rs, sb, best); break;
+            case 128: best = wf16c_strip<2, STD, TEAM, POT2>(w, P, i0, rs, sb, best); break;
+            default:  best = wf16c_strip<1, STD, TEAM, POT2>(w, P, i0, rs, sb, best); break;
             }
         }
         i0 += s.rows;
@@ -705,7 +752,7 @@ __device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__
 // retry16t / retry32: work lists of the exact kernels behind this one (pairs with n <= WF16T_MAX_N go to
 // the table kernel); *retry16t_n / *retry32_n are their fill counts (the host may have pre-filled them).
 // TEAM = 1: one warp per pair.  TEAM = warps per CTA: one CTA per pair (few, long pairs: the relax chain).
-template <bool STD, int TEAM>
+template <bool STD, int TEAM, bool POT2>
 __global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
 overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                      const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
@@ -745,7 +792,7 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
         const int m = (int)w.pd.m, n = (int)w.pd.n;
         const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system(packed, w.pd);
         w.g = wf16c_make_pass(m, n, P, sys0, false, 0);
-        const long long key = wf16c_pass<STD, TEAM>(w, P, team_keys);
+        const long long key = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
         uint32_t origin = wf16c_certified_origin(w.g, key);
         DevResult r;
         store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
@@ -754,7 +801,7 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
             __syncwarp();
             if (leader) atomicAdd(counters, 1u);
             w.g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score);
-            const long long key2 = wf16c_pass<STD, TEAM>(w, P, team_keys);
+            const long long key2 = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
             origin = wf16c_certified_origin(w.g, key2);
         }
         if (leader) {
@@ -773,21 +820,23 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
 
 constexpr int WF16C_TEAM = WF16C_THREADS / 32;
 
-template <bool STD, int TEAM>
+template <bool STD, int TEAM, bool POT2>
 inline cudaError_t wf16c_configure_one()
 {
-    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM, POT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM, POT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 inline cudaError_t wf16c_configure()
 {
     cudaError_t e;
-    if ((e = wf16c_configure_one<true, 1>()) != cudaSuccess) return e;
-    if ((e = wf16c_configure_one<false, 1>()) != cudaSuccess) return e;
-    if ((e = wf16c_configure_one<true, WF16C_TEAM>()) != cudaSuccess) return e;
-    return wf16c_configure_one<false, WF16C_TEAM>();
+    if ((e = wf16c_configure_one<true, 1, false>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<false, 1, false>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<true, WF16C_TEAM, false>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<false, WF16C_TEAM, false>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<true, 1, true>()) != cudaSuccess) return e;
+    return wf16c_configure_one<true, WF16C_TEAM, true>();
 }
 
 // Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
@@ -809,12 +858,13 @@ inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packe
         if (e != cudaSuccess) return (int)e;
         *scratch_cap = need;
     }
-#define GP_WF16C_LAUNCH(STD_, TEAM_)                                                                                   \
-    overlap_wf16c_kernel<STD_, TEAM_><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(                              \
+#define GP_WF16C_LAUNCH(STD_, TEAM_, POT2_)                                                                            \
+    overlap_wf16c_kernel<STD_, TEAM_, POT2_><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(                       \
         packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, \
         counters, force_sys, out)
-    if (P.std_scores) { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM); else GP_WF16C_LAUNCH(true, 1); }
-    else              { if (team) GP_WF16C_LAUNCH(false, WF16C_TEAM); else GP_WF16C_LAUNCH(false, 1); }
+    if (P.pot2 && P.std_scores) { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, true); else GP_WF16C_LAUNCH(true, 1, true); }
+    else if (P.std_scores)      { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, false); else GP_WF16C_LAUNCH(true, 1, false); }
+    else                        { if (team) GP_WF16C_LAUNCH(false, WF16C_TEAM, false); else GP_WF16C_LAUNCH(false, 1, false); }
 #undef GP_WF16C_LAUNCH
     return (int)cudaGetLastError();
 }

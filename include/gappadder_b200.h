@@ -179,6 +179,14 @@ int gp_set_cert_system(gp_ctx *ctx, uint32_t system);
  * depend on it.  gp_last_team: 1 if the last launch on this context used the CTA-per-pair form. */
 int gp_set_team_mode(gp_ctx *ctx, uint32_t mode);
 int gp_last_team(const gp_ctx *ctx);
+/* The certificate kernel has two value layouts.  The column-potential layout (every move costs, two add-max
+ * instructions per cell pair) works for column sequences up to 16382 bases; the free-moves layout (row and column
+ * potential under which the up and left moves add nothing: one 3-input max per cell pair) needs the standard
+ * scores (mismatch -2, indel -2) and every column sequence of the launch <= 3800 bases.  mode 0: the library uses
+ * the free-moves layout whenever a launch allows it (default); 1: always the column-potential layout.  Results
+ * never depend on it.  gp_last_layout: 1 if the last launch used the free-moves layout. */
+int gp_set_cert_layout(gp_ctx *ctx, uint32_t mode);
+int gp_last_layout(const gp_ctx *ctx);
 /* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).
  * Pairs no allowed kernel accepts go to the general 32-bit kernel; results never depend on the mask. */
 #define GP_KERNEL_TABLE16 1u

@@ -285,7 +285,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
         for (int x = 0; x < 2 * K; ++x) rc[x] = itop + x < m ? hp.row[itop + x] : 0u;
         for (uint32_t combo = 0; combo < 16; ++combo)
             for (int k = 0; k < K; ++k) tab[((size_t)lane * 16 + combo) * K + k] = wf16c_table_word(rc[k], rc[K + k], combo & 3u, combo >> 2, P);
-        lane16c_begin<K>(st[lane], g, itop);
+        lane16c_begin<K>(st[lane], g, itop, lane * 2 * K);
     }
     int S0 = -1000000000;
     for (int lane = 0; lane < 32; ++lane) { const int sc = (int)(lane_best[lane] >> 32); S0 = sc > S0 ? sc : S0; }
@@ -298,7 +298,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
     for (int lane = 0; lane < 32; ++lane) { snapj[lane] = 0; snapA[lane] = WF16C_NO_SNAP; }
     auto scan_pending = [&](int lane) {
         ++g_slow_calls;
-        lane_best[lane] = lane16c_scan_mn<K>(snapW[lane], g.m, g.n, g.C, false, i0 + lane * 2 * K, snapj[lane], S0, lane_best[lane]);
+        lane_best[lane] = lane16c_scan_mn<K>(snapW[lane], g.m, g.n, g.C, false, i0 + lane * 2 * K, snapj[lane], S0, g.pot2 ? lane * 2 * K : -1, lane_best[lane]);
     };
     constexpr int D = WF16C_SKEW;
     const int t_end = n + 1 + 31 * D;
@@ -321,16 +321,21 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
                 const uint32_t combo = (top[j] >> 16) & 15u;
                 uint32_t inc[K];
                 for (int k = 0; k < K; ++k) inc[k] = tab[((size_t)lane * 16 + combo) * K + k];
-                lane16c_step<K>(st[lane], recv[lane], inc, g.gup, g.gleft);
-                if (j == 1) lane16c_fix_first<K>(st[lane], g);
-                if (store_bottom && lane == 31 && j >= 2 && j - 1 <= n) bnd16[2 * (j - 1)] = (uint16_t)(st[lane].W[K - 1] >> 16);
+                const int irel_top = lane * 2 * K, pot2 = g.pot2 ? irel_top : -1;
+                lane16c_step<K>(st[lane], recv[lane], inc, g.gup, g.gleft, g.pot2);
+                if (j == 1) lane16c_fix_first<K>(st[lane], g, itop, irel_top);
+                if (store_bottom && lane == 31 && j >= 2 && j - 1 <= n) {
+                    int vb = (int)(st[lane].W[K - 1] >> 16);
+                    if (g.pot2) { vb -= 4 * 64 * K; vb = vb > 0 ? vb : 0; }       // row 0 of the next strip
+                    bnd16[2 * (j - 1)] = (uint16_t)vb;
+                }
                 if (filt) {
                     const bool rowlane = rowscan && (itop + 2 * K >= m - g.C) && (itop + 1 <= m);
-                    const uint32_t acc = p_add2(lane16c_max<K>(st[lane]), wf16c_nthr(g, j));
+                    const uint32_t acc = p_add2(g.pot2 ? lane16c_max_pot2<K>(st[lane]) : lane16c_max<K>(st[lane]), wf16c_nthr<K>(g, j, irel_top));
                     if (filter_fired(acc, j >= (rowlane ? 1 : jswitch) ? thrS[lane] : WF16C_UNARMED)) {
                         any_fired = true;
                         if (wf16c_deferrable(n, g.C, g.cell, j)) {                      // wf16c_fire_cold
-                            const int a = wf16c_exact_step_score<K>(st[lane].W, m, n, g.C, itop, j);
+                            const int a = wf16c_exact_step_score<K>(st[lane].W, m, n, g.C, itop, j, pot2);
                             if (!(a == WF16C_NO_SNAP || wf16c_score_of(a) < (S0 > 1 ? S0 : 1))) {
                                 if (snapA[lane] != WF16C_NO_SNAP && a <= snapA[lane] && wf16c_score_of(snapA[lane]) >= S0) scan_pending(lane);
                                 for (int k = 0; k < K; ++k) snapW[lane][k] = st[lane].W[k];
@@ -338,7 +343,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
                             }
                         } else {
                             ++g_slow_calls;
-                            lane_best[lane] = lane16c_scan_mn<K>(st[lane].W, g.m, g.n, g.C, g.cell, itop, j, S0, lane_best[lane]);
+                            lane_best[lane] = lane16c_scan_mn<K>(st[lane].W, g.m, g.n, g.C, g.cell, itop, j, S0, pot2, lane_best[lane]);
                         }
                     }
                 }
@@ -394,7 +399,12 @@ extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col
                              int mismatch, int indel, int max_clip, int first_sys, int32_t* out)
 {
     if (!wf16_params_ok(mismatch, indel) || !wf16c_pair_ok((uint32_t)m, (uint32_t)n)) return -1;
-    const Wf16cParams P = wf16c_make_params(mismatch, indel, max_clip);
+    Wf16cParams P = wf16c_make_params(mismatch, indel, max_clip);
+    if (first_sys >= 4) {                              // bit 2: the free-moves layout (standard scores, short columns)
+        if (!P.std_scores || (uint32_t)n > WF16C_POT2_MAX_N) return -1;
+        P.pot2 = 1;
+        first_sys -= 4;
+    }
     HostPair hp;
     hp.row.assign(row_codes, row_codes + m);
     hp.col.assign(col_codes, col_codes + n);

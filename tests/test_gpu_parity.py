@@ -30,13 +30,18 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         want.append((o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained))
     first = None
     try:
-        runs = []        # (kernel mask, certificate system to start with, team mode)
+        runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout)
         for mask in masks:
-            runs += [(mask, 0, 0), (mask, 1, 1), (mask, 2, 2), (mask, 3, 0), (mask, 0, 2)] if mask & KERNEL_CERT16 else [(mask, 0, 0)]
-        for mask, system, team in runs:
+            if mask & KERNEL_CERT16:      # layout 0: free moves whenever the launch allows it, 1: column potential only
+                runs += [(mask, 0, 0, 0), (mask, 1, 1, 0), (mask, 2, 2, 0), (mask, 3, 0, 0), (mask, 0, 2, 0),
+                         (mask, 0, 0, 1), (mask, 1, 2, 1), (mask, 2, 1, 1), (mask, 3, 0, 1)]
+            else:
+                runs += [(mask, 0, 0, 0)]
+        for mask, system, team, layout in runs:
             ctx.set_kernel_mask(mask)
             ctx.set_cert_system(system)
             ctx.set_team_mode(team)
+            ctx.set_cert_layout(layout)
             res = ctx.overlap_batch(seqs, pairs, params)
             assert len(res) == len(pairs)
             bad = []
@@ -45,13 +50,15 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
                        int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
                 if w != got:
                     bad.append(((a, b), len(seqs[a]), len(seqs[b]), w, got))
-            assert not bad, "kernel mask %d system %d team %d: first mismatches (pair, m, n, oracle, gpu): %r" % (mask, system, team, bad[:5])
+            assert not bad, "kernel mask %d system %d team %d layout %d (free moves used: %d): first mismatches (pair, m, n, oracle, gpu): %r" % (
+                mask, system, team, layout, ctx.last_layout, bad[:5])
             if first is None:
                 first = res
     finally:
         ctx.set_kernel_mask(KERNEL_ALL)
         ctx.set_cert_system(0)
         ctx.set_team_mode(0)
+        ctx.set_cert_layout(0)
     return first
 
 
