@@ -436,28 +436,42 @@ __device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
 template <int K> struct CVals { uint32_t W[K]; };
 
 // The cold side of the candidate bookkeeping: ONE function for every strip height (K at run time; scalars and
-// pointers only).  `cur` holds the lane's K registers of the fired step, `slot` the lane's pending step (K registers,
-// the lo column, the score), both in local memory so that the steady loops carry no extra live registers.
-//   flush == 0: the lane fired at lo column j.  A deferrable step becomes the pending step (the old pending step is
-//               scanned first when it ties or beats the new one and can still win); any other step is scanned now.
+// pointers only).  `bufs` is the lane's scratch in local memory (so that the steady loops carry no extra live
+// registers): two buffers of K registers and three words of state -- the pending step's lo column, its score, and
+// which buffer holds it.  The caller has put the fired step's registers into the OTHER buffer; deferring a step
+// flips the buffers instead of copying.
+//   flush == 0: the lane fired at lo column j; acc is the filter's accumulator of that step.  A deferrable step
+//               becomes the pending step (the old pending step is scanned first when it ties or beats the new one and
+//               can still win); any other step is scanned now.
 //   flush != 0: end of the strip, the pending step is scanned.
-// Returns the lane's best key; slot[K+1] holds the pending score afterwards.
-__device__ __noinline__ long long wf16c_cold(const uint32_t* cur, uint32_t* slot, int K, int flush, int m, int n, int C_or_cell,
+// Returns the lane's best key.
+__device__ __noinline__ long long wf16c_cold(uint32_t* bufs, int K, int flush, uint32_t acc, int m, int n, int C_or_cell,
                                              int itop, int j, int s_floor, int pot2, long long best)
 {
     const bool cell = C_or_cell < 0;
     const int C = cell ? 0 : C_or_cell;
-    if (flush) return lane16c_scan_rt(slot, K, m, n, C, false, itop, (int)slot[K], s_floor, pot2, best);
+    uint32_t* meta = bufs + 2 * K;
+    const uint32_t idx = meta[2];
+    const uint32_t* pend = bufs + idx * K;
+    const uint32_t* cur = bufs + (1u - idx) * K;
+    if (flush) return lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best);
     if (!wf16c_deferrable(n, C, cell, j)) return lane16c_scan_rt(cur, K, m, n, C, cell, itop, j, s_floor, pot2, best);
-    const int a = wf16c_exact_step_score_rt(cur, K, m, n, C, itop, j, pot2);
+    const int jswitch = n - C > 1 ? n - C : 1;
+    const int rlo = j - 1 >= jswitch ? 1 : m - C;              // candidate rows rlo..m
+    int a;
+    if (itop + 1 >= rlo && itop + 2 * K <= m) {                 // every cell of the lane is a candidate: the filter's maximum is exact
+        const int lo = (int)(int16_t)(acc & 0xffffu), hi = (int)(int16_t)(acc >> 16);
+        a = (lo > hi ? lo : hi) | 1;
+    } else {
+        a = wf16c_exact_step_score_rt(cur, K, m, n, C, itop, j, pot2);
+    }
     if (a == WF16C_NO_SNAP || wf16c_score_of(a) < (s_floor > 1 ? s_floor : 1)) return best;   // no candidate can matter
-    const int old = (int)slot[K + 1];
+    const int old = (int)meta[1];
     if (old != WF16C_NO_SNAP && a <= old && wf16c_score_of(old) >= s_floor)
-        best = lane16c_scan_rt(slot, K, m, n, C, false, itop, (int)slot[K], s_floor, pot2, best);
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) slot[k] = cur[k];
-    slot[K] = (uint32_t)j;
-    slot[K + 1] = (uint32_t)a;
+        best = lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best);
+    meta[0] = (uint32_t)j;
+    meta[1] = (uint32_t)a;
+    meta[2] = 1u - idx;
     return best;
 }
 
@@ -552,16 +566,19 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     const bool do_store = store_bottom && lane == 31;
     uint32_t recv_next = 0;                                               // shuffle issued one step ahead
 
-    // deferred exact scan (see wf16c_exact_step_score): the pending step's score here, its registers in local memory
-    uint32_t snap_slot[K + 2];
+    // deferred exact scan (see wf16c_cold): the pending step's score and buffer index here, the rest in local memory
+    uint32_t snap_bufs[2 * K + 3];
     int snapA = WF16C_NO_SNAP;
-    snap_slot[K + 1] = (uint32_t)WF16C_NO_SNAP;
-    uint32_t cur_w[K];                                                    // the fired step's registers, for the cold function
-    auto fire_path = [&](int jj) {                                        // this lane fired at lo column jj
+    uint32_t snap_idx = 0;
+    snap_bufs[2 * K + 1] = (uint32_t)WF16C_NO_SNAP;
+    snap_bufs[2 * K + 2] = 0u;
+    auto fire_path = [&](int jj, uint32_t acc) {                          // this lane fired at lo column jj
+        uint32_t* cur = snap_bufs + (1u - snap_idx) * K;
 #pragma unroll
-        for (int k = 0; k < K; ++k) cur_w[k] = st.W[k];
-        best = wf16c_cold(cur_w, snap_slot, K, 0, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
-        snapA = (int)snap_slot[K + 1];
+        for (int k = 0; k < K; ++k) cur[k] = st.W[k];
+        best = wf16c_cold(snap_bufs, K, 0, acc, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
+        snapA = (int)snap_bufs[2 * K + 1];
+        snap_idx = snap_bufs[2 * K + 2];
     };
     // After any lane's fire the whole warp learns the new best score at once (one REDUX): without it the
     // lanes below an alignment path, whose cells all gain a point per column, fire at every column of the
@@ -610,7 +627,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             }
             if (FILT) {
                 if (__any_sync(FULL, fire)) {                             // warp-uniform: every lane runs every step
-                    if (fire) fire_path(jj);
+                    if (fire) fire_path(jj, acc);
                     share_floor();
                 }
                 nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
@@ -659,7 +676,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         __syncwarp();
     }
     if (snapA != WF16C_NO_SNAP && wf16c_score_of(snapA) >= S0)
-        best = wf16c_cold(snap_slot, snap_slot, K, 1, m, n, g.C, itop, 0, S0, pot2, best);
+        best = wf16c_cold(snap_bufs, K, 1, 0u, m, n, g.C, itop, 0, S0, pot2, best);
     __syncwarp();
     return best;
 }
