@@ -285,6 +285,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of overlap_wf16c_kernel on cfg1 (200 gaps), one launch, from the committed
+# ncu --set full capture (profiles/wf16c_r01final.ncu_summary.txt: 22.47 MB read, 9.23 MB written)
+NCU_DRAM_BYTES_PER_LAUNCH = 31.7e6
+
+
 def workload_config(args):
     return {"workload": WORKLOADS[args.config] % args.gaps +
                         ", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)",
@@ -416,7 +421,10 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tintop/s",
-                         "frac": achieved / peak_lane_ops, "traffic": None,
+                         "frac": achieved / peak_lane_ops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.config == "cfg1" and args.gaps == 200 else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the ncu --set full "
+                                         "capture summarised in profiles/wf16c_r01final.ncu_summary.txt (not measured in this run); HBM is idle, "
+                                         "the bound is the integer issue rate",
                          "kernel": kernel_fn, "kernel_ms": k_ms, "kernel_gcells": k_cells / 1e9, "ops_per_cell": OPS_PER_CELL,
                          "peak_source": "measured live (gp_int_peak): 2 lanes x VIMNMX.S16x2+VIADD.16x2 dual-issue rate; "
                                         "ALU pipe alone %.2f Tinst/s, both pipes %.2f Tinst/s" % (alu / 1e12, dual / 1e12)},
