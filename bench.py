@@ -239,7 +239,7 @@ def dropin_line(args):
         d = json.loads(p.stdout.strip().splitlines()[-1])
     except Exception as e:                                   # the bench line must not depend on it
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
-    keep = ("gaps", "gpus", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
+    keep = ("gaps", "gpus", "workers", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
             "relax_steps", "output_ms", "gaps_per_s", "gcups", "error")
     return {k: d[k] for k in keep if k in d}
 

@@ -7,7 +7,7 @@
 // libgappadder_b200.so.  Because one process per gap cannot amortise CUDA context creation, a batch
 // form runs any number of gaps through one context (and through several GPUs):
 //
-//   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--no-gml]
+//   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--streams S] [--no-gml]
 //
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
@@ -35,6 +35,7 @@ struct Cli {
     bool have_input = false;
     std::string batch;
     int gpus = 1;
+    int streams = 1;            // workers (host thread + context + stream) per GPU
     bool write_gml = true;
     bool stats = false;
 };
@@ -52,6 +53,7 @@ bool parse_args(int argc, char** argv, Cli& c)
         if (a[0] != '-') { c.input = a; c.have_input = true; ++pos; continue; }
         if (!strcmp(a, "--batch")) { if (!val) return false; c.batch = val; pos += 2; continue; }
         if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); pos += 2; continue; }
+        if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); pos += 2; continue; }
         if (!strcmp(a, "--no-gml")) { c.write_gml = false; ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; ++pos; continue; }
         switch (a[1]) {
@@ -109,8 +111,17 @@ int run_batch(const Cli& c)
             lines.push_back(b);
         }
     }
-    // balance gaps over GPUs by estimated pairwise cells (contig lengths only)
-    int n_gpus = c.gpus < 1 ? 1 : c.gpus;
+    // Balance gaps over workers by estimated pairwise cells (contig lengths only).  A worker is a host thread with
+    // its own context and stream; --streams S puts S of them on every GPU, so that one worker's host phases and the
+    // thin tail of its relax chains (a few long pairs per launch, 32 launches deep) run beside another worker's
+    // kernels.  Gaps are independent: no ordering between workers, results do not depend on the split.
+    const int n_dev = c.gpus < 1 ? 1 : c.gpus;
+    // Default 1.  Measured on cfg1 (200 gaps, one B200, several runs each): 1 worker 287-306 ms; 3 workers 237-430 ms:
+    // sometimes a quarter faster, sometimes slower, because a worker's short relax launch can queue behind another
+    // worker's persistent pairwise kernel, which holds every SM until its work queue is empty.
+    const int per_dev = c.streams >= 1 ? c.streams : 1;
+    int n_gpus = n_dev * per_dev;                                  // number of workers from here on
+    if ((size_t)n_gpus > lines.size() && !lines.empty()) n_gpus = (int)lines.size();
     std::vector<uint64_t> cost(lines.size(), 0);
     if (n_gpus > 1) {
         for (size_t g = 0; g < lines.size(); ++g) {
@@ -133,7 +144,7 @@ int run_batch(const Cli& c)
         for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(GapInput{lines[g].in}); which.push_back(g); }
         if (in.empty()) return;
         gp_ctx* ctx = nullptr;
-        int r = gp_create(dev, &ctx);
+        int r = gp_create(dev % n_dev, &ctx);
         if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
         std::vector<GapOutput> out;
         const auto w0 = std::chrono::steady_clock::now();
@@ -154,7 +165,7 @@ int run_batch(const Cli& c)
     for (int d = 0; d < n_gpus; ++d) th.emplace_back(worker, d);
     for (auto& t : th) t.join();
     for (int d = 0; d < n_gpus; ++d)
-        if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: GPU %d failed (%d): %s\n", d, rc[d], err[d].c_str()); return 3; }
+        if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: worker %d (GPU %d) failed (%d): %s\n", d, d % n_dev, rc[d], err[d].c_str()); return 3; }
     if (c.stats) {
         // one JSON line per run: cells and the slowest GPU's phase times (merge_gaps only, context creation excluded)
         uint64_t tot = 0, ptot = 0; for (uint64_t x : cells) tot += x; for (uint64_t x : pcells) ptot += x;
@@ -163,11 +174,11 @@ int run_batch(const Cli& c)
         // dp_gcells / pairwise_gcells: m*n of every Evaluate the reference runs for these gaps; closed_gcells of them
         // (a node against itself) are answered in closed form here, so computed cells = dp_gcells - closed_gcells
         uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;
-        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
+        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
                         "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
                         "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "
                         "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu}\n",
-                lines.size(), n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
+                lines.size(), n_dev, n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
                 t.relax_device_ms, t.relax_host_ms, t.relax_team_steps, (unsigned long long)t.relax_pairs,
                 (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries);
     }

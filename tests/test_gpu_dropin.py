@@ -42,13 +42,16 @@ def test_single_gap_golden(case):
     assert gml == open(os.path.join(GOLD, case + ".gml"), "rb").read()
 
 
-def test_batch_golden():
+@pytest.mark.parametrize("streams", [1, 3])
+def test_batch_golden(streams):
+    """--batch: many gaps through one process; with --streams 3 the gaps are split over three workers (host thread +
+    context + stream each) on the same GPU -- the outputs must not depend on the split."""
     with tempfile.TemporaryDirectory() as td:
         lst = os.path.join(td, "list.tsv")
         with open(lst, "w") as f:
             for c in CASES:
                 f.write("%s\t%s\t%s\n" % (os.path.join(GOLD, c + ".fa"), os.path.join(td, c + ".out"), os.path.join(td, c + ".info")))
-        p = subprocess.run([BIN] + FLAGS + ["--batch", lst], cwd=td, capture_output=True)
+        p = subprocess.run([BIN] + FLAGS + ["--batch", lst, "--streams", str(streams)], cwd=td, capture_output=True)
         assert p.returncode == 0, p.stderr
         for c in CASES:
             assert open(os.path.join(td, c + ".out"), "rb").read() == open(os.path.join(GOLD, c + ".stdout"), "rb").read(), c

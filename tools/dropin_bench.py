@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--gaps", type=int, default=200)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=1, help="workers (host thread + context + stream) per GPU")
     ap.add_argument("--ref-gaps", type=int, default=2, help="gaps also run through the reference binary (0: skip)")
     ap.add_argument("--config", default="cfg1")
     args = ap.parse_args()
@@ -37,7 +38,7 @@ def main():
                 synth_gaps.write_fasta(fa, synth_gaps.make_gap(args.seed + g, synth_gaps.CONFIGS[args.config]))
                 f.write("%s\t%s\t%s\n" % (fa, os.path.join(td, "g%d.out" % g), os.path.join(td, "g%d.info" % g)))
         t0 = time.perf_counter()
-        p = subprocess.run([binary] + FLAGS + ["-t", "5", "--batch", lst, "--gpus", str(args.gpus), "--no-gml", "--stats"],
+        p = subprocess.run([binary] + FLAGS + ["-t", "5", "--batch", lst, "--gpus", str(args.gpus), "--streams", str(args.streams), "--no-gml", "--stats"],
                            capture_output=True, text=True)
         wall = time.perf_counter() - t0
         if p.returncode != 0:
