@@ -633,15 +633,33 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
                 nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
             }
         };
+        if constexpr (!EDGE && !FILT) {
+            // the steady loop: full blocks (cnt == 32), four steps per iteration so that the loop-carried copies (ring
+            // words, increment registers) are paid once per four steps -- they run on the same pipe as the packed adds
 #pragma unroll 1
-        do {
-            const uint32_t w2 = lds32(p + 8);
-            step(w0, w1, p + OR_OFF, j);
-            const uint32_t w3 = lds32(p + 12);
-            step(w1, w2, p + OR_OFF + 4, j + 1);
-            w0 = w2; w1 = w3;
-            p += 8; j += 2;
-        } while (p != p_end);
+            do {
+                const uint32_t w2 = lds32(p + 8);
+                step(w0, w1, p + OR_OFF, j);
+                const uint32_t w3 = lds32(p + 12);
+                step(w1, w2, p + OR_OFF + 4, j + 1);
+                const uint32_t w4 = lds32(p + 16);
+                step(w2, w3, p + OR_OFF + 8, j + 2);
+                const uint32_t w5 = lds32(p + 20);
+                step(w3, w4, p + OR_OFF + 12, j + 3);
+                w0 = w4; w1 = w5;
+                p += 16; j += 4;
+            } while (p != p_end);
+        } else {
+#pragma unroll 1
+            do {
+                const uint32_t w2 = lds32(p + 8);
+                step(w0, w1, p + OR_OFF, j);
+                const uint32_t w3 = lds32(p + 12);
+                step(w1, w2, p + OR_OFF + 4, j + 1);
+                w0 = w2; w1 = w3;
+                p += 8; j += 2;
+            } while (p != p_end);
+        }
     };
     using std::true_type;
     using std::false_type;
