@@ -152,3 +152,17 @@ def test_certificate_kernel_resolves_overlaps_and_long_columns(emu):
         w = _want(x, y)
         got = [cert(x, y, fs) for fs in (0, 1, 2)]
         assert sorted(st for st, _ in got) == [0, 1, 1] and all(t == w for _, t in got)
+
+
+def test_free_moves_layout_at_its_range_edge(emu):
+    """Column sequences of exactly 3800 bases (WF16C_POT2_MAX_N) with scores that reach the top of the 15-bit range:
+    near-identical pairs (H ~ n in the last rows and columns), containment in a longer row sequence, random rows."""
+    rnd = random.Random(11)
+
+    def rs(n):
+        return bytes(rnd.choice(b"ACGT") for _ in range(n))
+    s = rs(3800)
+    t = bytearray(s)
+    t[1900] = ord("A") if t[1900] != ord("A") else ord("C")
+    for a, b in [(bytes(t), s), (rs(600) + s + rs(600), s), (s, s[:3799] + b"G"), (rs(5000), s)]:
+        assert emu(a, b) == _want(a, b)

@@ -275,3 +275,23 @@ def test_team_mode_many_long_pairs(ctx):
         assert (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained) == \
             (int(r["score"]), int(r["row_end"]), int(r["col_end"]), int(r["nclip"]), int(bool(r["flags"] & FLAG_ROW0)),
              int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED))), (a, b)
+
+
+def test_free_moves_layout_range_edge_and_fallback(ctx):
+    """The certificate kernel's free-moves layout is used when every column sequence of the launch has at most 3800
+    bases; exactly 3800 with near-identical sequences drives the values to the top of the 15-bit range.  One base more
+    and the launch takes the column-potential layout.  Results are the oracle's either way."""
+    rng = random.Random(12)
+    s = _rand(rng, 3800)
+    t = bytearray(s)
+    t[1900] = ord("A") if t[1900] != ord("A") else ord("C")
+    seqs = [bytes(t), s, _rand(rng, 600) + s + _rand(rng, 600), s[:3799] + b"G", _rand(rng, 5000)]
+    pairs = [(0, 1), (2, 1), (1, 3), (4, 1), (3, 0)]
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
+    ctx.overlap_batch(seqs, pairs)
+    assert ctx.last_layout == 1
+    seqs.append(s + b"A")                                    # 3801 bases as a column sequence
+    pairs.append((0, 5))
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
+    ctx.overlap_batch(seqs, pairs)
+    assert ctx.last_layout == 0
