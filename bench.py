@@ -286,8 +286,8 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of overlap_wf16c_kernel on cfg1 (200 gaps), one launch, from the committed
-# ncu --set full capture (profiles/wf16c_r01final.ncu_summary.txt: 22.47 MB read, 9.23 MB written)
-NCU_DRAM_BYTES_PER_LAUNCH = 31.7e6
+# ncu --set full capture (profiles/wf16c_r01final.ncu_summary.txt: 21.96 MB read, 9.42 MB written)
+NCU_DRAM_BYTES_PER_LAUNCH = 31.4e6
 
 
 def workload_config(args):

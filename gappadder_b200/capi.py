@@ -19,7 +19,7 @@ EXPORTS = [
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
-    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout",
+    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device",
 ]
 
 
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         L.gp_last_team.argtypes = [C.c_void_p]
         L.gp_set_cert_layout.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_last_layout.argtypes = [C.c_void_p]
+        L.gp_quick_check_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -295,6 +296,23 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_closed_form_stats(self._h, C.byref(a), C.byref(b)))
         return dict(pairs=a.value, cells=b.value)
+
+    def quick_check_device(self, gap_first, k: int = 10):
+        """Candidate filter on the device for the gaps [gap_first[g], gap_first[g+1]) of the current sequence table.
+        -> list of PAIR_DTYPE arrays (node indices local to the gap), in gp_candidate_pairs' order."""
+        gf = np.ascontiguousarray(np.asarray(gap_first, dtype=np.uint32))
+        n = (gf[1:] - gf[:-1]).astype(np.int64)
+        hit = np.zeros(int((n * n).sum()), dtype=np.uint8)
+        self._check(self._L.gp_quick_check_device(self._h, gf.ctypes.data, len(gf) - 1, k, hit.ctypes.data, hit.nbytes))
+        out, pos = [], 0
+        for ng in n:
+            m = hit[pos:pos + ng * ng].reshape(ng, ng)
+            pos += ng * ng
+            i, j = np.nonzero(m)                       # row-major: i ascending, then j
+            p = np.zeros(len(i), dtype=PAIR_DTYPE)
+            p["row_seq"], p["col_seq"] = i, j
+            out.append(p)
+        return out
 
     def set_cert_layout(self, mode: int):
         """Certificate kernel: 0 free-moves layout whenever a launch allows it (default), 1 always the column potential."""

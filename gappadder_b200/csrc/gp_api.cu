@@ -7,6 +7,7 @@
 #include "overlap_wf16.cuh"
 #include "overlap_wf16t.cuh"
 #include "overlap_wf16c.cuh"
+#include "quick_check.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -69,6 +70,7 @@ struct gp_ctx {
     uint32_t kernel_mask = GP_KERNEL_ALL;
 
     // pair work lists
+    DeviceBuf d_qc_meta, d_qc_hit;             // quick check on the device: offsets/lengths/gap bounds, hit matrices
     DeviceBuf d_pairs, d_order16c, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t, d_scratch16c;
     HostBuf h_stage, h_pack, h_results, h_queue;   // h_queue: [0,32) initial d_queue image, [32,64) counters read back
     std::vector<uint32_t> pack_off;
@@ -154,7 +156,7 @@ void gp_destroy(gp_ctx* c)
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
     c->d_scratch16t.release(); c->d_scratch16c.release(); c->d_order16c.release(); c->h_queue.release();
     c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
-    c->h_stage.release(); c->h_pack.release(); c->h_results.release();
+    c->h_stage.release(); c->h_pack.release(); c->h_results.release(); c->d_qc_meta.release(); c->d_qc_hit.release();
     delete c;
 }
 
@@ -231,6 +233,46 @@ int gp_set_team_mode(gp_ctx* c, uint32_t mode)
 }
 
 int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
+
+int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes)
+{
+    if (!c) return GP_ERR_INVALID;
+    if ((!gap_first || !hit) && n_gaps) return c->fail(GP_ERR_INVALID, "null gap bounds / hit buffer");
+    if (k <= 0 || k > gp::QC_MAX_K) return c->fail(GP_ERR_RANGE, "quick check on the device supports k <= %d", gp::QC_MAX_K);
+    if (n_gaps == 0) return GP_OK;
+    const uint32_t n_seq = (uint32_t)c->seq_len.size();
+    std::vector<uint64_t> hit_off(n_gaps + 1, 0);
+    for (uint32_t g = 0; g < n_gaps; ++g) {
+        if (gap_first[g + 1] < gap_first[g] || gap_first[g + 1] > n_seq) return c->fail(GP_ERR_INVALID, "gap %u: bad sequence range", g);
+        const uint64_t n = gap_first[g + 1] - gap_first[g];
+        if (n > (uint64_t)gp::QC_MAX_NODES) return c->fail(GP_ERR_RANGE, "gap %u has %llu nodes (device quick check: <= %d)", g, (unsigned long long)n, gp::QC_MAX_NODES);
+        hit_off[g + 1] = hit_off[g] + n * n;
+    }
+    const uint64_t total = hit_off[n_gaps];
+    if (total > hit_bytes) return c->fail(GP_ERR_INVALID, "hit buffer too small: %llu bytes needed", (unsigned long long)total);
+    GP_CUDA(c, cudaSetDevice(c->device));
+    // meta: [seq_off n_seq][seq_len n_seq][gap_first n_gaps+1][pad][hit_off (n_gaps+1) x u64]
+    const size_t w32 = (size_t)2 * n_seq + n_gaps + 1, w32p = (w32 + 1) & ~(size_t)1;
+    const size_t meta_bytes = w32p * 4 + (size_t)(n_gaps + 1) * 8;
+    GP_CUDA(c, c->d_qc_meta.reserve(meta_bytes));
+    GP_CUDA(c, c->d_qc_hit.reserve(total ? total : 16));
+    uint32_t* dm = (uint32_t*)c->d_qc_meta.p;
+    GP_CUDA(c, cudaMemcpyAsync(dm, c->seq_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(dm + n_seq, c->seq_len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(dm + 2 * (size_t)n_seq, gap_first, (size_t)(n_gaps + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(dm + w32p, hit_off.data(), (size_t)(n_gaps + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    const size_t smem = gp::qc_smem_bytes(k);
+    GP_CUDA(c, cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)std::min<uint32_t>(n_gaps, (uint32_t)c->sm_count);
+    gp::quick_check_kernel<<<blocks, gp::QC_THREADS, smem, c->stream>>>(
+        (const uint32_t*)c->d_packed.p, dm, dm + n_seq, dm + 2 * (size_t)n_seq, (const uint64_t*)(dm + w32p), n_gaps, (int)k,
+        gp::qc_max_probes(k), (uint8_t*)c->d_qc_hit.p);
+    GP_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    if (total) GP_CUDA(c, cudaMemcpyAsync(hit, c->d_qc_hit.p, total, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));       // hit_off (host vector) and the caller's buffers are free again
+    return GP_OK;
+}
 
 int gp_set_cert_layout(gp_ctx* c, uint32_t mode)
 {

@@ -185,6 +185,14 @@ int gp_last_team(const gp_ctx *ctx);
  * scores (mismatch -2, indel -2) and every column sequence of the launch <= 3800 bases.  mode 0: the library uses
  * the free-moves layout whenever a launch allows it (default); 1: always the column-potential layout.  Results
  * never depend on it.  gp_last_layout: 1 if the last launch used the free-moves layout. */
+/* The candidate filter on the device (quick check, ContigsCompactor.cpp:992-1100, :1982-2095; the host form is
+ * gp_candidate_pairs).  Works on the context's current sequence table (gp_set_sequences): gap g owns the sequences
+ * gap_first[g] .. gap_first[g+1]-1 (its graph nodes in order; n_g of them).  hit receives, gap after gap, n_g * n_g
+ * bytes: hit[i * n_g + j] = 1 iff pair (i, j), j >= i, is a candidate (entries with j < i are 0).  Enumerating the
+ * 1s row by row gives gp_candidate_pairs' list for upper-case input (bytes other than A C G T count as A in k-mers,
+ * as in the reference).  k <= 10 (GAPPadder uses 10), at most 256 nodes per gap; GP_ERR_RANGE otherwise -- the
+ * host function has no such limits.  Returns 0 or a negative error. */
+int gp_quick_check_device(gp_ctx *ctx, const uint32_t *gap_first, uint32_t n_gaps, int32_t k, uint8_t *hit, uint64_t hit_bytes);
 int gp_set_cert_layout(gp_ctx *ctx, uint32_t mode);
 int gp_last_layout(const gp_ctx *ctx);
 /* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).

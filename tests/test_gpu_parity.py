@@ -295,3 +295,27 @@ def test_free_moves_layout_range_edge_and_fallback(ctx):
     _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
     ctx.overlap_batch(seqs, pairs)
     assert ctx.last_layout == 0
+
+
+@pytest.mark.parametrize("config,n_gaps", [("cfg1", 6), ("cfg3", 8), ("noisy", 12), ("tiny", 5)])
+def test_quick_check_on_the_device_equals_the_host_filter(ctx, config, n_gaps):
+    """gp_quick_check_device on the packed table vs gp_candidate_pairs on the ASCII nodes (itself pinned to the
+    reference's candidate lists in tests/test_oracle_golden.py), gap by gap: same pairs in the same order.  `noisy`
+    has N bases (k-mer letter A), `tiny` has nodes around the 30-base window."""
+    seqs, gap_first, want = [], [0], []
+    for gi in range(n_gaps):
+        nodes = []
+        for _, s in synth_gaps.make_gap(100 + gi, synth_gaps.CONFIGS[config]):
+            nodes.append(s)
+            nodes.append(g.revcomp(s))
+        if gi == 1:
+            nodes += [b"ACGTACGTAC", b"ACGTACGTACG" * 2, b"ACG", b""]        # shorter than the window / than k / empty
+        seqs += nodes
+        gap_first.append(len(seqs))
+        want.append(g.candidate_pairs(nodes, 10))
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    ctx.set_sequences(packed, off, lens, nsym)
+    got = ctx.quick_check_device(gap_first, 10)
+    assert len(got) == n_gaps
+    for gi in range(n_gaps):
+        assert np.array_equal(got[gi]["row_seq"], want[gi]["row_seq"]) and np.array_equal(got[gi]["col_seq"], want[gi]["col_seq"]), (config, gi)
