@@ -54,6 +54,7 @@ bool parse_args(int argc, char** argv, Cli& c)
         if (!strcmp(a, "--batch")) { if (!val) return false; c.batch = val; pos += 2; continue; }
         if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); pos += 2; continue; }
         if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); pos += 2; continue; }
+        if (!strcmp(a, "--host-quick-check")) { c.opt.host_quick_check = true; pos += 1; continue; }
         if (!strcmp(a, "--no-gml")) { c.write_gml = false; ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; ++pos; continue; }
         switch (a[1]) {

@@ -30,6 +30,7 @@ struct GapState {
     uint64_t pair_begin = 0, pair_end = 0;           // slice of the batch pair list
     bool dead = false;                               // fatal input error, nothing more to do
     bool arranged = false;                           // candidate pairs were generated
+    bool want_pairs = false;                         // ... by the quick check on the device (after the parallel phase)
     std::vector<gp_pair> cand;                       // ... with node indices local to the gap
     int cand_rc = 0;
     std::vector<std::vector<int>> paths;             // after RemoveDupRevCompPaths
@@ -103,6 +104,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     }
     dp.indel = (int)opt.score_indel;
     const bool scan_runs = opt.max_overlap_clip_len >= 0;        // `for (c = 0; c <= maxOverlapClipLen; ...)` (:1679)
+    // the quick check runs on the device when the library's device form covers the k-mer length (k <= 10)
+    const bool device_qc = !opt.host_quick_check && opt.quick_kmer_len >= 1 && opt.quick_kmer_len <= 10;
     dp.max_clip = scan_runs ? (int)std::floor(opt.max_overlap_clip_len) : 0;
     gp_thresholds thr{opt.max_frac_score_loss, opt.min_frac_overlap, opt.min_overlap_len, opt.min_overlap_len_with_scaffold};
     const int max_per_root = opt.max_count_contig_in_path > 0 ? opt.max_count_contig_in_path : 20;   // :33-34,:168
@@ -150,6 +153,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         }
         s.arranged = true;
         if (!scan_runs) return;        // no scan => every Evaluate is rejected (:1674-1722): no edges
+        if (device_qc) { s.want_pairs = true; return; }                  // quick check on the device, below
         std::vector<const char*> nodes;
         std::vector<uint32_t> lens;
         for (const std::string& q : s.node_seq) { nodes.push_back(q.data()); lens.push_back((uint32_t)q.size()); }
@@ -160,23 +164,94 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         s.cand.resize((size_t)np);
     });
     // serial: one sequence table and one pair list for the batch (node_seq vectors no longer grow)
+    std::vector<uint32_t> gap_first;                 // device quick check: node range of every live gap, in table order
+    std::vector<size_t> gap_of;
+    bool device_qc_ok = device_qc;
     for (size_t g = 0; g < G; ++g) {
         GapState& s = st[g];
         if (s.dead) continue;
         if (s.cand_rc != 0) { error = "gp_candidate_pairs failed"; return s.cand_rc; }
         s.node_base = (uint32_t)seq_ptr.size();
         for (const std::string& q : s.node_seq) { seq_ptr.push_back(q.data()); seq_len.push_back((uint32_t)q.size()); }
+        gap_first.push_back(s.node_base);
+        gap_of.push_back(g);
+        if (s.node_seq.size() > 256) device_qc_ok = false;               // gp_quick_check_device's limit
         s.pair_begin = pairs.size();
         for (const gp_pair& c : s.cand) pairs.push_back(gp_pair{c.row_seq + s.node_base, c.col_seq + s.node_base});
         s.pair_end = pairs.size();
         std::vector<gp_pair>().swap(s.cand);
+    }
+    gap_first.push_back((uint32_t)seq_ptr.size());
+
+    // Quick check on the device: the nodes go to HBM first (they are needed there for the DP anyway), the filter
+    // runs on the packed table (gp_quick_check_device), the pair list is read off the hit matrices in the host
+    // filter's order (row by row, j >= i).  Gaps with more than 256 nodes send the batch through the host filter.
+    bool table_resident = false;
+    if (device_qc) {
+        bool any = false;
+        for (size_t g = 0; g < G; ++g) any = any || st[g].want_pairs;
+        if (any && device_qc_ok) {
+            const uint32_t n_seq = (uint32_t)seq_ptr.size();
+            const size_t bytes = gp_packed_size(seq_len.data(), n_seq);
+            std::vector<uint32_t> packed(bytes / sizeof(uint32_t) + 4), off(n_seq);
+            uint32_t nsym = 0;
+            int rc = gp_pack_sequences(seq_ptr.data(), seq_len.data(), n_seq, packed.data(), off.data(), &nsym);
+            if (rc == GP_OK) rc = gp_set_sequences(ctx, packed.data(), bytes, off.data(), seq_len.data(), n_seq, nsym);
+            if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+            table_resident = true;
+            std::vector<uint64_t> hoff(gap_of.size() + 1, 0);
+            for (size_t q = 0; q < gap_of.size(); ++q) { const uint64_t n = gap_first[q + 1] - gap_first[q]; hoff[q + 1] = hoff[q] + n * n; }
+            std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
+            rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)gap_of.size(), opt.quick_kmer_len, hit.data(), hit.size());
+            if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+            for (size_t q = 0; q < gap_of.size(); ++q) {
+                GapState& s = st[gap_of[q]];
+                s.pair_begin = pairs.size();
+                if (s.want_pairs) {
+                    const uint32_t n = gap_first[q + 1] - gap_first[q];
+                    const uint8_t* h = hit.data() + hoff[q];
+                    for (uint32_t i = 0; i < n; ++i)
+                        for (uint32_t j = i; j < n; ++j)
+                            if (h[(size_t)i * n + j]) pairs.push_back(gp_pair{i + s.node_base, j + s.node_base});
+                }
+                s.pair_end = pairs.size();
+            }
+        } else if (any) {                                                 // host filter after all
+            for_each_gap(G, host_threads, [&](size_t g) {
+                GapState& s = st[g];
+                if (!s.want_pairs) return;
+                std::vector<const char*> nodes;
+                std::vector<uint32_t> lens;
+                for (const std::string& q : s.node_seq) { nodes.push_back(q.data()); lens.push_back((uint32_t)q.size()); }
+                const uint64_t N = nodes.size(), cap = N * (N + 1) / 2;
+                s.cand.resize(cap);
+                const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), (uint32_t)N, opt.quick_kmer_len, s.cand.data(), cap);
+                if (np < 0) { s.cand_rc = (int)np; s.cand.clear(); return; }
+                s.cand.resize((size_t)np);
+            });
+            for (size_t g = 0; g < G; ++g) {
+                GapState& s = st[g];
+                if (s.cand_rc != 0) { error = "gp_candidate_pairs failed"; return s.cand_rc; }
+                s.pair_begin = pairs.size();
+                for (const gp_pair& c : s.cand) pairs.push_back(gp_pair{c.row_seq + s.node_base, c.col_seq + s.node_base});
+                s.pair_end = pairs.size();
+                std::vector<gp_pair>().swap(s.cand);
+            }
+        }
     }
 
     lap(&MergeTimings::read_ms);
     // ---- pairwise phase: one batch for all gaps (replaces runMultiThreadMergeV2, :696-721) ------
     std::vector<gp_result> res(pairs.size());
     if (!pairs.empty()) {
-        int rc = gp_overlap_batch(ctx, seq_ptr.data(), seq_len.data(), (uint32_t)seq_ptr.size(), pairs.data(), pairs.size(), &dp, res.data());
+        int rc;
+        if (table_resident) {                                            // the table is in HBM already: pairs up, kernels, results down
+            rc = gp_upload_pairs(ctx, pairs.data(), pairs.size(), &dp);
+            if (rc == GP_OK) rc = gp_launch_resident(ctx);
+            if (rc == GP_OK) rc = gp_fetch_results(ctx, res.data(), pairs.size());
+        } else {
+            rc = gp_overlap_batch(ctx, seq_ptr.data(), seq_len.data(), (uint32_t)seq_ptr.size(), pairs.data(), pairs.size(), &dp, res.data());
+        }
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
         if (timings) {
             uint64_t cp = 0, cc = 0;

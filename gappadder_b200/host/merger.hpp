@@ -28,6 +28,7 @@ struct MergeOptions {
     int max_contig_path_len = -1;            // -p1 (unused by CompactVer3)
     int max_count_contig_in_path = -1;       // -p2 (default MAX_CONTIG_IN_PATH_COUNT = 20)
     bool verbose = false;                    // -V  (accepted, ignored: it pollutes stdout in the reference)
+    bool host_quick_check = false;           // --host-quick-check (not a reference flag): candidate filter on the host
 };
 
 struct GapInput {

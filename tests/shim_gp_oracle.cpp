@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "gappadder_b200.h"
 
@@ -16,7 +17,12 @@ typedef struct { int32_t score, row_end, col_end, nclip, tb_row, tb_col, bcontai
 int gpo_evaluate(const char* s1, int m, const char* s2, int n, int mismatch, int indel, int maxclip, gpo_dp_result* r);
 }
 
-struct gp_ctx { std::string err; };
+struct gp_ctx {
+    std::string err;
+    std::vector<std::string> seqs;        // the table of gp_set_sequences, unpacked again
+    std::vector<gp_pair> pairs;           // gp_upload_pairs
+    gp_dp_params params{};
+};
 
 extern "C" {
 int gp_create(int, gp_ctx** out) { *out = new gp_ctx(); return GP_OK; }
@@ -33,6 +39,45 @@ int gp_overlap_batch(gp_ctx*, const char* const* seqs, const uint32_t* seq_len, 
         out[k].flags = (r.tb_row == 0 ? GP_FLAG_ROW0 : 0u) | (r.tb_col == 0 ? GP_FLAG_COL0 : 0u) | (r.bcontained ? GP_FLAG_CONTAINED : 0u);
     }
     return GP_OK;
+}
+// The resident-table path of the drop-in (table up, quick check on the device, pairs up, launch, fetch), served from
+// the same oracle: the packed codes are turned back into letters (A C G T N, then B D E F ... for any other byte:
+// equal codes <-> equal bytes, and none of the others is a k-mer letter), the device filter is the host filter.
+int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t, const uint32_t* off, const uint32_t* len, uint32_t n, uint32_t)
+{
+    static const char letters[] = "ACGTNBDEFHIJKLMO";
+    c->seqs.assign(n, std::string());
+    for (uint32_t s = 0; s < n; ++s) {
+        c->seqs[s].resize(len[s]);
+        for (uint32_t i = 0; i < len[s]; ++i) c->seqs[s][i] = letters[(packed[off[s] + (i >> 3)] >> ((i & 7u) * 4u)) & 15u];
+    }
+    return GP_OK;
+}
+int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes)
+{
+    uint64_t pos = 0;
+    for (uint32_t g = 0; g < n_gaps; ++g) {
+        const uint32_t first = gap_first[g], n = gap_first[g + 1] - first;
+        if (pos + (uint64_t)n * n > hit_bytes) return GP_ERR_INVALID;
+        std::vector<const char*> nodes; std::vector<uint32_t> lens;
+        for (uint32_t i = 0; i < n; ++i) { nodes.push_back(c->seqs[first + i].data()); lens.push_back((uint32_t)c->seqs[first + i].size()); }
+        std::vector<gp_pair> cand((size_t)n * (n + 1) / 2 + 1);
+        const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), n, k, cand.data(), cand.size());
+        if (np < 0) return (int)np;
+        memset(hit + pos, 0, (size_t)n * n);
+        for (int64_t q = 0; q < np; ++q) hit[pos + (uint64_t)cand[q].row_seq * n + cand[q].col_seq] = 1;
+        pos += (uint64_t)n * n;
+    }
+    return GP_OK;
+}
+int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n, const gp_dp_params* p) { c->pairs.assign(pairs, pairs + n); c->params = *p; return GP_OK; }
+int gp_launch_resident(gp_ctx*) { return GP_OK; }
+int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n)
+{
+    if (n != c->pairs.size()) return GP_ERR_INVALID;
+    std::vector<const char*> ptr; std::vector<uint32_t> len;
+    for (const std::string& s : c->seqs) { ptr.push_back(s.data()); len.push_back((uint32_t)s.size()); }
+    return gp_overlap_batch(c, ptr.data(), len.data(), (uint32_t)ptr.size(), c->pairs.data(), n, &c->params, out);
 }
 // statistics the merger reads after a batch: nothing to report from the CPU shim
 int gp_closed_form_stats(const gp_ctx*, uint64_t* pairs, uint64_t* cells) { if (pairs) *pairs = 0; if (cells) *cells = 0; return GP_OK; }
