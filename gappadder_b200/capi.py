@@ -19,7 +19,7 @@ EXPORTS = [
     "gp_overlap_size", "gp_candidate_pairs", "gp_revcomp", "gp_int_peak",
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
-    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device",
+    "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device", "gp_upload_sequences",
 ]
 
 

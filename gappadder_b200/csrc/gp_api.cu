@@ -30,7 +30,8 @@ struct DeviceBuf {
     {
         if (bytes <= cap) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = 2 * bytes + 4096;       // doubling: a relax chain's batches grow a little every step, and a
+                                              // (pinned) reallocation costs about a millisecond
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -45,7 +46,8 @@ struct HostBuf {   // pinned staging
     {
         if (bytes <= cap) return cudaSuccess;
         if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 4 + 256;
+        size_t want = 2 * bytes + 4096;       // doubling: a relax chain's batches grow a little every step, and a
+                                              // (pinned) reallocation costs about a millisecond
         cudaError_t e = cudaMallocHost(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;
@@ -320,6 +322,23 @@ int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t packed_bytes, con
     int rc = set_sequences_async(c, packed, packed_bytes, seq_word_off, seq_len, n_seq, n_symbols);
     if (rc != GP_OK) return rc;
     GP_CUDA(c, cudaStreamSynchronize(c->stream));   // caller may reuse `packed` after return
+    return GP_OK;
+}
+
+int gp_upload_sequences(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len, uint32_t n_seq)
+{
+    if (!c) return GP_ERR_INVALID;
+    if ((!seqs || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequences");
+    const size_t bytes = gp_packed_size(seq_len, n_seq);
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, c->h_pack.reserve(bytes ? bytes : 16));
+    c->pack_off.resize(n_seq);
+    uint32_t nsym = 0;
+    int rc = gp_pack_sequences(seqs, seq_len, n_seq, (uint32_t*)c->h_pack.p, c->pack_off.data(), &nsym);
+    if (rc != GP_OK) return c->fail(rc, rc == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed");
+    rc = set_sequences_async(c, (const uint32_t*)c->h_pack.p, bytes, c->pack_off.data(), seq_len, n_seq, nsym);
+    if (rc != GP_OK) return rc;
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
     return GP_OK;
 }
 

@@ -175,13 +175,16 @@ int run_batch(const Cli& c)
         // dp_gcells / pairwise_gcells: m*n of every Evaluate the reference runs for these gaps; closed_gcells of them
         // (a node against itself) are answered in closed form here, so computed cells = dp_gcells - closed_gcells
         uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;
+        uint64_t shared_pairs = 0, shared_cells = 0;      // relax steps shared between chains with a common path prefix: not computed twice
+        for (const MergeTimings& x : tim) { shared_pairs += x.relax_shared_pairs; shared_cells += x.relax_shared_cells; }
         fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
                         "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
                         "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "
-                        "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu}\n",
+                        "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu, \"relax_shared_pairs\": %llu, \"relax_shared_gcells\": %.6f, \"relax_call_ms\": %.3f, \"relax_pack_ms\": %.3f}\n",
                 lines.size(), n_dev, n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
                 t.relax_device_ms, t.relax_host_ms, t.relax_team_steps, (unsigned long long)t.relax_pairs,
-                (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries);
+                (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries,
+                (unsigned long long)shared_pairs, shared_cells / 1e9, t.relax_call_ms, t.relax_pack_ms);
     }
     return 0;
 }

@@ -192,11 +192,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         for (size_t g = 0; g < G; ++g) any = any || st[g].want_pairs;
         if (any && device_qc_ok) {
             const uint32_t n_seq = (uint32_t)seq_ptr.size();
-            const size_t bytes = gp_packed_size(seq_len.data(), n_seq);
-            std::vector<uint32_t> packed(bytes / sizeof(uint32_t) + 4), off(n_seq);
-            uint32_t nsym = 0;
-            int rc = gp_pack_sequences(seq_ptr.data(), seq_len.data(), n_seq, packed.data(), off.data(), &nsym);
-            if (rc == GP_OK) rc = gp_set_sequences(ctx, packed.data(), bytes, off.data(), seq_len.data(), n_seq, nsym);
+            int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
             if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
             table_resident = true;
             std::vector<uint64_t> hoff(gap_of.size() + 1, 0);
@@ -304,9 +300,22 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         std::vector<const char*> sp;
         std::vector<uint32_t> sl;
         std::vector<gp_pair> pp;
-        for (size_t c : active) {
-            const Chain& ch = chains[c];
+        // Chains of one gap whose paths share the prefix path[0..next] hold the same merged string and meet the same
+        // node: one Evaluate serves them all (the reference runs it once per path, :1463-1513, with the same result).
+        std::vector<size_t> rep(active.size());                           // active chain -> index into pp
+        std::map<std::pair<size_t, std::vector<int>>, size_t> seen;
+        for (size_t a = 0; a < active.size(); ++a) {
+            const Chain& ch = chains[active[a]];
             const std::string& nodeseq = st[ch.gap].node_seq[ch.path[ch.next]];
+            std::pair<size_t, std::vector<int>> key(ch.gap, std::vector<int>(ch.path.begin(), ch.path.begin() + ch.next + 1));
+            auto it = seen.find(key);
+            if (it != seen.end()) {
+                rep[a] = it->second;
+                if (timings) { ++timings->relax_shared_pairs; timings->relax_shared_cells += (uint64_t)ch.merged.size() * nodeseq.size(); }
+                continue;
+            }
+            rep[a] = pp.size();
+            seen.emplace(std::move(key), pp.size());
             pp.push_back(gp_pair{(uint32_t)sp.size(), (uint32_t)sp.size() + 1});
             sp.push_back(ch.merged.data()); sl.push_back((uint32_t)ch.merged.size());
             sp.push_back(nodeseq.data()); sl.push_back((uint32_t)nodeseq.size());
@@ -322,6 +331,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             double tm[GP_TIMING_SLOTS] = {0};
             gp_last_timing(ctx, tm, GP_TIMING_SLOTS);
             timings->relax_device_ms += tm[2];
+            timings->relax_call_ms += tm[3];
+            timings->relax_pack_ms += tm[0] + tm[1];
         }
         for (size_t a = 0; a < active.size(); ++a) {
             Chain& ch = chains[active[a]];
@@ -330,7 +341,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             out[ch.gap].n_relax += 1;
             std::string m(ch.merged.size() + nodeseq.size() + 1, '\0');
             const int32_t len = gp_merged_concat(ch.merged.data(), (int32_t)ch.merged.size(), nodeseq.data(),
-                                                 (int32_t)nodeseq.size(), &rr[a], &m[0]);   // ccAct.GetMerged() (:1512)
+                                                 (int32_t)nodeseq.size(), &rr[rep[a]], &m[0]);   // ccAct.GetMerged() (:1512)
             m.resize((size_t)len);
             ch.merged.swap(m);
             ++ch.next;

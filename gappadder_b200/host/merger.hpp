@@ -57,6 +57,8 @@ struct MergeTimings {
     uint32_t relax_team_steps = 0;     // relax steps the library ran one CTA per pair (gp_last_team)
     uint64_t relax_pairs = 0, relax_second_passes = 0, relax_exact_retries = 0;   // certificate kernel, relax chain
     uint64_t closed_pairs = 0, closed_cells = 0;   // pairwise phase: node-vs-itself pairs answered in closed form
+    double relax_call_ms = 0, relax_pack_ms = 0;   // relax chain: inside gp_overlap_batch in total / its packing+classification part
+    uint64_t relax_shared_pairs = 0, relax_shared_cells = 0;   // relax steps answered by another chain of the gap with the same path prefix
     double relax_device_ms = 0;        // of relax_ms: inside gp_overlap_batch from first launch to results on the host
     double relax_host_ms = 0;          // of relax_ms: building the step's batch and the merged strings
 };

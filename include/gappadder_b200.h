@@ -125,6 +125,11 @@ int gp_set_sequences(gp_ctx *ctx, const uint32_t *packed, size_t packed_bytes,
                      const uint32_t *seq_word_off, const uint32_t *seq_len, uint32_t n_seq,
                      uint32_t n_symbols);
 
+/* The same from ASCII sequences: packs them into the context's own pinned staging buffer (kept and reused by
+ * gp_overlap_batch, so that later, smaller batches -- the relax chain -- never allocate pinned memory again) and
+ * uploads the table.  Returns when the table is in HBM. */
+int gp_upload_sequences(gp_ctx *ctx, const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq);
+
 /* Runs Evaluate's DP + scan + walk-end for every pair against the uploaded table and copies the
  * results to `out` (n_pairs entries, host memory).  Blocking. */
 int gp_overlap_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs,

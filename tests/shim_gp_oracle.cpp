@@ -53,6 +53,12 @@ int gp_set_sequences(gp_ctx* c, const uint32_t* packed, size_t, const uint32_t* 
     }
     return GP_OK;
 }
+int gp_upload_sequences(gp_ctx* c, const char* const* seqs, const uint32_t* len, uint32_t n)
+{
+    c->seqs.assign(n, std::string());
+    for (uint32_t s = 0; s < n; ++s) c->seqs[s].assign(seqs[s], len[s]);
+    return GP_OK;
+}
 int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes)
 {
     uint64_t pos = 0;

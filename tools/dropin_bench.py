@@ -47,7 +47,8 @@ def main():
         stats = json.loads(p.stderr.strip().splitlines()[-1])
         line = {"impl": "b200", "config": args.config, "process_wall_s": wall, **stats,
                 "gaps_per_s": args.gaps / (stats["merge_ms"] * 1e-3),
-                "gcups": (stats["dp_gcells"] - stats.get("closed_gcells", 0.0)) / (stats["merge_ms"] * 1e-3)}
+                # cells actually computed: not the closed-form pairs, not the relax steps shared between chains
+                "gcups": (stats["dp_gcells"] - stats.get("closed_gcells", 0.0) - stats.get("relax_shared_gcells", 0.0)) / (stats["merge_ms"] * 1e-3)}
         if args.ref_gaps and os.path.exists(ref):
             t_ref, same = 0.0, True
             for g in range(min(args.ref_gaps, args.gaps)):
