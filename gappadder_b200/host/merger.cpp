@@ -334,18 +334,21 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             timings->relax_call_ms += tm[3];
             timings->relax_pack_ms += tm[0] + tm[1];
         }
-        for (size_t a = 0; a < active.size(); ++a) {
+        for (size_t a = 0; a < active.size(); ++a) {                       // per-gap counters: serial
+            const Chain& ch = chains[active[a]];
+            out[ch.gap].relax_cells += (uint64_t)ch.merged.size() * st[ch.gap].node_seq[ch.path[ch.next]].size();
+            out[ch.gap].n_relax += 1;
+        }
+        for_each_gap(active.size(), active.size() >= 64 ? host_threads : 1, [&](size_t a) {   // the merged strings: host threads
             Chain& ch = chains[active[a]];
             const std::string& nodeseq = st[ch.gap].node_seq[ch.path[ch.next]];
-            out[ch.gap].relax_cells += (uint64_t)ch.merged.size() * nodeseq.size();
-            out[ch.gap].n_relax += 1;
             std::string m(ch.merged.size() + nodeseq.size() + 1, '\0');
             const int32_t len = gp_merged_concat(ch.merged.data(), (int32_t)ch.merged.size(), nodeseq.data(),
                                                  (int32_t)nodeseq.size(), &rr[rep[a]], &m[0]);   // ccAct.GetMerged() (:1512)
             m.resize((size_t)len);
             ch.merged.swap(m);
             ++ch.next;
-        }
+        });
     }
     for (Chain& ch : chains) st[ch.gap].merged.push_back(std::move(ch.merged));
     lap(&MergeTimings::relax_ms);
