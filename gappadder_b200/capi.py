@@ -323,7 +323,8 @@ class Context:
         return int(self._L.gp_last_layout(self._h))
 
     def set_team_mode(self, mode: int):
-        """Certificate kernel: 0 library chooses per launch (default), 1 one warp per pair, 2 one CTA per pair."""
+        """Certificate kernel: 0 library chooses per launch (default), 1 one warp per pair, 2 one CTA of four warps per pair,
+        3 one CTA of eight warps per pair."""
         self._check(self._L.gp_set_team_mode(self._h, mode))
 
     @property

@@ -229,7 +229,7 @@ int gp_set_cert_system(gp_ctx* c, uint32_t system)
 
 int gp_set_team_mode(gp_ctx* c, uint32_t mode)
 {
-    if (!c || mode > 2) return GP_ERR_INVALID;
+    if (!c || mode > 3) return GP_ERR_INVALID;
     c->team_mode = mode;
     return GP_OK;
 }
@@ -482,15 +482,17 @@ int gp_launch_resident(gp_ctx* c)
     // max(largest pair, total / W) warp-seconds of DP in warp mode; a team runs a pair's strips concurrently
     // (about 3.4x faster per pair at 4 warps, 15 % less aggregate throughput).  Few long pairs -- the relax
     // chain's batches -- are bound by the largest pair and take the team kernel.
-    bool team = c->team_mode == 2;
+    // Eight warps per pair (one CTA per SM) go further the same way: about 6x per pair, 57 % of the aggregate.
+    int team = c->team_mode == 2 ? gp::WF16C_TEAM : c->team_mode == 3 ? gp::WF16C_TEAM_BIG : 0;
     if (cert && c->team_mode == 0) {
         const double W = (double)c->sm_count * gp::WF16C_CTAS_PER_SM * gp::WF16C_TEAM;
         const double total = (double)c->cells16c, big = (double)c->max_cells16c;
         const double warp_t = std::max(big, total / W);
         const double team_t = std::max(big / 3.4, total / (0.85 * W));
-        team = team_t < warp_t;
+        const double big_t = std::max(big / 6.0, total / (0.57 * W));
+        team = warp_t <= team_t && warp_t <= big_t ? 0 : team_t <= big_t ? gp::WF16C_TEAM : gp::WF16C_TEAM_BIG;
     }
-    c->last_team = cert && team;
+    c->last_team = cert && team != 0;
     c->p16c.pot2 = (cert && c->cert_layout == 0 && c->p16c.std_scores && c->max_n16c <= gp::WF16C_POT2_MAX_N) ? 1 : 0;
     c->last_pot2 = c->p16c.pot2 != 0;
     GP_CUDA(c, cudaEventRecord(c->kev[0], c->stream));

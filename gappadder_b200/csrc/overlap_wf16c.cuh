@@ -787,8 +787,9 @@ __device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__
 // retry16t / retry32: work lists of the exact kernels behind this one (pairs with n <= WF16T_MAX_N go to
 // the table kernel); *retry16t_n / *retry32_n are their fill counts (the host may have pre-filled them).
 // TEAM = 1: one warp per pair.  TEAM = warps per CTA: one CTA per pair (few, long pairs: the relax chain).
+// TEAM = 1: one warp per pair, 4-warp CTAs.  TEAM = 4 / 8: one CTA of TEAM warps per pair (8 warps: one CTA per SM).
 template <bool STD, int TEAM, bool POT2>
-__global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
+__global__ void __launch_bounds__(TEAM > 4 ? 32 * TEAM : WF16C_THREADS, TEAM > 4 ? 1 : WF16C_CTAS_PER_SM)
 overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs,
                      const uint32_t* __restrict__ order, uint32_t n_work, unsigned int* __restrict__ queue,
                      Wf16cParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride,
@@ -854,11 +855,14 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
 }
 
 constexpr int WF16C_TEAM = WF16C_THREADS / 32;
+constexpr int WF16C_TEAM_BIG = 8;                  // the few, long pairs of a late relax step: 8 warps per pair, one CTA per SM
+
+template <int TEAM> constexpr size_t wf16c_smem_bytes() { return (size_t)(TEAM > 4 ? TEAM : WF16C_THREADS / 32) * WF16C_WARP_WORDS * sizeof(uint32_t); }
 
 template <bool STD, int TEAM, bool POT2>
 inline cudaError_t wf16c_configure_one()
 {
-    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM, POT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WF16C_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM, POT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf16c_smem_bytes<TEAM>());
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(overlap_wf16c_kernel<STD, TEAM, POT2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
@@ -871,19 +875,26 @@ inline cudaError_t wf16c_configure()
     if ((e = wf16c_configure_one<true, WF16C_TEAM, false>()) != cudaSuccess) return e;
     if ((e = wf16c_configure_one<false, WF16C_TEAM, false>()) != cudaSuccess) return e;
     if ((e = wf16c_configure_one<true, 1, true>()) != cudaSuccess) return e;
-    return wf16c_configure_one<true, WF16C_TEAM, true>();
+    if ((e = wf16c_configure_one<true, WF16C_TEAM, true>()) != cudaSuccess) return e;
+    if ((e = wf16c_configure_one<true, WF16C_TEAM_BIG, false>()) != cudaSuccess) return e;
+    return wf16c_configure_one<true, WF16C_TEAM_BIG, true>();
 }
 
 // Launches the kernel on `stream`; grows *scratch (device) as needed.  Returns a cudaError_t as int.
-// team: one CTA (WF16C_TEAM warps) per pair instead of one warp per pair.
+// team: 0 one warp per pair; WF16C_TEAM / WF16C_TEAM_BIG: one CTA of that many warps per pair (the big team exists for
+// the standard scores only; other scores take the 4-warp team).
 inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packed, const PairDesc* pairs,
                         const uint32_t* order, uint32_t n_work, unsigned int* queue, const Wf16cParams& P,
                         uint32_t max_n, void** scratch, size_t* scratch_cap,
                         uint32_t* retry16t, unsigned int* retry16t_n, uint32_t* retry32, unsigned int* retry32_n,
-                        unsigned int* counters, uint32_t force_sys, bool team, DevResult* out)
+                        unsigned int* counters, uint32_t force_sys, int team, DevResult* out)
 {
-    const int blocks = sm_count * WF16C_CTAS_PER_SM;
-    const uint32_t warps = (uint32_t)blocks * (WF16C_THREADS / 32);
+    if (team == WF16C_TEAM_BIG && !P.std_scores) team = WF16C_TEAM;
+    const bool big = team == WF16C_TEAM_BIG;
+    const int blocks = big ? sm_count : sm_count * WF16C_CTAS_PER_SM;
+    const int threads = big ? 32 * WF16C_TEAM_BIG : WF16C_THREADS;
+    const size_t smem = big ? wf16c_smem_bytes<WF16C_TEAM_BIG>() : wf16c_smem_bytes<1>();
+    const uint32_t warps = (uint32_t)blocks * (uint32_t)(threads / 32);
     const uint32_t stride = (max_n + 2 + 31 + 32) & ~31u;
     const size_t need = (size_t)warps * stride * sizeof(uint32_t);
     if (need > *scratch_cap) {
@@ -894,12 +905,16 @@ inline int wf16c_launch(cudaStream_t stream, int sm_count, const uint32_t* packe
         *scratch_cap = need;
     }
 #define GP_WF16C_LAUNCH(STD_, TEAM_, POT2_)                                                                            \
-    overlap_wf16c_kernel<STD_, TEAM_, POT2_><<<blocks, WF16C_THREADS, WF16C_SMEM_BYTES, stream>>>(                       \
+    overlap_wf16c_kernel<STD_, TEAM_, POT2_><<<blocks, threads, smem, stream>>>(                                        \
         packed, pairs, order, n_work, queue, P, (uint32_t*)*scratch, stride, retry16t, retry16t_n, retry32, retry32_n, \
         counters, force_sys, out)
-    if (P.pot2 && P.std_scores) { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, true); else GP_WF16C_LAUNCH(true, 1, true); }
-    else if (P.std_scores)      { if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, false); else GP_WF16C_LAUNCH(true, 1, false); }
-    else                        { if (team) GP_WF16C_LAUNCH(false, WF16C_TEAM, false); else GP_WF16C_LAUNCH(false, 1, false); }
+    if (P.pot2 && P.std_scores) {
+        if (big) GP_WF16C_LAUNCH(true, WF16C_TEAM_BIG, true); else if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, true); else GP_WF16C_LAUNCH(true, 1, true);
+    } else if (P.std_scores) {
+        if (big) GP_WF16C_LAUNCH(true, WF16C_TEAM_BIG, false); else if (team) GP_WF16C_LAUNCH(true, WF16C_TEAM, false); else GP_WF16C_LAUNCH(true, 1, false);
+    } else {
+        if (team) GP_WF16C_LAUNCH(false, WF16C_TEAM, false); else GP_WF16C_LAUNCH(false, 1, false);
+    }
 #undef GP_WF16C_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -180,7 +180,8 @@ int gp_set_cert_system(gp_ctx *ctx, uint32_t system);
 /* The certificate kernel runs one warp per pair (many pairs: the pairwise phase) or one CTA of four warps per
  * pair, the pair's 512-row strips pipelined across the warps through the boundary line (few long pairs: a relax
  * chain step, whose duration is its longest pair's).  mode 0: the library chooses per launch from the batch's
- * total and largest m*n (default); 1: always one warp per pair; 2: always one CTA per pair.  Results never
+ * total and largest m*n (default); 1: always one warp per pair; 2: always one CTA of four warps per pair; 3: always
+ * one CTA of eight warps per pair (one CTA per SM: the last steps of a relax chain, a handful of long pairs).  Results never
  * depend on it.  gp_last_team: 1 if the last launch on this context used the CTA-per-pair form. */
 int gp_set_team_mode(gp_ctx *ctx, uint32_t mode);
 int gp_last_team(const gp_ctx *ctx);

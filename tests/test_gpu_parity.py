@@ -33,7 +33,7 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout)
         for mask in masks:
             if mask & KERNEL_CERT16:      # layout 0: free moves whenever the launch allows it, 1: column potential only
-                runs += [(mask, 0, 0, 0), (mask, 1, 1, 0), (mask, 2, 2, 0), (mask, 3, 0, 0), (mask, 0, 2, 0),
+                runs += [(mask, 0, 0, 0), (mask, 1, 1, 0), (mask, 2, 2, 0), (mask, 3, 0, 0), (mask, 0, 2, 0), (mask, 0, 3, 0), (mask, 2, 3, 1),
                          (mask, 0, 0, 1), (mask, 1, 2, 1), (mask, 2, 1, 1), (mask, 3, 0, 1)]
             else:
                 runs += [(mask, 0, 0, 0)]
@@ -262,11 +262,18 @@ def test_team_mode_many_long_pairs(ctx):
         ctx.set_team_mode(2)
         team = ctx.overlap_batch(seqs, pairs)
         assert ctx.last_team
+        for layout in (0, 1):                        # eight warps per pair, both value layouts
+            ctx.set_cert_layout(layout)
+            ctx.set_team_mode(3)
+            big = ctx.overlap_batch(seqs, pairs)
+            assert ctx.last_team and (big == warp).all()
+        ctx.set_cert_layout(0)
         ctx.set_team_mode(0)
         ctx.overlap_batch(seqs, pairs[:40])          # few long pairs: the library picks the team form itself
         assert ctx.last_team
     finally:
         ctx.set_team_mode(0)
+        ctx.set_cert_layout(0)
     assert (warp == team).all()
     for k in range(0, len(pairs), 23):
         a, b = pairs[k]
