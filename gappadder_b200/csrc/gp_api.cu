@@ -422,14 +422,20 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
     auto by_cells = [&](uint32_t* ord, uint64_t cnt) {
         if (cnt < 2) return;
         uint64_t mx = 0;
-        for (uint64_t k = 0; k < cnt; ++k) mx = std::max<uint64_t>(mx, (uint64_t)hd[ord[k]].m * hd[ord[k]].n);
+        std::vector<uint64_t> cells(cnt);
+        for (uint64_t k = 0; k < cnt; ++k) { cells[k] = (uint64_t)hd[ord[k]].m * hd[ord[k]].n; mx = std::max(mx, cells[k]); }
         constexpr uint32_t B = 2048;
-        const uint64_t width = mx / B + 1;
-        std::vector<uint32_t> start(B + 1, 0), tmp(ord, ord + cnt);
-        for (uint64_t k = 0; k < cnt; ++k) ++start[B - 1 - (uint32_t)(((uint64_t)hd[tmp[k]].m * hd[tmp[k]].n) / width)];
+        const double inv_width = (double)B / ((double)mx + 1.0);            // size class without a division per pair
+        std::vector<uint32_t> start(B + 1, 0), tmp(ord, ord + cnt), cls(cnt);
+        for (uint64_t k = 0; k < cnt; ++k) {
+            uint32_t b = (uint32_t)((double)cells[k] * inv_width);
+            b = b < B ? b : B - 1;
+            cls[k] = B - 1 - b;                                             // largest class first
+            ++start[cls[k]];
+        }
         uint32_t run = 0;
         for (uint32_t b = 0; b <= B; ++b) { const uint32_t v = start[b]; start[b] = run; run += v; }
-        for (uint64_t k = 0; k < cnt; ++k) ord[start[B - 1 - (uint32_t)(((uint64_t)hd[tmp[k]].m * hd[tmp[k]].n) / width)]++] = tmp[k];
+        for (uint64_t k = 0; k < cnt; ++k) ord[start[cls[k]]++] = tmp[k];
     };
     by_cells(ho16c, c->n16c);
     by_cells(ho16t, c->n16t);
