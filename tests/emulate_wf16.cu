@@ -375,7 +375,7 @@ long long pass_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams&
     for (int l = 0; l < 32; ++l) lane_best[l] = wf16c_initial_best(g);
     int i0 = 0;
     while (i0 < m) {
-        const Wf16Strip s = wf16_next_strip(i0, m, g.C);
+        const Wf16Strip s = wf16c_next_strip(i0, m, g.C);
         const bool rs = s.rowscan && !g.cell;
         switch (s.rows) {
         case 512: strip_host_c<8>(hp, g, P, bnd, i0, rs, !s.last, lane_best); break;
