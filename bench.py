@@ -14,15 +14,24 @@ on the data path.
 
   value     GCUPS with sequences and pair lists already resident in HBM (CUDA events on the library's
             stream around gp_launch_resident, L2 flushed between steps, max over ranks)
-  e2e       GCUPS through the public call gp_overlap_batch on HOST buffers: packing into pinned memory,
-            H2D, kernels, D2H of the results, every step (wall clock of the blocking call)
+  e2e       GCUPS through the public C call gp_overlap_batch on HOST buffers (ASCII sequences as char pointers,
+            the pair list): packing into pinned memory, H2D, kernels, D2H of the results, every step (wall clock
+            of the blocking call; the pointer array is built once, as a C++ caller holds it)
   roofline  integer issue-rate roofline of the dominant kernel (overlap_wf16c_kernel on cfg1): achieved =
             GCUPS * 6 integer ops per cell / peak = 2 lanes * measured dual-pipe packed
             16x2 instruction rate (gp_int_peak, measured live on this GPU)
+            (traffic: DRAM bytes of one launch from the committed ncu capture; HBM is idle on this path)
   cpu_baseline  the reference's own Evaluate (oracle/_ref/libcm_ref.so, kind "reference") or the C
             restatement (kind "port") on the host cores, on a bounded sample of the same pair list
+  parity_sample  (with cpu_baseline) 48 pairs spread over the pair list: the timed end-to-end step's results
+            against the oracle, field by field
+  dropin    (N = 1, cfg1) whole gaps per second through build/ContigsMerger_b200 --batch on the same gaps as FASTA
+            files -- read, quick check on the device, pairwise phase, graph, relax chains, output; outside
+            every timed region above (tools/dropin_bench.py)
 
-`--impl reference` times only that CPU path (rank 0 only under torchrun).
+`--impl reference` times only that CPU path (rank 0 only under torchrun).  `--config cfg3|cfg5` runs the other
+BASELINE shapes (cfg5: 10 kb contigs, use --gaps 2); `--cert-layout 1` forces the certificate kernel's
+column-potential layout (A/B); the bench line the driver reads is the default cfg1 run.
 """
 from __future__ import annotations
 
