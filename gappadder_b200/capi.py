@@ -20,6 +20,7 @@ EXPORTS = [
     "gp_estimate_gap_cells", "gp_partition_gaps", "gp_pair_split", "gp_set_kernel_mask", "gp_last_timing",
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
     "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device", "gp_upload_sequences",
+    "gp_quick_check_stats",
 ]
 
 
@@ -119,6 +120,7 @@ def lib() -> C.CDLL:
         L.gp_set_cert_layout.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_last_layout.argtypes = [C.c_void_p]
         L.gp_quick_check_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
+        L.gp_quick_check_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -313,6 +315,12 @@ class Context:
             p["row_seq"], p["col_seq"] = i, j
             out.append(p)
         return out
+
+    def quick_check_stats(self) -> dict:
+        """Of the last quick_check_device: kernel ms (CUDA events), bases scanned, work items."""
+        ms, bases, items = C.c_double(0), C.c_uint64(0), C.c_uint32(0)
+        self._check(self._L.gp_quick_check_stats(self._h, C.byref(ms), C.byref(bases), C.byref(items)))
+        return dict(kernel_ms=ms.value, bases=bases.value, items=items.value)
 
     def set_cert_layout(self, mode: int):
         """Certificate kernel: 0 free-moves layout whenever a launch allows it (default), 1 always the column potential."""

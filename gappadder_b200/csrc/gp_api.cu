@@ -72,7 +72,11 @@ struct gp_ctx {
     uint32_t kernel_mask = GP_KERNEL_ALL;
 
     // pair work lists
-    DeviceBuf d_qc_meta, d_qc_hit;             // quick check on the device: offsets/lengths/gap bounds, hit matrices
+    DeviceBuf d_qc_meta, d_qc_hit, d_qc_slab;  // quick check on the device: offsets/lengths/gap bounds/items, hit matrices, probe slabs
+    cudaEvent_t qc_ev[2] = {nullptr, nullptr};
+    double qc_kernel_ms = 0;
+    uint64_t qc_bases = 0;
+    uint32_t qc_items = 0;
     DeviceBuf d_pairs, d_order16c, d_order16t, d_order16, d_order32, d_results, d_queue, d_scratch32, d_scratch16, d_scratch16t, d_scratch16c;
     HostBuf h_stage, h_pack, h_results, h_queue;   // h_queue: [0,32) initial d_queue image, [32,64) counters read back
     std::vector<uint32_t> pack_off;
@@ -139,6 +143,7 @@ int gp_create(int device, gp_ctx** out)
     if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete c; return GP_ERR_CUDA;
     }
+    for (auto& ev : c->qc_ev) cudaEventCreate(&ev);
     for (auto& ev : c->kev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA; }
     if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess) {
@@ -155,6 +160,8 @@ void gp_destroy(gp_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->qc_ev) if (ev) cudaEventDestroy(ev);
+    c->d_qc_slab.release();
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
     c->d_scratch16t.release(); c->d_scratch16c.release(); c->d_order16c.release(); c->h_queue.release();
     c->d_results.release(); c->d_queue.release(); c->d_scratch32.release(); c->d_scratch16.release();
@@ -244,35 +251,78 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     if (n_gaps == 0) return GP_OK;
     const uint32_t n_seq = (uint32_t)c->seq_len.size();
     std::vector<uint64_t> hit_off(n_gaps + 1, 0);
+    uint64_t total_bases = 0, max_nodes = 0;
     for (uint32_t g = 0; g < n_gaps; ++g) {
         if (gap_first[g + 1] < gap_first[g] || gap_first[g + 1] > n_seq) return c->fail(GP_ERR_INVALID, "gap %u: bad sequence range", g);
         const uint64_t n = gap_first[g + 1] - gap_first[g];
         if (n > (uint64_t)gp::QC_MAX_NODES) return c->fail(GP_ERR_RANGE, "gap %u has %llu nodes (device quick check: <= %d)", g, (unsigned long long)n, gp::QC_MAX_NODES);
         hit_off[g + 1] = hit_off[g] + n * n;
+        max_nodes = std::max(max_nodes, n);
+        for (uint32_t s = gap_first[g]; s < gap_first[g + 1]; ++s) total_bases += c->seq_len[s];
     }
     const uint64_t total = hit_off[n_gaps];
     if (total > hit_bytes) return c->fail(GP_ERR_INVALID, "hit buffer too small: %llu bytes needed", (unsigned long long)total);
+    // Work items: every gap cut into node ranges of about `item_bases` bases.  An item's first cost is the gap's probe
+    // set (42 k-mers per node, rebuilt by every CTA that meets the gap), so items are at least 64 kbases; beyond that
+    // they are sized for four items per SM so that few large gaps still fill the chip.
+    const uint64_t item_bases = std::min<uint64_t>(1u << 20, std::max<uint64_t>(64u << 10, total_bases / (4ull * (uint64_t)c->sm_count) + 1));
+    std::vector<gp::QcItem> items;
+    for (uint32_t g = 0; g < n_gaps; ++g) {
+        const uint32_t first = gap_first[g], n = gap_first[g + 1] - first;
+        uint32_t lo = 0;
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            acc += c->seq_len[first + i];
+            if (acc >= item_bases || i + 1 == n) { items.push_back(gp::QcItem{g, lo, i + 1, 0u}); lo = i + 1; acc = 0; }
+        }
+    }
+    c->qc_bases = total_bases;
+    c->qc_items = (uint32_t)items.size();
+    if (items.empty()) { memset(hit, 0, (size_t)total); return GP_OK; }
     GP_CUDA(c, cudaSetDevice(c->device));
-    // meta: [seq_off n_seq][seq_len n_seq][gap_first n_gaps+1][pad][hit_off (n_gaps+1) x u64]
+    // meta: [seq_off n_seq][seq_len n_seq][gap_first n_gaps+1][pad][hit_off (n_gaps+1) x u64][items][queue]
     const size_t w32 = (size_t)2 * n_seq + n_gaps + 1, w32p = (w32 + 1) & ~(size_t)1;
-    const size_t meta_bytes = w32p * 4 + (size_t)(n_gaps + 1) * 8;
+    const size_t items_at = w32p * 4 + (size_t)(n_gaps + 1) * 8;
+    const size_t queue_at = items_at + items.size() * sizeof(gp::QcItem);
+    const size_t meta_bytes = queue_at + 16;
     GP_CUDA(c, c->d_qc_meta.reserve(meta_bytes));
     GP_CUDA(c, c->d_qc_hit.reserve(total ? total : 16));
-    uint32_t* dm = (uint32_t*)c->d_qc_meta.p;
+    const int blocks = (int)std::min<size_t>(items.size(), (size_t)c->sm_count);
+    const uint32_t slab_probes = (uint32_t)max_nodes * gp::qc_probes_per_node(k) + 32u;
+    GP_CUDA(c, c->d_qc_slab.reserve((size_t)blocks * 3u * slab_probes * sizeof(uint32_t)));
+    char* dmb = (char*)c->d_qc_meta.p;
+    uint32_t* dm = (uint32_t*)dmb;
     GP_CUDA(c, cudaMemcpyAsync(dm, c->seq_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dm + n_seq, c->seq_len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dm + 2 * (size_t)n_seq, gap_first, (size_t)(n_gaps + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dm + w32p, hit_off.data(), (size_t)(n_gaps + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(dmb + items_at, items.data(), items.size() * sizeof(gp::QcItem), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(dmb + queue_at, 0, 16, c->stream));
+    if (total) GP_CUDA(c, cudaMemsetAsync(c->d_qc_hit.p, 0, total, c->stream));
     const size_t smem = gp::qc_smem_bytes(k);
     GP_CUDA(c, cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = (int)std::min<uint32_t>(n_gaps, (uint32_t)c->sm_count);
+    GP_CUDA(c, cudaEventRecord(c->qc_ev[0], c->stream));
     gp::quick_check_kernel<<<blocks, gp::QC_THREADS, smem, c->stream>>>(
-        (const uint32_t*)c->d_packed.p, dm, dm + n_seq, dm + 2 * (size_t)n_seq, (const uint64_t*)(dm + w32p), n_gaps, (int)k,
-        gp::qc_max_probes(k), (uint8_t*)c->d_qc_hit.p);
+        (const uint32_t*)c->d_packed.p, dm, dm + n_seq, dm + 2 * (size_t)n_seq, (const uint64_t*)(dm + w32p),
+        (const gp::QcItem*)(dmb + items_at), (uint32_t)items.size(), (unsigned int*)(dmb + queue_at), (int)k,
+        (uint32_t*)c->d_qc_slab.p, slab_probes, (uint8_t*)c->d_qc_hit.p);
     GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->qc_ev[1], c->stream));
     c->launches += 1;
     if (total) GP_CUDA(c, cudaMemcpyAsync(hit, c->d_qc_hit.p, total, cudaMemcpyDeviceToHost, c->stream));
-    GP_CUDA(c, cudaStreamSynchronize(c->stream));       // hit_off (host vector) and the caller's buffers are free again
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));       // the host vectors and the caller's buffers are free again
+    float ms = 0.f;
+    GP_CUDA(c, cudaEventElapsedTime(&ms, c->qc_ev[0], c->qc_ev[1]));
+    c->qc_kernel_ms = ms;
+    return GP_OK;
+}
+
+int gp_quick_check_stats(const gp_ctx* c, double* kernel_ms, uint64_t* bases, uint32_t* items)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = c->qc_kernel_ms;
+    if (bases) *bases = c->qc_bases;
+    if (items) *items = c->qc_items;
     return GP_OK;
 }
 
@@ -360,7 +410,14 @@ static void patch_closed(const gp_ctx* c, gp_result* out)
     for (uint32_t id : c->closed_ids) closed_form_self(out + id, hd[id].m);
 }
 
-static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+static void reset_pairs(gp_ctx* c)
+{
+    c->n_pairs = 0; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
+    c->cells16c = c->cells16t = c->cells16 = c->cells32 = 0; c->kev_valid = false;
+    c->closed_ids.clear(); c->cells_closed = 0; c->max_cells16c = 0;
+}
+
+static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
 {
     if (!params || (!pairs && n_pairs)) return c->fail(GP_ERR_INVALID, "null pairs/params");
     if (params->max_clip < 0) return c->fail(GP_ERR_INVALID, "max_clip must be >= 0");
@@ -402,8 +459,8 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
         // A sequence against itself has a closed form (closed_form_self below): no DP cells are computed.
         if (closed_ok && a == b && m >= 1) { c->closed_ids.push_back((uint32_t)i); c->cells_closed += (uint64_t)m * n; continue; }
         c->cells += (uint64_t)m * n;
-        // certificate kernel: everything A/C/G/T except a sequence against itself (its walk ends in the corner
-        // (0,0), which no certificate covers: straight to an exact kernel)
+        // certificate kernel: everything A/C/G/T except a sequence against itself (closed form above when the scores
+        // allow it; otherwise an exact kernel -- system C would certify its corner walk, but it is not worth a probe)
         if (params16c && a != b && gp::wf16c_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) {
             ho16c[c->n16c++] = (uint32_t)i; c->max_n16c = std::max(c->max_n16c, n); c->cells16c += (uint64_t)m * n;
             c->max_cells16c = std::max(c->max_cells16c, (uint64_t)m * n);
@@ -462,6 +519,15 @@ static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs,
     if (c->n16) GP_CUDA(c, cudaMemcpyAsync(c->d_order16.p, ho16, c->n16 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     if (c->n32) GP_CUDA(c, cudaMemcpyAsync(c->d_order32.p, ho32, c->n32 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     return GP_OK;       // h_stage is the context's own pinned memory: no need to wait for the copies here
+}
+
+// A failed upload leaves NO batch behind: a later gp_launch_resident is then a no-op instead of a launch on work lists
+// that were never written.
+static int upload_pairs_async(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+{
+    const int rc = upload_pairs_impl(c, pairs, n_pairs, params);
+    if (rc != GP_OK) reset_pairs(c);
+    return rc;
 }
 
 int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
@@ -630,7 +696,10 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     const auto t1 = clk::now();
     if (rc_pack != GP_OK || rc != GP_OK || off_check != c->pack_off) {
         cudaStreamSynchronize(c->stream);
-        c->n_pairs = 0;
+        reset_pairs(c);
+        // the host metadata describes the NEW table, the device still holds the old one: drop both, so that later
+        // calls on this context fail with GP_ERR_INVALID (pair indices out of range) instead of reading stale bases
+        c->seq_off.clear(); c->seq_len.clear(); c->seq_acgt.clear(); c->n_symbols = 0;
         if (rc_pack != GP_OK) return c->fail(rc_pack, rc_pack == GP_ERR_ALPHABET ? "more than 16 distinct sequence symbols" : "gp_pack_sequences failed");
         if (rc != GP_OK) return rc;
         return c->fail(GP_ERR_INVALID, "internal: table layout mismatch");
@@ -640,9 +709,8 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     if (nsym > 4) {                               // N or other letters somewhere: exact per-sequence flags, classify again
         GP_CUDA(c, cudaStreamSynchronize(c->stream));            // the staging buffer of the first classification is in flight
         rc = set_sequences_async(c, (const uint32_t*)c->h_pack.p, 0, c->pack_off.data(), seq_len, n_seq, nsym);
-        if (rc != GP_OK) return rc;
-        rc = upload_pairs_async(c, pairs, n_pairs, params);
-        if (rc != GP_OK) return rc;
+        if (rc == GP_OK) rc = upload_pairs_async(c, pairs, n_pairs, params);
+        if (rc != GP_OK) { reset_pairs(c); c->seq_off.clear(); c->seq_len.clear(); c->seq_acgt.clear(); c->n_symbols = 0; return rc; }
     }
     (void)t_cls;
     const auto t2 = clk::now();

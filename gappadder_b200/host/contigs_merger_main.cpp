@@ -12,6 +12,7 @@
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
 // OUT.fa.gml in batch mode (the reference drops ./tmp.gml in the working directory of each process).
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -139,6 +140,7 @@ int run_batch(const Cli& c)
     std::vector<uint64_t> cells(n_gpus, 0), pcells(n_gpus, 0);
     std::vector<MergeTimings> tim(n_gpus);
     std::vector<double> wall(n_gpus, 0);
+    std::atomic<bool> gap_failed(false);
     auto worker = [&](int dev) {
         std::vector<GapInput> in;
         std::vector<size_t> which;
@@ -155,6 +157,11 @@ int run_batch(const Cli& c)
         if (r != GP_OK) { rc[dev] = r; return; }
         for (size_t k = 0; k < which.size(); ++k) {
             const BatchLine& b = lines[which[k]];
+            if (!out[k].error.empty()) {                       // this gap only: nothing written, the others go on
+                fprintf(stderr, "ContigsMerger_b200: %s\n", out[k].error.c_str());
+                gap_failed = true;
+                continue;
+            }
             if (!write_file(b.out, out[k].stdout_text)) { rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + b.out; return; }
             if (out[k].wrote_info) write_file(b.info, out[k].info_text);
             if (c.write_gml && out[k].wrote_info) write_file(b.out + ".gml", out[k].gml_text);
@@ -186,7 +193,7 @@ int run_batch(const Cli& c)
                 (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries,
                 (unsigned long long)shared_pairs, shared_cells / 1e9, t.relax_call_ms, t.relax_pack_ms);
     }
-    return 0;
+    return gap_failed ? 3 : 0;
 }
 
 } // namespace
@@ -206,6 +213,7 @@ int main(int argc, char** argv)
     rc = merge_gaps(ctx, c.opt, {GapInput{c.input}}, out, err);
     gp_destroy(ctx);
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s\n", err.c_str()); return 3; }   // never partial stdout
+    if (!out[0].error.empty()) { fprintf(stderr, "ContigsMerger_b200: %s\n", out[0].error.c_str()); return 3; }
     fwrite(out[0].stdout_text.data(), 1, out[0].stdout_text.size(), stdout);
     if (out[0].wrote_info) {
         if (c.write_gml) write_file("tmp.gml", out[0].gml_text);

@@ -126,9 +126,17 @@ std::vector<std::vector<int>> OverlapGraph::find_paths(int max_per_root) const
     std::set<std::vector<int>> all;
     for (int root : roots) {
         std::vector<std::vector<int>> found = paths_from(root, order, rank, ends);
-        // longest first; equal lengths in the order the reference's std::set<const vector*> yields,
-        // taken here as insertion order (GraphUtils.cpp:719-753).  max_per_root+1 paths are kept:
-        // the reference tests `numOut > maxNodeOccurInPath` after the insert.
+        // Longest first; max_per_root+1 paths are kept: the reference tests `numOut > maxNodeOccurInPath` after
+        // the insert (GraphUtils.cpp:719-753).  Among EQUAL lengths the reference iterates a
+        // std::set<const vector*>, i.e. by the heap address of the std::set nodes that hold the paths -- the
+        // result then depends on the C library's allocator and on every allocation the process made before
+        // (probed with the reference binary on fan-shaped graphs, tests/golden/make_golden_big.py: mostly the
+        // LAST inserted paths survive, with tcache-sized groups of 7 out of order).  That order is not a property
+        // of the algorithm and cannot be reproduced in general; this implementation uses the deterministic rule
+        // closest to what glibc yields: equal lengths in reverse insertion order.  With at most max_per_root+1
+        // paths of the cut's length per root (every synthetic gap of BASELINE's shapes) nothing is cut among
+        // equals and the output is byte-identical whatever the order.
+        std::reverse(found.begin(), found.end());
         std::stable_sort(found.begin(), found.end(),
                          [](const std::vector<int>& a, const std::vector<int>& b) { return a.size() > b.size(); });
         int num_out = 0;

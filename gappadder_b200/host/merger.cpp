@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <numeric>
 #include <thread>
@@ -26,6 +27,13 @@ struct Chain {               // one path being merged left to right (FormMergedS
 struct GapState {
     std::vector<FastaRecord> contigs;
     std::vector<std::string> node_seq, node_name;   // [c0, c0_R, c1, c1_R, ...]  (:794-799)
+    // Letters other than A C G T N.  The DP only tests bytes for equality (:1641) and pairs never cross gaps, so such a
+    // gap's nodes go to the packer with its own letters renamed to a fixed placeholder set: the batch table's 16-code
+    // alphabet is then a per-gap limit (11 letters besides A C G T N), not a limit on the union over the batch.
+    // dp_seq is empty when the gap needs no renaming; outputs are always built from node_seq.
+    std::vector<std::string> dp_seq;
+    unsigned char letter_map[256];
+    const std::string& dp(size_t v) const { return dp_seq.empty() ? node_seq[v] : dp_seq[v]; }
     uint32_t node_base = 0;                          // index of node 0 in the batch sequence table
     uint64_t pair_begin = 0, pair_end = 0;           // slice of the batch pair list
     bool dead = false;                               // fatal input error, nothing more to do
@@ -105,7 +113,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     dp.indel = (int)opt.score_indel;
     const bool scan_runs = opt.max_overlap_clip_len >= 0;        // `for (c = 0; c <= maxOverlapClipLen; ...)` (:1679)
     // the quick check runs on the device when the library's device form covers the k-mer length (k <= 10)
-    const bool device_qc = !opt.host_quick_check && opt.quick_kmer_len >= 1 && opt.quick_kmer_len <= 10;
+    const bool device_qc = !opt.host_quick_check && opt.quick_kmer_len >= 1 && opt.quick_kmer_len <= GP_QC_MAX_K;
     dp.max_clip = scan_runs ? (int)std::floor(opt.max_overlap_clip_len) : 0;
     gp_thresholds thr{opt.max_frac_score_loss, opt.min_frac_overlap, opt.min_overlap_len, opt.min_overlap_len_with_scaffold};
     const int max_per_root = opt.max_count_contig_in_path > 0 ? opt.max_count_contig_in_path : 20;   // :33-34,:168
@@ -134,6 +142,30 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             s.node_seq.push_back(rc);
             s.node_name.push_back(r.name + "_R");                         // :785-787
         }
+        {   // letters besides A C G T N: rename per gap (see GapState::dp_seq)
+            static const char placeholder[] = "BDEFHIJKLMO";
+            bool seen[256] = {false};
+            int n_other = 0;
+            for (int b = 0; b < 256; ++b) s.letter_map[b] = (unsigned char)b;
+            for (const FastaRecord& r : s.contigs)
+                for (unsigned char ch : r.seq)
+                    if (!seen[ch] && ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') {
+                        seen[ch] = true;
+                        if (n_other < 11) s.letter_map[ch] = (unsigned char)placeholder[n_other];
+                        ++n_other;
+                    }
+            if (n_other > 11) {
+                out[g].error = in[g].fasta_path + ": " + std::to_string(n_other + 5) + " distinct sequence letters; this implementation "
+                               "handles A C G T N plus 11 others per gap (the reference accepts any letter)";
+                out[g].exit_code = 3;
+                s.dead = true;
+                return;
+            }
+            if (n_other > 0) {
+                s.dp_seq = s.node_seq;
+                for (std::string& q : s.dp_seq) for (char& ch : q) ch = (char)s.letter_map[(unsigned char)ch];
+            }
+        }
         // QuickCheckerContigsMatch::Init on every node (:843-849): a node shorter than k is fatal there
         bool too_short = false;
         for (const std::string& q : s.node_seq) if ((int)q.size() < opt.quick_kmer_len) too_short = true;
@@ -153,7 +185,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         }
         s.arranged = true;
         if (!scan_runs) return;        // no scan => every Evaluate is rejected (:1674-1722): no edges
-        if (device_qc) { s.want_pairs = true; return; }                  // quick check on the device, below
+        if (device_qc && N <= GP_QC_MAX_NODES) { s.want_pairs = true; return; }   // quick check on the device, below
         std::vector<const char*> nodes;
         std::vector<uint32_t> lens;
         for (const std::string& q : s.node_seq) { nodes.push_back(q.data()); lens.push_back((uint32_t)q.size()); }
@@ -163,77 +195,60 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         if (np < 0) { s.cand_rc = (int)np; s.cand.clear(); return; }
         s.cand.resize((size_t)np);
     });
-    // serial: one sequence table and one pair list for the batch (node_seq vectors no longer grow)
-    std::vector<uint32_t> gap_first;                 // device quick check: node range of every live gap, in table order
-    std::vector<size_t> gap_of;
-    bool device_qc_ok = device_qc;
-    for (size_t g = 0; g < G; ++g) {
-        GapState& s = st[g];
-        if (s.dead) continue;
+    // serial: one sequence table and one pair list for the batch (node_seq vectors no longer grow).  Gaps whose
+    // candidate filter runs on the device come first: gp_quick_check_device takes contiguous node ranges.  A gap
+    // beyond the device filter's limits (GP_QC_MAX_NODES) was filtered on the host above -- that gap only.
+    std::vector<size_t> order;
+    for (size_t g = 0; g < G; ++g) if (!st[g].dead && st[g].want_pairs) order.push_back(g);
+    const size_t n_dev = order.size();
+    for (size_t g = 0; g < G; ++g) if (!st[g].dead && !st[g].want_pairs) order.push_back(g);
+    std::vector<uint32_t> gap_first;                 // device quick check: node range of every device-filtered gap
+    for (size_t q = 0; q < order.size(); ++q) {
+        GapState& s = st[order[q]];
         if (s.cand_rc != 0) { error = "gp_candidate_pairs failed"; return s.cand_rc; }
         s.node_base = (uint32_t)seq_ptr.size();
-        for (const std::string& q : s.node_seq) { seq_ptr.push_back(q.data()); seq_len.push_back((uint32_t)q.size()); }
-        gap_first.push_back(s.node_base);
-        gap_of.push_back(g);
-        if (s.node_seq.size() > 256) device_qc_ok = false;               // gp_quick_check_device's limit
+        if (q < n_dev) gap_first.push_back(s.node_base);
+        if (q == n_dev) gap_first.push_back(s.node_base);
+        for (size_t v = 0; v < s.node_seq.size(); ++v) { seq_ptr.push_back(s.dp(v).data()); seq_len.push_back((uint32_t)s.node_seq[v].size()); }
+    }
+    if (order.size() == n_dev) gap_first.push_back((uint32_t)seq_ptr.size());
+
+    // Quick check on the device: the nodes go to HBM first (they are needed there for the DP anyway), the filter
+    // runs on the packed table (gp_quick_check_device), the pair list is read off the hit matrices in the host
+    // filter's order (row by row, j >= i).
+    bool table_resident = false;
+    if (n_dev > 0) {
+        const uint32_t n_seq = (uint32_t)seq_ptr.size();
+        int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
+        if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        table_resident = true;
+        std::vector<uint64_t> hoff(n_dev + 1, 0);
+        for (size_t q = 0; q < n_dev; ++q) { const uint64_t n = gap_first[q + 1] - gap_first[q]; hoff[q + 1] = hoff[q] + n * n; }
+        std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
+        rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)n_dev, opt.quick_kmer_len, hit.data(), hit.size());
+        if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        if (timings) {
+            double ms = 0; uint64_t bases = 0; uint32_t items = 0;
+            gp_quick_check_stats(ctx, &ms, &bases, &items);
+            timings->qc_kernel_ms += ms; timings->qc_bases += bases; timings->qc_items += items;
+        }
+        for (size_t q = 0; q < n_dev; ++q) {
+            GapState& s = st[order[q]];
+            s.pair_begin = pairs.size();
+            const uint32_t n = gap_first[q + 1] - gap_first[q];
+            const uint8_t* h = hit.data() + hoff[q];
+            for (uint32_t i = 0; i < n; ++i)
+                for (uint32_t j = i; j < n; ++j)
+                    if (h[(size_t)i * n + j]) pairs.push_back(gp_pair{i + s.node_base, j + s.node_base});
+            s.pair_end = pairs.size();
+        }
+    }
+    for (size_t q = n_dev; q < order.size(); ++q) {                       // host-filtered gaps
+        GapState& s = st[order[q]];
         s.pair_begin = pairs.size();
         for (const gp_pair& c : s.cand) pairs.push_back(gp_pair{c.row_seq + s.node_base, c.col_seq + s.node_base});
         s.pair_end = pairs.size();
         std::vector<gp_pair>().swap(s.cand);
-    }
-    gap_first.push_back((uint32_t)seq_ptr.size());
-
-    // Quick check on the device: the nodes go to HBM first (they are needed there for the DP anyway), the filter
-    // runs on the packed table (gp_quick_check_device), the pair list is read off the hit matrices in the host
-    // filter's order (row by row, j >= i).  Gaps with more than 256 nodes send the batch through the host filter.
-    bool table_resident = false;
-    if (device_qc) {
-        bool any = false;
-        for (size_t g = 0; g < G; ++g) any = any || st[g].want_pairs;
-        if (any && device_qc_ok) {
-            const uint32_t n_seq = (uint32_t)seq_ptr.size();
-            int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
-            if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
-            table_resident = true;
-            std::vector<uint64_t> hoff(gap_of.size() + 1, 0);
-            for (size_t q = 0; q < gap_of.size(); ++q) { const uint64_t n = gap_first[q + 1] - gap_first[q]; hoff[q + 1] = hoff[q] + n * n; }
-            std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
-            rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)gap_of.size(), opt.quick_kmer_len, hit.data(), hit.size());
-            if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
-            for (size_t q = 0; q < gap_of.size(); ++q) {
-                GapState& s = st[gap_of[q]];
-                s.pair_begin = pairs.size();
-                if (s.want_pairs) {
-                    const uint32_t n = gap_first[q + 1] - gap_first[q];
-                    const uint8_t* h = hit.data() + hoff[q];
-                    for (uint32_t i = 0; i < n; ++i)
-                        for (uint32_t j = i; j < n; ++j)
-                            if (h[(size_t)i * n + j]) pairs.push_back(gp_pair{i + s.node_base, j + s.node_base});
-                }
-                s.pair_end = pairs.size();
-            }
-        } else if (any) {                                                 // host filter after all
-            for_each_gap(G, host_threads, [&](size_t g) {
-                GapState& s = st[g];
-                if (!s.want_pairs) return;
-                std::vector<const char*> nodes;
-                std::vector<uint32_t> lens;
-                for (const std::string& q : s.node_seq) { nodes.push_back(q.data()); lens.push_back((uint32_t)q.size()); }
-                const uint64_t N = nodes.size(), cap = N * (N + 1) / 2;
-                s.cand.resize(cap);
-                const int64_t np = gp_candidate_pairs(nodes.data(), lens.data(), (uint32_t)N, opt.quick_kmer_len, s.cand.data(), cap);
-                if (np < 0) { s.cand_rc = (int)np; s.cand.clear(); return; }
-                s.cand.resize((size_t)np);
-            });
-            for (size_t g = 0; g < G; ++g) {
-                GapState& s = st[g];
-                if (s.cand_rc != 0) { error = "gp_candidate_pairs failed"; return s.cand_rc; }
-                s.pair_begin = pairs.size();
-                for (const gp_pair& c : s.cand) pairs.push_back(gp_pair{c.row_seq + s.node_base, c.col_seq + s.node_base});
-                s.pair_end = pairs.size();
-                std::vector<gp_pair>().swap(s.cand);
-            }
-        }
     }
 
     lap(&MergeTimings::read_ms);
@@ -302,6 +317,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         std::vector<gp_pair> pp;
         // Chains of one gap whose paths share the prefix path[0..next] hold the same merged string and meet the same
         // node: one Evaluate serves them all (the reference runs it once per path, :1463-1513, with the same result).
+        std::deque<std::string> renamed;                                  // keeps the renamed merged strings alive
         std::vector<size_t> rep(active.size());                           // active chain -> index into pp
         std::map<std::pair<size_t, std::vector<int>>, size_t> seen;
         for (size_t a = 0; a < active.size(); ++a) {
@@ -317,8 +333,18 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             rep[a] = pp.size();
             seen.emplace(std::move(key), pp.size());
             pp.push_back(gp_pair{(uint32_t)sp.size(), (uint32_t)sp.size() + 1});
-            sp.push_back(ch.merged.data()); sl.push_back((uint32_t)ch.merged.size());
-            sp.push_back(nodeseq.data()); sl.push_back((uint32_t)nodeseq.size());
+            const GapState& gs = st[ch.gap];
+            if (gs.dp_seq.empty()) {
+                sp.push_back(ch.merged.data());
+                sp.push_back(nodeseq.data());
+            } else {                                                       // renamed letters (GapState::dp_seq)
+                renamed.emplace_back(ch.merged);
+                for (char& b : renamed.back()) b = (char)gs.letter_map[(unsigned char)b];
+                sp.push_back(renamed.back().data());
+                sp.push_back(gs.dp_seq[ch.path[ch.next]].data());
+            }
+            sl.push_back((uint32_t)ch.merged.size());
+            sl.push_back((uint32_t)nodeseq.size());
         }
         std::vector<gp_result> rr(pp.size());
         int rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());

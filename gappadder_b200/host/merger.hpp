@@ -41,6 +41,9 @@ struct GapOutput {
     std::string gml_text;      // contents of ./tmp.gml ("" when the reference would not reach it)
     bool wrote_info = false;   // the reference creates the -o file only when it gets that far
     int exit_code = 0;
+    // Set when THIS gap is outside the implementation's contract (more than 16 distinct letters: see merger.cpp);
+    // nothing is written for it (exit code 3 in the single-gap form), the other gaps of the batch are unaffected.
+    std::string error;
     // statistics
     uint64_t pair_cells = 0, relax_cells = 0;
     uint32_t n_pairs = 0, n_relax = 0;
@@ -61,6 +64,9 @@ struct MergeTimings {
     uint64_t relax_shared_pairs = 0, relax_shared_cells = 0;   // relax steps answered by another chain of the gap with the same path prefix
     double relax_device_ms = 0;        // of relax_ms: inside gp_overlap_batch from first launch to results on the host
     double relax_host_ms = 0;          // of relax_ms: building the step's batch and the merged strings
+    double qc_kernel_ms = 0;           // device quick check: kernel time, bases scanned (0.5 B each), work items
+    uint64_t qc_bases = 0;
+    uint32_t qc_items = 0;
 };
 
 // Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure

@@ -196,9 +196,14 @@ int gp_last_team(const gp_ctx *ctx);
  * gap_first[g] .. gap_first[g+1]-1 (its graph nodes in order; n_g of them).  hit receives, gap after gap, n_g * n_g
  * bytes: hit[i * n_g + j] = 1 iff pair (i, j), j >= i, is a candidate (entries with j < i are 0).  Enumerating the
  * 1s row by row gives gp_candidate_pairs' list for upper-case input (bytes other than A C G T count as A in k-mers,
- * as in the reference).  k <= 10 (GAPPadder uses 10), at most 256 nodes per gap; GP_ERR_RANGE otherwise -- the
+ * as in the reference).  k <= 10 (GAPPadder uses 10), at most 4096 nodes per gap; GP_ERR_RANGE otherwise -- the
  * host function has no such limits.  Returns 0 or a negative error. */
 int gp_quick_check_device(gp_ctx *ctx, const uint32_t *gap_first, uint32_t n_gaps, int32_t k, uint8_t *hit, uint64_t hit_bytes);
+#define GP_QC_MAX_K 10
+#define GP_QC_MAX_NODES 4096
+/* Of the last gp_quick_check_device on this context: device time of the filter kernel (CUDA events on the context's
+ * stream), the bases it scanned (it reads 0.5 byte per base of packed codes, once) and the work items it was cut into. */
+int gp_quick_check_stats(const gp_ctx *ctx, double *kernel_ms, uint64_t *bases, uint32_t *items);
 int gp_set_cert_layout(gp_ctx *ctx, uint32_t mode);
 int gp_last_layout(const gp_ctx *ctx);
 /* Testing / A-B measurement: restricts which 16-bit kernels gp_upload_pairs may choose (default all).

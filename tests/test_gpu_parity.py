@@ -2,7 +2,9 @@
 
 Bit-exact (integer work): (score, row_end, col_end, nclip, row0/col0/contained flags) per pair.
 """
+import os
 import random
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import pytest
@@ -24,10 +26,15 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
     per pair and one CTA per pair --, then the table kernel, then the PRMT kernel / general kernel; KERNEL_DP_ALL
     is the same without the closed form) against the oracle.  Returns the default routing's results."""
     params = params or g.GAPPADDER_DP
-    want = []
-    for a, b in pairs:
-        o = oracle_evaluate(seqs[a], seqs[b], params.mismatch, params.indel, params.max_clip, full=full)
-        want.append((o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained))
+
+    def one(ab):
+        o = oracle_evaluate(seqs[ab[0]], seqs[ab[1]], params.mismatch, params.indel, params.max_clip, full=full)
+        return (o.score, o.row_end, o.col_end, o.nclip, int(o.tb_row == 0), int(o.tb_col == 0), o.bcontained)
+    if len(pairs) >= 64:                    # realistic-size gaps: the oracle (ctypes, GIL released) on every host core
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+            want = list(ex.map(one, pairs))
+    else:
+        want = [one(ab) for ab in pairs]
     first = None
     try:
         runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout)
@@ -326,3 +333,74 @@ def test_quick_check_on_the_device_equals_the_host_filter(ctx, config, n_gaps):
     assert len(got) == n_gaps
     for gi in range(n_gaps):
         assert np.array_equal(got[gi]["row_seq"], want[gi]["row_seq"]) and np.array_equal(got[gi]["col_seq"], want[gi]["col_seq"]), (config, gi)
+
+
+def _gap_nodes_and_candidates(config, seed):
+    nodes = []
+    for _, s in synth_gaps.make_gap(seed, synth_gaps.CONFIGS[config]):
+        nodes += [s, g.revcomp(s)]
+    cand = g.candidate_pairs(nodes, 10)
+    return nodes, [(int(p["row_seq"]), int(p["col_seq"])) for p in cand]
+
+
+def test_cfg3_gap_80_contigs_every_candidate_pair(ctx):
+    """BASELINE cfg3/cfg4 shape at its upper end: the 80-contig gap whose whole-binary output is a committed reference
+    golden (tests/golden/big/cfg3_s15): every candidate pair, every layout / team / starting system."""
+    nodes, pairs = _gap_nodes_and_candidates("cfg3", 15)
+    assert len(nodes) == 160 and len(pairs) > 2000
+    _check(ctx, nodes, pairs, masks=(KERNEL_ALL, KERNEL_TAGGED))
+
+
+def test_cfg5_reduced_repeat_rich_long_columns(ctx):
+    """The tie-heaviest input: 8 kb contigs of a repeat-rich locus (reduced cfg5, golden tests/golden/big/cfg5r_s1).
+    Columns beyond 3800 bases: the column-potential layout, second passes, exact retries if any; every layout / team /
+    starting system on every candidate pair; and two full-size cfg5 contig pairs (10 kb x 10 kb)."""
+    nodes, pairs = _gap_nodes_and_candidates("cfg5r", 1)
+    assert len(nodes) == 28 and max(len(s) for s in nodes) == 8000 and len(pairs) > 100
+    _check(ctx, nodes, pairs, masks=(KERNEL_ALL,))
+    ctx.overlap_batch(nodes, pairs)
+    assert ctx.last_layout == 0                       # 8000 columns: not the free-moves layout
+    big, bp = _gap_nodes_and_candidates("cfg5", 3)
+    bp = [ab for ab in bp if ab[0] != ab[1]][:400:100]
+    assert len(bp) >= 2 and len(big[bp[0][0]]) == 10000
+    _check(ctx, big, bp, masks=(KERNEL_ALL,))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 9])
+def test_quick_check_on_the_device_small_k(ctx, k):
+    """k = 1, 2 (a k-mer set smaller than one word), and other k below GAPPadder's 10."""
+    seqs, gap_first, want = [], [0], []
+    for gi in range(4):
+        nodes = []
+        for _, s in synth_gaps.make_gap(300 + gi, synth_gaps.CONFIGS["noisy" if gi % 2 else "small"]):
+            nodes += [s, g.revcomp(s)]
+        seqs += nodes
+        gap_first.append(len(seqs))
+        want.append(g.candidate_pairs(nodes, k))
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    ctx.set_sequences(packed, off, lens, nsym)
+    got = ctx.quick_check_device(gap_first, k)
+    for gi in range(4):
+        assert np.array_equal(got[gi]["row_seq"], want[gi]["row_seq"]) and np.array_equal(got[gi]["col_seq"], want[gi]["col_seq"]), (k, gi)
+
+
+def test_quick_check_on_the_device_big_gaps_and_many_items(ctx):
+    """A full cfg5 gap (400 nodes of 10 kb: more nodes than one CTA's old limit, cut into dozens of work items), next to
+    small gaps and an empty one: same candidate lists as the host filter."""
+    seqs, gap_first, want = [], [0], []
+    for config, seed in (("cfg5", 1), ("tiny", 7), ("cfg3", 15), ("tiny", 8)):
+        nodes = []
+        for _, s in synth_gaps.make_gap(seed, synth_gaps.CONFIGS[config]):
+            nodes += [s, g.revcomp(s)]
+        seqs += nodes
+        gap_first.append(len(seqs))
+        want.append(g.candidate_pairs(nodes, 10))
+    gap_first.append(len(seqs))                      # an empty gap
+    want.append(g.candidate_pairs([], 10))
+    packed, off, lens, nsym = g.pack_sequences(seqs)
+    ctx.set_sequences(packed, off, lens, nsym)
+    got = ctx.quick_check_device(gap_first, 10)
+    st = ctx.quick_check_stats()
+    assert st["bases"] == sum(len(s) for s in seqs) and st["items"] > 8
+    for gi in range(len(want)):
+        assert np.array_equal(got[gi]["row_seq"], want[gi]["row_seq"]) and np.array_equal(got[gi]["col_seq"], want[gi]["col_seq"]), gi

@@ -42,6 +42,8 @@ CONFIGS = {
     # configs[4]: long-contig stress, 200 contigs x 10 kb on a 40 kb repeat-rich locus
     "cfg5": GapSpec(n_contigs=(200, 200), length=(10000, 10000), locus=40000,
                     sub_rate=0.002, repeats=(2, 4, 1000, 3000)),
+    # reduced cfg5 the reference binary can finish (golden outputs): 14 contigs x 8 kb on a repeat-rich 20 kb locus
+    "cfg5r": GapSpec(n_contigs=(14, 14), length=(8000, 8000), locus=20000, sub_rate=0.002, repeats=(2, 4, 1000, 3000)),
     # small shapes for unit tests
     "tiny": GapSpec(n_contigs=(6, 6), length=(60, 220), locus=500, sub_rate=0.01),
     "small": GapSpec(n_contigs=(12, 12), length=(100, 600), locus=1500, sub_rate=0.005, indel_rate=0.001),
