@@ -23,7 +23,7 @@ on the data path.
             (traffic: DRAM bytes of one launch from the committed ncu capture; HBM is idle on this path)
   cpu_baseline  the reference's own Evaluate (oracle/_ref/libcm_ref.so, kind "reference") or the C
             restatement (kind "port") on the host cores, on a bounded sample of the same pair list
-  parity_sample  (with cpu_baseline) 48 pairs spread over the pair list: the timed end-to-end step's results
+  parity_sample  (with cpu_baseline) 512 pairs (cfg5: 96) spread over the pair list: the timed end-to-end step's results
             against the oracle, field by field
   dropin    (N = 1, cfg1) whole gaps per second through build/ContigsMerger_b200 --batch on the same gaps as FASTA
             files -- read, quick check on the device, pairwise phase, graph, relax chains, output; outside
@@ -56,11 +56,11 @@ OPS_PER_CELL = 6  # 1 compare/select + 3 adds + 2 max
 
 
 def build_workload(n_gaps: int, first_seed: int, config: str = "cfg1"):
-    """-> (seqs: list[bytes], pairs: structured array, cells, per-gap pair counts)"""
+    """-> (seqs: list[bytes], pairs: structured array, cells, per-gap pair counts, per-gap node counts)"""
     import gappadder_b200 as g
     import synth_gaps
     from gappadder_b200.capi import PAIR_DTYPE
-    seqs, chunks, per_gap = [], [], []
+    seqs, chunks, per_gap, nodes_per_gap = [], [], [], []
     spec = synth_gaps.CONFIGS[config]
     for gi in range(n_gaps):
         recs = synth_gaps.make_gap(first_seed + gi, spec)
@@ -75,10 +75,11 @@ def build_workload(n_gaps: int, first_seed: int, config: str = "cfg1"):
         seqs.extend(nodes)
         chunks.append(cand)
         per_gap.append(len(cand))
+        nodes_per_gap.append(len(nodes))
     pairs = np.concatenate(chunks) if chunks else np.zeros(0, dtype=PAIR_DTYPE)
     lens = np.array([len(s) for s in seqs], dtype=np.int64)
     cells = int((lens[pairs["row_seq"]] * lens[pairs["col_seq"]]).sum()) if len(pairs) else 0
-    return seqs, pairs, cells, per_gap
+    return seqs, pairs, cells, per_gap, nodes_per_gap
 
 
 def rank_first_seed(first_seed: int, rank: int, gaps_per_rank: int) -> int:
@@ -204,7 +205,7 @@ def cpu_sample(seqs, pairs, cores: int, budget_s: float, run):
     return pairs[:n], int(csum[n - 1])
 
 
-def parity_sample(seqs, pairs, res, cores: int, n: int = 48):
+def parity_sample(seqs, pairs, res, cores: int, n: int = 512):
     """Checker (part of the cpu_baseline leg): n pairs spread over this run's pair list, the timed end-to-end
     step's results against the oracle's Evaluate, field by field."""
     import _oracle
@@ -234,23 +235,46 @@ def parity_sample(seqs, pairs, res, cores: int, n: int = 48):
     return {"pairs": int(len(idx)), "mismatches": len(bad), "first_bad": bad[:4], "against": "oracle/overlap_oracle.c gpo_evaluate"}
 
 
-def dropin_line(args):
-    """Whole-gap throughput beside the bench line (not part of any timed region above): the drop-in binary
-    build/ContigsMerger_b200 --batch on the same gaps as FASTA files -- read, quick check, pairwise phase, graph,
-    relax chains, output -- timed by tools/dropin_bench.py.  gaps_per_s here is whole gaps merged per second."""
+def _dropin_tool(cli, timeout=600):
     tool = os.path.join(ROOT, "tools", "dropin_bench.py")
-    binary = os.path.join(ROOT, "build", "ContigsMerger_b200")
-    if not os.path.exists(binary):
+    if not os.path.exists(os.path.join(ROOT, "build", "ContigsMerger_b200")):
         return {"unavailable": "build/ContigsMerger_b200 not built"}
     try:
-        p = subprocess.run([sys.executable, tool, "--gaps", str(args.gaps), "--seed", str(args.seed), "--ref-gaps", "0"],
-                           capture_output=True, text=True, timeout=300)
-        d = json.loads(p.stdout.strip().splitlines()[-1])
+        p = subprocess.run([sys.executable, tool] + cli, capture_output=True, text=True, timeout=timeout)
+        return json.loads(p.stdout.strip().splitlines()[-1])
     except Exception as e:                                   # the bench line must not depend on it
         return {"unavailable": "%s: %s" % (type(e).__name__, e)}
-    keep = ("gaps", "gpus", "workers", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
-            "relax_steps", "output_ms", "gaps_per_s", "gcups", "error")
-    return {k: d[k] for k in keep if k in d}
+
+
+DROPIN_KEEP = ("gaps", "gpus", "workers", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
+               "relax_steps", "output_ms", "partition_ms", "qc_kernel_ms", "gaps_per_s", "gaps_per_s_process", "process_wall_s", "gcups",
+               "worker_wall_ms", "worker_gaps", "worker_gcells", "imbalance_max_over_mean", "vs_gpus1", "reference", "error", "unavailable")
+
+
+def dropin_line(args, world):
+    """Whole-gap throughput beside the bench line (not part of any timed region above): the drop-in binary
+    build/ContigsMerger_b200 --batch on gaps as FASTA files -- read, LPT partition, quick check, pairwise phase, graph,
+    relax chains, output -- timed by tools/dropin_bench.py.  gaps_per_s is whole gaps merged per second.
+      cfg1    (N = 1) the bench workload's own 200 gaps on one GPU, one of them also through the reference binary (bytes compared)
+      strong  the product's multi-GPU path: ONE fixed job (args.dropin_gaps cfg3-shaped gaps, 10-80 contigs each: BASELINE
+              configs[2]/[3] shape) through `--batch --gpus N`, gaps assigned to GPUs by gp_partition_gaps (LPT on estimated
+              cells), results gathered by the host; per-GPU wall, imbalance, and the first 32 gaps byte-compared with --gpus 1."""
+    out = {}
+    if world == 1 and args.config == "cfg1":
+        d = _dropin_tool(["--gaps", str(args.gaps), "--seed", str(args.seed), "--ref-gaps", "1", "--repeat", "2"])
+        out["cfg1"] = {k: d[k] for k in DROPIN_KEEP if k in d}
+    d = _dropin_tool(["--config", "cfg3", "--gaps", str(args.dropin_gaps), "--seed", "5000", "--gpus", str(world), "--ref-gaps", "0",
+                      "--verify-gpus1", "32" if world > 1 else "0", "--repeat", "2"])
+    out["strong"] = {k: d[k] for k in DROPIN_KEEP if k in d}
+    out["strong"]["job"] = "%d cfg3-shaped gaps (seeds 5000..), fixed for every N: strong scaling of whole gaps/s" % args.dropin_gaps
+    walls = out["strong"].get("worker_wall_ms")
+    if walls:
+        t = out["strong"]
+        host = t.get("read_ms", 0) + t.get("graph_ms", 0) + t.get("output_ms", 0)
+        out["strong"]["limiter"] = ("host phases (FASTA read + graph + output: %.0f of %.0f ms on the slowest worker)" % (host, t["merge_ms"])
+                                    if host > 0.5 * t["merge_ms"] else "device phases (pairwise + relax: %.0f of %.0f ms on the slowest worker)"
+                                    % (t.get("pairwise_ms", 0) + t.get("relax_ms", 0), t["merge_ms"]))
+    return out
 
 
 def host_cores():
@@ -267,7 +291,7 @@ def run_reference(args):
     kind, run = cpu_path()
     cores = min(host_cores(), 64)
     n_gaps = max(1, min(args.gaps, 8))
-    seqs, pairs, _, _ = build_workload(n_gaps, args.seed, args.config)
+    seqs, pairs, _, _, _ = build_workload(n_gaps, args.seed, args.config)
     sample, cells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
     for _ in range(min(args.warmup, 1)):
         cpu_run_pairs(run, seqs, sample[:max(cores, len(sample) // 8)], cores)
@@ -294,9 +318,26 @@ WORKLOADS = {
 }
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of overlap_wf16c_kernel on cfg1 (200 gaps), one launch, from the committed
-# ncu --set full capture (profiles/wf16c_r01final.ncu_summary.txt: 21.96 MB read, 9.42 MB written)
-NCU_DRAM_BYTES_PER_LAUNCH = 31.4e6
+def committed_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one overlap_wf16c_kernel launch on cfg1 (200 gaps), read from the
+    newest committed `ncu --set full` summary under profiles/ (tools/ncu_summary.py output) -> (bytes, file name)."""
+    import glob
+    import re
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "wf16c_r*.ncu_summary.txt"))):
+        txt = open(f).read()
+        rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+) Mbyte", txt)
+        wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+) Mbyte", txt)
+        if rd and wr and "<1, 1, 1>" in txt:
+            best = ((float(rd.group(1)) + float(wr.group(1))) * 1e6, os.path.relpath(f, ROOT))
+    return best
+
+
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6545.0, "B200_PROFILING.md fallback"
 
 
 def workload_config(args):
@@ -327,7 +368,7 @@ def run_gpu(args):
 
     ctx = g.Context(local_rank)                 # fails loudly without the CUDA library / a B200
     ctx.set_cert_layout(args.cert_layout)
-    seqs, pairs, cells, per_gap = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps), args.config)
+    seqs, pairs, cells, per_gap, nodes_per_gap = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps), args.config)
     packed, off, lens, nsym = g.pack_sequences(seqs)
     ctx.set_sequences(packed, off, lens, nsym)
     ctx.set_kernel_mask(args.kernel_mask)
@@ -395,6 +436,40 @@ def run_gpu(args):
     checksum = int(res["score"].astype(np.int64).sum()) if res is not None and len(res) else 0
     cert = ctx.cert_stats()
 
+    # --- HBM / PCIe-bound byte phases (rank 0): packing + table upload, quick check on the device, result scatter ----
+    hbm = None
+    if rank == 0:
+        n_bases = int(sum(len(x) for x in seqs))
+        peak_gbs, peak_src = measured_hbm_peak()
+        t_up = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ctx.upload_host_sequences(hb)                      # ASCII -> 4-bit codes in pinned memory (host threads) -> HBM
+            t_up.append(time.perf_counter() - t0)
+        up_ms = min(t_up) * 1e3
+        gap_first = np.concatenate([[0], np.cumsum(nodes_per_gap)]).astype(np.uint32)
+        qc_ms, qc_items, qc_equal = None, None, None
+        if max(nodes_per_gap) <= 4096:
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            qc = ctx.quick_check_device(gap_first, 10)
+            st = ctx.quick_check_stats()
+            qc_ms, qc_items = st["kernel_ms"], st["items"]
+            qc_pairs = sum(len(x) for x in qc)
+            qc_equal = bool(qc_pairs == len(pairs))               # same candidate list size as the host filter that built the workload
+        qc_bytes = n_bases // 2 + n_bases // 8                     # packed codes once + 4 B of carry-in per 32 bases
+        hbm = {
+            "peak_GBps": peak_gbs, "peak_source": peak_src, "bases": n_bases,
+            "pack_and_upload": {"what": "gp_upload_sequences: 1 B/base ASCII read + 0.5 B/base written to pinned memory (host threads), 0.5 B/base H2D",
+                                "bytes": int(n_bases * 2), "ms": up_ms, "GBps": n_bases * 2 / (up_ms * 1e-3) / 1e9,
+                                "bound": "host memory + PCIe, not HBM"},
+            "quick_check": {"what": "quick_check_kernel on the packed table in HBM, L2 flushed before it", "bytes": int(qc_bytes), "kernel_ms": qc_ms,
+                            "GBps": (qc_bytes / (qc_ms * 1e-3) / 1e9) if qc_ms else None,
+                            "frac_of_hbm_peak": (qc_bytes / (qc_ms * 1e-3) / 1e9 / peak_gbs) if qc_ms else None,
+                            "work_items": qc_items, "candidate_count_equals_host_filter": qc_equal},
+            "result_scatter": {"what": "20 B per pair written by the DP kernels, one D2H copy", "bytes": d2h},
+        }
+
     # --- reduce over ranks ---------------------------------------------------------------------
     tot_cells, tot_gaps, max_ms, max_e2e_ms = reduce_over_ranks(dist, dev, cells, args.gaps, my_ms, my_e2e_ms)
 
@@ -402,6 +477,7 @@ def run_gpu(args):
         value = tot_cells / (max_ms * 1e-3) / 1e9
         e2e_v = tot_cells / (max_e2e_ms * 1e-3) / 1e9
         alu, dual = ctx.int_peak()
+        traffic = committed_ncu_traffic()
         peak_lane_ops = 2.0 * dual                             # two 16-bit lanes per packed instruction
         # dominant kernel: the one with the most host-routed cells; its own launch time (library events around it)
         kname = max(ktimes, key=lambda k: ktimes[k]["cells"])
@@ -414,7 +490,7 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s16x2", "data": "synthetic", "config": workload_config(args),
-            "gaps_per_s": tot_gaps / (max_ms * 1e-3),
+            "pairwise_gaps_per_s": tot_gaps / (max_ms * 1e-3),      # pairwise phase only; whole gaps/s is dropin.*.gaps_per_s
             "pairs_per_step": int(len(pairs)) * world, "gcells_per_step": tot_cells / 1e9,
             "kernel_split": {"pairs_cert16": cert["cert16"], "pairs_table16": split["table16"], "pairs_prmt16": split["prmt16"],
                              "pairs_wide32": split["wide32"], "cert_second_passes": cert["second_passes"],
@@ -425,15 +501,16 @@ def run_gpu(args):
             "kernel_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in ktimes.items()},
             "kernel_gcells": {k: v["cells"] / 1e9 for k, v in ktimes.items()},
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": max_e2e_ms, "gaps_per_s": tot_gaps / (max_e2e_ms * 1e-3), "timing": "wall clock of the blocking gp_overlap_batch call",
+                    "ms_per_step": max_e2e_ms, "pairwise_gaps_per_s": tot_gaps / (max_e2e_ms * 1e-3), "timing": "wall clock of the blocking gp_overlap_batch call",
                     "last_call_breakdown_ms": {k: round(v, 3) for k, v in breakdown.items()}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tintop/s",
-                         "frac": achieved / peak_lane_ops, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if args.config == "cfg1" and args.gaps == 200 else None,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the ncu --set full "
-                                         "capture summarised in profiles/wf16c_r01final.ncu_summary.txt (not measured in this run); HBM is idle, "
-                                         "the bound is the integer issue rate",
+                         "frac": achieved / peak_lane_ops, "traffic": traffic[0] if traffic and args.config == "cfg1" and args.gaps == 200 else None,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, read from the committed "
+                                         "ncu --set full summary %s (ncu cannot run inside a timed bench); algorithmic bytes per launch: %d "
+                                         "(packed table + pair descriptors + work order + results); HBM is idle, the bound is the integer issue rate"
+                                         % (traffic[1] if traffic else "(none)", h2d + d2h),
                          "kernel": kernel_fn, "kernel_ms": k_ms, "kernel_gcells": k_cells / 1e9, "ops_per_cell": OPS_PER_CELL,
                          "peak_source": "measured live (gp_int_peak): 2 lanes x VIMNMX.S16x2+VIADD.16x2 dual-issue rate; "
                                         "ALU pipe alone %.2f Tinst/s, both pipes %.2f Tinst/s" % (alu / 1e12, dual / 1e12)},
@@ -446,11 +523,30 @@ def run_gpu(args):
             t = cpu_run_pairs(run, seqs, sample, cores)
             line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "first %d candidate pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
-            line["parity_sample"] = parity_sample(seqs, pairs, res, cores)
-        if world == 1 and not args.no_dropin and args.config == "cfg1":
-            line["dropin"] = dropin_line(args)
-        print(json.dumps(line))
+            line["parity_sample"] = parity_sample(seqs, pairs, res, cores, 96 if args.config == "cfg5" else 512)
+        line["hbm"] = hbm
+        print_line = line
+    else:
+        print_line = None
     ctx.close()
+    # Whole-gap throughput through the drop-in binary (the product's own multi-GPU path at N > 1): rank 0 runs it as a
+    # subprocess on all N GPUs while the other ranks wait on the CPU (a store key, not an NCCL barrier, whose kernel
+    # would spin on their GPUs).
+    if not args.no_dropin:
+        if dist is not None:
+            store = dist.distributed_c10d._get_default_store()
+            torch.cuda.synchronize(dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            if rank == 0:
+                print_line["dropin"] = dropin_line(args, world)
+                store.set("gp_dropin_done", "1")
+            else:
+                store.wait(["gp_dropin_done"])
+        elif args.config == "cfg1":
+            print_line["dropin"] = dropin_line(args, world)
+    if rank == 0:
+        print(json.dumps(print_line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -463,7 +559,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gaps", type=int, default=200, help="gaps per GPU per step (cfg1 = 200)")
+    ap.add_argument("--gaps", type=int, default=None, help="gaps per GPU per step (default: cfg1/cfg3 200, cfg5 20 = BASELINE's counts)")
+    ap.add_argument("--dropin-gaps", type=int, default=1600, help="size of the fixed cfg3-shaped job of the drop-in's strong-scaling run")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--config", default="cfg1", choices=sorted(WORKLOADS), help="workload shape (tools/synth_gaps.py); the bench line is cfg1")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work in the cpu_baseline sample")
@@ -472,6 +569,8 @@ def main():
     ap.add_argument("--cert-layout", type=int, default=0, help="A/B: certificate kernel value layout (0 free moves when a launch allows it, 1 column potential only)")
     ap.add_argument("--kernel-mask", type=int, default=15, help="A/B: what the library may use (1 table, 2 PRMT, 4 certificate kernel, 8 closed form for s-vs-s)")
     args = ap.parse_args()
+    if args.gaps is None:
+        args.gaps = 20 if args.config == "cfg5" else 200
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

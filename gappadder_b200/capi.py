@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
         L.gp_set_cert_layout.argtypes = [C.c_void_p, C.c_uint32]
         L.gp_last_layout.argtypes = [C.c_void_p]
         L.gp_quick_check_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
+        L.gp_upload_sequences.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32]
         L.gp_quick_check_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -358,6 +359,10 @@ class Context:
     def set_sequences(self, packed: np.ndarray, off: np.ndarray, lens: np.ndarray, n_symbols: int):
         self._check(self._L.gp_set_sequences(self._h, packed.ctypes.data, packed.nbytes, off.ctypes.data,
                                              lens.ctypes.data, len(lens), n_symbols))
+
+    def upload_host_sequences(self, batch: "HostBatch"):
+        """gp_upload_sequences: ASCII sequences -> 4-bit codes in the context's pinned buffer -> HBM.  Blocking."""
+        self._check(self._L.gp_upload_sequences(self._h, batch.arr, batch.lens.ctypes.data, batch.n_seq))
 
     def upload_pairs(self, pairs: np.ndarray, params: DpParams = GAPPADDER_DP):
         pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)

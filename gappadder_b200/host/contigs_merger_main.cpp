@@ -12,6 +12,7 @@
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
 // OUT.fa.gml in batch mode (the reference drops ./tmp.gml in the working directory of each process).
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -125,16 +126,30 @@ int run_batch(const Cli& c)
     int n_gpus = n_dev * per_dev;                                  // number of workers from here on
     if ((size_t)n_gpus > lines.size() && !lines.empty()) n_gpus = (int)lines.size();
     std::vector<uint64_t> cost(lines.size(), 0);
-    if (n_gpus > 1) {
-        for (size_t g = 0; g < lines.size(); ++g) {
-            std::vector<FastaRecord> recs; std::string fatal;
-            read_fasta(lines[g].in, recs, fatal);
-            std::vector<uint32_t> lens;
-            for (const FastaRecord& r : recs) lens.push_back((uint32_t)r.seq.size());
-            cost[g] = estimate_gap_cells(lens);
-        }
+    const auto part0 = std::chrono::steady_clock::now();
+    // Every FASTA is read once, here, on the host cores: the contig lengths balance the gaps over the workers
+    // (gp_partition_gaps), the records go to the workers as they are.
+    std::vector<GapInput> loaded(lines.size());
+    {
+        std::atomic<size_t> next(0);
+        auto reader = [&] {
+            for (size_t g = next.fetch_add(1); g < lines.size(); g = next.fetch_add(1)) {
+                GapInput& gi = loaded[g];
+                gi.fasta_path = lines[g].in;
+                gi.read_ok = read_fasta(gi.fasta_path, gi.records, gi.fatal);
+                gi.loaded = true;
+                std::vector<uint32_t> lens;
+                for (const FastaRecord& r : gi.records) lens.push_back((uint32_t)r.seq.size());
+                cost[g] = estimate_gap_cells(lens);
+            }
+        };
+        const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> rd;
+        for (unsigned t = 0; t < T; ++t) rd.emplace_back(reader);
+        for (auto& t : rd) t.join();
     }
     const std::vector<int> part = partition_gaps(cost, n_gpus);
+    const double partition_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - part0).count();
     std::vector<int> rc(n_gpus, 0);
     std::vector<std::string> err(n_gpus);
     std::vector<uint64_t> cells(n_gpus, 0), pcells(n_gpus, 0);
@@ -144,7 +159,7 @@ int run_batch(const Cli& c)
     auto worker = [&](int dev) {
         std::vector<GapInput> in;
         std::vector<size_t> which;
-        for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(GapInput{lines[g].in}); which.push_back(g); }
+        for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(std::move(loaded[g])); which.push_back(g); }
         if (in.empty()) return;
         gp_ctx* ctx = nullptr;
         int r = gp_create(dev % n_dev, &ctx);
@@ -184,14 +199,25 @@ int run_batch(const Cli& c)
         uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;
         uint64_t shared_pairs = 0, shared_cells = 0;      // relax steps shared between chains with a common path prefix: not computed twice
         for (const MergeTimings& x : tim) { shared_pairs += x.relax_shared_pairs; shared_cells += x.relax_shared_cells; }
+        double qc_ms = 0; uint64_t qc_bases = 0; uint32_t qc_items = 0;
+        for (const MergeTimings& x : tim) { qc_ms = std::max(qc_ms, x.qc_kernel_ms); qc_bases += x.qc_bases; qc_items += x.qc_items; }
+        std::string per_worker = "\"worker_wall_ms\": [";
+        for (int d = 0; d < n_gpus; ++d) per_worker += (d ? ", " : "") + std::to_string(wall[d]);
+        per_worker += "], \"worker_gcells\": [";
+        for (int d = 0; d < n_gpus; ++d) per_worker += (d ? ", " : "") + std::to_string(cells[d] / 1e9);
+        per_worker += "], \"worker_gaps\": [";
+        for (int d = 0; d < n_gpus; ++d) { size_t cnt = 0; for (size_t g = 0; g < lines.size(); ++g) cnt += part[g] == d; per_worker += (d ? ", " : "") + std::to_string(cnt); }
+        per_worker += "]";
         fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
                         "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
                         "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "
-                        "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu, \"relax_shared_pairs\": %llu, \"relax_shared_gcells\": %.6f, \"relax_call_ms\": %.3f, \"relax_pack_ms\": %.3f}\n",
+                        "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu, \"relax_shared_pairs\": %llu, \"relax_shared_gcells\": %.6f, \"relax_call_ms\": %.3f, \"relax_pack_ms\": %.3f, "
+                        "\"qc_kernel_ms\": %.4f, \"qc_bases\": %llu, \"qc_items\": %u, \"partition_ms\": %.3f, %s}\n",
                 lines.size(), n_dev, n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
                 t.relax_device_ms, t.relax_host_ms, t.relax_team_steps, (unsigned long long)t.relax_pairs,
                 (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries,
-                (unsigned long long)shared_pairs, shared_cells / 1e9, t.relax_call_ms, t.relax_pack_ms);
+                (unsigned long long)shared_pairs, shared_cells / 1e9, t.relax_call_ms, t.relax_pack_ms,
+                qc_ms, (unsigned long long)qc_bases, qc_items, partition_ms, per_worker.c_str());
     }
     return gap_failed ? 3 : 0;
 }
@@ -210,7 +236,8 @@ int main(int argc, char** argv)
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s (no CPU fallback)\n", gp_last_error(nullptr)); return 3; }
     std::vector<GapOutput> out;
     std::string err;
-    rc = merge_gaps(ctx, c.opt, {GapInput{c.input}}, out, err);
+    GapInput single; single.fasta_path = c.input;
+    rc = merge_gaps(ctx, c.opt, {single}, out, err);
     gp_destroy(ctx);
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s\n", err.c_str()); return 3; }   // never partial stdout
     if (!out[0].error.empty()) { fprintf(stderr, "ContigsMerger_b200: %s\n", out[0].error.c_str()); return 3; }

@@ -126,7 +126,10 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     for_each_gap(G, host_threads, [&](size_t g) {
         GapState& s = st[g];
         std::string fatal;
-        if (!read_fasta(in[g].fasta_path, s.contigs, fatal)) {
+        bool ok;
+        if (in[g].loaded) { s.contigs = in[g].records; ok = in[g].read_ok; fatal = in[g].fatal; }
+        else ok = read_fasta(in[g].fasta_path, s.contigs, fatal);
+        if (!ok) {
             out[g].stdout_text = "FATAL ERROR: " + fatal + "\n";          // THROW, fastareader.cpp:11-15
             out[g].exit_code = 1;
             s.dead = true;

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "fasta.hpp"
 #include "gappadder_b200.h"
 
 namespace gpm {
@@ -33,6 +34,12 @@ struct MergeOptions {
 
 struct GapInput {
     std::string fasta_path;
+    // Optional: the file's records when the caller has read it already (the batch driver reads every gap once, in
+    // parallel, to balance the gaps over GPUs by contig lengths).  read_ok / fatal are read_fasta's results.
+    bool loaded = false;
+    bool read_ok = true;
+    std::string fatal;
+    std::vector<FastaRecord> records;
 };
 
 struct GapOutput {

@@ -30,7 +30,7 @@ def _worker(rank, world, port, q):
     import bench
     gaps = 3
     first = bench.rank_first_seed(100, rank, gaps)
-    seqs, pairs, cells, per_gap = bench.build_workload(gaps, first, config="tiny")
+    seqs, pairs, cells, per_gap, _ = bench.build_workload(gaps, first, config="tiny")
     seeds = [None] * world
     dist.all_gather_object(seeds, list(range(first, first + gaps)))
     my_ms, my_e2e = 10.0 * (rank + 1), 30.0 - 5.0 * rank

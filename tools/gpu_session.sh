@@ -1,0 +1,36 @@
+#!/bin/bash
+# tools/gpu_session.sh TAG [what...] -- one gpurun call's worth of work on the GPU box; everything lands in gpurun_out/TAG_*.
+# what: tests bench ref cfg3 cfg5 ncu_pair ncu_relax launches dropin qc   (default: tests bench)
+TAG=$1; shift
+WHAT="${*:-tests bench}"
+O=gpurun_out
+mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_gpu.txt 2>&1
+for w in $WHAT; do
+  case $w in
+    tests)   timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; tail -5 $O/${TAG}_pytest.log ;;
+    bench)   timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.json ;;
+    benchq)  timeout 600 python bench.py --no-dropin --no-cpu > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; tail -c 400 $O/${TAG}_benchq.json ;;
+    ref)     timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2>&1 ;;
+    cfg3)    timeout 600 python bench.py --config cfg3 --no-dropin > $O/${TAG}_bench_cfg3.json 2> $O/${TAG}_bench_cfg3.err ;;
+    cfg5)    timeout 900 python bench.py --config cfg5 --steps 3 --no-dropin > $O/${TAG}_bench_cfg5.json 2> $O/${TAG}_bench_cfg5.err ;;
+    cfg2)    timeout 600 python bench.py --config cfg2 --no-dropin > $O/${TAG}_bench_cfg2.json 2> $O/${TAG}_bench_cfg2.err; tail -c 400 $O/${TAG}_bench_cfg2.json ;;
+    dropin)  timeout 600 python tools/dropin_bench.py --gaps 200 --ref-gaps 1 --repeat 3 > $O/${TAG}_dropin.json 2> $O/${TAG}_dropin.err; cat $O/${TAG}_dropin.json ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-dropin > $O/${TAG}_ncu_launches.log 2>&1 ;;
+    ncu_pair) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:overlap_wf16c -s 1 -c 1 -o $O/${TAG}_wf16c -f python bench.py --steps 1 --warmup 1 --no-cpu --no-dropin > $O/${TAG}_ncu_full.log 2>&1 ;;
+    ncu_relax) python tools/dropin_bench.py --gaps 200 --ref-gaps 0 > /dev/null 2>&1
+             mkdir -p /tmp/rl && python - <<'PY'
+import sys, os
+sys.path.insert(0, 'tools')
+import synth_gaps
+with open('/tmp/rl/list.tsv', 'w') as f:
+    for g in range(200):
+        fa = '/tmp/rl/g%d.fa' % g
+        synth_gaps.write_fasta(fa, synth_gaps.make_gap(1 + g, synth_gaps.CONFIGS['cfg1']))
+        f.write('%s\t/tmp/rl/g%d.out\t/tmp/rl/g%d.info\n' % (fa, g, g))
+PY
+             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"overlap_wf16c|relax" -s 3 -c 6 -o $O/${TAG}_relax -f build/ContigsMerger_b200 -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1 -t 5 --batch /tmp/rl/list.tsv --no-gml > $O/${TAG}_ncu_relax.log 2>&1 ;;
+    qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
+    *) echo "unknown: $w" ;;
+  esac
+done

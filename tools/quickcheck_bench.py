@@ -50,12 +50,21 @@ def main():
         ctx._check(ctx._L.gp_quick_check_device(ctx._h, gf.ctypes.data, len(gf) - 1, 10, hit.ctypes.data, hit.nbytes))
         ts.append(time.perf_counter() - t0)
     dev_s = float(np.median(ts))
+    st = ctx.quick_check_stats()                                  # kernel alone (CUDA events), last call
+    kernel_bytes = bases // 2 + bases // 8                        # packed codes once + 4 B carry-in per 32 bases
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6545.0
     algo_bytes = packed.nbytes + hit.nbytes                       # packed codes read once (0.5 B/base) + hit matrices written
     print(json.dumps({"config": a.config, "gaps": a.gaps, "nodes": len(seqs), "mbases": bases / 1e6, "pairs": int(sum(len(x) for x in want)),
                       "identical": bool(same), "host_ms": host_s * 1e3, "host_note": "gp_candidate_pairs, one call per gap, one thread",
                       "device_ms": dev_s * 1e3, "device_note": "blocking gp_quick_check_device call, sequences resident in HBM",
                       "device_gbases_per_s": bases / dev_s / 1e9, "algorithmic_bytes": int(algo_bytes),
-                      "device_algorithmic_gb_per_s": algo_bytes / dev_s / 1e9}))
+                      "device_algorithmic_gb_per_s": algo_bytes / dev_s / 1e9,
+                      "kernel_ms": st["kernel_ms"], "kernel_items": st["items"], "kernel_bytes": int(kernel_bytes),
+                      "kernel_gb_per_s": kernel_bytes / (st["kernel_ms"] * 1e-3) / 1e9, "hbm_peak_gb_per_s": peak,
+                      "kernel_frac_of_hbm_peak": kernel_bytes / (st["kernel_ms"] * 1e-3) / 1e9 / peak}))
 
 
 if __name__ == "__main__":
