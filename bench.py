@@ -30,7 +30,9 @@ on the data path.
             every timed region above (tools/dropin_bench.py)
 
 `--impl reference` times only that CPU path (rank 0 only under torchrun).  `--config cfg3|cfg5` runs the other
-BASELINE shapes (cfg5: 10 kb contigs, use --gaps 2); `--cert-layout 1` forces the certificate kernel's
+BASELINE shapes (cfg5: 10 kb contigs, 20 gaps); `--config cfg2` is BASELINE configs[1], flank placement: the semi-global kernel
+(gp_semiglobal_batch) on 2 flanks x 80 nodes per gap, bit-exact against the oracle's builder-written definition -- the reference's
+own arithmetic there is BWA's, absent from the reference tree (parity unpinned), so its CPU arm is the oracle port; `--cert-layout 1` forces the certificate kernel's
 column-potential layout (A/B); the bench line the driver reads is the default cfg1 run.
 """
 from __future__ import annotations
@@ -312,6 +314,8 @@ def run_reference(args):
 
 
 WORKLOADS = {
+    "cfg2": "cfg2 (BASELINE configs[1], flank placement): %d synthetic gaps/GPU x 2 flanks (995 bp) x 40 contigs and their reverse "
+            "complements (300-3000 bp), semi-global (flank end to end inside the contig); BWA parity unpinned",
     "cfg1": "cfg1: %d synthetic gaps/GPU x 40 contigs (300-3000 bp, 8 kb locus, 0.2%% subst, 50%% RC)",
     "cfg3": "cfg3 (BASELINE configs[2]/[3] shape): %d synthetic gaps/GPU x 10-80 contigs, six k-mer sets (300-3000 bp, 8 kb locus)",
     "cfg5": "cfg5 (BASELINE configs[4], long-contig stress): %d synthetic gaps/GPU x 200 contigs x 10 kb on a 40 kb repeat-rich locus",
@@ -342,9 +346,192 @@ def measured_hbm_peak():
 
 def workload_config(args):
     return {"workload": WORKLOADS[args.config] % args.gaps +
-                        ", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)",
+                        (", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)" if args.config != "cfg2"
+                         else ", every flank against every node, scores +1 / -2 / -2"),
             "gaps_per_gpu": args.gaps, "first_seed": args.seed, "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": "gaps sharded by rank, no collective"}
+
+
+# ---------------------------------------------------------------------------------------------
+# cfg2: flank placement (semi-global).  Same contract as the overlap arm; the CPU arm is the oracle's builder-written
+# definition (kind "port"): GAPPadder's own arithmetic here is BWA's, which is not in /root/reference (parity unpinned).
+
+def build_flank_workload(n_gaps: int, first_seed: int):
+    import gappadder_b200 as g
+    import synth_gaps
+    from gappadder_b200.capi import PAIR_DTYPE
+    spec = synth_gaps.CONFIGS["cfg1"]
+    seqs, rows, cols = [], [], []
+    for gi in range(n_gaps):
+        base = len(seqs)
+        seqs += [s for _, s in synth_gaps.make_flanks(first_seed + gi, spec)]
+        for _, s in synth_gaps.make_gap(first_seed + gi, spec):
+            seqs += [s, g.revcomp(s)]
+            for f in (base, base + 1):
+                rows += [f, f]
+                cols += [len(seqs) - 2, len(seqs) - 1]
+    pairs = np.zeros(len(rows), dtype=PAIR_DTYPE)
+    pairs["row_seq"], pairs["col_seq"] = rows, cols
+    lens = np.array([len(s) for s in seqs], dtype=np.int64)
+    return seqs, pairs, int((lens[pairs["row_seq"]] * lens[pairs["col_seq"]]).sum())
+
+
+def cpu_flank_path():
+    import ctypes as C
+    import _oracle
+    lib = _oracle.oracle_lib()
+
+    def run(a, b):
+        r = _oracle.PlaceResult()
+        lib.gpo_semiglobal(a, len(a), b, len(b), -2, -2, C.byref(r))
+        return r
+    return "port", run
+
+
+def flank_parity_sample(seqs, pairs, res, cores, n=512):
+    _, run = cpu_flank_path()
+    idx = np.unique(np.linspace(0, len(pairs) - 1, num=min(n, len(pairs)), dtype=np.int64))
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(k):
+        o = run(seqs[int(pairs["row_seq"][k])], seqs[int(pairs["col_seq"][k])])
+        r = res[k]
+        return (o.score, o.col_start, o.col_end) == (int(r["score"]), int(r["col_start"]), int(r["col_end"]))
+    with ThreadPoolExecutor(max_workers=max(1, cores)) as ex:
+        ok = list(ex.map(one, idx))
+    bad = [int(k) for k, good in zip(idx, ok) if not good]
+    return {"pairs": int(len(idx)), "mismatches": len(bad), "first_bad": bad[:4],
+            "against": "oracle/overlap_oracle.c gpo_semiglobal (builder-written definition; BWA parity unpinned)"}
+
+
+def run_reference_cfg2(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    kind, run = cpu_flank_path()
+    cores = min(host_cores(), 64)
+    seqs, pairs, _ = build_flank_workload(max(1, min(args.gaps, 4)), args.seed)
+    sample, cells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run_pairs(run, seqs, sample[:max(cores, len(sample) // 8)], cores)
+    t = float(np.mean([cpu_run_pairs(run, seqs, sample, cores) for _ in range(args.steps)]))
+    v = cells / t / 1e9
+    desc = "first %d flank-node pairs (%.3f Gcells) of the cfg2 pair list, seeds %d.., per step" % (len(sample), cells / 1e9, args.seed)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc,
+                         "note": "the reference's own arithmetic for this path is BWA's (pick_contigs.py:83-86), absent from /root/reference: "
+                                 "this is the oracle's semi-global restatement, rolling rows, one pair per thread"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def run_gpu_cfg2(args):
+    import torch
+    import gappadder_b200 as g
+    from gappadder_b200.capi import HostBatch, PLACE_DTYPE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = g.Context(local_rank)
+    seqs, pairs, cells = build_flank_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps))
+    hb = HostBatch(seqs, pairs)
+    ctx.upload_host_sequences(hb)
+    ctx.semiglobal_upload_pairs(pairs, g.GAPPADDER_DP)
+    st = ctx.semiglobal_stats()
+    assert st["cells"] == cells
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        ctx.semiglobal_launch()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k_ms = 0.0
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        ctx.semiglobal_launch()
+        e1.record(stream)
+        stream.synchronize()
+        k_ms += ctx.semiglobal_stats()["kernel_ms"]
+    barrier()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev]))
+    k_ms /= args.steps
+    # end to end: the blocking C call on host ASCII buffers (pack into pinned memory, H2D, kernels, D2H)
+    out = np.zeros(len(pairs), dtype=PLACE_DTYPE)
+    for _ in range(min(args.warmup, 2)):
+        ctx.semiglobal_host_batch(hb, out, g.GAPPADDER_DP)
+    barrier()
+    e2e_t = []
+    for _ in range(args.steps):
+        out[:] = 0
+        t0 = time.perf_counter()
+        ctx.semiglobal_host_batch(hb, out, g.GAPPADDER_DP)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    my_e2e_ms = float(np.mean(e2e_t)) * 1e3
+    n_bases = int(sum(len(x) for x in seqs))
+    h2d = int(n_bases // 2 + len(pairs) * (16 + 4))
+    d2h = int(len(pairs) * 16)
+    tot_cells, tot_gaps, max_ms, max_e2e_ms = reduce_over_ranks(dist, dev, cells, args.gaps, my_ms, my_e2e_ms)
+    if rank == 0:
+        alu, dual = ctx.int_peak()
+        peak_lane_ops = 2.0 * dual
+        achieved = cells / (k_ms * 1e-3) * OPS_PER_CELL
+        line = {
+            "metric": METRIC, "value": tot_cells / (max_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32", "data": "synthetic",
+            "config": workload_config(args), "pairs_per_step": int(len(pairs)) * world, "gcells_per_step": tot_cells / 1e9,
+            "placement_gaps_per_s": tot_gaps / (max_ms * 1e-3),
+            "parity_status": "bit-exact against the builder-written semi-global definition (oracle gpo_semiglobal); BWA parity unpinned (SURVEY.md 8c)",
+            "kernel_split": {"pairs_table": st["table_pairs"], "pairs_generic": st["generic_pairs"]},
+            "e2e": {"value": tot_cells / (max_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": max_e2e_ms, "timing": "wall clock of the blocking gp_semiglobal_batch call"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tintop/s", "frac": achieved / peak_lane_ops,
+                         "traffic": None, "kernel": "flank_place_kernel", "kernel_ms": k_ms, "kernel_gcells": cells / 1e9, "ops_per_cell": OPS_PER_CELL,
+                         "peak_source": "measured live (gp_int_peak): 2 lanes x VIMNMX.S16x2+VIADD.16x2 dual-issue rate, the same denominator as the "
+                                        "overlap kernels; this kernel computes one 32-bit cell per instruction pair (score and start column in one word)"},
+            "result_checksum": int(out["score"].astype(np.int64).sum()),
+        }
+        if world == 1 and not args.no_cpu:
+            kind, run = cpu_flank_path()
+            cores = min(host_cores(), 64)
+            sample, scells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+            t = cpu_run_pairs(run, seqs, sample, cores)
+            line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "first %d flank-node pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
+            line["parity_sample"] = flank_parity_sample(seqs, pairs, out, cores)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -571,6 +758,8 @@ def main():
     args = ap.parse_args()
     if args.gaps is None:
         args.gaps = 20 if args.config == "cfg5" else 200
+    if args.config == "cfg2":
+        return run_reference_cfg2(args) if args.impl == "reference" else run_gpu_cfg2(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -21,6 +21,7 @@ EXPORTS = [
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
     "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device", "gp_upload_sequences",
     "gp_quick_check_stats",
+    "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
 ]
 
 
@@ -50,6 +51,7 @@ class Thresholds(C.Structure):
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
+PLACE_DTYPE = np.dtype([("score", "<i4"), ("col_start", "<i4"), ("col_end", "<i4"), ("flags", "<u4")])
 FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16, FLAG_CLOSED = 1, 2, 4, 8, 16
 KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_CLOSED, KERNEL_ALL = 1, 2, 4, 8, 15
 KERNEL_DP_ALL = KERNEL_TABLE16 | KERNEL_PRMT16 | KERNEL_CERT16      # every kernel, no closed form
@@ -122,6 +124,11 @@ def lib() -> C.CDLL:
         L.gp_quick_check_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
         L.gp_upload_sequences.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32]
         L.gp_quick_check_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.gp_semiglobal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(DpParams), C.c_void_p]
+        L.gp_semiglobal_upload_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(DpParams)]
+        L.gp_semiglobal_launch.argtypes = [C.c_void_p]
+        L.gp_semiglobal_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.gp_semiglobal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -316,6 +323,38 @@ class Context:
             p["row_seq"], p["col_seq"] = i, j
             out.append(p)
         return out
+
+    # ---- flank placement (semi-global; parity unpinned: bit-exact against oracle gpo_semiglobal) ----
+    def semiglobal_batch(self, seqs: Sequence[bytes], pairs, params: DpParams = GAPPADDER_DP) -> np.ndarray:
+        """pairs: (flank index, contig index).  -> PLACE_DTYPE array (score, col_start, col_end, flags)."""
+        hb = HostBatch(seqs, pairs)
+        out = np.zeros(len(hb.pairs), dtype=PLACE_DTYPE)
+        self._check(self._L.gp_semiglobal_batch(self._h, hb.arr, hb.lens.ctypes.data, hb.n_seq, hb.pairs.ctypes.data, len(hb.pairs),
+                                                C.byref(params), out.ctypes.data))
+        return out
+
+    def semiglobal_host_batch(self, hb: "HostBatch", out: np.ndarray, params: DpParams = GAPPADDER_DP) -> np.ndarray:
+        self._check(self._L.gp_semiglobal_batch(self._h, hb.arr, hb.lens.ctypes.data, hb.n_seq, hb.pairs.ctypes.data, len(hb.pairs),
+                                                C.byref(params), out.ctypes.data))
+        return out
+
+    def semiglobal_upload_pairs(self, pairs: np.ndarray, params: DpParams = GAPPADDER_DP):
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        self._check(self._L.gp_semiglobal_upload_pairs(self._h, pairs.ctypes.data, len(pairs), C.byref(params)))
+        self._n_place = len(pairs)
+
+    def semiglobal_launch(self):
+        self._check(self._L.gp_semiglobal_launch(self._h))
+
+    def semiglobal_fetch(self) -> np.ndarray:
+        out = np.zeros(self._n_place, dtype=PLACE_DTYPE)
+        self._check(self._L.gp_semiglobal_fetch(self._h, out.ctypes.data, self._n_place))
+        return out
+
+    def semiglobal_stats(self) -> dict:
+        cells, t, g, ms = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        self._check(self._L.gp_semiglobal_stats(self._h, C.byref(cells), C.byref(t), C.byref(g), C.byref(ms)))
+        return dict(cells=cells.value, table_pairs=t.value, generic_pairs=g.value, kernel_ms=ms.value)
 
     def quick_check_stats(self) -> dict:
         """Of the last quick_check_device: kernel ms (CUDA events), bases scanned, work items."""

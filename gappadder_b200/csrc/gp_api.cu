@@ -8,6 +8,7 @@
 #include "overlap_wf16t.cuh"
 #include "overlap_wf16c.cuh"
 #include "quick_check.cuh"
+#include "flank_place.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -73,6 +74,15 @@ struct gp_ctx {
 
     // pair work lists
     DeviceBuf d_qc_meta, d_qc_hit, d_qc_slab;  // quick check on the device: offsets/lengths/gap bounds/items, hit matrices, probe slabs
+    // flank placement (semi-global; flank_place.cuh)
+    DeviceBuf d_fp_pairs, d_fp_order, d_fp_results, d_fp_queue, d_fp_scratch;
+    HostBuf h_fp_stage;
+    uint64_t fp_pairs = 0, fp_n_table = 0, fp_n_generic = 0, fp_cells = 0;
+    uint32_t fp_max_n = 0;
+    std::vector<uint32_t> fp_host_ids;         // pairs with an empty flank or contig: answered on the host
+    gp_dp_params fp_params{};
+    cudaEvent_t fp_ev[2] = {nullptr, nullptr};
+    bool fp_ev_valid = false;
     cudaEvent_t qc_ev[2] = {nullptr, nullptr};
     double qc_kernel_ms = 0;
     uint64_t qc_bases = 0;
@@ -144,9 +154,10 @@ int gp_create(int device, gp_ctx** out)
         g_create_error = cudaGetErrorString(e); delete c; return GP_ERR_CUDA;
     }
     for (auto& ev : c->qc_ev) cudaEventCreate(&ev);
+    for (auto& ev : c->fp_ev) cudaEventCreate(&ev);
     for (auto& ev : c->kev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA; }
-    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess) {
+    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess || (e = gp::fp_configure()) != cudaSuccess) {
         g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
         cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA;
     }
@@ -161,6 +172,8 @@ void gp_destroy(gp_ctx* c)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->qc_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->fp_ev) if (ev) cudaEventDestroy(ev);
+    c->d_fp_pairs.release(); c->d_fp_order.release(); c->d_fp_results.release(); c->d_fp_queue.release(); c->d_fp_scratch.release(); c->h_fp_stage.release();
     c->d_qc_slab.release();
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
     c->d_scratch16t.release(); c->d_scratch16c.release(); c->d_order16c.release(); c->h_queue.release();
@@ -263,9 +276,11 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     const uint64_t total = hit_off[n_gaps];
     if (total > hit_bytes) return c->fail(GP_ERR_INVALID, "hit buffer too small: %llu bytes needed", (unsigned long long)total);
     // Work items: every gap cut into node ranges of about `item_bases` bases.  An item's first cost is the gap's probe
-    // set (42 k-mers per node, rebuilt by every CTA that meets the gap), so items are at least 64 kbases; beyond that
+    // table (42 k-mers per node, rebuilt by every CTA that meets the gap), so items are at least 32 kbases; beyond that
     // they are sized for four items per SM so that few large gaps still fill the chip.
-    const uint64_t item_bases = std::min<uint64_t>(1u << 20, std::max<uint64_t>(64u << 10, total_bases / (4ull * (uint64_t)c->sm_count) + 1));
+    const uint64_t item_bases = std::min<uint64_t>(1u << 20, std::max<uint64_t>(32u << 10, total_bases / (4ull * (uint64_t)c->sm_count) + 1));
+    std::vector<uint32_t> chunk_off(n_seq + 1, 0);                       // 32-base chunks before every table sequence
+    for (uint32_t s = 0; s < n_seq; ++s) chunk_off[s + 1] = chunk_off[s] + (c->seq_len[s] + gp::QC_CHUNK - 1) / gp::QC_CHUNK;
     std::vector<gp::QcItem> items;
     for (uint32_t g = 0; g < n_gaps; ++g) {
         const uint32_t first = gap_first[g], n = gap_first[g + 1] - first;
@@ -273,39 +288,50 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
         uint64_t acc = 0;
         for (uint32_t i = 0; i < n; ++i) {
             acc += c->seq_len[first + i];
-            if (acc >= item_bases || i + 1 == n) { items.push_back(gp::QcItem{g, lo, i + 1, 0u}); lo = i + 1; acc = 0; }
+            if (acc >= item_bases || i + 1 == n) {
+                gp::QcItem it{};
+                it.gap = g; it.node_lo = lo; it.node_hi = i + 1;
+                it.chunk_begin = chunk_off[first + lo]; it.n_chunks = chunk_off[first + i + 1] - chunk_off[first + lo];
+                items.push_back(it);
+                lo = i + 1; acc = 0;
+            }
         }
     }
     c->qc_bases = total_bases;
     c->qc_items = (uint32_t)items.size();
     if (items.empty()) { memset(hit, 0, (size_t)total); return GP_OK; }
     GP_CUDA(c, cudaSetDevice(c->device));
-    // meta: [seq_off n_seq][seq_len n_seq][gap_first n_gaps+1][pad][hit_off (n_gaps+1) x u64][items][queue]
-    const size_t w32 = (size_t)2 * n_seq + n_gaps + 1, w32p = (w32 + 1) & ~(size_t)1;
-    const size_t items_at = w32p * 4 + (size_t)(n_gaps + 1) * 8;
+    // meta: [seq_off n_seq][seq_len n_seq][chunk_off n_seq+1][gap_first n_gaps+1][pad][hit_off (n_gaps+1) x u64][items][queue]
+    const size_t w32 = (size_t)3 * n_seq + 1 + n_gaps + 1, w32p = (w32 + 3) & ~(size_t)3;
+    const size_t items_at = w32p * 4 + (((size_t)(n_gaps + 1) * 8 + 15) & ~(size_t)15);
     const size_t queue_at = items_at + items.size() * sizeof(gp::QcItem);
     const size_t meta_bytes = queue_at + 16;
     GP_CUDA(c, c->d_qc_meta.reserve(meta_bytes));
     GP_CUDA(c, c->d_qc_hit.reserve(total ? total : 16));
     const int blocks = (int)std::min<size_t>(items.size(), (size_t)c->sm_count);
-    const uint32_t slab_probes = (uint32_t)max_nodes * gp::qc_probes_per_node(k) + 32u;
-    GP_CUDA(c, c->d_qc_slab.reserve((size_t)blocks * 3u * slab_probes * sizeof(uint32_t)));
+    const uint32_t need_probes = (uint32_t)max_nodes * gp::qc_probes_per_node(k);
+    const uint32_t smem_probes = std::min(need_probes, gp::qc_smem_probe_capacity(k));
+    const uint32_t slab_probes = need_probes > smem_probes ? need_probes + 32u : 0u;   // only gaps too big for shared memory use it
+    GP_CUDA(c, c->d_qc_slab.reserve(slab_probes ? (size_t)blocks * slab_probes * sizeof(uint32_t) : 16));
     char* dmb = (char*)c->d_qc_meta.p;
     uint32_t* dm = (uint32_t*)dmb;
+    uint32_t* d_chunk = dm + 2 * (size_t)n_seq;
+    uint32_t* d_gapfirst = d_chunk + n_seq + 1;
     GP_CUDA(c, cudaMemcpyAsync(dm, c->seq_off.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dm + n_seq, c->seq_len.data(), (size_t)n_seq * 4, cudaMemcpyHostToDevice, c->stream));
-    GP_CUDA(c, cudaMemcpyAsync(dm + 2 * (size_t)n_seq, gap_first, (size_t)(n_gaps + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(d_chunk, chunk_off.data(), (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(d_gapfirst, gap_first, (size_t)(n_gaps + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dm + w32p, hit_off.data(), (size_t)(n_gaps + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemcpyAsync(dmb + items_at, items.data(), items.size() * sizeof(gp::QcItem), cudaMemcpyHostToDevice, c->stream));
     GP_CUDA(c, cudaMemsetAsync(dmb + queue_at, 0, 16, c->stream));
     if (total) GP_CUDA(c, cudaMemsetAsync(c->d_qc_hit.p, 0, total, c->stream));
-    const size_t smem = gp::qc_smem_bytes(k);
+    const size_t smem = gp::qc_smem_bytes(k, smem_probes);
     GP_CUDA(c, cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GP_CUDA(c, cudaEventRecord(c->qc_ev[0], c->stream));
     gp::quick_check_kernel<<<blocks, gp::QC_THREADS, smem, c->stream>>>(
-        (const uint32_t*)c->d_packed.p, dm, dm + n_seq, dm + 2 * (size_t)n_seq, (const uint64_t*)(dm + w32p),
+        (const uint32_t*)c->d_packed.p, dm, dm + n_seq, d_chunk, d_gapfirst, (const uint64_t*)(dm + w32p),
         (const gp::QcItem*)(dmb + items_at), (uint32_t)items.size(), (unsigned int*)(dmb + queue_at), (int)k,
-        (uint32_t*)c->d_qc_slab.p, slab_probes, (uint8_t*)c->d_qc_hit.p);
+        smem_probes, (uint32_t*)c->d_qc_slab.p, slab_probes, (uint8_t*)c->d_qc_hit.p);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->qc_ev[1], c->stream));
     c->launches += 1;
@@ -721,6 +747,138 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     c->timing[2] = ms(t2, t3);      // copies + kernels + result copy, until the stream is idle
     c->timing[3] = ms(t0, t3);
     return rc;
+}
+
+// ---- flank placement: semi-global alignment of a flank inside a contig (flank_place.cuh) -------------------------------
+
+static void sort_longest_first(const gp::PairDesc* hd, uint32_t* ord, uint64_t cnt)
+{
+    std::stable_sort(ord, ord + cnt, [&](uint32_t a, uint32_t b) { return (uint64_t)hd[a].m * hd[a].n > (uint64_t)hd[b].m * hd[b].n; });
+}
+
+int gp_semiglobal_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params)
+{
+    if (!c) return GP_ERR_INVALID;
+    c->fp_pairs = 0; c->fp_n_table = c->fp_n_generic = 0; c->fp_cells = 0; c->fp_max_n = 0; c->fp_host_ids.clear(); c->fp_ev_valid = false;
+    if (!params || (!pairs && n_pairs)) return c->fail(GP_ERR_INVALID, "null pairs/params");
+    if (params->indel > 0) return c->fail(GP_ERR_INVALID, "flank placement needs indel <= 0");
+    if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
+    if (n_pairs == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n_seq = (uint32_t)c->seq_len.size();
+    const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
+    GP_CUDA(c, c->h_fp_stage.reserve(desc_bytes + n_pairs * sizeof(uint32_t)));
+    gp::PairDesc* hd = (gp::PairDesc*)c->h_fp_stage.p;
+    uint32_t* ord = (uint32_t*)((char*)c->h_fp_stage.p + desc_bytes);
+    std::vector<uint32_t> generic;
+    uint64_t n_table = 0, cells = 0;
+    uint32_t max_n = 0;
+    for (uint64_t i = 0; i < n_pairs; ++i) {
+        const uint32_t a = pairs[i].row_seq, b = pairs[i].col_seq;
+        if (a >= n_seq || b >= n_seq) return c->fail(GP_ERR_INVALID, "pair %llu references sequence out of range", (unsigned long long)i);
+        const uint32_t m = c->seq_len[a], n = c->seq_len[b];
+        hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
+        if (m == 0 || n == 0) { c->fp_host_ids.push_back((uint32_t)i); continue; }
+        if (!gp::fp_pair_ok(m, n, params->indel) || std::abs(params->mismatch) > 1000)
+            return c->fail(GP_ERR_RANGE, "pair %llu (flank %u, contig %u bases) exceeds the placement kernel's range (contig <= %u bases, m + |indel|*(m+n) < 2^17)",
+                           (unsigned long long)i, m, n, gp::FP_MAX_N);
+        cells += (uint64_t)m * n;
+        max_n = std::max(max_n, n);
+        if (c->seq_acgt[a] && c->seq_acgt[b]) ord[n_table++] = (uint32_t)i; else generic.push_back((uint32_t)i);
+    }
+    std::copy(generic.begin(), generic.end(), ord + n_table);
+    sort_longest_first(hd, ord, n_table);
+    sort_longest_first(hd, ord + n_table, generic.size());
+    GP_CUDA(c, c->d_fp_pairs.reserve(desc_bytes));
+    GP_CUDA(c, c->d_fp_order.reserve(n_pairs * sizeof(uint32_t)));
+    GP_CUDA(c, c->d_fp_results.reserve(n_pairs * sizeof(gp::DevPlace)));
+    GP_CUDA(c, c->d_fp_queue.reserve(64));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_fp_pairs.p, hd, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_fp_order.p, ord, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->fp_pairs = n_pairs; c->fp_n_table = n_table; c->fp_n_generic = generic.size(); c->fp_cells = cells; c->fp_max_n = max_n;
+    c->fp_params = *params;
+    return GP_OK;
+}
+
+int gp_semiglobal_launch(gp_ctx* c)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (c->fp_n_table + c->fp_n_generic == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const int blocks = c->sm_count * gp::FP_CTAS_PER_SM;
+    const uint32_t warps = (uint32_t)blocks * (gp::FP_THREADS / 32);
+    const uint32_t stride = (c->fp_max_n + 1 + 64 + 31) & ~31u;
+    GP_CUDA(c, c->d_fp_scratch.reserve((size_t)warps * stride * sizeof(uint32_t)));
+    GP_CUDA(c, cudaMemsetAsync(c->d_fp_queue.p, 0, 64, c->stream));
+    unsigned int* queue = (unsigned int*)c->d_fp_queue.p;
+    const uint32_t* ord = (const uint32_t*)c->d_fp_order.p;
+    GP_CUDA(c, cudaEventRecord(c->fp_ev[0], c->stream));
+    if (c->fp_n_table) {
+        gp::flank_place_kernel<true><<<blocks, gp::FP_THREADS, gp::FP_SMEM_BYTES, c->stream>>>(
+            (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_fp_pairs.p, ord, (uint32_t)c->fp_n_table, queue,
+            c->fp_params.mismatch, c->fp_params.indel, (uint32_t*)c->d_fp_scratch.p, stride, (gp::DevPlace*)c->d_fp_results.p);
+        GP_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    if (c->fp_n_generic) {
+        gp::flank_place_kernel<false><<<blocks, gp::FP_THREADS, gp::FP_SMEM_BYTES, c->stream>>>(
+            (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_fp_pairs.p, ord + c->fp_n_table, (uint32_t)c->fp_n_generic, queue + 8,
+            c->fp_params.mismatch, c->fp_params.indel, (uint32_t*)c->d_fp_scratch.p, stride, (gp::DevPlace*)c->d_fp_results.p);
+        GP_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    GP_CUDA(c, cudaEventRecord(c->fp_ev[1], c->stream));
+    c->fp_ev_valid = true;
+    return GP_OK;
+}
+
+int gp_semiglobal_fetch(gp_ctx* c, gp_place_result* out, uint64_t n_pairs)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (n_pairs != c->fp_pairs) return c->fail(GP_ERR_INVALID, "n_pairs does not match the uploaded batch");
+    if (n_pairs == 0) return GP_OK;
+    if (!out) return c->fail(GP_ERR_INVALID, "null output");
+    static_assert(sizeof(gp_place_result) == sizeof(gp::DevPlace), "result layouts must match");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, cudaMemcpyAsync(out, c->d_fp_results.p, n_pairs * sizeof(gp_place_result), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    const gp::PairDesc* hd = (const gp::PairDesc*)c->h_fp_stage.p;
+    for (uint32_t id : c->fp_host_ids) {            // an empty flank scores 0 at column 0; an empty contig takes m indels
+        out[id].score = hd[id].n == 0 ? (int32_t)hd[id].m * c->fp_params.indel : 0;
+        out[id].col_start = 0; out[id].col_end = 0; out[id].flags = 2u;
+    }
+    return GP_OK;
+}
+
+int gp_semiglobal_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len, uint32_t n_seq,
+                        const gp_pair* pairs, uint64_t n_pairs, const gp_dp_params* params, gp_place_result* out)
+{
+    if (!c) return GP_ERR_INVALID;
+    int rc = gp_upload_sequences(c, seqs, seq_len, n_seq);
+    if (rc == GP_OK) rc = gp_semiglobal_upload_pairs(c, pairs, n_pairs, params);
+    if (rc == GP_OK) rc = gp_semiglobal_launch(c);
+    if (rc == GP_OK) rc = gp_semiglobal_fetch(c, out, n_pairs);
+    return rc;
+}
+
+int gp_semiglobal_stats(gp_ctx* c, uint64_t* cells, uint64_t* table_pairs, uint64_t* generic_pairs, double* kernel_ms)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (cells) *cells = c->fp_cells;
+    if (table_pairs) *table_pairs = c->fp_n_table;
+    if (generic_pairs) *generic_pairs = c->fp_n_generic;
+    if (kernel_ms) {
+        *kernel_ms = 0.0;
+        if (c->fp_ev_valid) {
+            GP_CUDA(c, cudaSetDevice(c->device));
+            GP_CUDA(c, cudaEventSynchronize(c->fp_ev[1]));
+            float t = 0.f;
+            GP_CUDA(c, cudaEventElapsedTime(&t, c->fp_ev[0], c->fp_ev[1]));
+            *kernel_ms = t;
+        }
+    }
+    return GP_OK;
 }
 
 int gp_last_timing(const gp_ctx* c, double* out_ms, int n)

@@ -11,17 +11,18 @@
 // bases so that a batch of any shape -- 50 000 small gaps, or 20 gaps of 400 long contigs -- fills the chip.
 // Persistent CTAs (one per SM: the set takes most of its shared memory) pull items from an atomic queue.  Per item:
 //   phase 1  the probe k-mers of the WHOLE gap (the k-mers of the first and last 30 bases of every node) go into a
-//            4^k-bit set in shared memory (128 KB for k = 10, GAPPadder's value) and into hash chains (heads in shared
-//            memory, (k-mer, owner) records in a per-CTA slab of global scratch that stays in L1/L2);
-//   phase 2  the item's nodes stream past the set: a thread takes 32 consecutive bases (one 16-byte load of packed
-//            codes plus the word before it), rolls the k-mer along them -- a shift, an or and one shared-memory bit
-//            test per base -- and on a hit walks the chain and stores hit(i, owner) = 1 (a plain byte store:
-//            idempotent, no atomics; the matrix is zeroed before the launch).
-// The packed codes arrive at 0.5 B per base and are read exactly once (plus 4 B of carry-in per 32 bases): an
+//            4^k-bit set in shared memory (128 KB for k = 10, GAPPadder's value) and, as (k-mer | owner << 20) words
+//            sorted by hash bucket (count, scan, scatter), into shared memory next to it; a gap with more probes
+//            than fit there (about 400 nodes at k = 10) keeps them in a per-CTA slab of global scratch instead;
+//   phase 2  the item's nodes stream past the set as one flat list of 32-base chunks: a thread takes a chunk (one
+//            16-byte load of packed codes plus the two words before it), rolls the k-mer along it -- a shift, an or
+//            and one shared-memory bit test per base -- and on a hit compares the bucket's probes and stores
+//            hit(i, owner) = 1 (a plain byte store: idempotent, no atomics; the matrix is zeroed before the launch).
+// The packed codes arrive at 0.5 B per base and are read exactly once (plus 8 B of carry-in per 32 bases): an
 // HBM-bound byte-stream scan with no arithmetic to speak of.  bench.py reports its achieved GB/s.
 //
-// Limits: k <= 10 (the set must fit shared memory), QC_MAX_NODES nodes per gap (the hit matrix is n x n bytes);
-// gp_quick_check_device returns GP_ERR_RANGE beyond them and the host filter has no such limits.
+// Limits: k <= 10 (the set must fit shared memory), QC_MAX_NODES nodes per gap (12-bit owner field; the hit matrix is
+// n x n bytes); gp_quick_check_device returns GP_ERR_RANGE beyond them and the host filter has no such limits.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -31,20 +32,23 @@ namespace gp {
 
 constexpr int QC_THREADS = 512;
 constexpr int QC_MAX_K = 10;                      // 4^10 bits = 128 KB of shared memory
-constexpr int QC_MAX_NODES = 4096;                // nodes per gap (contigs and their reverse complements)
+constexpr int QC_MAX_NODES = 4096;                // nodes per gap (contigs and their reverse complements): 12-bit owner field
 constexpr int QC_WINDOW = 30;                     // lenContigLen, ContigsCompactor.cpp:2024
-constexpr int QC_HEADS = 8192;                    // hash heads (32-bit indices into the probe slab)
+constexpr int QC_BUCKETS = 4096;                  // hash buckets of the probe table
 constexpr int QC_CHUNK = 32;                      // bases per thread step: four packed words, one 16-byte load
+constexpr size_t QC_SMEM_MAX = 227 * 1024 - 2048; // dynamic shared memory the kernel may ask for
 
 struct QcItem {                                   // one unit of work: scan nodes [node_lo, node_hi) of gap `gap`
-    uint32_t gap, node_lo, node_hi, pad;
+    uint32_t gap, node_lo, node_hi;
+    uint32_t chunk_begin, n_chunks;               // the nodes' 32-base chunks in the table-wide chunk numbering
+    uint32_t pad[3];
 };
 
-inline uint32_t qc_probes_per_node(int k) { return 2u * (uint32_t)(QC_WINDOW - k + 1); }
-inline size_t qc_smem_bytes(int k)
-{
-    return std::max<size_t>(16, ((size_t)1 << (2 * k)) / 8) + (size_t)QC_HEADS * 4 + 64;     // 160 KB for k = 10
-}
+__host__ __device__ inline uint32_t qc_probes_per_node(int k) { return 2u * (uint32_t)(QC_WINDOW - k + 1); }
+inline size_t qc_set_bytes(int k) { return std::max<size_t>(16, ((size_t)1 << (2 * k)) / 8); }
+// shared memory: the set, the bucket ends, and room for `smem_probes` probe words
+inline size_t qc_smem_bytes(int k, uint32_t smem_probes) { return qc_set_bytes(k) + (size_t)QC_BUCKETS * 4 + (size_t)smem_probes * 4 + 64; }
+inline uint32_t qc_smem_probe_capacity(int k) { return (uint32_t)((QC_SMEM_MAX - qc_set_bytes(k) - (size_t)QC_BUCKETS * 4 - 64) / 4); }
 
 // 2-bit k-mer letters of eight packed 4-bit codes: A C G T -> 0..3, everything else 0 (KmerUtils.cpp:22-58)
 __device__ __forceinline__ uint32_t qc_letters(uint32_t w)
@@ -69,26 +73,42 @@ __device__ __forceinline__ uint32_t qc_kmer(const uint32_t* __restrict__ packed,
     return v;
 }
 
-__device__ __forceinline__ uint32_t qc_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - 13); }
+__device__ __forceinline__ uint32_t qc_hash(uint32_t v) { return (v * 0x9E3779B1u) >> (32 - 12); }
+
+// The window k-mer number e of a gap (e = node * per_node + side * per_side + a): its value and owner; false when the
+// window is shorter than a + k bases.
+__device__ __forceinline__ bool qc_probe(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ seq_off,
+                                         const uint32_t* __restrict__ seq_len, uint32_t first, uint32_t e, int k, uint32_t& v, uint32_t& j)
+{
+    const uint32_t per_side = (uint32_t)(QC_WINDOW - k + 1), per_node = 2u * per_side;
+    j = e / per_node;
+    const uint32_t r = e % per_node, side = r / per_side, a = r % per_side;
+    const uint32_t len = seq_len[first + j], wlen = len < (uint32_t)QC_WINDOW ? len : (uint32_t)QC_WINDOW;
+    if (a + (uint32_t)k > wlen) return false;
+    const uint32_t start = side == 0 ? 0u : len - wlen;
+    v = qc_kmer(packed, seq_off[first + j], start + a + (uint32_t)k - 1u, k);
+    return true;
+}
 
 // hit: for gap g, n_g * n_g bytes at hit_off[g] (zeroed by the caller), hit[i * n_g + j] = 1 iff (i, j), j >= i, is a candidate.
-// slab: per CTA, 3 * slab_probes words of global scratch: probe k-mers, their owner nodes, the chain links.
+// chunk_off: per table sequence, the number of 32-base chunks of all sequences before it (n_seq + 1 entries).
+// slab: per CTA, slab_probes words of global scratch for gaps whose probes do not fit shared memory (smem_probes words).
 __global__ void __launch_bounds__(QC_THREADS, 1)
 quick_check_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_len,
-                   const uint32_t* __restrict__ gap_first, const uint64_t* __restrict__ hit_off, const QcItem* __restrict__ items,
-                   uint32_t n_items, unsigned int* __restrict__ queue, int k, uint32_t* __restrict__ slab, uint32_t slab_probes,
-                   uint8_t* __restrict__ hit)
+                   const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ gap_first, const uint64_t* __restrict__ hit_off,
+                   const QcItem* __restrict__ items, uint32_t n_items, unsigned int* __restrict__ queue, int k,
+                   uint32_t smem_probes, uint32_t* __restrict__ slab, uint32_t slab_probes, uint8_t* __restrict__ hit)
 {
     extern __shared__ uint32_t qc_smem[];
-    const uint32_t set_words = k >= 3 ? (1u << (2 * k)) / 32u : 1u;       // k = 1, 2: 4 / 16 bits still take a whole word
+    const uint32_t set_words = k >= 3 ? (1u << (2 * k)) / 32u : 4u;       // k = 1, 2: 4 / 16 bits still take whole words
     uint32_t* kset = qc_smem;
-    uint32_t* head = kset + (set_words < 4u ? 4u : set_words);            // QC_HEADS chain heads, 0xffffffff ends a chain
-    uint32_t* pk = slab + (size_t)blockIdx.x * 3u * slab_probes;          // probe k-mers
-    uint32_t* po = pk + slab_probes;                                      // probe owners
-    uint32_t* pn = po + slab_probes;                                      // chain links
-    __shared__ uint32_t n_probes, item_idx;
-    const uint32_t kmask = k >= 16 ? 0xffffffffu : ((1u << (2 * k)) - 1u);
+    uint32_t* bend = kset + set_words;                                    // QC_BUCKETS bucket ends (exclusive prefix while filling)
+    uint32_t* sprobes = bend + QC_BUCKETS;
+    __shared__ uint32_t item_idx, warp_sums[QC_THREADS / 32];
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t cur_gap = 0xffffffffu;
+    const uint32_t* probes = sprobes;
     for (;;) {
         if (threadIdx.x == 0) item_idx = atomicAdd(queue, 1u);
         __syncthreads();
@@ -99,56 +119,77 @@ quick_check_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restri
         const uint32_t first = gap_first[item.gap], n = gap_first[item.gap + 1] - first;
         if (item.gap != cur_gap) {                // consecutive items of one gap reuse the set (the queue hands them out in order)
             cur_gap = item.gap;
+            const uint32_t n_probe_slots = n * qc_probes_per_node(k);
+            uint32_t* wprobes = n_probe_slots <= smem_probes ? sprobes : slab + (size_t)blockIdx.x * slab_probes;
+            probes = wprobes;
             for (uint32_t e = threadIdx.x; e < set_words; e += blockDim.x) kset[e] = 0u;
-            for (uint32_t e = threadIdx.x; e < QC_HEADS; e += blockDim.x) head[e] = 0xffffffffu;
-            if (threadIdx.x == 0) n_probes = 0;
+            for (uint32_t e = threadIdx.x; e < QC_BUCKETS; e += blockDim.x) bend[e] = 0u;
             __syncthreads();
-            // phase 1: the k-mers of the first and last 30 bases of every node (:2026-2029); windows are clipped to the node
-            const uint32_t per_side = (uint32_t)(QC_WINDOW - k + 1), per_node = 2u * per_side;
-            for (uint32_t e = threadIdx.x; e < n * per_node; e += blockDim.x) {
-                const uint32_t j = e / per_node, r = e % per_node, side = r / per_side, a = r % per_side;
-                const uint32_t len = seq_len[first + j], wlen = len < (uint32_t)QC_WINDOW ? len : (uint32_t)QC_WINDOW;
-                if (a + (uint32_t)k > wlen) continue;
-                const uint32_t start = side == 0 ? 0u : len - wlen;
-                const uint32_t v = qc_kmer(packed, seq_off[first + j], start + a + (uint32_t)k - 1u, k);
+            // phase 1a: the k-mers of the first and last 30 bases of every node (:2026-2029) into the set; bucket counts
+            for (uint32_t e = threadIdx.x; e < n_probe_slots; e += blockDim.x) {
+                uint32_t v, j;
+                if (!qc_probe(packed, seq_off, seq_len, first, e, k, v, j)) continue;
                 atomicOr(&kset[v >> 5], 1u << (v & 31u));
-                const uint32_t q = atomicAdd(&n_probes, 1u);
-                pk[q] = v;
-                po[q] = j;
-                pn[q] = atomicExch(&head[qc_hash(v)], q);            // push front
+                atomicAdd(&bend[qc_hash(v)], 1u);
+            }
+            __syncthreads();
+            // phase 1b: exclusive prefix sum of the counts (QC_BUCKETS / QC_THREADS = 8 buckets per thread)
+            {
+                constexpr int PER = QC_BUCKETS / QC_THREADS;
+                uint32_t local[PER], sum = 0;
+#pragma unroll
+                for (int x = 0; x < PER; ++x) { local[x] = bend[threadIdx.x * PER + x]; sum += local[x]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+                if (lane == 31) warp_sums[warp] = incl;
+                __syncthreads();
+                uint32_t base = 0;
+                for (int w = 0; w < warp; ++w) base += warp_sums[w];
+                uint32_t run = base + incl - sum;
+#pragma unroll
+                for (int x = 0; x < PER; ++x) { bend[threadIdx.x * PER + x] = run; run += local[x]; }
+            }
+            __syncthreads();
+            // phase 1c: scatter (k-mer | owner << 20) into the buckets; afterwards bend[h] is the END of bucket h
+            for (uint32_t e = threadIdx.x; e < n_probe_slots; e += blockDim.x) {
+                uint32_t v, j;
+                if (!qc_probe(packed, seq_off, seq_len, first, e, k, v, j)) continue;
+                wprobes[atomicAdd(&bend[qc_hash(v)], 1u)] = v | (j << 20);
             }
             __threadfence_block();
             __syncthreads();
         }
-        // phase 2: the item's nodes against the set, 32 bases per thread step
+        // phase 2: the item's nodes against the set, as one flat list of 32-base chunks
         uint8_t* out = hit + hit_off[item.gap];
-        for (uint32_t i = item.node_lo; i < item.node_hi; ++i) {
-            const uint32_t len = seq_len[first + i], off = seq_off[first + i];
+        for (uint32_t f = threadIdx.x; f < item.n_chunks; f += blockDim.x) {
+            const uint32_t gchunk = item.chunk_begin + f;
+            uint32_t lo = first + item.node_lo, hi = first + item.node_hi;      // the sequence s with chunk_off[s] <= gchunk < chunk_off[s+1]
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(chunk_off + mid) <= gchunk) lo = mid; else hi = mid; }
+            const uint32_t i = lo - first, c = gchunk - __ldg(chunk_off + lo);
+            const uint32_t len = seq_len[lo], off = seq_off[lo];
             if (len < (uint32_t)k) continue;
-            const uint32_t n_chunks = (len + QC_CHUNK - 1) / QC_CHUNK;
-            for (uint32_t c = threadIdx.x; c < n_chunks; c += blockDim.x) {
-                const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(packed + off) + c);       // sequences start 16-byte aligned
-                const uint32_t prev = c ? qc_letters(__ldg(packed + off + 4u * c - 1u)) : 0u, prev2 = c ? qc_letters(__ldg(packed + off + 4u * c - 2u)) : 0u;
-                // carry-in: the k-1 <= 9 bases before the chunk (the previous two words hold 16)
-                uint32_t v = 0;
+            const uint4 w4 = __ldg(reinterpret_cast<const uint4*>(packed + off) + c);       // sequences start 16-byte aligned
+            const uint32_t prev = c ? qc_letters(__ldg(packed + off + 4u * c - 1u)) : 0u, prev2 = c ? qc_letters(__ldg(packed + off + 4u * c - 2u)) : 0u;
+            // carry-in: the k-1 <= 9 bases before the chunk (the previous two words hold 16)
+            uint32_t v = 0;
 #pragma unroll
-                for (int t = 0; t < 8; ++t) v = (v << 2) | ((prev2 >> (4 * t)) & 3u);
+            for (int t = 0; t < 8; ++t) v = (v << 2) | ((prev2 >> (4 * t)) & 3u);
 #pragma unroll
-                for (int t = 0; t < 8; ++t) v = (v << 2) | ((prev >> (4 * t)) & 3u);
-                const uint32_t words[4] = {qc_letters(w4.x), qc_letters(w4.y), qc_letters(w4.z), qc_letters(w4.w)};
-                const uint32_t base0 = c * QC_CHUNK;
+            for (int t = 0; t < 8; ++t) v = (v << 2) | ((prev >> (4 * t)) & 3u);
+            const uint32_t words[4] = {qc_letters(w4.x), qc_letters(w4.y), qc_letters(w4.z), qc_letters(w4.w)};
+            const uint32_t base0 = c * QC_CHUNK;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        v = ((v << 2) | ((words[q] >> (4 * t)) & 3u)) & kmask;
-                        const uint32_t pos = base0 + 8u * q + t;
-                        if (pos < len && pos + 1u >= (uint32_t)k && ((kset[v >> 5] >> (v & 31u)) & 1u)) {
-                            for (uint32_t p = head[qc_hash(v)]; p != 0xffffffffu; p = __ldcg(pn + p)) {     // slab reads through L2
-                                if (__ldcg(pk + p) != v) continue;
-                                const uint32_t j = __ldcg(po + p);
-                                if (j >= i) out[(size_t)i * n + j] = 1;
-                            }
+                for (int t = 0; t < 8; ++t) {
+                    v = ((v << 2) | ((words[q] >> (4 * t)) & 3u)) & kmask;
+                    const uint32_t pos = base0 + 8u * q + t;
+                    if (pos < len && pos + 1u >= (uint32_t)k && ((kset[v >> 5] >> (v & 31u)) & 1u)) {
+                        const uint32_t h = qc_hash(v);
+                        for (uint32_t p = h ? bend[h - 1] : 0u, pe = bend[h]; p < pe; ++p) {
+                            const uint32_t pv = probes[p];
+                            if ((pv & 0xfffffu) == v && (pv >> 20) >= i) out[(size_t)i * n + (pv >> 20)] = 1;
                         }
                     }
                 }

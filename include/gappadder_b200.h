@@ -222,6 +222,35 @@ int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
  * cells are NOT part of gp_pair_stats' cells (no cell update is computed for them). */
 int gp_closed_form_stats(const gp_ctx *ctx, uint64_t *pairs, uint64_t *cells);
 
+/* ---- flank placement: semi-global alignment (BASELINE configs[1]) ------------------------------------------------------
+ * What GAPPadder does here is `bwa mem -T <s> -a contigs.fa flanks.fa` (pick_contigs.py:83-86); BWA is not vendored and
+ * not pinned, so PARITY IS UNPINNED at this boundary: these entry points are bit-exact against the builder-written
+ * definition in oracle/overlap_oracle.c (gpo_semiglobal), not against GAPPadder's output.  The flank (row_seq) is aligned
+ * end to end inside the contig (col_seq, free ends) with Evaluate's linear scoring (match +1, params->mismatch,
+ * params->indel <= 0; max_clip unused):
+ *   score     max over j of H(m, j)
+ *   col_end   the smallest j that reaches it; the flank occupies contig[col_start, col_end) (0-based)
+ *   col_start the largest start column over all optimal alignments that end there
+ *   flags     informational: 1 shared-memory-table kernel (pure A/C/G/T pair), 0 compare-per-cell kernel, 2 empty sequence
+ * Strand: give the contig and its reverse complement as two table entries (as ContigsMerger's nodes are).
+ * Limits: contig <= 16383 bases, m + |indel| * (m + n) < 2^17; GP_ERR_RANGE beyond. */
+typedef struct gp_place_result {
+    int32_t score;
+    int32_t col_start;
+    int32_t col_end;
+    uint32_t flags;
+} gp_place_result;
+/* One call on host ASCII sequences: pack + upload + kernels + results.  Blocking. */
+int gp_semiglobal_batch(gp_ctx *ctx, const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
+                        const gp_pair *pairs, uint64_t n_pairs, const gp_dp_params *params, gp_place_result *out);
+/* Split form on the context's current sequence table (device-resident timing): upload once, launch any number of times
+ * (gp_semiglobal_launch only enqueues on gp_stream(ctx)), fetch once. */
+int gp_semiglobal_upload_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs, const gp_dp_params *params);
+int gp_semiglobal_launch(gp_ctx *ctx);
+int gp_semiglobal_fetch(gp_ctx *ctx, gp_place_result *out, uint64_t n_pairs);
+/* Of the uploaded batch: DP cells (sum of m*n), pairs per kernel; of the last launch: device time (CUDA events). */
+int gp_semiglobal_stats(gp_ctx *ctx, uint64_t *cells, uint64_t *table_pairs, uint64_t *generic_pairs, double *kernel_ms);
+
 /* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):
  * thread-level instructions per second of VIADDMNMX.S16x2 alone (ALU pipe) and of the
  * VIMNMX.S16x2 + VIADD.16x2 dual-issue mix (both integer pipes).  bench.py's roofline denominator. */

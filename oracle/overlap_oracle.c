@@ -354,3 +354,55 @@ int64_t gpo_candidate_pairs(const char *const *seqs, const int32_t *lens, int nn
     free(codes);
     return np;
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * Flank placement (BASELINE.json configs[1]) -- PARITY UNPINNED.
+ *
+ * GAPPadder places the two flanks of a gap on every contig with `bwa mem -T <s> -a contigs.fa flanks.fa`
+ * (/root/reference/pick_contigs.py:83-86) and keeps, per contig and side, strand, clip type, the number of
+ * aligned columns and the leftmost contig position of the best record (:99-147).  The arithmetic is BWA's,
+ * which is neither vendored nor version-pinned (README.md:28), and the reference holds no test or vector for it:
+ * nothing here is checked against GAPPadder's own output.  What follows is the BUILDER-WRITTEN definition that
+ * the B200 kernel (gappadder_b200/csrc/flank_place.cuh) is bit-exact against -- the semi-global form the
+ * survey prescribes: the flank is aligned end to end inside the contig, with Evaluate's linear scoring
+ * (match +1, mismatch, indel; ContigsCompactor.cpp:1596,1640,1654).
+ *
+ *   rows = flank s1 (m bases, consumed entirely), columns = contig s2 (n bases, free ends)
+ *   H(0,j) = 0,  H(i,0) = i*indel,  H(i,j) = max(H(i-1,j-1) + s(i,j), H(i-1,j) + indel, H(i,j-1) + indel)
+ *   score     = max_j H(m,j)
+ *   col_end   = the smallest j that reaches it            (flank occupies contig[col_start, col_end), 0-based)
+ *   col_start = the LARGEST start column over all optimal alignments that end in (m, col_end)
+ *               (an order-free definition: start(i,j) = max of start over the predecessors that reach H(i,j);
+ *                start(0,j) = j, start(i,0) = 0)
+ * m = 0 gives score 0, col_end = 0, col_start = 0. */
+typedef struct {
+    int32_t score;
+    int32_t col_start;
+    int32_t col_end;
+} gpo_place_result;
+
+int gpo_semiglobal(const char *s1, int m, const char *s2, int n, int mismatch, int indel, gpo_place_result *r)
+{
+    int32_t *H = (int32_t *)malloc(((size_t)n + 1) * sizeof(int32_t));
+    int32_t *S = (int32_t *)malloc(((size_t)n + 1) * sizeof(int32_t));
+    if (!H || !S) { free(H); free(S); return -1; }
+    for (int j = 0; j <= n; ++j) { H[j] = 0; S[j] = j; }
+    for (int i = 1; i <= m; ++i) {
+        int32_t dh = H[0], ds = S[0];              /* (i-1, j-1) */
+        H[0] = i * indel; S[0] = 0;
+        for (int j = 1; j <= n; ++j) {
+            const int32_t uh = H[j], us = S[j];    /* (i-1, j) */
+            int32_t h = dh + (s1[i - 1] == s2[j - 1] ? 1 : mismatch), s = ds;
+            const int32_t hu = uh + indel, hl = H[j - 1] + indel;
+            if (hu > h || (hu == h && us > s)) { h = hu; s = us; }
+            if (hl > h || (hl == h && S[j - 1] > s)) { h = hl; s = S[j - 1]; }
+            dh = uh; ds = us;
+            H[j] = h; S[j] = s;
+        }
+    }
+    int best = 0;
+    for (int j = 1; j <= n; ++j) if (H[j] > H[best]) best = j;
+    r->score = H[best]; r->col_end = best; r->col_start = S[best];
+    free(H); free(S);
+    return 0;
+}

@@ -39,6 +39,10 @@ def gappadder_thresholds() -> Thresholds:
 _oracle = None
 
 
+class PlaceResult(C.Structure):
+    _fields_ = [("score", C.c_int32), ("col_start", C.c_int32), ("col_end", C.c_int32)]
+
+
 def oracle_lib() -> C.CDLL:
     global _oracle
     if _oracle is None:
@@ -59,6 +63,7 @@ def oracle_lib() -> C.CDLL:
         lib.gpo_quickcheck.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int]
         lib.gpo_candidate_pairs.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int32), C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int64]
         lib.gpo_candidate_pairs.restype = C.c_int64
+        lib.gpo_semiglobal.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(PlaceResult)]
         _oracle = lib
     return _oracle
 
@@ -67,6 +72,14 @@ def oracle_evaluate(s1: bytes, s2: bytes, mismatch=-2, indel=-2, maxclip=50, ful
     r = DPResult()
     fn = oracle_lib().gpo_evaluate_full if full else oracle_lib().gpo_evaluate
     rc = fn(s1, len(s1), s2, len(s2), mismatch, indel, maxclip, C.byref(r))
+    assert rc == 0
+    return r
+
+
+def oracle_semiglobal(flank: bytes, contig: bytes, mismatch=-2, indel=-2) -> PlaceResult:
+    """Flank end to end inside the contig (builder-written definition, BWA parity unpinned: see overlap_oracle.c)."""
+    r = PlaceResult()
+    rc = oracle_lib().gpo_semiglobal(flank, len(flank), contig, len(contig), mismatch, indel, C.byref(r))
     assert rc == 0
     return r
 

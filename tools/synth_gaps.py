@@ -72,6 +72,18 @@ def make_locus(rng: np.random.Generator, spec: GapSpec) -> np.ndarray:
     return locus
 
 
+FLANK_LENGTH = 995     # flank_length - 5 with GAPPadder's flank_length = 1000 (gnrt_pos_true_seqs.py:93-99)
+
+
+def make_flanks(seed: int, spec: GapSpec) -> List[Tuple[str, bytes]]:
+    """The two flanks of the gap make_gap(seed, spec) draws its contigs from (BASELINE cfg2): the first and the last
+    995 bases of the same locus, named <scaffold>_<gap>_left / _right like gnrt_pos_true_seqs.py:93-99."""
+    rng = np.random.default_rng(int(seed))
+    locus = make_locus(rng, spec)
+    L = min(FLANK_LENGTH, spec.locus)
+    return [("0_%d_left" % seed, locus[:L].tobytes()), ("0_%d_right" % seed, locus[spec.locus - L:].tobytes())]
+
+
 def make_gap(seed: int, spec: GapSpec) -> List[Tuple[str, bytes]]:
     """Returns [(name, sequence bytes)] for one gap."""
     rng = np.random.default_rng(int(seed))
