@@ -31,6 +31,12 @@ __device__ __forceinline__ uint32_t load_code(const uint32_t* __restrict__ packe
     return (__ldg(packed + off + (pos >> 3)) >> ((pos & 7u) * 4u)) & 15u;
 }
 
+// The same through L2 (ld.global.cg): for sequences written by other CTAs of the same launch (relax chain arena).
+__device__ __forceinline__ uint32_t load_code_cg(const uint32_t* packed, uint32_t off, uint32_t pos)
+{
+    return (__ldcg(packed + off + (pos >> 3)) >> ((pos & 7u) * 4u)) & 15u;
+}
+
 // Best-cell bookkeeping.  The reference scans, for c = 0..C, column n-c top to bottom and then row
 // m-c left to right, and keeps the FIRST strict maximum (ContigsCompactor.cpp:1679-1709).  That is
 // an order-independent reduction with key (score descending, scan rank ascending) where

@@ -9,6 +9,7 @@
 #include "overlap_wf16c.cuh"
 #include "quick_check.cuh"
 #include "flank_place.cuh"
+#include "relax_chain.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -74,6 +75,12 @@ struct gp_ctx {
 
     // pair work lists
     DeviceBuf d_qc_meta, d_qc_hit, d_qc_slab;  // quick check on the device: offsets/lengths/gap bounds/items, hit matrices, probe slabs
+    // relax chains on the device (relax_chain.cuh)
+    DeviceBuf d_arena, d_rx_items, d_rx_order, d_rx_status, d_rx_results, d_rx_queue;
+    HostBuf h_rx_stage, h_rx_out;
+    uint64_t rx_second_passes = 0, rx_unresolved = 0, rx_cells_bound = 0;
+    double rx_kernel_ms = 0;
+    cudaEvent_t rx_ev[2] = {nullptr, nullptr};
     // flank placement (semi-global; flank_place.cuh)
     DeviceBuf d_fp_pairs, d_fp_order, d_fp_results, d_fp_queue, d_fp_scratch;
     HostBuf h_fp_stage;
@@ -155,9 +162,12 @@ int gp_create(int device, gp_ctx** out)
     }
     for (auto& ev : c->qc_ev) cudaEventCreate(&ev);
     for (auto& ev : c->fp_ev) cudaEventCreate(&ev);
+    for (auto& ev : c->rx_ev) cudaEventCreate(&ev);
     for (auto& ev : c->kev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA; }
-    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess || (e = gp::fp_configure()) != cudaSuccess) {
+    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess || (e = gp::fp_configure()) != cudaSuccess || (e = gp::relax_configure()) != cudaSuccess ||
+        // set once, to the maximum: function attributes are per device, and several contexts (workers) may launch concurrently
+        (e = cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp::QC_SMEM_MAX)) != cudaSuccess) {
         g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
         cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA;
     }
@@ -173,6 +183,8 @@ void gp_destroy(gp_ctx* c)
     for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->qc_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->fp_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->rx_ev) if (ev) cudaEventDestroy(ev);
+    c->d_arena.release(); c->d_rx_items.release(); c->d_rx_order.release(); c->d_rx_status.release(); c->d_rx_results.release(); c->d_rx_queue.release(); c->h_rx_stage.release(); c->h_rx_out.release();
     c->d_fp_pairs.release(); c->d_fp_order.release(); c->d_fp_results.release(); c->d_fp_queue.release(); c->d_fp_scratch.release(); c->h_fp_stage.release();
     c->d_qc_slab.release();
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
@@ -326,7 +338,6 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     GP_CUDA(c, cudaMemsetAsync(dmb + queue_at, 0, 16, c->stream));
     if (total) GP_CUDA(c, cudaMemsetAsync(c->d_qc_hit.p, 0, total, c->stream));
     const size_t smem = gp::qc_smem_bytes(k, smem_probes);
-    GP_CUDA(c, cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GP_CUDA(c, cudaEventRecord(c->qc_ev[0], c->stream));
     gp::quick_check_kernel<<<blocks, gp::QC_THREADS, smem, c->stream>>>(
         (const uint32_t*)c->d_packed.p, dm, dm + n_seq, d_chunk, d_gapfirst, (const uint64_t*)(dm + w32p),
@@ -747,6 +758,125 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     c->timing[2] = ms(t2, t3);      // copies + kernels + result copy, until the stream is idle
     c->timing[3] = ms(t0, t3);
     return rc;
+}
+
+// ---- relax chains on the device (relax_chain.cuh) --------------------------------------------------------------------
+
+int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, const gp_dp_params* params, gp_result* out, uint32_t* merged_len)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (!params || ((!steps || !out || !merged_len) && n_steps)) return c->fail(GP_ERR_INVALID, "null steps/params/output");
+    c->rx_second_passes = c->rx_unresolved = 0; c->rx_cells_bound = 0; c->rx_kernel_ms = 0;
+    if (n_steps == 0) return GP_OK;
+    if (n_steps > 0x7ffffff0ull) return c->fail(GP_ERR_RANGE, "too many relax steps in one call");
+    if (!(params->mismatch == -2 && params->indel == -2) || params->max_clip < 0)
+        return c->fail(GP_ERR_RANGE, "gp_relax_chains runs the standard scores (-2, -2) only; use gp_overlap_batch step by step");
+    const uint32_t n_seq = (uint32_t)c->seq_len.size();
+    const uint32_t n = (uint32_t)n_steps;
+    // items, depth, merged-length bounds (len(merged) <= len(row) + len(column), :108-153), arena slots
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, c->h_rx_stage.reserve((size_t)n * (sizeof(gp::RelaxItem) + sizeof(uint32_t))));
+    gp::RelaxItem* items = (gp::RelaxItem*)c->h_rx_stage.p;
+    uint32_t* order = (uint32_t*)((char*)c->h_rx_stage.p + (size_t)n * sizeof(gp::RelaxItem));
+    std::vector<uint32_t> depth(n), bound(n);
+    std::vector<uint64_t> prio(n, 0);
+    uint64_t arena_words = 0, max_total = 0;
+    uint32_t max_n = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const gp_relax_step& st = steps[k];
+        if (st.col_seq >= n_seq || (st.parent < 0 && st.row_seq >= n_seq) || st.parent >= (int32_t)k)
+            return c->fail(GP_ERR_INVALID, "relax step %u: bad sequence index or parent (a parent must precede its children)", k);
+        const uint32_t cl = c->seq_len[st.col_seq];
+        if (!c->seq_acgt[st.col_seq] || cl < 1 || cl > gp::WF16C_MAX_N || (st.parent < 0 && (!c->seq_acgt[st.row_seq] || c->seq_len[st.row_seq] < 1)))
+            return c->fail(GP_ERR_RANGE, "relax step %u: sequences outside the certificate kernel's domain (A/C/G/T, 1..16382 column bases)", k);
+        gp::RelaxItem it{};
+        it.parent = st.parent;
+        it.col_off = c->seq_off[st.col_seq]; it.col_len = cl;
+        uint32_t rl;
+        if (st.parent < 0) { it.row_off = c->seq_off[st.row_seq]; it.row_len = c->seq_len[st.row_seq]; rl = it.row_len; depth[k] = 0; }
+        else { rl = bound[st.parent]; depth[k] = depth[st.parent] + 1; }
+        if ((uint64_t)rl + cl > 0xffffffull) return c->fail(GP_ERR_RANGE, "relax step %u: merged contig beyond 2^24 bases", k);
+        bound[k] = rl + cl;
+        prio[k] = (uint64_t)rl * cl;
+        c->rx_cells_bound += prio[k];
+        it.arena_off = (uint32_t)arena_words;
+        arena_words += (((uint64_t)bound[k] + 7) / 8 + 1 + 31) & ~31ull;          // 128-byte slots: no cache line is shared between items
+        if (arena_words > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "relax arena beyond 2^32 words; split the batch");
+        max_n = std::max(max_n, cl);
+        max_total = std::max<uint64_t>(max_total, (uint64_t)rl + cl);
+        items[k] = it;
+    }
+    if ((uint64_t)(params->max_clip + 1) * (max_total + 2) >= (1ull << 30)) return c->fail(GP_ERR_RANGE, "max_clip x length exceeds the kernels' rank range");
+    // priority = the longest chain from the item downwards (cells, upper bound); children come after parents in `steps`
+    {
+        std::vector<uint64_t> below(n, 0);
+        for (uint32_t k = n; k-- > 0;) {
+            prio[k] += below[k];
+            const int32_t p = steps[k].parent;
+            if (p >= 0) below[p] = std::max(below[p], prio[k]);
+        }
+    }
+    for (uint32_t k = 0; k < n; ++k) order[k] = k;
+    std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return depth[a] != depth[b] ? depth[a] < depth[b] : prio[a] > prio[b]; });
+
+    const size_t item_bytes = (size_t)n * sizeof(gp::RelaxItem);
+    GP_CUDA(c, c->d_rx_items.reserve(item_bytes));
+    GP_CUDA(c, c->d_rx_order.reserve((size_t)n * 4));
+    GP_CUDA(c, c->d_rx_status.reserve((size_t)n * 8));                   // status words, then merged lengths
+    GP_CUDA(c, c->d_rx_results.reserve((size_t)n * sizeof(gp::DevResult)));
+    GP_CUDA(c, c->d_rx_queue.reserve(64));
+    GP_CUDA(c, c->d_arena.reserve((size_t)arena_words * 4 + 256));
+    GP_CUDA(c, c->h_rx_out.reserve((size_t)n * (sizeof(gp::DevResult) + 4) + 64));
+    c->p16c = gp::wf16c_make_params(params->mismatch, params->indel, params->max_clip);
+    const bool pot2 = c->cert_layout == 0 && max_n <= gp::WF16C_POT2_MAX_N;
+    c->p16c.pot2 = pot2 ? 1 : 0;
+    c->last_pot2 = pot2;
+    const int blocks = c->sm_count * gp::WF16C_CTAS_PER_SM;
+    const uint32_t warps = (uint32_t)blocks * (gp::WF16C_THREADS / 32);
+    const uint32_t stride = (max_n + 2 + 31 + 32) & ~31u;
+    GP_CUDA(c, c->d_scratch16c.reserve((size_t)warps * stride * sizeof(uint32_t)));
+    uint32_t* d_status = (uint32_t*)c->d_rx_status.p;
+    uint32_t* d_mlen = d_status + n;
+    GP_CUDA(c, cudaMemcpyAsync(c->d_rx_items.p, items, item_bytes, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_rx_order.p, order, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(d_status, 0, (size_t)n * 8, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(c->d_rx_queue.p, 0, 64, c->stream));
+    unsigned int* queue = (unsigned int*)c->d_rx_queue.p;
+    const size_t smem = gp::wf16c_smem_bytes<gp::WF16C_THREADS / 32>();
+    GP_CUDA(c, cudaEventRecord(c->rx_ev[0], c->stream));
+    if (pot2)
+        gp::relax_chain_kernel<true><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, (const uint32_t*)c->d_rx_order.p, n,
+            queue, c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_status, d_mlen, queue + 8, (gp::DevResult*)c->d_rx_results.p);
+    else
+        gp::relax_chain_kernel<false><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, (const uint32_t*)c->d_rx_order.p, n,
+            queue, c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_status, d_mlen, queue + 8, (gp::DevResult*)c->d_rx_results.p);
+    GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->rx_ev[1], c->stream));
+    c->launches += 1;
+    char* ho = (char*)c->h_rx_out.p;
+    GP_CUDA(c, cudaMemcpyAsync(ho, c->d_rx_results.p, (size_t)n * sizeof(gp::DevResult), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(ho + (size_t)n * sizeof(gp::DevResult), d_mlen, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync((uint32_t*)c->h_queue.p + 32, c->d_rx_queue.p, 64, cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    memcpy(out, ho, (size_t)n * sizeof(gp_result));
+    memcpy(merged_len, ho + (size_t)n * sizeof(gp::DevResult), (size_t)n * 4);
+    c->rx_second_passes = ((const uint32_t*)c->h_queue.p)[32 + 8];
+    c->rx_unresolved = ((const uint32_t*)c->h_queue.p)[32 + 9];
+    float ms = 0.f;
+    GP_CUDA(c, cudaEventElapsedTime(&ms, c->rx_ev[0], c->rx_ev[1]));
+    c->rx_kernel_ms = ms;
+    return GP_OK;
+}
+
+int gp_relax_stats(const gp_ctx* c, double* kernel_ms, uint64_t* second_passes, uint64_t* unresolved)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = c->rx_kernel_ms;
+    if (second_passes) *second_passes = c->rx_second_passes;
+    if (unresolved) *unresolved = c->rx_unresolved;
+    return GP_OK;
 }
 
 // ---- flank placement: semi-global alignment of a flank inside a contig (flank_place.cuh) -------------------------------

@@ -416,7 +416,8 @@ GP_HD Wf16Strip wf16c_next_strip(int i0, int m, int C)
 // ---- device side ------------------------------------------------------------------------------
 
 struct Wf16cWarp {                      // warp-uniform state of one pass
-    const uint32_t* packed;
+    const uint32_t* packed;             // the column sequence's table
+    const uint32_t* packed_row;         // the row sequence's (the same table, or the relax chain's arena of merged contigs)
     PairDesc pd;
     Wf16cPass g;
     uint32_t* bnd;                      // boundary line in global scratch (see wf16c_line_word)
@@ -516,7 +517,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     {
         uint32_t rc[2 * K];
 #pragma unroll
-        for (int x = 0; x < 2 * K; ++x) rc[x] = (itop + x < m) ? load_code(w.packed, w.pd.row_off, (uint32_t)(itop + x)) : 0u;
+        for (int x = 0; x < 2 * K; ++x) rc[x] = (itop + x < m) ? (TEAM > 1 ? load_code_cg(w.packed_row, w.pd.row_off, (uint32_t)(itop + x)) : load_code(w.packed_row, w.pd.row_off, (uint32_t)(itop + x))) : 0u;
 #pragma unroll 1
         for (uint32_t combo = 0; combo < 16; ++combo) {
             const uint32_t ca = combo & 3u, cb = combo >> 2;
@@ -757,6 +758,9 @@ __device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P,
 
 // Does the 16-base word pair (plo, phi) occur in the sequence at word offset `off` with `len` bases?
 // Warp-wide; every lane returns the same answer.
+// CG: read through L2 (ld.global.cg) instead of the read-only path -- for a row sequence another CTA of the same launch wrote.
+template <bool CG> __device__ __forceinline__ uint32_t wf16c_ldw(const uint32_t* p) { return CG ? __ldcg(p) : __ldg(p); }
+template <bool CG = false>
 __device__ __forceinline__ bool wf16c_probe_hit(const uint32_t* __restrict__ packed, uint32_t off, uint32_t len, uint32_t plo, uint32_t phi)
 {
     const int lane = threadIdx.x & 31;
@@ -764,9 +768,9 @@ __device__ __forceinline__ bool wf16c_probe_hit(const uint32_t* __restrict__ pac
     bool hit = false;
     for (uint32_t q0 = 0; q0 < nw; q0 += 32) {
         const uint32_t q = q0 + lane;
-        const uint32_t w0 = q < nw ? __ldg(packed + off + q) : 0u;
-        const uint32_t w1 = q + 1 < nw ? __ldg(packed + off + q + 1) : 0u;
-        const uint32_t w2 = q + 2 < nw ? __ldg(packed + off + q + 2) : 0u;
+        const uint32_t w0 = q < nw ? wf16c_ldw<CG>(packed + off + q) : 0u;
+        const uint32_t w1 = q + 1 < nw ? wf16c_ldw<CG>(packed + off + q + 1) : 0u;
+        const uint32_t w2 = q + 2 < nw ? wf16c_ldw<CG>(packed + off + q + 2) : 0u;
 #pragma unroll
         for (uint32_t s = 0; s < 8; ++s) {
             const uint32_t lo = __funnelshift_r(w0, w1, 4 * s), hi = __funnelshift_r(w1, w2, 4 * s);
@@ -778,17 +782,44 @@ __device__ __forceinline__ bool wf16c_probe_hit(const uint32_t* __restrict__ pac
 }
 
 // Orientation probe: the system to start with (where the walk is expected to end).
-__device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__ packed, const PairDesc& pd)
+template <bool CG = false>
+__device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__ packed_row, const uint32_t* __restrict__ packed, const PairDesc& pd)
 {
     if (pd.m < (uint32_t)WF16C_PROBE || pd.n < (uint32_t)WF16C_PROBE) return WF16C_SYS_U;
     const uint32_t c0 = __ldg(packed + pd.col_off), c1 = __ldg(packed + pd.col_off + 1);
-    const uint32_t r0 = __ldg(packed + pd.row_off), r1 = __ldg(packed + pd.row_off + 1);
+    const uint32_t r0 = wf16c_ldw<CG>(packed_row + pd.row_off), r1 = wf16c_ldw<CG>(packed_row + pd.row_off + 1);
     // both sequences start with the same bases: the overlap starts in the corner
     if (c0 == r0 && c1 == r1) return WF16C_SYS_C;
     // the first bases of the column sequence occur in the row sequence: the overlap starts in column 0
-    if (wf16c_probe_hit(packed, pd.row_off, pd.m, c0, c1)) return WF16C_SYS_U;
+    if (wf16c_probe_hit<CG>(packed_row, pd.row_off, pd.m, c0, c1)) return WF16C_SYS_U;
     // the first bases of the row sequence occur in the column sequence: it starts in row 0
     return wf16c_probe_hit(packed, pd.col_off, pd.n, r0, r1) ? WF16C_SYS_L : WF16C_SYS_U;
+}
+
+// One pair, start to finish: probe, first pass (scan mode), up to two sub-table passes in the other systems.  Every
+// thread of the warp (TEAM = 1) or CTA (TEAM > 1) calls it with w.pd / w.packed / w.packed_row set.  r receives the exact
+// score / ends / clip; the return value is the certified origin (FLAG_ROW0 | FLAG_COL0 bits) or 0 when no system
+// certifies it (the caller hands the pair to an exact kernel); key_out the first pass's key without the origin bits.
+template <bool STD, int TEAM, bool POT2>
+__device__ __forceinline__ uint32_t wf16c_solve_pair(Wf16cWarp& w, const Wf16cParams& P, long long* team_keys, uint32_t force_sys,
+                                                     bool leader, unsigned int* __restrict__ counters, DevResult& r, long long& key_out)
+{
+    const int m = (int)w.pd.m, n = (int)w.pd.n;
+    const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system<(TEAM > 1)>(w.packed_row, w.packed, w.pd);
+    w.g = wf16c_make_pass(m, n, P, sys0, false, 0);
+    const long long key = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
+    uint32_t origin = wf16c_certified_origin(w.g, key);
+    store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
+    for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
+        // another system on the sub-table that ends at the best cell, that cell only
+        __syncwarp();
+        if (leader) atomicAdd(counters, 1u);
+        w.g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score);
+        const long long key2 = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
+        origin = wf16c_certified_origin(w.g, key2);
+    }
+    key_out = key & ~3ll;
+    return origin;
 }
 
 // counters[0] sub-table passes run (second and third passes), counters[1] pairs handed to an exact kernel.
@@ -814,6 +845,7 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Wf16cWarp w;
     w.packed = packed;
+    w.packed_row = packed;
     w.team_warp = TEAM > 1 ? (int)(threadIdx.x >> 5) : 0;
     w.strip_idx = 0;
     w.prog_addr = (uint32_t)__cvta_generic_to_shared(team_prog);
@@ -835,23 +867,12 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
         const uint32_t pid = order[qi];
         w.pd = pairs[pid];
         const int m = (int)w.pd.m, n = (int)w.pd.n;
-        const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system(packed, w.pd);
-        w.g = wf16c_make_pass(m, n, P, sys0, false, 0);
-        const long long key = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
-        uint32_t origin = wf16c_certified_origin(w.g, key);
         DevResult r;
-        store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
-        for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
-            // another system on the sub-table that ends at the best cell, that cell only
-            __syncwarp();
-            if (leader) atomicAdd(counters, 1u);
-            w.g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score);
-            const long long key2 = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
-            origin = wf16c_certified_origin(w.g, key2);
-        }
+        long long key;
+        const uint32_t origin = wf16c_solve_pair<STD, TEAM, POT2>(w, P, team_keys, force_sys, leader, counters, r, key);
         if (leader) {
             if (origin != 0u) {
-                store_result(out + pid, (key & ~3ll) | (long long)origin, m, n, FLAG_KERNEL16);
+                store_result(out + pid, key | (long long)origin, m, n, FLAG_KERNEL16);
             } else {
                 out[pid] = r;                                                // overwritten by the exact kernel
                 atomicAdd(counters + 1, 1u);

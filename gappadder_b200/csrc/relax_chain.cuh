@@ -1,0 +1,168 @@
+// relax_chain.cuh -- the relax chains of ContigsMerger on the device, as ONE dependency-driven launch (sm_100a).
+//
+// Reference: ContigsCompactor::FormMergedSeqFromPath, ContigsCompactor-v0.2.0/ContigsMerger/ContigsCompactor.cpp:1456-1515:
+//   merged = node_0;  for k = 1..: Evaluate(merged, node_k, relax) (:1491);  merged = ccAct.GetMerged() (:1512)
+// i.e. step k needs the merged contig step k-1 produced: sequential inside a path, independent across paths and gaps.
+// Paths of one gap that share a prefix share those steps, so the steps of a batch form a forest; a work item is one
+// node of it: Evaluate(merged contig of the parent item, node) followed by SetMergedStringConcat (:108-153).
+//
+// Round 1 ran the forest level by level from the host: 32 blocking calls (pack, copy, launch, copy back, build strings
+// on the host), each as long as its longest pair.  Here the merged contigs never leave the GPU:
+//   * items are handed out by an atomic ticket counter in topological order (by depth, longest remaining chain first);
+//   * a CTA of four warps takes an item, waits until the parent item's `status` word says its merged contig is in the
+//     arena (the parent holds a lower ticket, so it is running or done: no deadlock whatever the number of resident CTAs),
+//     runs the certificate kernel's CTA-per-pair machinery on (arena row, table column) -- the pair's 512-row strips
+//     pipelined across the four warps --, builds the new merged contig as 4-bit codes in its own arena slot (a
+//     funnel-shift nibble copy by all 128 threads) and publishes length and status with release semantics;
+//   * nothing synchronises levels: every chain advances as soon as its previous step is done.
+// The host gets one gp_result per item and rebuilds the strings from the original letters (gp_merged_concat).
+// An item whose walk end no certificate system proves (a genuine tie between walks ending on different borders; none
+// seen on any synthetic set) is marked unresolved together with its descendants; the caller runs those chains
+// through gp_overlap_batch (exact kernels) instead.
+#pragma once
+#include "overlap_wf16c.cuh"
+
+namespace gp {
+
+struct RelaxItem {                 // 32 bytes
+    int32_t parent;                // item that produced the row sequence, or -1: table sequence (row_off, row_len)
+    uint32_t row_off, row_len;     // parent < 0 only: the path's first node in the packed table (word offset, bases)
+    uint32_t col_off, col_len;     // the node met at this step, in the packed table
+    uint32_t arena_off;            // this item's merged contig in the arena (word offset, 128-byte aligned)
+    uint32_t pad[2];
+};
+
+constexpr uint32_t RELAX_PENDING = 0u, RELAX_DONE = 1u, RELAX_UNRESOLVED = 2u;
+constexpr uint32_t FLAG_UNRESOLVED = 32u;       // gp_result.flags: GP_FLAG_UNRESOLVED
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Eight 4-bit codes starting at base q of the sequence at word pointer s (through L2)
+__device__ __forceinline__ uint32_t relax_fetch8(const uint32_t* s, uint32_t q)
+{
+    const uint32_t w = q >> 3, sh = (q & 7u) * 4u;
+    const uint32_t lo = __ldcg(s + w), hi = sh ? __ldcg(s + w + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+// dst := A[a0, a0 + la) ++ B[b0, b0 + lb) as packed 4-bit codes, unused codes of the last word zero.  Whole CTA.
+__device__ __forceinline__ void relax_concat(uint32_t* __restrict__ dst, const uint32_t* A, uint32_t a0, uint32_t la,
+                                             const uint32_t* B, uint32_t b0, uint32_t lb)
+{
+    const uint32_t total = la + lb, nw = (total + 7u) >> 3;
+    for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+        const uint32_t p0 = 8u * w;
+        uint32_t v = 0u;
+        if (p0 < la) {
+            v = relax_fetch8(A, a0 + p0);
+            if (p0 + 8u > la) v &= (1u << (4u * (la - p0))) - 1u;
+        }
+        if (p0 + 8u > la && lb) {
+            const uint32_t ps = p0 > la ? p0 : la, sh = ps - p0;                 // first base of this word that comes from B
+            v |= relax_fetch8(B, b0 + (ps - la)) << (4u * sh);
+        }
+        if (p0 + 8u > total) v &= (1u << (4u * (total - p0))) - 1u;
+        dst[w] = v;
+    }
+}
+
+template <bool POT2>
+__global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
+relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ arena, const RelaxItem* __restrict__ items,
+                   const uint32_t* __restrict__ order, uint32_t n_items, unsigned int* __restrict__ queue, Wf16cParams P,
+                   uint32_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ status, uint32_t* __restrict__ mlen,
+                   unsigned int* __restrict__ counters, DevResult* __restrict__ out)
+{
+    constexpr int TEAM = WF16C_THREADS / 32;
+    extern __shared__ uint32_t wf16c_smem[];
+    __shared__ uint32_t team_prog[TEAM];
+    __shared__ long long team_keys[TEAM];
+    __shared__ uint32_t team_qi, parent_state;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    Wf16cWarp w;
+    w.packed = packed;
+    w.team_warp = (int)(threadIdx.x >> 5);
+    w.strip_idx = 0;
+    w.prog_addr = (uint32_t)__cvta_generic_to_shared(team_prog);
+    w.bnd = scratch + (size_t)(warp_global - (uint32_t)w.team_warp) * scratch_stride;
+    w.smem = wf16c_smem + (threadIdx.x >> 5) * WF16C_WARP_WORDS;
+    const bool leader = threadIdx.x == 0;
+    for (;;) {
+        if (leader) team_qi = atomicAdd(queue, 1u);
+        __syncthreads();
+        const uint32_t qi = team_qi;
+        __syncthreads();
+        if (qi >= n_items) break;
+        const uint32_t id = order[qi];
+        const RelaxItem it = items[id];
+        const uint32_t* row_base = packed;
+        uint32_t row_off = it.row_off, m = it.row_len;
+        if (it.parent >= 0) {
+            if (leader) {
+                uint32_t s;
+                while ((s = ld_acquire_u32(status + it.parent)) == RELAX_PENDING) __nanosleep(200);
+                parent_state = s;
+            }
+            __syncthreads();
+            const uint32_t ps = parent_state;
+            __syncthreads();
+            if (ps != RELAX_DONE) {                                   // the chain is handed back to the host from here on
+                if (leader) { out[id].flags = FLAG_UNRESOLVED; st_release_u32(status + id, RELAX_UNRESOLVED); }
+                continue;
+            }
+            row_base = arena;
+            row_off = items[it.parent].arena_off;
+            m = __ldcg(mlen + it.parent);
+        }
+        w.packed_row = row_base;
+        w.pd = PairDesc{row_off, m, it.col_off, it.col_len};
+        const int n = (int)it.col_len;
+        DevResult r;
+        long long key;
+        const uint32_t origin = wf16c_solve_pair<true, TEAM, POT2>(w, P, team_keys, 0u, leader, counters, r, key);
+        if (origin == 0u) {
+            if (leader) { r.flags |= FLAG_UNRESOLVED; out[id] = r; atomicAdd(counters + 1, 1u); st_release_u32(status + id, RELAX_UNRESOLVED); }
+            continue;
+        }
+        store_result(&r, key | (long long)origin, (int)m, n, FLAG_KERNEL16);
+        // SetMergedStringConcat (:108-153) on 4-bit codes
+        const bool contained = (r.flags & FLAG_CONTAINED) != 0u;
+        const uint32_t len1 = m, len2 = (uint32_t)n, rowe = (uint32_t)r.row_end, cole = (uint32_t)r.col_end, clip = (uint32_t)r.nclip;
+        uint32_t* dst = arena + it.arena_off;
+        uint32_t total;
+        const uint32_t* s1 = row_base + row_off;                      // word pointers of the two sequences
+        const uint32_t* s2 = packed + it.col_off;
+        if (contained && rowe + clip == len1 && len1 < len2) { relax_concat(dst, s2, 0u, len2, s2, 0u, 0u); total = len2; }            // merged = s2 (:116-121)
+        else if (contained && cole + clip == len2 && len2 < len1) { relax_concat(dst, s1, 0u, len1, s1, 0u, 0u); total = len1; }       // merged = s1 (:122-127)
+        else if (rowe + clip == len1) { relax_concat(dst, s1, 0u, len1 - clip, s2, cole, len2 - cole); total = len1 - clip + len2 - cole; }   // :131-139
+        else { relax_concat(dst, s2, 0u, len2 - clip, s1, rowe, len1 - rowe); total = len2 - clip + len1 - rowe; }                     // :141-149
+        __threadfence();
+        __syncthreads();
+        if (leader) {
+            out[id] = r;
+            mlen[id] = total;
+            st_release_u32(status + id, RELAX_DONE);
+        }
+    }
+}
+
+inline cudaError_t relax_configure()
+{
+    cudaError_t e = cudaFuncSetAttribute(relax_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf16c_smem_bytes<WF16C_THREADS / 32>());
+    if (e != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(relax_chain_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(relax_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wf16c_smem_bytes<WF16C_THREADS / 32>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(relax_chain_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+} // namespace gp

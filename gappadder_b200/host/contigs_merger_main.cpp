@@ -57,6 +57,7 @@ bool parse_args(int argc, char** argv, Cli& c)
         if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); pos += 2; continue; }
         if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); pos += 2; continue; }
         if (!strcmp(a, "--host-quick-check")) { c.opt.host_quick_check = true; pos += 1; continue; }
+        if (!strcmp(a, "--host-relax")) { c.opt.host_relax = true; pos += 1; continue; }
         if (!strcmp(a, "--no-gml")) { c.write_gml = false; ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; ++pos; continue; }
         switch (a[1]) {

@@ -37,6 +37,7 @@ struct GapState {
     uint32_t node_base = 0;                          // index of node 0 in the batch sequence table
     uint64_t pair_begin = 0, pair_end = 0;           // slice of the batch pair list
     bool dead = false;                               // fatal input error, nothing more to do
+    bool acgt_only = true;                           // every node is pure A/C/G/T and at most 16382 bases (device relax chains)
     bool arranged = false;                           // candidate pairs were generated
     bool want_pairs = false;                         // ... by the quick check on the device (after the parallel phase)
     std::vector<gp_pair> cand;                       // ... with node indices local to the gap
@@ -163,6 +164,10 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
                 out[g].exit_code = 3;
                 s.dead = true;
                 return;
+            }
+            for (const FastaRecord& r : s.contigs) {
+                if (r.seq.size() > 16382 || r.seq.empty()) s.acgt_only = false;
+                for (unsigned char ch : r.seq) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { s.acgt_only = false; break; }
             }
             if (n_other > 0) {
                 s.dp_seq = s.node_seq;
@@ -309,7 +314,105 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     for (size_t g = 0; g < G; ++g) for (Chain& c : gap_chains[g]) chains.push_back(std::move(c));
 
     lap(&MergeTimings::graph_ms);
-    // ---- relax chains: step k of every chain in one batch (replaces the loop at :1463-1513) ------
+    // ---- relax chains on the device: the whole forest of steps in one launch (gp_relax_chains) ------------------
+    // A step = Evaluate(merged contig so far, next node of the path) + SetMergedStringConcat (:1463-1513).  Chains of one
+    // gap whose paths share a prefix share those steps (the reference runs them once per path, with the same result), so
+    // the steps of a gap form a trie over its paths.  Gaps outside the device entry point's domain (letters other than
+    // A C G T, other scores, nodes beyond 16382 bases) and gaps with a step no certificate resolves take the step-by-step
+    // loop below (exact kernels through gp_overlap_batch).
+    if (!chains.empty() && !opt.host_relax) {
+        std::vector<gp_relax_step> steps;
+        std::vector<std::vector<int32_t>> chain_steps(chains.size());     // per chain: step index of path position 1, 2, ...
+        std::vector<char> gap_on_device(G, 0);
+        for (size_t g = 0; g < G; ++g) gap_on_device[g] = !st[g].dead && st[g].acgt_only && dp.mismatch == -2 && dp.indel == -2;
+        {
+            size_t c0 = 0;
+            while (c0 < chains.size()) {                                   // chains are grouped by gap
+                const int g = chains[c0].gap;
+                size_t c1 = c0;
+                while (c1 < chains.size() && chains[c1].gap == g) ++c1;
+                if (gap_on_device[g]) {
+                    std::map<std::vector<int>, int32_t> seen;             // path prefix -> step
+                    for (size_t c = c0; c < c1; ++c) {
+                        const std::vector<int>& p = chains[c].path;
+                        int32_t parent = -1;
+                        for (size_t k = 1; k < p.size(); ++k) {
+                            std::vector<int> key(p.begin(), p.begin() + k + 1);
+                            auto it = seen.find(key);
+                            if (it == seen.end()) {
+                                it = seen.emplace(std::move(key), (int32_t)steps.size()).first;
+                                steps.push_back(gp_relax_step{parent, st[g].node_base + (uint32_t)p[0], st[g].node_base + (uint32_t)p[k]});
+                            } else if (timings) ++timings->relax_shared_pairs;
+                            chain_steps[c].push_back(it->second);
+                            parent = it->second;
+                        }
+                    }
+                }
+                c0 = c1;
+            }
+        }
+        if (!steps.empty()) {
+            std::vector<gp_result> rr(steps.size());
+            std::vector<uint32_t> mlen(steps.size());
+            const int rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
+            if (rc == GP_ERR_RANGE) {
+                for (size_t g = 0; g < G; ++g) gap_on_device[g] = 0;       // outside the entry point's domain after all: step by step
+            } else if (rc != GP_OK) {
+                error = gp_last_error(ctx);
+                return rc;
+            } else {
+                if (timings) {
+                    double ms = 0; uint64_t sp2 = 0, un = 0;
+                    gp_relax_stats(ctx, &ms, &sp2, &un);
+                    timings->relax_device_ms += ms; timings->relax_pairs += steps.size(); timings->relax_second_passes += sp2;
+                    timings->relax_exact_retries += un; timings->relax_steps += 1; timings->relax_team_steps += 1;
+                }
+                for (size_t c = 0; c < chains.size(); ++c)
+                    for (int32_t k : chain_steps[c]) if (rr[k].flags & GP_FLAG_UNRESOLVED) gap_on_device[chains[c].gap] = 0;
+                // merged contigs from the original letters, chain by chain; consecutive chains of a gap share long prefixes
+                // (the paths come out of a sorted set), so a stack of the previous chain's intermediate contigs is reused
+                std::vector<size_t> first_chain_of_gap;
+                for (size_t c = 0; c < chains.size(); ++c) if (c == 0 || chains[c].gap != chains[c - 1].gap) first_chain_of_gap.push_back(c);
+                first_chain_of_gap.push_back(chains.size());
+                std::atomic<int> bad(0);
+                for_each_gap(first_chain_of_gap.size() - 1, host_threads, [&](size_t q) {
+                    const size_t c0 = first_chain_of_gap[q], c1 = first_chain_of_gap[q + 1];
+                    const int g = chains[c0].gap;
+                    if (!gap_on_device[g]) return;
+                    std::vector<std::string> stack;                        // stack[k] = merged contig after path position k+1
+                    std::vector<int32_t> stack_step;
+                    for (size_t c = c0; c < c1; ++c) {
+                        Chain& ch = chains[c];
+                        const std::vector<int32_t>& cs = chain_steps[c];
+                        size_t keep = 0;
+                        while (keep < cs.size() && keep < stack_step.size() && stack_step[keep] == cs[keep]) ++keep;
+                        stack.resize(keep); stack_step.resize(keep);
+                        for (size_t k = keep; k < cs.size(); ++k) {
+                            const std::string& prev = k == 0 ? st[g].node_seq[ch.path[0]] : stack[k - 1];
+                            const std::string& nodeseq = st[g].node_seq[ch.path[k + 1]];
+                            std::string m(prev.size() + nodeseq.size() + 1, '\0');
+                            const int32_t len = gp_merged_concat(prev.data(), (int32_t)prev.size(), nodeseq.data(), (int32_t)nodeseq.size(), &rr[cs[k]], &m[0]);
+                            if ((uint32_t)len != mlen[cs[k]]) bad = 1;     // the device built a different contig: never expected
+                            m.resize((size_t)len);
+                            stack.push_back(std::move(m));
+                            stack_step.push_back(cs[k]);
+                        }
+                        for (size_t k = 0; k < cs.size(); ++k) {
+                            const size_t rows = k == 0 ? st[g].node_seq[ch.path[0]].size() : stack[k - 1].size();
+                            out[g].relax_cells += (uint64_t)rows * st[g].node_seq[ch.path[k + 1]].size();
+                            out[g].n_relax += 1;
+                        }
+                        ch.merged = cs.empty() ? ch.merged : stack.back();
+                        ch.next = ch.path.size();
+                    }
+                });
+                if (bad) { error = "internal: merged contig lengths of the device relax chain and the host epilogue differ"; return GP_ERR_INVALID; }
+                // a gap with an unresolved step starts over in the loop below
+                for (Chain& ch : chains) if (!gap_on_device[ch.gap]) { ch.next = 1; ch.merged = st[ch.gap].node_seq[ch.path[0]]; }
+            }
+        }
+    }
+    // ---- relax chains, step by step: step k of every remaining chain in one batch (gaps the device path did not take) ------
     for (;;) {
         std::vector<size_t> active;
         for (size_t c = 0; c < chains.size(); ++c) if (chains[c].next < chains[c].path.size()) active.push_back(c);

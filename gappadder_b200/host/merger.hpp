@@ -30,6 +30,7 @@ struct MergeOptions {
     int max_count_contig_in_path = -1;       // -p2 (default MAX_CONTIG_IN_PATH_COUNT = 20)
     bool verbose = false;                    // -V  (accepted, ignored: it pollutes stdout in the reference)
     bool host_quick_check = false;           // --host-quick-check (not a reference flag): candidate filter on the host
+    bool host_relax = false;                 // --host-relax (not a reference flag): relax chains step by step from the host (round 1's form)
 };
 
 struct GapInput {

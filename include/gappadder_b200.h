@@ -222,6 +222,29 @@ int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
  * cells are NOT part of gp_pair_stats' cells (no cell update is computed for them). */
 int gp_closed_form_stats(const gp_ctx *ctx, uint64_t *pairs, uint64_t *cells);
 
+/* ---- relax chains on the device ------------------------------------------------------------------------------------------
+ * ContigsCompactor::FormMergedSeqFromPath (ContigsCompactor.cpp:1456-1515): merged = node_0; for every further node of the
+ * path, Evaluate(merged, node, relax) (:1491) and merged = GetMerged() (:1512).  A step needs the merged contig of the
+ * step before, so the steps of a batch form a forest: steps[k].parent is the step that produced the row sequence (it
+ * must precede k), or -1 when the row sequence is the table sequence steps[k].row_seq (the path's first node); col_seq
+ * is the node met at step k.  Paths with a common prefix share those steps.  The whole forest runs as ONE launch on the
+ * context's current sequence table; merged contigs stay on the device (csrc/relax_chain.cuh).
+ *   out[k]         Evaluate's result of step k (relax mode: no significance test)
+ *   merged_len[k]  length of the merged contig after step k (the caller rebuilds the letters with gp_merged_concat)
+ * A step whose walk end no certificate proves carries GP_FLAG_UNRESOLVED, and so do all steps below it (their other
+ * fields are undefined): run those chains through gp_overlap_batch.  GP_ERR_RANGE when the batch is outside this entry
+ * point's domain (scores other than -2/-2, letters other than A C G T, column sequences beyond 16382 bases): likewise. */
+typedef struct gp_relax_step {
+    int32_t parent;
+    uint32_t row_seq;
+    uint32_t col_seq;
+} gp_relax_step;
+#define GP_FLAG_UNRESOLVED 32u
+int gp_relax_chains(gp_ctx *ctx, const gp_relax_step *steps, uint64_t n_steps, const gp_dp_params *params,
+                    gp_result *out, uint32_t *merged_len);
+/* Of the last gp_relax_chains: device time of its launch, sub-table passes, unresolved steps (descendants not counted). */
+int gp_relax_stats(const gp_ctx *ctx, double *kernel_ms, uint64_t *second_passes, uint64_t *unresolved);
+
 /* ---- flank placement: semi-global alignment (BASELINE configs[1]) ------------------------------------------------------
  * What GAPPadder does here is `bwa mem -T <s> -a contigs.fa flanks.fa` (pick_contigs.py:83-86); BWA is not vendored and
  * not pinned, so PARITY IS UNPINNED at this boundary: these entry points are bit-exact against the builder-written

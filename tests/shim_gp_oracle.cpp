@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -101,6 +102,28 @@ int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n)
 int gp_closed_form_stats(const gp_ctx*, uint64_t* pairs, uint64_t* cells) { if (pairs) *pairs = 0; if (cells) *cells = 0; return GP_OK; }
 int gp_cert_stats(const gp_ctx*, uint64_t* a, uint64_t* b, uint64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GP_OK; }
 int gp_last_team(const gp_ctx*) { return 0; }
+// The device relax chain, served from the oracle step by step on the table of the last upload (parents precede children).
+// GP_SHIM_NO_RELAX=1 answers GP_ERR_RANGE instead, which sends the merger to its step-by-step loop.
+int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n, const gp_dp_params* p, gp_result* out, uint32_t* merged_len)
+{
+    if (getenv("GP_SHIM_NO_RELAX")) return GP_ERR_RANGE;
+    std::vector<std::string> merged(n);
+    for (uint64_t k = 0; k < n; ++k) {
+        const std::string& row = steps[k].parent < 0 ? c->seqs[steps[k].row_seq] : merged[steps[k].parent];
+        const std::string& col = c->seqs[steps[k].col_seq];
+        const char* ptr[2] = {row.data(), col.data()};
+        const uint32_t len[2] = {(uint32_t)row.size(), (uint32_t)col.size()};
+        const gp_pair pr{0, 1};
+        if (int rc = gp_overlap_batch(c, ptr, len, 2, &pr, 1, p, out + k)) return rc;
+        std::string m(row.size() + col.size() + 1, '\0');
+        const int32_t l = gp_merged_concat(row.data(), (int32_t)row.size(), col.data(), (int32_t)col.size(), out + k, &m[0]);
+        m.resize((size_t)l);
+        merged[k] = std::move(m);
+        merged_len[k] = (uint32_t)l;
+    }
+    return GP_OK;
+}
+int gp_relax_stats(const gp_ctx*, double* ms, uint64_t* a, uint64_t* b) { if (ms) *ms = 0; if (a) *a = 0; if (b) *b = 0; return GP_OK; }
 int gp_quick_check_stats(const gp_ctx*, double* ms, uint64_t* b, uint32_t* i) { if (ms) *ms = 0; if (b) *b = 0; if (i) *i = 0; return GP_OK; }
 int gp_last_timing(const gp_ctx*, double* out_ms, int n) { for (int i = 0; i < n; ++i) out_ms[i] = 0.0; return GP_OK; }
 }

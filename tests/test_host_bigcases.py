@@ -49,3 +49,13 @@ def test_gap_with_too_many_letters_fails_alone(hosttest_binary):  # noqa: F811
         p = subprocess.run([hosttest_binary] + B.FLAGS + ["--batch", lst], cwd=td, capture_output=True)
         assert p.returncode == 3 and not os.path.exists(os.path.join(td, "bad.out"))
         assert open(os.path.join(td, "good.out"), "rb").read() == B.golden("fan1", "stdout")
+
+
+def test_step_by_step_relax_path(hosttest_binary, monkeypatch):  # noqa: F811
+    """The merger's fallback for gaps outside gp_relax_chains' domain (and for unresolved steps): the relax chains step by
+    step through gp_overlap_batch, with prefix sharing -- same bytes."""
+    monkeypatch.setenv("GP_SHIM_NO_RELAX", "1")
+    with tempfile.TemporaryDirectory() as td:
+        B.check_single(hosttest_binary, "cfg3_s43", td)
+    with tempfile.TemporaryDirectory() as td:
+        B.check_batch(hosttest_binary, ["fan1", "fan3", "iupac1"], td, ("--host-relax",))
