@@ -21,7 +21,7 @@ EXPORTS = [
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
     "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device", "gp_upload_sequences",
     "gp_quick_check_stats",
-    "gp_relax_chains", "gp_relax_stats",
+    "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
     "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
 ]
 
@@ -125,6 +125,9 @@ def lib() -> C.CDLL:
         L.gp_quick_check_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64]
         L.gp_upload_sequences.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32]
         L.gp_quick_check_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.gp_set_orientation.argtypes = [C.c_void_p, C.c_uint32]
+        L.gp_transposed_pairs.argtypes = [C.c_void_p]
+        L.gp_transposed_pairs.restype = C.c_uint64
         L.gp_semiglobal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(DpParams), C.c_void_p]
         L.gp_semiglobal_upload_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(DpParams)]
         L.gp_semiglobal_launch.argtypes = [C.c_void_p]
@@ -370,6 +373,14 @@ class Context:
     @property
     def last_layout(self) -> int:
         return int(self._L.gp_last_layout(self._h))
+
+    def set_orientation(self, mode: int):
+        """Certificate kernel: 0 the cost model orients every pair (default), 1 never transpose, 2 always when allowed."""
+        self._check(self._L.gp_set_orientation(self._h, mode))
+
+    @property
+    def transposed_pairs(self) -> int:
+        return int(self._L.gp_transposed_pairs(self._h))
 
     def set_team_mode(self, mode: int):
         """Certificate kernel: 0 library chooses per launch (default), 1 one warp per pair, 2 one CTA of four warps per pair,

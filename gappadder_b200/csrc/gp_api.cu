@@ -99,7 +99,9 @@ struct gp_ctx {
     std::vector<uint32_t> pack_off;
     double timing[GP_TIMING_SLOTS] = {0};       // milliseconds of the last gp_overlap_batch, see gp_last_timing
     uint64_t n_pairs = 0, n16c = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
-    uint32_t max_n16c = 0, max_n16c_small = 0, max_n16t = 0, max_n16 = 0, max_n32 = 0;
+    uint32_t max_n16c = 0, max_n16c_small = 0, max_n16c_orig = 0, max_n16t = 0, max_n16 = 0, max_n32 = 0;
+    uint64_t n16c_transposed = 0;
+    uint32_t orientation = 0;                   // certificate kernel: 0 the host's cost model orients every pair, 1 never transpose, 2 always (tests)
     uint32_t cert_system = 0;                   // 0: probe decides, 1: start with system U, 2: with L, 3: with C (tests)
     uint32_t team_mode = 0;                     // certificate kernel: 0 auto, 1 one warp per pair, 2 one CTA per pair
     uint64_t max_cells16c = 0;                  // largest m*n routed to the certificate kernel
@@ -267,6 +269,15 @@ int gp_set_team_mode(gp_ctx* c, uint32_t mode)
 }
 
 int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
+
+int gp_set_orientation(gp_ctx* c, uint32_t mode)
+{
+    if (!c || mode > 2) return GP_ERR_INVALID;
+    c->orientation = mode;
+    return GP_OK;
+}
+
+uint64_t gp_transposed_pairs(const gp_ctx* c) { return c ? c->n16c_transposed : 0; }
 
 int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes)
 {
@@ -447,6 +458,19 @@ static void patch_closed(const gp_ctx* c, gp_result* out)
     for (uint32_t id : c->closed_ids) closed_form_self(out + id, hd[id].m);
 }
 
+// Relative cost of one certificate-kernel pass over a table of `rows` x `cols`: per strip (cols + pipeline fill and drain
+// + set-up) steps, a step costing a fixed part plus two instructions per register (K = strip rows / 64).
+static double wf16c_cost(uint32_t rows, uint32_t cols, int C)
+{
+    double cost = 0.5 * cols;
+    for (int i0 = 0; i0 < (int)rows;) {
+        const gp::Wf16Strip st = gp::wf16c_next_strip(i0, (int)rows, C);
+        cost += ((double)cols + 93.0 + 16.0) * (10.0 + 2.0 * (st.rows / 64));
+        i0 += st.rows;
+    }
+    return cost;
+}
+
 static void reset_pairs(gp_ctx* c)
 {
     c->n_pairs = 0; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
@@ -462,7 +486,7 @@ static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, 
     GP_CUDA(c, cudaSetDevice(c->device));
     c->params = *params;
     c->n_pairs = n_pairs; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
-    c->max_n16c = c->max_n16c_small = c->max_n16t = c->max_n16 = c->max_n32 = 0;
+    c->max_n16c = c->max_n16c_small = c->max_n16c_orig = c->max_n16t = c->max_n16 = c->max_n32 = 0; c->n16c_transposed = 0;
     c->cells16c = c->cells16t = c->cells16 = c->cells32 = 0; c->kev_valid = false;
     c->closed_ids.clear(); c->cells_closed = 0; c->max_cells16c = 0;
     if (n_pairs == 0) return GP_OK;
@@ -499,8 +523,17 @@ static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, 
         // certificate kernel: everything A/C/G/T except a sequence against itself (closed form above when the scores
         // allow it; otherwise an exact kernel -- system C would certify its corner walk, but it is not worth a probe)
         if (params16c && a != b && gp::wf16c_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) {
-            ho16c[c->n16c++] = (uint32_t)i; c->max_n16c = std::max(c->max_n16c, n); c->cells16c += (uint64_t)m * n;
+            // Orientation (Wf16cPass::tr): the kernel may compute the transposed table -- rows = the column sequence -- when
+            // that fills its 512-row strips better; results come back in the reference's orientation either way.  Never at
+            // the price of the launch's free-moves layout (columns <= WF16C_POT2_MAX_N).
+            bool tr = false;
+            if (c->orientation != 1 && gp::wf16c_pair_ok(n, m) && (m <= gp::WF16C_POT2_MAX_N || n > gp::WF16C_POT2_MAX_N))
+                tr = c->orientation == 2 || wf16c_cost(n, m, params->max_clip) < 0.97 * wf16c_cost(m, n, params->max_clip);
+            const uint32_t cn = tr ? m : n;                             // columns of the computed table
+            ho16c[c->n16c++] = (uint32_t)i | (tr ? 0x80000000u : 0u); c->max_n16c = std::max(c->max_n16c, cn); c->cells16c += (uint64_t)m * n;
+            c->n16c_transposed += tr ? 1 : 0;
             c->max_cells16c = std::max(c->max_cells16c, (uint64_t)m * n);
+            c->max_n16c_orig = std::max(c->max_n16c_orig, n);           // retries go to the exact kernels in the reference's orientation
             if (n <= gp::WF16T_MAX_N) c->max_n16c_small = std::max(c->max_n16c_small, n);
         }
         else if (params16t && gp::wf16t_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) { ho16t[c->n16t++] = (uint32_t)i; c->max_n16t = std::max(c->max_n16t, n); c->cells16t += (uint64_t)m * n; }
@@ -517,7 +550,7 @@ static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, 
         if (cnt < 2) return;
         uint64_t mx = 0;
         std::vector<uint64_t> cells(cnt);
-        for (uint64_t k = 0; k < cnt; ++k) { cells[k] = (uint64_t)hd[ord[k]].m * hd[ord[k]].n; mx = std::max(mx, cells[k]); }
+        for (uint64_t k = 0; k < cnt; ++k) { const gp::PairDesc& d = hd[ord[k] & 0x7fffffffu]; cells[k] = (uint64_t)d.m * d.n; mx = std::max(mx, cells[k]); }
         constexpr uint32_t B = 2048;
         const double inv_width = (double)B / ((double)mx + 1.0);            // size class without a division per pair
         std::vector<uint32_t> start(B + 1, 0), tmp(ord, ord + cnt), cls(cnt);
@@ -615,7 +648,7 @@ int gp_launch_resident(gp_ctx* c)
         c->launches += 1;
     }
     GP_CUDA(c, cudaEventRecord(c->kev[1], c->stream));
-    const bool big_retries = cert && c->max_n16c > gp::WF16T_MAX_N;      // retries the table kernel cannot take
+    const bool big_retries = cert && c->max_n16c_orig > gp::WF16T_MAX_N; // retries the table kernel cannot take
     if (c->n16t || cert) {
         int rc = gp::wf16t_launch(c->stream, c->sm_count, (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p,
                                   (const uint32_t*)c->d_order16t.p, (uint32_t)c->n16t, queue + 16, c->p16t,
@@ -637,7 +670,7 @@ int gp_launch_resident(gp_ctx* c)
         constexpr int R = 8, THREADS = 128;
         const int blocks = c->sm_count * 8;
         const uint32_t warps = (uint32_t)blocks * (THREADS / 32);
-        const uint32_t stride = (std::max(c->max_n32, big_retries ? c->max_n16c : 0u) + 1 + 31) & ~31u;
+        const uint32_t stride = (std::max(c->max_n32, big_retries ? c->max_n16c_orig : 0u) + 1 + 31) & ~31u;
         GP_CUDA(c, c->d_scratch32.reserve((size_t)warps * stride * sizeof(int32_t)));
         gp::overlap_wf32_kernel<R><<<blocks, THREADS, 0, c->stream>>>(
             (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_pairs.p, (const uint32_t*)c->d_order32.p,

@@ -103,6 +103,13 @@ struct Wf16cPass {
     int s_cell;
     uint32_t gup, gleft;
     bool pot2;                      // free-moves layout (see WF16C_POT2_MAX_N); rows are then strip-relative (irel)
+    // Transposed pair: the computed table's rows are the reference's COLUMN sequence and vice versa, cell (i,j) here is
+    // the reference's cell (j,i).  Scores are symmetric; what is not -- the scan order (ranks) and which border is
+    // "row 0" -- is translated where it is used: cell_rank with swapped arguments, the first scanned cell (0,N) sits at
+    // (m,0) here, and certified origins swap ROW0 <-> COL0.  The tie rule (diag > up > left) is not symmetric either, but
+    // this kernel never follows it: certificates hold for ALL optimal walks.  The host orients a pair so that the
+    // sequence that fills 512-row strips better is the row sequence.
+    bool tr;
     // V of a cell with score H and origin bit 0 / H of a cell value
     GP_HD int v_of(int H, int irel, int j) const { return pot2 ? 2 * (H + 2 * irel + 2 * j + n + 1) : 2 * (H + n - j + 1); }
     GP_HD int h_of(int vv, int irel, int j) const { return pot2 ? (vv >> 1) - (2 * irel + 2 * j + n + 1) : (vv >> 1) - 1 - (n - j); }
@@ -110,7 +117,7 @@ struct Wf16cPass {
     GP_HD uint32_t v_row0(int j) const { return (uint32_t)v_of(0, 0, j) + (j == 0 ? bcorner : brow); }
 };
 
-GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, bool cell, int s_cell)
+GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, bool cell, int s_cell, bool tr = false)
 {
     Wf16cPass g;
     g.m = m; g.n = n; g.C = cell ? 0 : P.max_clip;
@@ -121,6 +128,7 @@ GP_HD Wf16cPass wf16c_make_pass(int m, int n, const Wf16cParams& P, int sys, boo
     g.cell = cell; g.s_cell = s_cell;
     g.gup = P.gup; g.gleft = P.gleft;
     g.pot2 = P.pot2 != 0;
+    g.tr = tr;
     return g;
 }
 
@@ -270,7 +278,7 @@ GP_HD uint32_t wf16c_scan_thr(int S, int n, int pot2, int K, int k, int j)
 }
 // The exact scan takes K at run time and loops: it is cold code, and four unrolled copies of it (one per strip
 // height) made up a third of the kernel's instructions -- enough to push the kernel out of the instruction cache.
-GP_HD long long lane16c_scan_rt(const uint32_t* W, int K, int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best)
+GP_HD long long lane16c_scan_rt(const uint32_t* W, int K, int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best, bool tr = false)
 {
     if (cell) {
         for (int half = 0; half < 2; ++half) {
@@ -306,7 +314,7 @@ GP_HD long long lane16c_scan_rt(const uint32_t* W, int K, int m, int n, int C, b
             const int jh = j - half;
             const int vv = half ? (int)(w >> 16) : (int)(w & 0xffffu);
             const int i = itop + 1 + k + half * K;
-            const uint32_t rk = i <= m ? cell_rank(i, jh, m, n, C) : RANK_MAX + 1u;
+            const uint32_t rk = i <= m ? (tr ? cell_rank(jh, i, n, m, C) : cell_rank(i, jh, m, n, C)) : RANK_MAX + 1u;
             if (rk <= RANK_MAX) {
                 const long long key = make_key(wf16c_h_of(vv, n, pot2, 1 + k + half * K, jh), rk, (uint32_t)vv & 1u);
                 if (key > best) {
@@ -320,14 +328,14 @@ GP_HD long long lane16c_scan_rt(const uint32_t* W, int K, int m, int n, int C, b
     return best;
 }
 template <int K>
-GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best)
+GP_HD long long lane16c_scan_mn(const uint32_t (&W)[K], int m, int n, int C, bool cell, int itop, int j, int s_floor, int pot2, long long best, bool tr = false)
 {
-    return lane16c_scan_rt(W, K, m, n, C, cell, itop, j, s_floor, pot2, best);
+    return lane16c_scan_rt(W, K, m, n, C, cell, itop, j, s_floor, pot2, best, tr);
 }
 template <int K>
 GP_HD long long lane16c_scan(const uint32_t (&W)[K], const Wf16cPass& g, int itop, int irel_top, int j, long long best)
 {
-    return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, g.pot2 ? irel_top : -1, best);
+    return lane16c_scan_mn<K>(W, g.m, g.n, g.C, g.cell, itop, j, 0, g.pot2 ? irel_top : -1, best, g.tr);
 }
 
 // Deferred exact scans.  Along an alignment path inside the candidate zone a lane's best cell gains a point at
@@ -379,6 +387,7 @@ GP_HD int wf16c_exact_step_score(const uint32_t (&W)[K], int m, int n, int C, in
 GP_HD long long wf16c_initial_best(const Wf16cPass& g)
 {
     if (g.cell) return make_key(g.s_cell - 1, RANK_MAX, 0u);
+    if (g.tr) return make_key(0, 0u, g.m == 0 ? g.bcorner : g.bcol);      // the reference's (0,N) is cell (m,0) here
     return make_key(0, 0u, g.n == 0 ? g.bcorner : g.brow);
 }
 
@@ -387,12 +396,15 @@ GP_HD long long wf16c_initial_best(const Wf16cPass& g)
 GP_HD uint32_t wf16c_certified_origin(const Wf16cPass& g, long long key)
 {
     const uint32_t lo = (uint32_t)(key & 0xffffffffll);
-    if (!g.cell && (int)(key >> 32) == 0 && (RANK_MAX - (lo >> 2)) == 0u)     // the best cell is (0,n) itself
-        return FLAG_ROW0 | (g.n == 0 ? FLAG_COL0 : 0u);
-    if (g.cell && (int)(key >> 32) != g.s_cell) return 0u;                      // cannot happen; be safe
-    if (lo & 1u) return 0u;
+    uint32_t f;                                                                 // in the computed table's terms
+    if (!g.cell && (int)(key >> 32) == 0 && (RANK_MAX - (lo >> 2)) == 0u)     // the best cell is the first scanned cell itself
+        f = g.tr ? (FLAG_COL0 | (g.m == 0 ? FLAG_ROW0 : 0u)) : (FLAG_ROW0 | (g.n == 0 ? FLAG_COL0 : 0u));
+    else if (g.cell && (int)(key >> 32) != g.s_cell) return 0u;                 // cannot happen; be safe
+    else if (lo & 1u) return 0u;
     // system U proves column 0, system L proves row 0, system C proves the corner
-    return g.sys == WF16C_SYS_U ? FLAG_COL0 : g.sys == WF16C_SYS_L ? FLAG_ROW0 : (FLAG_ROW0 | FLAG_COL0);
+    else f = g.sys == WF16C_SYS_U ? FLAG_COL0 : g.sys == WF16C_SYS_L ? FLAG_ROW0 : (FLAG_ROW0 | FLAG_COL0);
+    if (g.tr) f = ((f & FLAG_ROW0) ? FLAG_COL0 : 0u) | ((f & FLAG_COL0) ? FLAG_ROW0 : 0u);   // to the reference's orientation
+    return f;
 }
 
 // The systems to try after `first` failed, in order.
@@ -461,12 +473,14 @@ __device__ __noinline__ long long wf16c_cold(uint32_t* bufs, int K, int flush, u
 {
     const bool cell = C_or_cell < 0;
     const int C = cell ? 0 : C_or_cell;
+    const bool tr = (flush & 2) != 0;                         // bit 1 of `flush`: transposed pair (ranks with swapped coordinates)
+    flush &= 1;
     uint32_t* meta = bufs + 2 * K;
     const uint32_t idx = meta[2];
     const uint32_t* pend = bufs + idx * K;
     const uint32_t* cur = bufs + (1u - idx) * K;
-    if (flush) return lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best);
-    if (!wf16c_deferrable(n, C, cell, j)) return lane16c_scan_rt(cur, K, m, n, C, cell, itop, j, s_floor, pot2, best);
+    if (flush) return lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best, tr);
+    if (!wf16c_deferrable(n, C, cell, j)) return lane16c_scan_rt(cur, K, m, n, C, cell, itop, j, s_floor, pot2, best, tr);
     const int jswitch = n - C > 1 ? n - C : 1;
     const int rlo = j - 1 >= jswitch ? 1 : m - C;              // candidate rows rlo..m
     int a;
@@ -479,7 +493,7 @@ __device__ __noinline__ long long wf16c_cold(uint32_t* bufs, int K, int flush, u
     if (a == WF16C_NO_SNAP || wf16c_score_of(a) < (s_floor > 1 ? s_floor : 1)) return best;   // no candidate can matter
     const int old = (int)meta[1];
     if (old != WF16C_NO_SNAP && a <= old && wf16c_score_of(old) >= s_floor)
-        best = lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best);
+        best = lane16c_scan_rt(pend, K, m, n, C, false, itop, (int)meta[0], s_floor, pot2, best, tr);
     meta[0] = (uint32_t)j;
     meta[1] = (uint32_t)a;
     meta[2] = 1u - idx;
@@ -587,7 +601,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         uint32_t* cur = snap_bufs + (1u - snap_idx) * K;
 #pragma unroll
         for (int k = 0; k < K; ++k) cur[k] = st.W[k];
-        best = wf16c_cold(snap_bufs, K, 0, acc, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
+        best = wf16c_cold(snap_bufs, K, g.tr ? 2 : 0, acc, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
         snapA = (int)snap_bufs[2 * K + 1];
         snap_idx = snap_bufs[2 * K + 2];
     };
@@ -705,7 +719,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         __syncwarp();
     }
     if (snapA != WF16C_NO_SNAP && wf16c_score_of(snapA) >= S0)
-        best = wf16c_cold(snap_bufs, K, 1, 0u, m, n, g.C, itop, 0, S0, pot2, best);
+        best = wf16c_cold(snap_bufs, K, g.tr ? 3 : 1, 0u, m, n, g.C, itop, 0, S0, pot2, best);
     __syncwarp();
     return best;
 }
@@ -802,19 +816,19 @@ __device__ __forceinline__ int wf16c_predict_system(const uint32_t* __restrict__
 // certifies it (the caller hands the pair to an exact kernel); key_out the first pass's key without the origin bits.
 template <bool STD, int TEAM, bool POT2>
 __device__ __forceinline__ uint32_t wf16c_solve_pair(Wf16cWarp& w, const Wf16cParams& P, long long* team_keys, uint32_t force_sys,
-                                                     bool leader, unsigned int* __restrict__ counters, DevResult& r, long long& key_out)
+                                                     bool leader, unsigned int* __restrict__ counters, DevResult& r, long long& key_out, bool tr = false)
 {
-    const int m = (int)w.pd.m, n = (int)w.pd.n;
+    const int m = (int)w.pd.m, n = (int)w.pd.n;                           // of the computed table (tr: the reference's n, m)
     const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system<(TEAM > 1)>(w.packed_row, w.packed, w.pd);
-    w.g = wf16c_make_pass(m, n, P, sys0, false, 0);
+    w.g = wf16c_make_pass(m, n, P, sys0, false, 0, tr);
     const long long key = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
     uint32_t origin = wf16c_certified_origin(w.g, key);
-    store_result(&r, key & ~3ll, m, n, FLAG_KERNEL16);                 // exact score / ends / clip; origin still open
+    store_result(&r, key & ~3ll, tr ? n : m, tr ? m : n, FLAG_KERNEL16);  // exact score / ends / clip, the reference's orientation; origin still open
     for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
         // another system on the sub-table that ends at the best cell, that cell only
         __syncwarp();
         if (leader) atomicAdd(counters, 1u);
-        w.g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score);
+        w.g = wf16c_make_pass(tr ? r.col_end : r.row_end, tr ? r.row_end : r.col_end, P, wf16c_next_system(sys0, attempt), true, r.score, tr);
         const long long key2 = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
         origin = wf16c_certified_origin(w.g, key2);
     }
@@ -864,12 +878,15 @@ overlap_wf16c_kernel(const uint32_t* __restrict__ packed, const PairDesc* __rest
             qi = __shfl_sync(0xffffffffu, qi, 0);
         }
         if (qi >= n_work) break;
-        const uint32_t pid = order[qi];
+        const uint32_t ord = order[qi];
+        const uint32_t pid = ord & 0x7fffffffu;
+        const bool tr = (ord >> 31) != 0u;                                 // the host's orientation choice (Wf16cPass::tr)
         w.pd = pairs[pid];
-        const int m = (int)w.pd.m, n = (int)w.pd.n;
+        const int m = (int)w.pd.m, n = (int)w.pd.n;                        // the reference's orientation
+        if (tr) w.pd = PairDesc{w.pd.col_off, w.pd.n, w.pd.row_off, w.pd.m};
         DevResult r;
         long long key;
-        const uint32_t origin = wf16c_solve_pair<STD, TEAM, POT2>(w, P, team_keys, force_sys, leader, counters, r, key);
+        const uint32_t origin = wf16c_solve_pair<STD, TEAM, POT2>(w, P, team_keys, force_sys, leader, counters, r, key, tr);
         if (leader) {
             if (origin != 0u) {
                 store_result(out + pid, key | (long long)origin, m, n, FLAG_KERNEL16);

@@ -4,6 +4,8 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -350,6 +352,18 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
                 }
                 c0 = c1;
             }
+        }
+        if (!steps.empty() && getenv("GP_RELAX_DEBUG")) {                  // per depth: steps, cells (upper bound: rows = sum of the prefix's nodes)
+            std::vector<uint32_t> depth(steps.size()), bound(steps.size());
+            std::map<uint32_t, std::pair<uint64_t, uint64_t>> per;
+            for (size_t k = 0; k < steps.size(); ++k) {
+                const uint32_t cl = seq_len[steps[k].col_seq];
+                const uint32_t rl = steps[k].parent < 0 ? seq_len[steps[k].row_seq] : bound[steps[k].parent];
+                depth[k] = steps[k].parent < 0 ? 0 : depth[steps[k].parent] + 1;
+                bound[k] = rl + cl;
+                per[depth[k]].first += 1; per[depth[k]].second += (uint64_t)rl * cl;
+            }
+            for (const auto& kv : per) fprintf(stderr, "relax depth %u: %llu steps, %.3f Gcells (bound)\n", kv.first, (unsigned long long)kv.second.first, kv.second.second / 1e9);
         }
         if (!steps.empty()) {
             std::vector<gp_result> rr(steps.size());

@@ -298,7 +298,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
     for (int lane = 0; lane < 32; ++lane) { snapj[lane] = 0; snapA[lane] = WF16C_NO_SNAP; }
     auto scan_pending = [&](int lane) {
         ++g_slow_calls;
-        lane_best[lane] = lane16c_scan_mn<K>(snapW[lane], g.m, g.n, g.C, false, i0 + lane * 2 * K, snapj[lane], S0, g.pot2 ? lane * 2 * K : -1, lane_best[lane]);
+        lane_best[lane] = lane16c_scan_mn<K>(snapW[lane], g.m, g.n, g.C, false, i0 + lane * 2 * K, snapj[lane], S0, g.pot2 ? lane * 2 * K : -1, lane_best[lane], g.tr);
     };
     constexpr int D = WF16C_SKEW;
     const int t_end = n + 1 + 31 * D;
@@ -343,7 +343,7 @@ void strip_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams& P, 
                             }
                         } else {
                             ++g_slow_calls;
-                            lane_best[lane] = lane16c_scan_mn<K>(st[lane].W, g.m, g.n, g.C, g.cell, itop, j, S0, pot2, lane_best[lane]);
+                            lane_best[lane] = lane16c_scan_mn<K>(st[lane].W, g.m, g.n, g.C, g.cell, itop, j, S0, pot2, lane_best[lane], g.tr);
                         }
                     }
                 }
@@ -398,18 +398,22 @@ long long pass_host_c(const HostPair& hp, const Wf16cPass& g, const Wf16cParams&
 extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col_codes, int n,
                              int mismatch, int indel, int max_clip, int first_sys, int32_t* out)
 {
-    if (!wf16_params_ok(mismatch, indel) || !wf16c_pair_ok((uint32_t)m, (uint32_t)n)) return -1;
+    if (!wf16_params_ok(mismatch, indel)) return -1;
     Wf16cParams P = wf16c_make_params(mismatch, indel, max_clip);
+    bool tr = false;
+    if (first_sys >= 8) { tr = true; first_sys -= 8; }  // bit 3: transposed (the computed table's rows are the column sequence)
+    const int cm = tr ? n : m, cn = tr ? m : n;         // the computed table
+    if (!wf16c_pair_ok((uint32_t)cm, (uint32_t)cn)) return -1;
     if (first_sys >= 4) {                              // bit 2: the free-moves layout (standard scores, short columns)
-        if (!P.std_scores || (uint32_t)n > WF16C_POT2_MAX_N) return -1;
+        if (!P.std_scores || (uint32_t)cn > WF16C_POT2_MAX_N) return -1;
         P.pot2 = 1;
         first_sys -= 4;
     }
     HostPair hp;
-    hp.row.assign(row_codes, row_codes + m);
-    hp.col.assign(col_codes, col_codes + n);
+    if (tr) { hp.row.assign(col_codes, col_codes + n); hp.col.assign(row_codes, row_codes + m); }
+    else { hp.row.assign(row_codes, row_codes + m); hp.col.assign(col_codes, col_codes + n); }
     if (first_sys < 0 || first_sys > 2) return -1;
-    Wf16cPass g = wf16c_make_pass(m, n, P, first_sys, false, 0);
+    Wf16cPass g = wf16c_make_pass(cm, cn, P, first_sys, false, 0, tr);
     const long long key = pass_host_c(hp, g, P);
     uint32_t origin = wf16c_certified_origin(g, key);
     DevResult r;
@@ -417,7 +421,7 @@ extern "C" int wf16c_emulate(const uint8_t* row_codes, int m, const uint8_t* col
     int status = 0;
     for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {
         status = 1;
-        g = wf16c_make_pass(r.row_end, r.col_end, P, wf16c_next_system(first_sys, attempt), true, r.score);
+        g = wf16c_make_pass(tr ? r.col_end : r.row_end, tr ? r.row_end : r.col_end, P, wf16c_next_system(first_sys, attempt), true, r.score, tr);
         origin = wf16c_certified_origin(g, pass_host_c(hp, g, P));
     }
     if (origin == 0u) status = 2;

@@ -49,9 +49,15 @@ def emu():
             assert L.wf16t_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, out) == 0
             f = out[4]
             res.append((out[0], out[1], out[2], out[3], f & 1, (f >> 1) & 1, (f >> 2) & 1))
-        if four and len(b) <= 16382:                   # the certificate kernel's domain; every starting system
-            layouts = (0, 4) if (mm, ind) == (-2, -2) and len(b) <= 3800 else (0,)      # + 4: the free-moves layout
-            for first_sys in [s + l for l in layouts for s in (0, 1, 2)]:
+        # the certificate kernel's domain; every starting system, both layouts (+ 4: free moves), both orientations
+        # (+ 8: transposed -- the computed table's rows are b, its columns a; results in the reference's orientation)
+        variants = []
+        for tr, cols in ((0, b), (8, a)):
+            if four and len(cols) <= 16382:
+                layouts = (0, 4) if (mm, ind) == (-2, -2) and len(cols) <= 3800 else (0,)
+                variants += [s + l + tr for l in layouts for s in (0, 1, 2)]
+        if variants:
+            for first_sys in variants:
                 out = (C.c_int32 * 5)()
                 st = L.wf16c_emulate(a.translate(CODE), len(a), b.translate(CODE), len(b), mm, ind, clip, first_sys, out)
                 assert st in (0, 1, 2)

@@ -43,7 +43,7 @@ def test_fan2_modulo_allocator_order():
         B.check_paths_modulo_ties(info, out, gml, "fan2")
 
 
-@pytest.mark.parametrize("extra", [(), ("--streams", "2"), ("--host-quick-check",)])
+@pytest.mark.parametrize("extra", [(), ("--streams", "2"), ("--host-quick-check",), ("--host-relax",)])
 def test_batch_reference_bytes(extra):
     """All cases in one process (one sequence table, one pairwise launch, relax chains of all gaps together); the
     outputs must not depend on the batch, on the worker split or on where the quick check runs."""

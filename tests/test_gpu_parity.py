@@ -37,18 +37,21 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         want = [one(ab) for ab in pairs]
     first = None
     try:
-        runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout)
+        runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout, orientation)
         for mask in masks:
             if mask & KERNEL_CERT16:      # layout 0: free moves whenever the launch allows it, 1: column potential only
-                runs += [(mask, 0, 0, 0), (mask, 1, 1, 0), (mask, 2, 2, 0), (mask, 3, 0, 0), (mask, 0, 2, 0), (mask, 0, 3, 0), (mask, 2, 3, 1),
-                         (mask, 0, 0, 1), (mask, 1, 2, 1), (mask, 2, 1, 1), (mask, 3, 0, 1)]
+                # orientation 0: the host's cost model transposes pairs that fill the strips better; 1 never; 2 every pair it can
+                runs += [(mask, 0, 0, 0, 0), (mask, 1, 1, 0, 0), (mask, 2, 2, 0, 0), (mask, 3, 0, 0, 0), (mask, 0, 2, 0, 0), (mask, 0, 3, 0, 0), (mask, 2, 3, 1, 0),
+                         (mask, 0, 0, 1, 0), (mask, 1, 2, 1, 0), (mask, 2, 1, 1, 0), (mask, 3, 0, 1, 0),
+                         (mask, 0, 0, 0, 1), (mask, 0, 0, 0, 2), (mask, 1, 2, 1, 2), (mask, 2, 0, 1, 2), (mask, 3, 3, 0, 2), (mask, 0, 2, 0, 2)]
             else:
-                runs += [(mask, 0, 0, 0)]
-        for mask, system, team, layout in runs:
+                runs += [(mask, 0, 0, 0, 0)]
+        for mask, system, team, layout, orient in runs:
             ctx.set_kernel_mask(mask)
             ctx.set_cert_system(system)
             ctx.set_team_mode(team)
             ctx.set_cert_layout(layout)
+            ctx.set_orientation(orient)
             res = ctx.overlap_batch(seqs, pairs, params)
             assert len(res) == len(pairs)
             bad = []
@@ -57,8 +60,8 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
                        int(bool(r["flags"] & FLAG_ROW0)), int(bool(r["flags"] & FLAG_COL0)), int(bool(r["flags"] & FLAG_CONTAINED)))
                 if w != got:
                     bad.append(((a, b), len(seqs[a]), len(seqs[b]), w, got))
-            assert not bad, "kernel mask %d system %d team %d layout %d (free moves used: %d): first mismatches (pair, m, n, oracle, gpu): %r" % (
-                mask, system, team, layout, ctx.last_layout, bad[:5])
+            assert not bad, "kernel mask %d system %d team %d layout %d orientation %d (free moves used: %d, transposed pairs: %d): first mismatches (pair, m, n, oracle, gpu): %r" % (
+                mask, system, team, layout, orient, ctx.last_layout, ctx.transposed_pairs, bad[:5])
             if first is None:
                 first = res
     finally:
@@ -66,6 +69,7 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         ctx.set_cert_system(0)
         ctx.set_team_mode(0)
         ctx.set_cert_layout(0)
+        ctx.set_orientation(0)
     return first
 
 
