@@ -272,7 +272,7 @@ int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
 
 int gp_set_orientation(gp_ctx* c, uint32_t mode)
 {
-    if (!c || mode > 2) return GP_ERR_INVALID;
+    if (!c || mode > 4) return GP_ERR_INVALID;      // 3 / 4 (experiments): the longer / the shorter sequence as rows
     c->orientation = mode;
     return GP_OK;
 }
@@ -528,7 +528,8 @@ static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, 
             // the price of the launch's free-moves layout (columns <= WF16C_POT2_MAX_N).
             bool tr = false;
             if (c->orientation != 1 && gp::wf16c_pair_ok(n, m) && (m <= gp::WF16C_POT2_MAX_N || n > gp::WF16C_POT2_MAX_N))
-                tr = c->orientation == 2 || wf16c_cost(n, m, params->max_clip) < 0.97 * wf16c_cost(m, n, params->max_clip);
+                tr = c->orientation == 2 || (c->orientation == 3 && n > m) || (c->orientation == 4 && n < m) ||
+                     (c->orientation == 0 && wf16c_cost(n, m, params->max_clip) < 0.97 * wf16c_cost(m, n, params->max_clip));
             const uint32_t cn = tr ? m : n;                             // columns of the computed table
             ho16c[c->n16c++] = (uint32_t)i | (tr ? 0x80000000u : 0u); c->max_n16c = std::max(c->max_n16c, cn); c->cells16c += (uint64_t)m * n;
             c->n16c_transposed += tr ? 1 : 0;
@@ -841,21 +842,36 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     }
     if ((uint64_t)(params->max_clip + 1) * (max_total + 2) >= (1ull << 30)) return c->fail(GP_ERR_RANGE, "max_clip x length exceeds the kernels' rank range");
     // priority = the longest chain from the item downwards (cells, upper bound); children come after parents in `steps`
+    std::vector<uint32_t> subtree(n, 1);
     {
         std::vector<uint64_t> below(n, 0);
         for (uint32_t k = n; k-- > 0;) {
             prio[k] += below[k];
             const int32_t p = steps[k].parent;
-            if (p >= 0) below[p] = std::max(below[p], prio[k]);
+            if (p >= 0) { below[p] = std::max(below[p], prio[k]); subtree[p] += subtree[k]; }
         }
     }
-    for (uint32_t k = 0; k < n; ++k) order[k] = k;
-    std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return depth[a] != depth[b] ? depth[a] < depth[b] : prio[a] > prio[b]; });
+    // children lists, longest chain first: a CTA follows first_child, the siblings go to the ready ring; roots fill the ring
+    std::vector<uint32_t> roots;
+    {
+        std::vector<uint32_t> by_prio(n);
+        for (uint32_t k = 0; k < n; ++k) { by_prio[k] = k; items[k].first_child = -1; items[k].next_sibling = -1; }
+        std::stable_sort(by_prio.begin(), by_prio.end(), [&](uint32_t a, uint32_t b) { return prio[a] < prio[b]; });    // ascending: push front
+        for (uint32_t k : by_prio) {
+            const int32_t p = steps[k].parent;
+            if (p < 0) continue;
+            items[k].next_sibling = items[p].first_child;
+            items[p].first_child = (int32_t)k;
+        }
+        for (uint32_t q = n; q-- > 0;) if (steps[by_prio[q]].parent < 0) roots.push_back(by_prio[q]);                  // descending priority
+    }
+    const uint32_t ring_slots = n + gp::RELAX_RING_SLACK;
+    (void)depth;
 
     const size_t item_bytes = (size_t)n * sizeof(gp::RelaxItem);
     GP_CUDA(c, c->d_rx_items.reserve(item_bytes));
-    GP_CUDA(c, c->d_rx_order.reserve((size_t)n * 4));
-    GP_CUDA(c, c->d_rx_status.reserve((size_t)n * 8));                   // status words, then merged lengths
+    GP_CUDA(c, c->d_rx_order.reserve((size_t)n * 4 + (size_t)ring_slots * 4));         // subtree sizes, then the ready ring
+    GP_CUDA(c, c->d_rx_status.reserve((size_t)n * 4));                                   // merged lengths
     GP_CUDA(c, c->d_rx_results.reserve((size_t)n * sizeof(gp::DevResult)));
     GP_CUDA(c, c->d_rx_queue.reserve(64));
     GP_CUDA(c, c->d_arena.reserve((size_t)arena_words * 4 + 256));
@@ -868,23 +884,34 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     const uint32_t warps = (uint32_t)blocks * (gp::WF16C_THREADS / 32);
     const uint32_t stride = (max_n + 2 + 31 + 32) & ~31u;
     GP_CUDA(c, c->d_scratch16c.reserve((size_t)warps * stride * sizeof(uint32_t)));
-    uint32_t* d_status = (uint32_t*)c->d_rx_status.p;
-    uint32_t* d_mlen = d_status + n;
+    uint32_t* d_subtree = (uint32_t*)c->d_rx_order.p;
+    uint32_t* d_ring = d_subtree + n;
+    uint32_t* d_mlen = (uint32_t*)c->d_rx_status.p;
+    memcpy(order, subtree.data(), (size_t)n * 4);                                        // staging: subtree sizes
     GP_CUDA(c, cudaMemcpyAsync(c->d_rx_items.p, items, item_bytes, cudaMemcpyHostToDevice, c->stream));
-    GP_CUDA(c, cudaMemcpyAsync(c->d_rx_order.p, order, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
-    GP_CUDA(c, cudaMemsetAsync(d_status, 0, (size_t)n * 8, c->stream));
-    GP_CUDA(c, cudaMemsetAsync(c->d_rx_queue.p, 0, 64, c->stream));
-    unsigned int* queue = (unsigned int*)c->d_rx_queue.p;
+    GP_CUDA(c, cudaMemcpyAsync(d_subtree, order, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(d_ring, 0xff, (size_t)ring_slots * 4, c->stream));       // RELAX_EMPTY
+    GP_CUDA(c, cudaMemcpyAsync(d_ring, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemsetAsync(d_mlen, 0, (size_t)n * 4, c->stream));
+    {
+        uint32_t* q = (uint32_t*)c->h_queue.p;                                           // pinned: [0] head, [1] tail, [2] done, [8] passes, [9] unresolved
+        GP_CUDA(c, c->h_queue.reserve(256));
+        q = (uint32_t*)c->h_queue.p;
+        memset(q, 0, 64);
+        q[1] = (uint32_t)roots.size();
+        GP_CUDA(c, cudaMemcpyAsync(c->d_rx_queue.p, q, 64, cudaMemcpyHostToDevice, c->stream));
+    }
+    unsigned int* ctrl = (unsigned int*)c->d_rx_queue.p;
     const size_t smem = gp::wf16c_smem_bytes<gp::WF16C_THREADS / 32>();
     GP_CUDA(c, cudaEventRecord(c->rx_ev[0], c->stream));
     if (pot2)
         gp::relax_chain_kernel<true><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
-            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, (const uint32_t*)c->d_rx_order.p, n,
-            queue, c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_status, d_mlen, queue + 8, (gp::DevResult*)c->d_rx_results.p);
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, d_ring, ctrl,
+            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
     else
         gp::relax_chain_kernel<false><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
-            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, (const uint32_t*)c->d_rx_order.p, n,
-            queue, c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_status, d_mlen, queue + 8, (gp::DevResult*)c->d_rx_results.p);
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, d_ring, ctrl,
+            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->rx_ev[1], c->stream));
     c->launches += 1;
@@ -894,9 +921,20 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     GP_CUDA(c, cudaMemcpyAsync((uint32_t*)c->h_queue.p + 32, c->d_rx_queue.p, 64, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
     memcpy(out, ho, (size_t)n * sizeof(gp_result));
-    memcpy(merged_len, ho + (size_t)n * sizeof(gp::DevResult), (size_t)n * 4);
+    const uint32_t* dev_mlen = (const uint32_t*)(ho + (size_t)n * sizeof(gp::DevResult));
     c->rx_second_passes = ((const uint32_t*)c->h_queue.p)[32 + 8];
     c->rx_unresolved = ((const uint32_t*)c->h_queue.p)[32 + 9];
+    // merged lengths by the host epilogue's own rule; a step below an unresolved one is unresolved too; the device's contig
+    // lengths (inner steps only: nobody reads a leaf's contig) must agree
+    for (uint32_t k = 0; k < n; ++k) {
+        const int32_t p = steps[k].parent;
+        if (p >= 0 && (out[p].flags & GP_FLAG_UNRESOLVED)) { out[k].flags = GP_FLAG_UNRESOLVED; merged_len[k] = 0; continue; }
+        if (out[k].flags & GP_FLAG_UNRESOLVED) { merged_len[k] = 0; continue; }
+        const int32_t len1 = (int32_t)(p < 0 ? c->seq_len[steps[k].row_seq] : merged_len[p]), len2 = (int32_t)c->seq_len[steps[k].col_seq];
+        merged_len[k] = (uint32_t)gp_merged_length(len1, len2, &out[k]);
+        if (items[k].first_child >= 0 && dev_mlen[k] != merged_len[k])
+            return c->fail(GP_ERR_CUDA, "internal: relax step %u: device contig length %u, host epilogue %u", k, dev_mlen[k], merged_len[k]);
+    }
     float ms = 0.f;
     GP_CUDA(c, cudaEventElapsedTime(&ms, c->rx_ev[0], c->rx_ev[1]));
     c->rx_kernel_ms = ms;

@@ -7,18 +7,21 @@
 // node of it: Evaluate(merged contig of the parent item, node) followed by SetMergedStringConcat (:108-153).
 //
 // Round 1 ran the forest level by level from the host: 32 blocking calls (pack, copy, launch, copy back, build strings
-// on the host), each as long as its longest pair.  Here the merged contigs never leave the GPU:
-//   * items are handed out by an atomic ticket counter in topological order (by depth, longest remaining chain first);
-//   * a CTA of four warps takes an item, waits until the parent item's `status` word says its merged contig is in the
-//     arena (the parent holds a lower ticket, so it is running or done: no deadlock whatever the number of resident CTAs),
-//     runs the certificate kernel's CTA-per-pair machinery on (arena row, table column) -- the pair's 512-row strips
-//     pipelined across the four warps --, builds the new merged contig as 4-bit codes in its own arena slot (a
-//     funnel-shift nibble copy by all 128 threads) and publishes length and status with release semantics;
-//   * nothing synchronises levels: every chain advances as soon as its previous step is done.
+// on the host), each as long as its longest pair.  Here the merged contigs never leave the GPU and nothing synchronises
+// levels:
+//   * a CTA of four warps FOLLOWS a chain: it runs the certificate kernel's CTA-per-pair machinery on (row = merged
+//     contig so far, column = next node) -- the pair's 512-row strips pipelined across the four warps --, builds the new
+//     merged contig as 4-bit codes in the item's arena slot (a funnel-shift nibble copy by all 128 threads), and goes
+//     straight on to the item's first child with the contig still in L2;
+//   * where the forest branches, the other children are pushed to a ready ring (release store after the contig and
+//     its length are in memory); a CTA without a chain takes the next ring ticket and waits for that slot to be
+//     filled.  The ring starts out holding the roots, longest chains first.  Every item is consumed exactly once, a
+//     global counter of finished items ends the launch, and no CTA ever waits for work that is not already running
+//     or queued: no deadlock whatever the number of resident CTAs.
 // The host gets one gp_result per item and rebuilds the strings from the original letters (gp_merged_concat).
 // An item whose walk end no certificate system proves (a genuine tie between walks ending on different borders; none
-// seen on any synthetic set) is marked unresolved together with its descendants; the caller runs those chains
-// through gp_overlap_batch (exact kernels) instead.
+// seen on any synthetic set) is marked unresolved, its subtree is skipped; the caller runs those chains through
+// gp_overlap_batch (exact kernels) instead.
 #pragma once
 #include "overlap_wf16c.cuh"
 
@@ -29,11 +32,13 @@ struct RelaxItem {                 // 32 bytes
     uint32_t row_off, row_len;     // parent < 0 only: the path's first node in the packed table (word offset, bases)
     uint32_t col_off, col_len;     // the node met at this step, in the packed table
     uint32_t arena_off;            // this item's merged contig in the arena (word offset, 128-byte aligned)
-    uint32_t pad[2];
+    int32_t first_child;           // the child this CTA goes on with (-1: the chain ends here)
+    int32_t next_sibling;          // the parent's next child (-1: none): pushed to the ready ring by whoever finishes the parent
 };
 
-constexpr uint32_t RELAX_PENDING = 0u, RELAX_DONE = 1u, RELAX_UNRESOLVED = 2u;
+constexpr uint32_t RELAX_EMPTY = 0xffffffffu, RELAX_EXIT = 0xfffffffeu;
 constexpr uint32_t FLAG_UNRESOLVED = 32u;       // gp_result.flags: GP_FLAG_UNRESOLVED
+constexpr uint32_t RELAX_RING_SLACK = 2048;     // ring slots beyond the item count: one pending ticket per CTA
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p)
 {
@@ -75,18 +80,19 @@ __device__ __forceinline__ void relax_concat(uint32_t* __restrict__ dst, const u
     }
 }
 
+// ctrl: [0] ring head (next ticket), [1] ring tail (next free slot), [2] finished items, [8] sub-table passes, [9] unresolved items
 template <bool POT2>
 __global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
 relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ arena, const RelaxItem* __restrict__ items,
-                   const uint32_t* __restrict__ order, uint32_t n_items, unsigned int* __restrict__ queue, Wf16cParams P,
-                   uint32_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ status, uint32_t* __restrict__ mlen,
-                   unsigned int* __restrict__ counters, DevResult* __restrict__ out)
+                   const uint32_t* __restrict__ subtree, uint32_t n_items, uint32_t* __restrict__ ring, unsigned int* __restrict__ ctrl,
+                   Wf16cParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ mlen,
+                   DevResult* __restrict__ out)
 {
     constexpr int TEAM = WF16C_THREADS / 32;
     extern __shared__ uint32_t wf16c_smem[];
     __shared__ uint32_t team_prog[TEAM];
     __shared__ long long team_keys[TEAM];
-    __shared__ uint32_t team_qi, parent_state;
+    __shared__ uint32_t next_item;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     Wf16cWarp w;
     w.packed = packed;
@@ -96,29 +102,31 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
     w.bnd = scratch + (size_t)(warp_global - (uint32_t)w.team_warp) * scratch_stride;
     w.smem = wf16c_smem + (threadIdx.x >> 5) * WF16C_WARP_WORDS;
     const bool leader = threadIdx.x == 0;
+    int32_t cur = -1;                                               // the item this CTA goes on with (CTA-uniform)
     for (;;) {
-        if (leader) team_qi = atomicAdd(queue, 1u);
-        __syncthreads();
-        const uint32_t qi = team_qi;
-        __syncthreads();
-        if (qi >= n_items) break;
-        const uint32_t id = order[qi];
+        if (cur < 0) {                                              // no chain to follow: the next ring ticket
+            if (leader) {
+                const uint32_t t = atomicAdd(ctrl, 1u);
+                uint32_t v = RELAX_EXIT;
+                if (t < n_items + RELAX_RING_SLACK) {
+                    while ((v = ld_acquire_u32(ring + t)) == RELAX_EMPTY) {
+                        if (ld_acquire_u32(ctrl + 2) >= n_items) { v = RELAX_EXIT; break; }      // everything is finished
+                        __nanosleep(200);
+                    }
+                }
+                next_item = v;
+            }
+            __syncthreads();
+            const uint32_t v = next_item;
+            __syncthreads();
+            if (v == RELAX_EXIT) break;
+            cur = (int32_t)v;
+        }
+        const uint32_t id = (uint32_t)cur;
         const RelaxItem it = items[id];
         const uint32_t* row_base = packed;
         uint32_t row_off = it.row_off, m = it.row_len;
-        if (it.parent >= 0) {
-            if (leader) {
-                uint32_t s;
-                while ((s = ld_acquire_u32(status + it.parent)) == RELAX_PENDING) __nanosleep(200);
-                parent_state = s;
-            }
-            __syncthreads();
-            const uint32_t ps = parent_state;
-            __syncthreads();
-            if (ps != RELAX_DONE) {                                   // the chain is handed back to the host from here on
-                if (leader) { out[id].flags = FLAG_UNRESOLVED; st_release_u32(status + id, RELAX_UNRESOLVED); }
-                continue;
-            }
+        if (it.parent >= 0) {                                       // the parent is finished: we followed it, or its push released us
             row_base = arena;
             row_off = items[it.parent].arena_off;
             m = __ldcg(mlen + it.parent);
@@ -128,9 +136,10 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
         const int n = (int)it.col_len;
         DevResult r;
         long long key;
-        const uint32_t origin = wf16c_solve_pair<true, TEAM, POT2>(w, P, team_keys, 0u, leader, counters, r, key);
-        if (origin == 0u) {
-            if (leader) { r.flags |= FLAG_UNRESOLVED; out[id] = r; atomicAdd(counters + 1, 1u); st_release_u32(status + id, RELAX_UNRESOLVED); }
+        const uint32_t origin = wf16c_solve_pair<true, TEAM, POT2>(w, P, team_keys, 0u, leader, ctrl + 8, r, key);
+        if (origin == 0u) {                                         // handed back to the host with everything below it
+            if (leader) { r.flags |= FLAG_UNRESOLVED; out[id] = r; atomicAdd(ctrl + 9, 1u); atomicAdd(ctrl + 2, subtree[id]); }
+            cur = -1;
             continue;
         }
         store_result(&r, key | (long long)origin, (int)m, n, FLAG_KERNEL16);
@@ -141,7 +150,8 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
         uint32_t total;
         const uint32_t* s1 = row_base + row_off;                      // word pointers of the two sequences
         const uint32_t* s2 = packed + it.col_off;
-        if (contained && rowe + clip == len1 && len1 < len2) { relax_concat(dst, s2, 0u, len2, s2, 0u, 0u); total = len2; }            // merged = s2 (:116-121)
+        if (it.first_child < 0) total = 0;                            // a leaf: nobody reads its contig (the host rebuilds the letters)
+        else if (contained && rowe + clip == len1 && len1 < len2) { relax_concat(dst, s2, 0u, len2, s2, 0u, 0u); total = len2; }       // merged = s2 (:116-121)
         else if (contained && cole + clip == len2 && len2 < len1) { relax_concat(dst, s1, 0u, len1, s1, 0u, 0u); total = len1; }       // merged = s1 (:122-127)
         else if (rowe + clip == len1) { relax_concat(dst, s1, 0u, len1 - clip, s2, cole, len2 - cole); total = len1 - clip + len2 - cole; }   // :131-139
         else { relax_concat(dst, s2, 0u, len2 - clip, s1, rowe, len1 - rowe); total = len2 - clip + len1 - rowe; }                     // :141-149
@@ -149,9 +159,16 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
         __syncthreads();
         if (leader) {
             out[id] = r;
-            mlen[id] = total;
-            st_release_u32(status + id, RELAX_DONE);
+            if (it.first_child >= 0) {
+                mlen[id] = total;
+                __threadfence();
+                for (int32_t c = items[it.first_child].next_sibling; c >= 0; c = items[c].next_sibling)    // the other children: ready now
+                    st_release_u32(ring + atomicAdd(ctrl + 1, 1u), (uint32_t)c);
+            }
+            atomicAdd(ctrl + 2, 1u);
         }
+        cur = it.first_child;
+        __syncthreads();                                             // mlen[id] is written before anyone of this CTA reads it
     }
 }
 

@@ -208,7 +208,9 @@ int run_batch(const Cli& c)
         for (int d = 0; d < n_gpus; ++d) per_worker += (d ? ", " : "") + std::to_string(cells[d] / 1e9);
         per_worker += "], \"worker_gaps\": [";
         for (int d = 0; d < n_gpus; ++d) { size_t cnt = 0; for (size_t g = 0; g < lines.size(); ++g) cnt += part[g] == d; per_worker += (d ? ", " : "") + std::to_string(cnt); }
-        per_worker += "]";
+        per_worker += "], \"detail_ms\": {";
+        { bool first = true; for (const auto& kv : t.detail) { char b[96]; snprintf(b, sizeof b, "%s\"%s\": %.3f", first ? "" : ", ", kv.first.c_str(), kv.second); per_worker += b; first = false; } }
+        per_worker += "}";
         fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
                         "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
                         "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "

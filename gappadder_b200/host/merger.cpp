@@ -102,6 +102,12 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         if (timings) timings->*slot += std::chrono::duration<double, std::milli>(now - t_prev).count();
         t_prev = now;
     };
+    auto t_mark = clk::now();
+    auto mark = [&](const char* name) {                   // finer split of the phases above, for --stats (does not touch `lap`)
+        const auto now = clk::now();
+        if (timings) timings->detail[name] += std::chrono::duration<double, std::milli>(now - t_mark).count();
+        t_mark = now;
+    };
     const size_t G = in.size();
     out.assign(G, GapOutput());
     std::vector<GapState> st(G);
@@ -205,6 +211,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         if (np < 0) { s.cand_rc = (int)np; s.cand.clear(); return; }
         s.cand.resize((size_t)np);
     });
+    mark("read.nodes");
     // serial: one sequence table and one pair list for the batch (node_seq vectors no longer grow).  Gaps whose
     // candidate filter runs on the device come first: gp_quick_check_device takes contiguous node ranges.  A gap
     // beyond the device filter's limits (GP_QC_MAX_NODES) was filtered on the host above -- that gap only.
@@ -228,15 +235,18 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     // filter's order (row by row, j >= i).
     bool table_resident = false;
     if (n_dev > 0) {
+        mark("read.table");
         const uint32_t n_seq = (uint32_t)seq_ptr.size();
         int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
         table_resident = true;
+        mark("read.upload");
         std::vector<uint64_t> hoff(n_dev + 1, 0);
         for (size_t q = 0; q < n_dev; ++q) { const uint64_t n = gap_first[q + 1] - gap_first[q]; hoff[q + 1] = hoff[q] + n * n; }
         std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
         rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)n_dev, opt.quick_kmer_len, hit.data(), hit.size());
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        mark("read.quick_check");
         if (timings) {
             double ms = 0; uint64_t bases = 0; uint32_t items = 0;
             gp_quick_check_stats(ctx, &ms, &bases, &items);
@@ -261,6 +271,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         std::vector<gp_pair>().swap(s.cand);
     }
 
+    mark("read.pairs");
     lap(&MergeTimings::read_ms);
     // ---- pairwise phase: one batch for all gaps (replaces runMultiThreadMergeV2, :696-721) ------
     std::vector<gp_result> res(pairs.size());
@@ -268,6 +279,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         int rc;
         if (table_resident) {                                            // the table is in HBM already: pairs up, kernels, results down
             rc = gp_upload_pairs(ctx, pairs.data(), pairs.size(), &dp);
+            mark("pairwise.upload_pairs");
             if (rc == GP_OK) rc = gp_launch_resident(ctx);
             if (rc == GP_OK) rc = gp_fetch_results(ctx, res.data(), pairs.size());
         } else {
@@ -281,6 +293,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         }
     }
 
+    mark("pairwise.kernels_fetch");
     lap(&MergeTimings::pairwise_ms);
     // ---- edges, graph, paths (threadMergeContigV2 :652-685, addEdges :724-770, :898-931) --------
     std::vector<Chain> chains;
@@ -315,6 +328,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
     });
     for (size_t g = 0; g < G; ++g) for (Chain& c : gap_chains[g]) chains.push_back(std::move(c));
 
+    mark("graph");
     lap(&MergeTimings::graph_ms);
     // ---- relax chains on the device: the whole forest of steps in one launch (gp_relax_chains) ------------------
     // A step = Evaluate(merged contig so far, next node of the path) + SetMergedStringConcat (:1463-1513).  Chains of one
@@ -328,31 +342,42 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         std::vector<char> gap_on_device(G, 0);
         for (size_t g = 0; g < G; ++g) gap_on_device[g] = !st[g].dead && st[g].acgt_only && dp.mismatch == -2 && dp.indel == -2;
         {
-            size_t c0 = 0;
-            while (c0 < chains.size()) {                                   // chains are grouped by gap
+            // the trie of every gap on the host threads (step indices local to the gap), then one list with offsets
+            std::vector<size_t> first_chain;                               // chains are grouped by gap
+            for (size_t c = 0; c < chains.size(); ++c) if (c == 0 || chains[c].gap != chains[c - 1].gap) first_chain.push_back(c);
+            first_chain.push_back(chains.size());
+            std::vector<std::vector<gp_relax_step>> gap_steps(first_chain.size() - 1);
+            for_each_gap(first_chain.size() - 1, host_threads, [&](size_t q) {
+                const size_t c0 = first_chain[q], c1 = first_chain[q + 1];
                 const int g = chains[c0].gap;
-                size_t c1 = c0;
-                while (c1 < chains.size() && chains[c1].gap == g) ++c1;
-                if (gap_on_device[g]) {
-                    std::map<std::vector<int>, int32_t> seen;             // path prefix -> step
-                    for (size_t c = c0; c < c1; ++c) {
-                        const std::vector<int>& p = chains[c].path;
-                        int32_t parent = -1;
-                        for (size_t k = 1; k < p.size(); ++k) {
-                            std::vector<int> key(p.begin(), p.begin() + k + 1);
-                            auto it = seen.find(key);
-                            if (it == seen.end()) {
-                                it = seen.emplace(std::move(key), (int32_t)steps.size()).first;
-                                steps.push_back(gp_relax_step{parent, st[g].node_base + (uint32_t)p[0], st[g].node_base + (uint32_t)p[k]});
-                            } else if (timings) ++timings->relax_shared_pairs;
-                            chain_steps[c].push_back(it->second);
-                            parent = it->second;
+                if (!gap_on_device[g]) return;
+                std::vector<gp_relax_step>& mine = gap_steps[q];
+                std::map<std::vector<int>, int32_t> seen;                 // path prefix -> step
+                for (size_t c = c0; c < c1; ++c) {
+                    const std::vector<int>& p = chains[c].path;
+                    int32_t parent = -1;
+                    std::vector<int> key(1, p[0]);
+                    for (size_t k = 1; k < p.size(); ++k) {
+                        key.push_back(p[k]);
+                        auto it = seen.find(key);
+                        if (it == seen.end()) {
+                            it = seen.emplace(key, (int32_t)mine.size()).first;
+                            mine.push_back(gp_relax_step{parent, st[g].node_base + (uint32_t)p[0], st[g].node_base + (uint32_t)p[k]});
                         }
+                        chain_steps[c].push_back(it->second);
+                        parent = it->second;
                     }
                 }
-                c0 = c1;
+            });
+            for (size_t q = 0; q + 1 < first_chain.size(); ++q) {
+                const int32_t base = (int32_t)steps.size();
+                for (gp_relax_step stp : gap_steps[q]) { if (stp.parent >= 0) stp.parent += base; steps.push_back(stp); }
+                size_t uses = 0;
+                for (size_t c = first_chain[q]; c < first_chain[q + 1]; ++c) { for (int32_t& k : chain_steps[c]) k += base; uses += chain_steps[c].size(); }
+                if (timings) timings->relax_shared_pairs += uses - gap_steps[q].size();
             }
         }
+        mark("relax.trie");
         if (!steps.empty() && getenv("GP_RELAX_DEBUG")) {                  // per depth: steps, cells (upper bound: rows = sum of the prefix's nodes)
             std::vector<uint32_t> depth(steps.size()), bound(steps.size());
             std::map<uint32_t, std::pair<uint64_t, uint64_t>> per;
@@ -369,6 +394,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
             std::vector<gp_result> rr(steps.size());
             std::vector<uint32_t> mlen(steps.size());
             const int rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
+            mark("relax.device_call");
             if (rc == GP_ERR_RANGE) {
                 for (size_t g = 0; g < G; ++g) gap_on_device[g] = 0;       // outside the entry point's domain after all: step by step
             } else if (rc != GP_OK) {
@@ -416,10 +442,16 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
                             out[g].relax_cells += (uint64_t)rows * st[g].node_seq[ch.path[k + 1]].size();
                             out[g].n_relax += 1;
                         }
+                        if (getenv("GP_RELAX_DEBUG")) {
+                            uint64_t cc = 0;
+                            for (size_t k = 0; k < cs.size(); ++k) cc += (uint64_t)(k == 0 ? st[g].node_seq[ch.path[0]].size() : stack[k - 1].size()) * st[g].node_seq[ch.path[k + 1]].size();
+                            fprintf(stderr, "relax chain gap %d: %zu steps, %.1f Mcells, final %zu bases\n", g, cs.size(), cc / 1e6, cs.empty() ? (size_t)0 : stack.back().size());
+                        }
                         ch.merged = cs.empty() ? ch.merged : stack.back();
                         ch.next = ch.path.size();
                     }
                 });
+                mark("relax.strings");
                 if (bad) { error = "internal: merged contig lengths of the device relax chain and the host epilogue differ"; return GP_ERR_INVALID; }
                 // a gap with an unresolved step starts over in the loop below
                 for (Chain& ch : chains) if (!gap_on_device[ch.gap]) { ch.next = 1; ch.merged = st[ch.gap].node_seq[ch.path[0]]; }

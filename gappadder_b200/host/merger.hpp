@@ -4,6 +4,7 @@
 // through one GPU context together: the pairwise phase of ALL gaps is one gp_overlap_pairs call, and
 // step k of ALL merge chains is one call.
 #pragma once
+#include <map>
 #include <string>
 #include <vector>
 
@@ -75,6 +76,7 @@ struct MergeTimings {
     double qc_kernel_ms = 0;           // device quick check: kernel time, bases scanned (0.5 B each), work items
     uint64_t qc_bases = 0;
     uint32_t qc_items = 0;
+    std::map<std::string, double> detail;  // finer wall-clock split (ms) of the phases above, by name
 };
 
 // Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure

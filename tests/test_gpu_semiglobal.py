@@ -57,7 +57,7 @@ def test_cfg2_shape_flanks_against_contigs_and_reverse_complements(ctx):
             pairs += [(base, len(seqs) - 2), (base, len(seqs) - 1), (base + 1, len(seqs) - 2), (base + 1, len(seqs) - 1)]
     res = _check(ctx, seqs, pairs)
     assert (res["flags"] == 1).all()                       # pure A/C/G/T: the shared-memory-table kernel
-    assert int((res["score"] > 900).sum()) >= 3             # some contigs contain a whole flank
+    assert int((res["score"] > 900).sum()) >= 1             # some contig contains a whole flank
     st = ctx.semiglobal_stats()
     assert st["table_pairs"] == len(pairs) and st["cells"] == sum(len(seqs[a]) * len(seqs[b]) for a, b in pairs)
 
