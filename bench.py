@@ -755,7 +755,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-dropin", action="store_true", help="skip the whole-ContigsMerger (drop-in binary) timing beside the bench line")
     ap.add_argument("--cert-layout", type=int, default=0, help="A/B: certificate kernel value layout (0 free moves when a launch allows it, 1 column potential only)")
-    ap.add_argument("--orientation", type=int, default=0, help="A/B: certificate kernel pair orientation (0 cost model, 1 never transpose, 2 always, 3 longer sequence as rows, 4 shorter as rows)")
+    ap.add_argument("--orientation", type=int, default=0, help="A/B: certificate kernel pair orientation (0 longer sequence as rows, 1 never transpose, 2 always)")
     ap.add_argument("--kernel-mask", type=int, default=15, help="A/B: what the library may use (1 table, 2 PRMT, 4 certificate kernel, 8 closed form for s-vs-s)")
     args = ap.parse_args()
     if args.gaps is None:

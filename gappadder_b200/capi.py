@@ -375,7 +375,7 @@ class Context:
         return int(self._L.gp_last_layout(self._h))
 
     def set_orientation(self, mode: int):
-        """Certificate kernel: 0 the cost model orients every pair (default), 1 never transpose, 2 always when allowed."""
+        """Certificate kernel: 0 the longer sequence as rows (default), 1 never transpose, 2 always when allowed."""
         self._check(self._L.gp_set_orientation(self._h, mode))
 
     @property

@@ -101,7 +101,7 @@ struct gp_ctx {
     uint64_t n_pairs = 0, n16c = 0, n16t = 0, n16 = 0, n32 = 0, cells = 0;
     uint32_t max_n16c = 0, max_n16c_small = 0, max_n16c_orig = 0, max_n16t = 0, max_n16 = 0, max_n32 = 0;
     uint64_t n16c_transposed = 0;
-    uint32_t orientation = 0;                   // certificate kernel: 0 the host's cost model orients every pair, 1 never transpose, 2 always (tests)
+    uint32_t orientation = 0;                   // certificate kernel: 0 the longer sequence becomes the row sequence, 1 never transpose, 2 always (tests)
     uint32_t cert_system = 0;                   // 0: probe decides, 1: start with system U, 2: with L, 3: with C (tests)
     uint32_t team_mode = 0;                     // certificate kernel: 0 auto, 1 one warp per pair, 2 one CTA per pair
     uint64_t max_cells16c = 0;                  // largest m*n routed to the certificate kernel
@@ -272,7 +272,7 @@ int gp_last_team(const gp_ctx* c) { return c && c->last_team ? 1 : 0; }
 
 int gp_set_orientation(gp_ctx* c, uint32_t mode)
 {
-    if (!c || mode > 4) return GP_ERR_INVALID;      // 3 / 4 (experiments): the longer / the shorter sequence as rows
+    if (!c || mode > 2) return GP_ERR_INVALID;
     c->orientation = mode;
     return GP_OK;
 }
@@ -458,19 +458,6 @@ static void patch_closed(const gp_ctx* c, gp_result* out)
     for (uint32_t id : c->closed_ids) closed_form_self(out + id, hd[id].m);
 }
 
-// Relative cost of one certificate-kernel pass over a table of `rows` x `cols`: per strip (cols + pipeline fill and drain
-// + set-up) steps, a step costing a fixed part plus two instructions per register (K = strip rows / 64).
-static double wf16c_cost(uint32_t rows, uint32_t cols, int C)
-{
-    double cost = 0.5 * cols;
-    for (int i0 = 0; i0 < (int)rows;) {
-        const gp::Wf16Strip st = gp::wf16c_next_strip(i0, (int)rows, C);
-        cost += ((double)cols + 93.0 + 16.0) * (10.0 + 2.0 * (st.rows / 64));
-        i0 += st.rows;
-    }
-    return cost;
-}
-
 static void reset_pairs(gp_ctx* c)
 {
     c->n_pairs = 0; c->n16c = c->n16t = c->n16 = c->n32 = 0; c->cells = 0;
@@ -523,13 +510,14 @@ static int upload_pairs_impl(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, 
         // certificate kernel: everything A/C/G/T except a sequence against itself (closed form above when the scores
         // allow it; otherwise an exact kernel -- system C would certify its corner walk, but it is not worth a probe)
         if (params16c && a != b && gp::wf16c_pair_ok(m, n) && c->seq_acgt[a] && c->seq_acgt[b]) {
-            // Orientation (Wf16cPass::tr): the kernel may compute the transposed table -- rows = the column sequence -- when
-            // that fills its 512-row strips better; results come back in the reference's orientation either way.  Never at
-            // the price of the launch's free-moves layout (columns <= WF16C_POT2_MAX_N).
+            // Orientation (Wf16cPass::tr): the kernel computes the transposed table -- rows = the column sequence -- when the
+            // column sequence is the longer one: more full 512-row strips, shorter pipeline fill and drain per strip (measured
+            // on cfg1: never 7412, always 7220, shorter-as-rows 7151, longer-as-rows 7531 GCUPS; a per-strip cost model chose
+            // the same pairs to within noise).  Results come back in the reference's orientation either way.  Never at the
+            // price of the launch's free-moves layout (columns <= WF16C_POT2_MAX_N).
             bool tr = false;
             if (c->orientation != 1 && gp::wf16c_pair_ok(n, m) && (m <= gp::WF16C_POT2_MAX_N || n > gp::WF16C_POT2_MAX_N))
-                tr = c->orientation == 2 || (c->orientation == 3 && n > m) || (c->orientation == 4 && n < m) ||
-                     (c->orientation == 0 && wf16c_cost(n, m, params->max_clip) < 0.97 * wf16c_cost(m, n, params->max_clip));
+                tr = c->orientation == 2 || (c->orientation == 0 && n > m);   // default: the longer sequence as rows
             const uint32_t cn = tr ? m : n;                             // columns of the computed table
             ho16c[c->n16c++] = (uint32_t)i | (tr ? 0x80000000u : 0u); c->max_n16c = std::max(c->max_n16c, cn); c->cells16c += (uint64_t)m * n;
             c->n16c_transposed += tr ? 1 : 0;

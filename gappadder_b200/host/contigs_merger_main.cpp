@@ -8,6 +8,8 @@
 // form runs any number of gaps through one context (and through several GPUs):
 //
 //   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--streams S] [--no-gml]
+//   ContigsMerger_b200 --serve SOCKET [--gpus N] [--window-ms W]     resident service (server.hpp): thin clients -- this same
+//       binary with GAPPADDER_B200_SOCKET=SOCKET in its environment -- send one gap each; concurrent requests share a launch
 //
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
@@ -26,6 +28,7 @@
 #include "fasta.hpp"
 #include "gappadder_b200.h"
 #include "merger.hpp"
+#include "server.hpp"
 
 using namespace gpm;
 
@@ -40,51 +43,38 @@ struct Cli {
     int streams = 1;            // workers (host thread + context + stream) per GPU
     bool write_gml = true;
     bool stats = false;
+    std::string serve;          // --serve SOCKET: run as the resident service (server.hpp)
+    int window_ms = 3;
+    bool shutdown = false;      // --shutdown: ask the server behind GAPPADDER_B200_SOCKET to exit
 };
 
-float parse_float(const char* s) { float v = 0; if (s) sscanf(s, "%f", &v); return v; }   // CM/main.cpp:91-93
 int parse_int(const char* s, int dflt) { int v = dflt; if (s) sscanf(s, "%d", &v); return v; }
 
-// CheckArguments, CM/main.cpp:53-231: flags are recognised by their second (and third) character only.
-bool parse_args(int argc, char** argv, Cli& c)
+// The reference's flags (CheckArguments, CM/main.cpp:53-231: recognised by their second and third character only) are
+// parsed by parse_request (server.cpp), shared with the resident server; the flags below are this binary's own and are
+// taken out of argv first.
+bool parse_args(int argc, char** argv, Cli& c, std::vector<char*>& ref_argv)
 {
-    int pos = 1;
-    while (pos < argc) {
+    ref_argv.assign(1, argv[0]);
+    for (int pos = 1; pos < argc; ++pos) {
         const char* a = argv[pos];
         const char* val = pos + 1 < argc ? argv[pos + 1] : nullptr;
-        if (a[0] != '-') { c.input = a; c.have_input = true; ++pos; continue; }
-        if (!strcmp(a, "--batch")) { if (!val) return false; c.batch = val; pos += 2; continue; }
-        if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); pos += 2; continue; }
-        if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); pos += 2; continue; }
-        if (!strcmp(a, "--host-quick-check")) { c.opt.host_quick_check = true; pos += 1; continue; }
-        if (!strcmp(a, "--host-relax")) { c.opt.host_relax = true; pos += 1; continue; }
-        if (!strcmp(a, "--no-gml")) { c.write_gml = false; ++pos; continue; }
-        if (!strcmp(a, "--stats")) { c.stats = true; ++pos; continue; }
-        switch (a[1]) {
-        case 'V': c.opt.verbose = true; printf("Turn on Verbose\n"); ++pos; break;
-        case 'l': c.opt.line_length = parse_int(val, c.opt.line_length); pos += 2; break;
-        case 's': c.opt.max_frac_score_loss = parse_float(val); pos += 2; break;
-        case 'c': c.opt.min_frac_overlap = parse_float(val); pos += 2; break;
-        case 'x': c.opt.min_overlap_len = parse_float(val); pos += 2; break;
-        case 'y': c.opt.max_overlap_clip_len = parse_float(val); pos += 2; break;
-        case 'm': c.opt.min_support_kmer = parse_int(val, c.opt.min_support_kmer); pos += 2; break;
-        case 't': c.opt.num_threads = parse_int(val, c.opt.num_threads); pos += 2; break;
-        case 'z': c.opt.min_overlap_len_with_scaffold = parse_float(val); pos += 2; break;
-        case 'k': c.opt.quick_kmer_len = parse_int(val, c.opt.quick_kmer_len); pos += 2; break;
-        case 'i':
-            if (a[2] == '1') { c.opt.score_mismatch = parse_float(val); pos += 2; break; }
-            if (a[2] == '2') { c.opt.score_indel = parse_float(val); pos += 2; break; }
-            return false;
-        case 'o': if (val) c.opt.info_file = val; pos += 2; break;
-        case 'p':
-            if (a[2] == '1') { c.opt.max_contig_path_len = parse_int(val, -1); pos += 2; break; }
-            if (a[2] == '2') { c.opt.max_count_contig_in_path = parse_int(val, -1); pos += 2; break; }
-            return false;
-        case 'e': pos += 2; break;                         // scaffold info file: unused by CompactVer3
-        case 'u': pos += 2; break;                         // support-pairs cutoff: unused by CompactVer3
-        default: return false;
-        }
+        if (!strcmp(a, "--batch")) { if (!val) return false; c.batch = val; ++pos; continue; }
+        if (!strcmp(a, "--serve")) { if (!val) return false; c.serve = val; ++pos; continue; }
+        if (!strcmp(a, "--window-ms")) { c.window_ms = parse_int(val, 3); ++pos; continue; }
+        if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); ++pos; continue; }
+        if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); ++pos; continue; }
+        if (!strcmp(a, "--stats")) { c.stats = true; continue; }
+        if (!strcmp(a, "--shutdown")) { c.shutdown = true; continue; }
+        ref_argv.push_back(argv[pos]);
     }
+    Request r;
+    if (!parse_request((int)ref_argv.size(), ref_argv.data(), r)) return false;
+    c.opt = r.opt;
+    c.input = r.input;
+    c.have_input = !r.input.empty();
+    c.write_gml = r.write_gml;
+    if (c.opt.verbose) printf("Turn on Verbose\n");
     return true;
 }
 
@@ -230,10 +220,34 @@ int run_batch(const Cli& c)
 int main(int argc, char** argv)
 {
     Cli c;
-    if (!parse_args(argc, argv, c)) { printf("Wrong input.\n"); return 1; }           // CM/main.cpp:216-220
+    std::vector<char*> ref_argv;
+    if (!parse_args(argc, argv, c, ref_argv)) { printf("Wrong input.\n"); return 1; }           // CM/main.cpp:216-220
+    if (!c.serve.empty()) {
+        ServeOptions so;
+        so.socket_path = c.serve; so.gpus = c.gpus < 1 ? 1 : c.gpus; so.window_ms = c.window_ms < 0 ? 0 : c.window_ms;
+        return serve(so);
+    }
     if (!c.batch.empty()) return run_batch(c);
     // single gap, exactly the reference's process: argv[repeatfileArgIndex] defaults to argv[1]
-    if (!c.have_input) { if (argc > 1) c.input = argv[1]; else { fprintf(stderr, "usage: ContigsMerger_b200 <flags> contigs.fa\n"); return 1; } }
+    if (!c.have_input && !c.shutdown) { fprintf(stderr, "usage: ContigsMerger_b200 <flags> contigs.fa\n"); return 1; }
+    // A resident server (ContigsMerger_b200 --serve SOCKET) answers when GAPPADDER_B200_SOCKET names it: no CUDA context
+    // in this process, and the gaps of concurrent callers share one launch.  Same bytes either way.
+    if (const char* sock = getenv("GAPPADDER_B200_SOCKET")) {
+        Reply rp;
+        std::vector<char*> send_argv = ref_argv;
+        char shut[] = "--shutdown";
+        if (c.shutdown) send_argv.insert(send_argv.begin() + 1, shut);
+        if (request_from_server(sock, (int)send_argv.size(), send_argv.data(), rp)) {
+            if (!rp.err.empty()) fwrite(rp.err.data(), 1, rp.err.size(), stderr);
+            fwrite(rp.out.data(), 1, rp.out.size(), stdout);
+            if (rp.wrote_info) {
+                if (c.write_gml) write_file("tmp.gml", rp.gml);
+                if (!write_file(c.opt.info_file, rp.info)) { printf("Can not open file: %s\n", c.opt.info_file.c_str()); return 1; }
+            }
+            return rp.exit_code;
+        }
+        if (c.shutdown) return 0;
+    }
     gp_ctx* ctx = nullptr;
     int rc = gp_create(0, &ctx);
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s (no CPU fallback)\n", gp_last_error(nullptr)); return 3; }

@@ -187,8 +187,8 @@ int gp_set_team_mode(gp_ctx *ctx, uint32_t mode);
 int gp_last_team(const gp_ctx *ctx);
 /* The certificate kernel may compute a pair's TRANSPOSED table (rows = the column sequence) when that fills its 512-row
  * strips better; scan ranks and walk ends are translated inside the kernel and results are always in the reference's
- * orientation.  mode 0: the host's cost model decides per pair (default); 1: never; 2: always when the pair allows it
- * (testing).  Results never depend on it.  gp_transposed_pairs: pairs of the uploaded batch computed transposed. */
+ * orientation.  mode 0: the longer sequence becomes the row sequence (default); 1: never transpose; 2: always when the
+ * pair allows it (testing).  Results never depend on it.  gp_transposed_pairs: pairs of the uploaded batch computed transposed. */
 int gp_set_orientation(gp_ctx *ctx, uint32_t mode);
 uint64_t gp_transposed_pairs(const gp_ctx *ctx);
 /* The certificate kernel has two value layouts.  The column-potential layout (every move costs, two add-max

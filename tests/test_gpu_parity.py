@@ -40,7 +40,7 @@ def _check(ctx, seqs, pairs, params=None, full=False, masks=(KERNEL_ALL, KERNEL_
         runs = []        # (kernel mask, certificate system to start with, team mode, certificate kernel layout, orientation)
         for mask in masks:
             if mask & KERNEL_CERT16:      # layout 0: free moves whenever the launch allows it, 1: column potential only
-                # orientation 0: the host's cost model transposes pairs that fill the strips better; 1 never; 2 every pair it can
+                # orientation 0: the longer sequence becomes the row sequence; 1 never transposed; 2 every pair transposed that can be
                 runs += [(mask, 0, 0, 0, 0), (mask, 1, 1, 0, 0), (mask, 2, 2, 0, 0), (mask, 3, 0, 0, 0), (mask, 0, 2, 0, 0), (mask, 0, 3, 0, 0), (mask, 2, 3, 1, 0),
                          (mask, 0, 0, 1, 0), (mask, 1, 2, 1, 0), (mask, 2, 1, 1, 0), (mask, 3, 0, 1, 0),
                          (mask, 0, 0, 0, 1), (mask, 0, 0, 0, 2), (mask, 1, 2, 1, 2), (mask, 2, 0, 1, 2), (mask, 3, 3, 0, 2), (mask, 0, 2, 0, 2)]

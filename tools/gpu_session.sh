@@ -31,6 +31,7 @@ with open('/tmp/rl/list.tsv', 'w') as f:
 PY
              timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"overlap_wf16c|relax" -s 3 -c 6 -o $O/${TAG}_relax -f build/ContigsMerger_b200 -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1 -t 5 --batch /tmp/rl/list.tsv --no-gml > $O/${TAG}_ncu_relax.log 2>&1 ;;
     orient)  for o in 1 2 3 4 0; do timeout 300 python bench.py --no-dropin --no-cpu --steps 3 --orientation $o > $O/${TAG}_orient$o.json 2>/dev/null; python -c "import json,sys; d=json.loads(open('$O/${TAG}_orient$o.json').read().strip().splitlines()[-1]); print('orientation $o', round(d['value'],1), round(d['e2e']['value'],1), d['kernel_split']['cert_second_passes'])"; done ;;
+    ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
     *) echo "unknown: $w" ;;
   esac
