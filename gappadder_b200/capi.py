@@ -21,7 +21,7 @@ EXPORTS = [
     "gp_cert_stats", "gp_set_cert_system", "gp_kernel_times",
     "gp_closed_form_stats", "gp_set_team_mode", "gp_last_team", "gp_set_cert_layout", "gp_last_layout", "gp_quick_check_device", "gp_upload_sequences",
     "gp_quick_check_stats",
-    "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
+    "gp_reserve", "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
     "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
 ]
 

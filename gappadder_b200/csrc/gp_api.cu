@@ -782,6 +782,40 @@ int gp_overlap_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len
     return rc;
 }
 
+// One-time allocations up front (pinned staging and device buffers grow on demand otherwise, the first batch paying for
+// them: about 20 ms for a 200-gap batch).  Sizes are hints; everything still grows when a batch needs more.
+int gp_reserve(gp_ctx* c, uint64_t n_bases, uint32_t n_seq, uint64_t n_pairs, uint64_t n_relax_steps)
+{
+    if (!c) return GP_ERR_INVALID;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const size_t packed = (size_t)(n_bases / 2 + (uint64_t)n_seq * 16 + 64);
+    GP_CUDA(c, c->h_pack.reserve(packed));
+    GP_CUDA(c, c->d_packed.reserve(packed));
+    if (n_pairs) {
+        GP_CUDA(c, c->h_stage.reserve((size_t)n_pairs * (sizeof(gp::PairDesc) + 4 * sizeof(uint32_t))));
+        GP_CUDA(c, c->d_pairs.reserve((size_t)n_pairs * sizeof(gp::PairDesc)));
+        GP_CUDA(c, c->d_order16c.reserve((size_t)n_pairs * 4));
+        GP_CUDA(c, c->d_order16t.reserve((size_t)n_pairs * 4));
+        GP_CUDA(c, c->d_order16.reserve((size_t)n_pairs * 4));
+        GP_CUDA(c, c->d_order32.reserve((size_t)n_pairs * 4));
+        GP_CUDA(c, c->d_results.reserve((size_t)n_pairs * sizeof(gp::DevResult)));
+        GP_CUDA(c, c->h_results.reserve((size_t)n_pairs * sizeof(gp::DevResult)));
+        GP_CUDA(c, c->d_queue.reserve(128));
+        GP_CUDA(c, c->h_queue.reserve(256));
+    }
+    if (n_relax_steps) {
+        GP_CUDA(c, c->h_rx_stage.reserve((size_t)n_relax_steps * (sizeof(gp::RelaxItem) + sizeof(uint32_t))));
+        GP_CUDA(c, c->d_rx_items.reserve((size_t)n_relax_steps * sizeof(gp::RelaxItem)));
+        GP_CUDA(c, c->d_rx_order.reserve((size_t)n_relax_steps * 8 + (size_t)gp::RELAX_RING_SLACK * 4));
+        GP_CUDA(c, c->d_rx_status.reserve((size_t)n_relax_steps * 4));
+        GP_CUDA(c, c->d_rx_results.reserve((size_t)n_relax_steps * sizeof(gp::DevResult)));
+        GP_CUDA(c, c->h_rx_out.reserve((size_t)n_relax_steps * (sizeof(gp::DevResult) + 4) + 64));
+        GP_CUDA(c, c->d_rx_queue.reserve(64));
+        GP_CUDA(c, c->h_queue.reserve(256));
+    }
+    return GP_OK;
+}
+
 // ---- relax chains on the device (relax_chain.cuh) --------------------------------------------------------------------
 
 int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, const gp_dp_params* params, gp_result* out, uint32_t* merged_len)

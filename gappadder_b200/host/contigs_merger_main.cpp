@@ -155,6 +155,16 @@ int run_batch(const Cli& c)
         gp_ctx* ctx = nullptr;
         int r = gp_create(dev % n_dev, &ctx);
         if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
+        {   // buffers for this worker's share up front (sizes from the FASTA records: every contig and its reverse complement,
+            // every node pair of a gap at most, about two relax steps per node)
+            uint64_t bases = 0, pairs = 0, nodes = 0;
+            for (const GapInput& gi : in) {
+                const uint64_t n = 2 * gi.records.size();
+                nodes += n; pairs += n * (n + 1) / 2;
+                for (const FastaRecord& rec : gi.records) bases += 2 * rec.seq.size();
+            }
+            gp_reserve(ctx, bases, (uint32_t)nodes, pairs / 2, 2 * nodes);
+        }
         std::vector<GapOutput> out;
         const auto w0 = std::chrono::steady_clock::now();
         r = merge_gaps(ctx, c.opt, in, out, err[dev], &tim[dev]);
@@ -253,8 +263,9 @@ int main(int argc, char** argv)
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s (no CPU fallback)\n", gp_last_error(nullptr)); return 3; }
     std::vector<GapOutput> out;
     std::string err;
-    GapInput single; single.fasta_path = c.input;
-    rc = merge_gaps(ctx, c.opt, {single}, out, err);
+    std::vector<GapInput> single(1);
+    single[0].fasta_path = c.input;
+    rc = merge_gaps(ctx, c.opt, single, out, err);
     gp_destroy(ctx);
     if (rc != GP_OK) { fprintf(stderr, "ContigsMerger_b200: %s\n", err.c_str()); return 3; }   // never partial stdout
     if (!out[0].error.empty()) { fprintf(stderr, "ContigsMerger_b200: %s\n", out[0].error.c_str()); return 3; }

@@ -92,7 +92,7 @@ std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts)
     return std::vector<int>(part.begin(), part.end());
 }
 
-int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
+int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
                std::string& error, MergeTimings* timings)
 {
     using clk = std::chrono::steady_clock;
@@ -136,7 +136,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>
         GapState& s = st[g];
         std::string fatal;
         bool ok;
-        if (in[g].loaded) { s.contigs = in[g].records; ok = in[g].read_ok; fatal = in[g].fatal; }
+        if (in[g].loaded) { s.contigs = std::move(in[g].records); ok = in[g].read_ok; fatal = in[g].fatal; }
         else ok = read_fasta(in[g].fasta_path, s.contigs, fatal);
         if (!ok) {
             out[g].stdout_text = "FATAL ERROR: " + fatal + "\n";          // THROW, fastareader.cpp:11-15

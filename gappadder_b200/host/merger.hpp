@@ -79,10 +79,10 @@ struct MergeTimings {
     std::map<std::string, double> detail;  // finer wall-clock split (ms) of the phases above, by name
 };
 
-// Runs every gap.  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
+// Runs every gap (preloaded records are moved out of `in`).  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
 // here is a GPU/library failure, never an input problem (those are reported per gap like the
 // reference does, on stdout with exit code 1).
-int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, const std::vector<GapInput>& in, std::vector<GapOutput>& out,
+int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
                std::string& error, MergeTimings* timings = nullptr);
 
 // Estimated DP cells of one gap's pairwise phase from contig lengths alone (all node pairs i <= j):

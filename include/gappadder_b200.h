@@ -228,6 +228,11 @@ int gp_set_kernel_mask(gp_ctx *ctx, uint32_t mask);
  * cells are NOT part of gp_pair_stats' cells (no cell update is computed for them). */
 int gp_closed_form_stats(const gp_ctx *ctx, uint64_t *pairs, uint64_t *cells);
 
+/* Optional: allocates the context's pinned staging and device buffers up front for batches of about this size (bases and
+ * sequences of the table, pairs of the pairwise phase, steps of gp_relax_chains), so that the first batch does not pay for
+ * them.  Hints only: every buffer still grows on demand. */
+int gp_reserve(gp_ctx *ctx, uint64_t n_bases, uint32_t n_seq, uint64_t n_pairs, uint64_t n_relax_steps);
+
 /* ---- relax chains on the device ------------------------------------------------------------------------------------------
  * ContigsCompactor::FormMergedSeqFromPath (ContigsCompactor.cpp:1456-1515): merged = node_0; for every further node of the
  * path, Evaluate(merged, node, relax) (:1491) and merged = GetMerged() (:1512).  A step needs the merged contig of the

@@ -102,6 +102,7 @@ int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n)
 int gp_closed_form_stats(const gp_ctx*, uint64_t* pairs, uint64_t* cells) { if (pairs) *pairs = 0; if (cells) *cells = 0; return GP_OK; }
 int gp_cert_stats(const gp_ctx*, uint64_t* a, uint64_t* b, uint64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GP_OK; }
 int gp_last_team(const gp_ctx*) { return 0; }
+int gp_reserve(gp_ctx*, uint64_t, uint32_t, uint64_t, uint64_t) { return GP_OK; }
 // The device relax chain, served from the oracle step by step on the table of the last upload (parents precede children).
 // GP_SHIM_NO_RELAX=1 answers GP_ERR_RANGE instead, which sends the merger to its step-by-step loop.
 int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n, const gp_dp_params* p, gp_result* out, uint32_t* merged_len)

@@ -18,8 +18,7 @@ for w in $WHAT; do
     dropin)  timeout 600 python tools/dropin_bench.py --gaps 200 --ref-gaps 1 --repeat 3 > $O/${TAG}_dropin.json 2> $O/${TAG}_dropin.err; cat $O/${TAG}_dropin.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-dropin > $O/${TAG}_ncu_launches.log 2>&1 ;;
     ncu_pair) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:overlap_wf16c -s 1 -c 1 -o $O/${TAG}_wf16c -f python bench.py --steps 1 --warmup 1 --no-cpu --no-dropin > $O/${TAG}_ncu_full.log 2>&1 ;;
-    ncu_relax) python tools/dropin_bench.py --gaps 200 --ref-gaps 0 > /dev/null 2>&1
-             mkdir -p /tmp/rl && python - <<'PY'
+    ncu_relax) mkdir -p /tmp/rl && python - <<'PY'
 import sys, os
 sys.path.insert(0, 'tools')
 import synth_gaps
@@ -29,8 +28,10 @@ with open('/tmp/rl/list.tsv', 'w') as f:
         synth_gaps.write_fasta(fa, synth_gaps.make_gap(1 + g, synth_gaps.CONFIGS['cfg1']))
         f.write('%s\t/tmp/rl/g%d.out\t/tmp/rl/g%d.info\n' % (fa, g, g))
 PY
-             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"overlap_wf16c|relax" -s 3 -c 6 -o $O/${TAG}_relax -f build/ContigsMerger_b200 -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1 -t 5 --batch /tmp/rl/list.tsv --no-gml > $O/${TAG}_ncu_relax.log 2>&1 ;;
-    orient)  for o in 1 2 3 4 0; do timeout 300 python bench.py --no-dropin --no-cpu --steps 3 --orientation $o > $O/${TAG}_orient$o.json 2>/dev/null; python -c "import json,sys; d=json.loads(open('$O/${TAG}_orient$o.json').read().strip().splitlines()[-1]); print('orientation $o', round(d['value'],1), round(d['e2e']['value'],1), d['kernel_split']['cert_second_passes'])"; done ;;
+             timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"relax_chain" -c 1 -o $O/${TAG}_relax -f build/ContigsMerger_b200 -s 0.4 -i1 -2.0 -i2 -2.0 -x 12 -y 50 -k 10 -m 1 -t 5 --batch /tmp/rl/list.tsv --no-gml > $O/${TAG}_ncu_relax.log 2>&1 ;;
+    ncu_flank) timeout 900 ncu --set full --clock-control none --import-source on -k regex:flank_place -s 1 -c 1 -o $O/${TAG}_flank -f python bench.py --config cfg2 --steps 1 --warmup 1 --no-cpu > $O/${TAG}_ncu_flank.log 2>&1 ;;
+    ncu_qc)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:quick_check -s 1 -c 1 -o $O/${TAG}_qc -f python tools/quickcheck_bench.py --reps 2 > $O/${TAG}_ncu_qc.log 2>&1 ;;
+    streams) for sN in 1 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --repeat 3 --streams $sN > $O/${TAG}_dropin_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_dropin_s$sN.json').read().strip().splitlines()[-1]); print('streams $sN', d['merge_ms'], d['gaps_per_s'], d.get('detail_ms'))"; done ;;
     ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
     *) echo "unknown: $w" ;;
