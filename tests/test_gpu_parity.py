@@ -308,11 +308,21 @@ def test_free_moves_layout_range_edge_and_fallback(ctx):
     _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
     ctx.overlap_batch(seqs, pairs)
     assert ctx.last_layout == 1
-    seqs.append(s + b"A")                                    # 3801 bases as a column sequence
-    pairs.append((0, 5))
+    seqs.append(s + b"A")                                    # 3801 bases as a column sequence ...
+    pairs.append((0, 5))                                     # ... of a 3800-base row sequence: computed transposed (the
+    _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))            # longer sequence as rows), the columns still fit the layout
+    ctx.overlap_batch(seqs, pairs)
+    assert ctx.last_layout == 1
+    pairs.append((4, 5))                                     # 5000 rows x 3801 columns: no orientation keeps the layout
     _check(ctx, seqs, pairs, masks=(KERNEL_ALL,))
     ctx.overlap_batch(seqs, pairs)
     assert ctx.last_layout == 0
+    ctx.set_orientation(1)                                   # never transpose: (0, 5) alone already forces the fallback
+    try:
+        ctx.overlap_batch(seqs, pairs[:-1])
+        assert ctx.last_layout == 0
+    finally:
+        ctx.set_orientation(0)
 
 
 @pytest.mark.parametrize("config,n_gaps", [("cfg1", 6), ("cfg3", 8), ("noisy", 12), ("tiny", 5)])

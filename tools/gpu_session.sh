@@ -8,7 +8,7 @@ mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/${TAG}_gpu.txt 2>&1
 for w in $WHAT; do
   case $w in
-    tests)   timeout 1500 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; tail -5 $O/${TAG}_pytest.log ;;
+    tests)   timeout 1500 python -m pytest tests -m gpu -q > $O/${TAG}_pytest.log 2>&1; tail -5 $O/${TAG}_pytest.log ;;
     bench)   timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 600 $O/${TAG}_bench.json ;;
     benchq)  timeout 600 python bench.py --no-dropin --no-cpu > $O/${TAG}_benchq.json 2> $O/${TAG}_benchq.err; tail -c 400 $O/${TAG}_benchq.json ;;
     ref)     timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.json 2>&1 ;;
