@@ -250,7 +250,8 @@ def _dropin_tool(cli, timeout=600):
 
 DROPIN_KEEP = ("gaps", "gpus", "workers", "dp_gcells", "pairwise_gcells", "merge_ms", "read_ms", "pairwise_ms", "graph_ms", "relax_ms",
                "relax_steps", "output_ms", "partition_ms", "qc_kernel_ms", "gaps_per_s", "gaps_per_s_process", "process_wall_s", "gcups",
-               "worker_wall_ms", "worker_gaps", "worker_gcells", "imbalance_max_over_mean", "vs_gpus1", "reference", "error", "unavailable")
+               "worker_wall_ms", "worker_gaps", "worker_gcells", "worker_chunks", "mergers_per_gpu", "chunk_gaps", "detail_ms",
+               "imbalance_max_over_mean", "vs_gpus1", "reference", "error", "unavailable")
 
 
 def dropin_line(args, world):
@@ -272,10 +273,13 @@ def dropin_line(args, world):
     walls = out["strong"].get("worker_wall_ms")
     if walls:
         t = out["strong"]
-        host = t.get("read_ms", 0) + t.get("graph_ms", 0) + t.get("output_ms", 0)
-        out["strong"]["limiter"] = ("host phases (FASTA read + graph + output: %.0f of %.0f ms on the slowest worker)" % (host, t["merge_ms"])
-                                    if host > 0.5 * t["merge_ms"] else "device phases (pairwise + relax: %.0f of %.0f ms on the slowest worker)"
-                                    % (t.get("pairwise_ms", 0) + t.get("relax_ms", 0), t["merge_ms"]))
+        # phases of different chunks overlap (two mergers per GPU alternate on the device): what matters is how long the
+        # slowest GPU's device lock was held
+        dt = t.get("detail_ms", {})
+        dev = sum(dt.get(k, 0) for k in ("read.upload", "read.quick_check", "pairwise.upload_pairs", "pairwise.kernels_fetch", "relax.device_call"))
+        out["strong"]["device_busy_ms"] = dev
+        out["strong"]["limiter"] = ("device phases (upload + quick check + pairwise + relax hold the slowest GPU %.0f of %.0f ms)" % (dev, t["merge_ms"])
+                                    if dev > 0.6 * t["merge_ms"] else "host phases and pipeline fill (the slowest GPU is busy only %.0f of %.0f ms)" % (dev, t["merge_ms"]))
     return out
 
 

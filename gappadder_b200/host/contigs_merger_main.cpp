@@ -7,20 +7,26 @@
 // libgappadder_b200.so.  Because one process per gap cannot amortise CUDA context creation, a batch
 // form runs any number of gaps through one context (and through several GPUs):
 //
-//   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--streams S] [--no-gml]
+//   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--streams S] [--chunk-gaps C] [--chunk-mb M] [--no-gml]
 //   ContigsMerger_b200 --serve SOCKET [--gpus N] [--window-ms W]     resident service (server.hpp): thin clients -- this same
 //       binary with GAPPADDER_B200_SOCKET=SOCKET in its environment -- send one gap each; concurrent requests share a launch
 //
 // LIST holds one gap per line: IN.fa <TAB> OUT.fa <TAB> INFO.  Each OUT/INFO pair is byte-identical
 // to what the single-gap form (and the reference) writes.  tmp.gml is written next to each OUT.fa as
 // OUT.fa.gml in batch mode (the reference drops ./tmp.gml in the working directory of each process).
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -40,7 +46,9 @@ struct Cli {
     bool have_input = false;
     std::string batch;
     int gpus = 1;
-    int streams = 1;            // workers (host thread + context + stream) per GPU
+    int streams = 2;            // mergers (host thread + context + stream) per GPU; they alternate on the device (run_batch)
+    int chunk_gaps = 512;       // batch pipeline: gaps per chunk at most ...
+    int chunk_mb = 256;         // ... and MB of FASTA per chunk at most
     bool write_gml = true;
     bool stats = false;
     std::string serve;          // --serve SOCKET: run as the resident service (server.hpp)
@@ -63,7 +71,9 @@ bool parse_args(int argc, char** argv, Cli& c, std::vector<char*>& ref_argv)
         if (!strcmp(a, "--serve")) { if (!val) return false; c.serve = val; ++pos; continue; }
         if (!strcmp(a, "--window-ms")) { c.window_ms = parse_int(val, 3); ++pos; continue; }
         if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); ++pos; continue; }
-        if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 1); ++pos; continue; }
+        if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 2); ++pos; continue; }
+        if (!strcmp(a, "--chunk-gaps")) { c.chunk_gaps = parse_int(val, 512); ++pos; continue; }
+        if (!strcmp(a, "--chunk-mb")) { c.chunk_mb = parse_int(val, 256); ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; continue; }
         if (!strcmp(a, "--shutdown")) { c.shutdown = true; continue; }
         ref_argv.push_back(argv[pos]);
@@ -89,8 +99,28 @@ bool write_file(const std::string& path, const std::string& data)
 
 struct BatchLine { std::string in, out, info; };
 
+// One unit of the batch pipeline: some gaps of one GPU's share, read, merged and written together.
+struct Chunk {
+    std::vector<size_t> gaps;                       // indices into the batch list
+    std::vector<GapInput> in;
+    std::vector<GapOutput> out;
+    std::atomic<size_t> to_read{0};                 // gaps whose FASTA is not in memory yet
+};
+
+// The batch driver.  Gaps are independent, so the batch is a pipeline over CHUNKS of gaps:
+//   partition  gaps -> GPUs, longest-processing-time on (FASTA bytes)^2 (a stat per gap; no sequence is read for it), then
+//              each GPU's share is cut into chunks of at most --chunk-gaps gaps / --chunk-mb MB of FASTA;
+//   readers    a pool of host threads parses the FASTA files chunk by chunk, a bounded number of chunks ahead of the GPU;
+//   mergers    --streams S host threads per GPU (default 2), each with its own context, take that GPU's chunks in order
+//              and run merge_gaps on them; they share one mutex per GPU that is held around the device phases only, so
+//              the host phases of one chunk (nodes, graph, strings, output text) run beside the kernels of another and
+//              the GPU never runs two persistent kernels at once;
+//   writers    one thread per GPU writes the finished chunks' files and frees them.
+// Memory is bounded by the chunks in flight, whatever the batch size (BASELINE configs[3]: 50 000 gaps).  Results do not
+// depend on the split: every gap's bytes are what the single-gap form writes.
 int run_batch(const Cli& c)
 {
+    using clk = std::chrono::steady_clock;
     std::vector<BatchLine> lines;
     {
         std::ifstream f(c.batch);
@@ -105,122 +135,230 @@ int run_batch(const Cli& c)
             lines.push_back(b);
         }
     }
-    // Balance gaps over workers by estimated pairwise cells (contig lengths only).  A worker is a host thread with
-    // its own context and stream; --streams S puts S of them on every GPU, so that one worker's host phases and the
-    // thin tail of its relax chains (a few long pairs per launch, 32 launches deep) run beside another worker's
-    // kernels.  Gaps are independent: no ordering between workers, results do not depend on the split.
+    const auto t_start = clk::now();
+    auto ms_since = [&](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
     const int n_dev = c.gpus < 1 ? 1 : c.gpus;
-    // Default 1.  Measured on cfg1 (200 gaps, one B200, several runs each): 1 worker 287-306 ms; 3 workers 237-430 ms:
-    // sometimes a quarter faster, sometimes slower, because a worker's short relax launch can queue behind another
-    // worker's persistent pairwise kernel, which holds every SM until its work queue is empty.
-    const int per_dev = c.streams >= 1 ? c.streams : 1;
-    int n_gpus = n_dev * per_dev;                                  // number of workers from here on
-    if ((size_t)n_gpus > lines.size() && !lines.empty()) n_gpus = (int)lines.size();
-    std::vector<uint64_t> cost(lines.size(), 0);
-    const auto part0 = std::chrono::steady_clock::now();
-    // Every FASTA is read once, here, on the host cores: the contig lengths balance the gaps over the workers
-    // (gp_partition_gaps), the records go to the workers as they are.
-    std::vector<GapInput> loaded(lines.size());
-    {
-        std::atomic<size_t> next(0);
-        auto reader = [&] {
-            for (size_t g = next.fetch_add(1); g < lines.size(); g = next.fetch_add(1)) {
-                GapInput& gi = loaded[g];
-                gi.fasta_path = lines[g].in;
-                gi.read_ok = read_fasta(gi.fasta_path, gi.records, gi.fatal);
-                gi.loaded = true;
-                std::vector<uint32_t> lens;
-                for (const FastaRecord& r : gi.records) lens.push_back((uint32_t)r.seq.size());
-                cost[g] = estimate_gap_cells(lens);
-            }
-        };
-        const unsigned T = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-        std::vector<std::thread> rd;
-        for (unsigned t = 0; t < T; ++t) rd.emplace_back(reader);
-        for (auto& t : rd) t.join();
+    const size_t L = lines.size();
+
+    // ---- partition: cost from the file size alone ---------------------------------------------------------------
+    std::vector<uint64_t> fsize(L, 0), cost(L, 0);
+    for (size_t g = 0; g < L; ++g) {
+        struct stat sb;
+        if (stat(lines[g].in.c_str(), &sb) == 0) fsize[g] = (uint64_t)sb.st_size;
+        cost[g] = fsize[g] * fsize[g] + 1;                       // pairwise cells grow with the square of the bases
     }
-    const std::vector<int> part = partition_gaps(cost, n_gpus);
-    const double partition_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - part0).count();
-    std::vector<int> rc(n_gpus, 0);
-    std::vector<std::string> err(n_gpus);
-    std::vector<uint64_t> cells(n_gpus, 0), pcells(n_gpus, 0);
-    std::vector<MergeTimings> tim(n_gpus);
-    std::vector<double> wall(n_gpus, 0);
-    std::atomic<bool> gap_failed(false);
-    auto worker = [&](int dev) {
-        std::vector<GapInput> in;
-        std::vector<size_t> which;
-        for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(std::move(loaded[g])); which.push_back(g); }
-        if (in.empty()) return;
-        gp_ctx* ctx = nullptr;
-        int r = gp_create(dev % n_dev, &ctx);
-        if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
-        {   // buffers for this worker's share up front (sizes from the FASTA records: every contig and its reverse complement,
-            // every node pair of a gap at most, about two relax steps per node)
-            uint64_t bases = 0, pairs = 0, nodes = 0;
-            for (const GapInput& gi : in) {
-                const uint64_t n = 2 * gi.records.size();
-                nodes += n; pairs += n * (n + 1) / 2;
-                for (const FastaRecord& rec : gi.records) bases += 2 * rec.seq.size();
-            }
-            gp_reserve(ctx, bases, (uint32_t)nodes, pairs / 2, 2 * nodes);
+    const std::vector<int> part = partition_gaps(cost, n_dev);
+    const uint64_t chunk_bytes = (uint64_t)(c.chunk_mb < 1 ? 1 : c.chunk_mb) << 20;
+    const size_t chunk_gaps = (size_t)(c.chunk_gaps < 1 ? 1 : c.chunk_gaps);
+    std::vector<std::vector<std::unique_ptr<Chunk>>> chunks(n_dev);
+    for (int d = 0; d < n_dev; ++d) {
+        // an even split of the share (the last chunk is not a sliver), each chunk within both limits
+        std::vector<size_t> mine;
+        uint64_t bytes = 0;
+        for (size_t g = 0; g < L; ++g) if (part[g] == d) { mine.push_back(g); bytes += fsize[g]; }
+        if (mine.empty()) continue;
+        size_t n_chunks = std::max<size_t>((mine.size() + chunk_gaps - 1) / chunk_gaps, (size_t)((bytes + chunk_bytes - 1) / chunk_bytes));
+        n_chunks = std::max<size_t>(1, std::min(n_chunks, mine.size()));
+        for (size_t k = 0; k < n_chunks; ++k) {
+            std::unique_ptr<Chunk> ch(new Chunk);
+            for (size_t q = k * mine.size() / n_chunks; q < (k + 1) * mine.size() / n_chunks; ++q) ch->gaps.push_back(mine[q]);
+            ch->in.resize(ch->gaps.size());
+            ch->to_read = ch->gaps.size();
+            chunks[d].push_back(std::move(ch));
         }
-        std::vector<GapOutput> out;
-        const auto w0 = std::chrono::steady_clock::now();
-        r = merge_gaps(ctx, c.opt, in, out, err[dev], &tim[dev]);
-        wall[dev] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
-        gp_destroy(ctx);
-        if (r != GP_OK) { rc[dev] = r; return; }
-        for (size_t k = 0; k < which.size(); ++k) {
-            const BatchLine& b = lines[which[k]];
-            if (!out[k].error.empty()) {                       // this gap only: nothing written, the others go on
-                fprintf(stderr, "ContigsMerger_b200: %s\n", out[k].error.c_str());
-                gap_failed = true;
-                continue;
+    }
+    const double partition_ms = ms_since(t_start);
+
+    // ---- pipeline state -------------------------------------------------------------------------------------------
+    std::mutex mu;                                               // guards the counters below
+    std::condition_variable cv;
+    std::vector<size_t> merged_chunks(n_dev, 0);                 // chunks a merger has taken (readers stay LOOKAHEAD ahead)
+    std::vector<size_t> next_chunk(n_dev, 0);                    // next chunk a merger takes
+    std::vector<std::deque<Chunk*>> to_write(n_dev);
+    std::vector<size_t> written(n_dev, 0);
+    std::atomic<bool> failed(false), gap_failed(false);
+    constexpr size_t LOOKAHEAD = 3;
+    // read tasks in the order the GPUs need them: round r of every GPU, then round r + 1
+    struct ReadTask { int dev; size_t chunk, slot; };
+    std::vector<ReadTask> tasks;
+    {
+        size_t rounds = 0;
+        for (int d = 0; d < n_dev; ++d) rounds = std::max(rounds, chunks[d].size());
+        for (size_t r = 0; r < rounds; ++r)
+            for (int d = 0; d < n_dev; ++d)
+                if (r < chunks[d].size())
+                    for (size_t q = 0; q < chunks[d][r]->gaps.size(); ++q) tasks.push_back(ReadTask{d, r, q});
+    }
+    std::atomic<size_t> next_task(0);
+    auto reader = [&] {
+        for (size_t t = next_task.fetch_add(1); t < tasks.size(); t = next_task.fetch_add(1)) {
+            const ReadTask& rt = tasks[t];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || rt.chunk < merged_chunks[rt.dev] + LOOKAHEAD; });
+                if (failed) return;
             }
-            if (!write_file(b.out, out[k].stdout_text)) { rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + b.out; return; }
-            if (out[k].wrote_info) write_file(b.info, out[k].info_text);
-            if (c.write_gml && out[k].wrote_info) write_file(b.out + ".gml", out[k].gml_text);
-            cells[dev] += out[k].pair_cells + out[k].relax_cells;
-            pcells[dev] += out[k].pair_cells;
+            Chunk& ch = *chunks[rt.dev][rt.chunk];
+            GapInput& gi = ch.in[rt.slot];
+            gi.fasta_path = lines[ch.gaps[rt.slot]].in;
+            gi.read_ok = read_fasta(gi.fasta_path, gi.records, gi.fatal);
+            gi.loaded = true;
+            if (ch.to_read.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
+        }
+    };
+
+    const int per_dev = c.streams >= 1 ? c.streams : 1;
+    const int n_workers = n_dev * per_dev;
+    std::vector<int> rc(n_workers, 0);
+    std::vector<std::string> err(n_workers);
+    std::vector<MergeTimings> tim(n_workers);
+    std::vector<uint64_t> cells(n_dev, 0), pcells(n_dev, 0);
+    std::vector<double> wall(n_dev, 0);
+    std::vector<std::mutex> dev_mu(n_dev);
+    auto add_timings = [](MergeTimings& a, const MergeTimings& b) {
+        a.read_ms += b.read_ms; a.pairwise_ms += b.pairwise_ms; a.graph_ms += b.graph_ms; a.relax_ms += b.relax_ms; a.output_ms += b.output_ms;
+        a.relax_steps += b.relax_steps; a.relax_team_steps += b.relax_team_steps; a.relax_pairs += b.relax_pairs;
+        a.relax_second_passes += b.relax_second_passes; a.relax_exact_retries += b.relax_exact_retries;
+        a.closed_pairs += b.closed_pairs; a.closed_cells += b.closed_cells; a.relax_call_ms += b.relax_call_ms; a.relax_pack_ms += b.relax_pack_ms;
+        a.relax_shared_pairs += b.relax_shared_pairs; a.relax_shared_cells += b.relax_shared_cells;
+        a.relax_device_ms += b.relax_device_ms; a.relax_host_ms += b.relax_host_ms;
+        a.qc_kernel_ms += b.qc_kernel_ms; a.qc_bases += b.qc_bases; a.qc_items += b.qc_items;
+        for (const auto& kv : b.detail) a.detail[kv.first] += kv.second;
+    };
+    // Contexts first (CUDA context, module load, buffers for the largest chunk: a per-process constant of a second or
+    // so, reported as setup_ms), in parallel; the batch clock starts when they exist.
+    std::vector<gp_ctx*> ctxs(n_workers, nullptr);
+    {
+        std::vector<std::thread> mk;
+        for (int w = 0; w < n_workers; ++w) mk.emplace_back([&, w] {
+            const int dev = w % n_dev;
+            if (chunks[dev].size() <= (size_t)(w / n_dev)) return;        // fewer chunks than mergers on this GPU
+            const int r = gp_create(dev, &ctxs[w]);
+            if (r != GP_OK) { rc[w] = r; err[w] = gp_last_error(nullptr); return; }
+            // sizes from the FASTA bytes: every contig and its reverse complement, every node pair of a gap at most,
+            // about two relax steps per node
+            uint64_t bases = 0, pairs = 0, nodes = 0;
+            for (const auto& ch : chunks[dev]) {
+                uint64_t b = 0, p = 0, n = 0;
+                for (size_t g : ch->gaps) { b += 2 * fsize[g]; const uint64_t k = 2 * (fsize[g] / 1000 + 2); n += k; p += k * (k + 1) / 2; }
+                bases = std::max(bases, b); pairs = std::max(pairs, p); nodes = std::max(nodes, n);
+            }
+            gp_reserve(ctxs[w], bases, (uint32_t)std::min<uint64_t>(nodes, 0x7fffffffu), pairs / 2, 2 * nodes);
+        });
+        for (auto& t : mk) t.join();
+        for (int w = 0; w < n_workers; ++w)
+            if (rc[w] != 0) {
+                fprintf(stderr, "ContigsMerger_b200: worker %d (GPU %d) failed (%d): %s\n", w, w % n_dev, rc[w], err[w].c_str());
+                for (gp_ctx* x : ctxs) if (x) gp_destroy(x);
+                return 3;
+            }
+    }
+    const double setup_ms = ms_since(t_start) - partition_ms;
+    const auto t_run = clk::now();
+    auto merger = [&](int w) {
+        const int dev = w % n_dev;
+        gp_ctx* ctx = ctxs[w];
+        if (!ctx) return;
+        int r;
+        for (;;) {
+            Chunk* ch = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (failed || next_chunk[dev] >= chunks[dev].size()) break;
+                ch = chunks[dev][next_chunk[dev]++].get();
+                merged_chunks[dev] = next_chunk[dev];
+                cv.notify_all();
+                cv.wait(lk, [&] { return failed || ch->to_read.load() == 0; });
+                if (failed) break;
+            }
+            MergeTimings t;
+            r = merge_gaps(ctx, c.opt, ch->in, ch->out, err[w], &t, &dev_mu[dev]);
+            add_timings(tim[w], t);
+            if (r != GP_OK) { rc[w] = r; failed = true; std::lock_guard<std::mutex> lk(mu); cv.notify_all(); break; }
+            std::vector<GapInput>().swap(ch->in);
+            { std::lock_guard<std::mutex> lk(mu); to_write[dev].push_back(ch); cv.notify_all(); }
+        }
+    };
+    auto writer = [&](int dev) {
+        for (;;) {
+            Chunk* ch = nullptr;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return failed || !to_write[dev].empty() || written[dev] == chunks[dev].size(); });
+                if (to_write[dev].empty()) break;                 // everything written, or a failure with nothing queued
+                ch = to_write[dev].front(); to_write[dev].pop_front();
+            }
+            for (size_t k = 0; k < ch->gaps.size(); ++k) {
+                const BatchLine& b = lines[ch->gaps[k]];
+                GapOutput& o = ch->out[k];
+                if (!o.error.empty()) {                          // this gap only: nothing written, the others go on
+                    fprintf(stderr, "ContigsMerger_b200: %s\n", o.error.c_str());
+                    gap_failed = true;
+                    continue;
+                }
+                if (!write_file(b.out, o.stdout_text)) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + b.out; failed = true; cv.notify_all();
+                    return;
+                }
+                if (o.wrote_info) write_file(b.info, o.info_text);
+                if (c.write_gml && o.wrote_info) write_file(b.out + ".gml", o.gml_text);
+                cells[dev] += o.pair_cells + o.relax_cells;
+                pcells[dev] += o.pair_cells;
+            }
+            std::vector<GapOutput>().swap(ch->out);
+            wall[dev] = partition_ms + ms_since(t_run);
+            { std::lock_guard<std::mutex> lk(mu); ++written[dev]; cv.notify_all(); }
         }
     };
     std::vector<std::thread> th;
-    for (int d = 0; d < n_gpus; ++d) th.emplace_back(worker, d);
+    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    for (unsigned t = 0; t < T; ++t) th.emplace_back(reader);
+    for (int w = 0; w < n_workers; ++w) th.emplace_back(merger, w);
+    for (int d = 0; d < n_dev; ++d) th.emplace_back(writer, d);
     for (auto& t : th) t.join();
-    for (int d = 0; d < n_gpus; ++d)
-        if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: worker %d (GPU %d) failed (%d): %s\n", d, d % n_dev, rc[d], err[d].c_str()); return 3; }
+    const double batch_ms = partition_ms + ms_since(t_run);
+    for (gp_ctx* x : ctxs) if (x) gp_destroy(x);
+    for (int w = 0; w < n_workers; ++w)
+        if (rc[w] != 0) { fprintf(stderr, "ContigsMerger_b200: worker %d (GPU %d) failed (%d): %s\n", w, w % n_dev, rc[w], err[w].c_str()); return 3; }
     if (c.stats) {
-        // one JSON line per run: cells and the slowest GPU's phase times (merge_gaps only, context creation excluded)
+        // One JSON line per run.  merge_ms = the whole batch: partition, then from the moment the contexts exist to the last
+        // output file written (FASTA reading, every phase, file writing); creating the contexts (setup_ms) is a per-process
+        // constant outside it.  The phase times are SUMS over
+        // the chunks of the slowest GPU's mergers: phases of different chunks overlap, so they can add up to more than
+        // merge_ms.
         uint64_t tot = 0, ptot = 0; for (uint64_t x : cells) tot += x; for (uint64_t x : pcells) ptot += x;
-        int slow = 0; for (int d = 1; d < n_gpus; ++d) if (wall[d] > wall[slow]) slow = d;
-        const MergeTimings& t = tim[slow];
+        int slow = 0; for (int d = 1; d < n_dev; ++d) if (wall[d] > wall[slow]) slow = d;
+        MergeTimings t;
+        for (int w = slow; w < n_workers; w += n_dev) add_timings(t, tim[w]);
         // dp_gcells / pairwise_gcells: m*n of every Evaluate the reference runs for these gaps; closed_gcells of them
         // (a node against itself) are answered in closed form here, so computed cells = dp_gcells - closed_gcells
         uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;
         uint64_t shared_pairs = 0, shared_cells = 0;      // relax steps shared between chains with a common path prefix: not computed twice
         for (const MergeTimings& x : tim) { shared_pairs += x.relax_shared_pairs; shared_cells += x.relax_shared_cells; }
         double qc_ms = 0; uint64_t qc_bases = 0; uint32_t qc_items = 0;
-        for (const MergeTimings& x : tim) { qc_ms = std::max(qc_ms, x.qc_kernel_ms); qc_bases += x.qc_bases; qc_items += x.qc_items; }
+        for (const MergeTimings& x : tim) { qc_ms += x.qc_kernel_ms; qc_bases += x.qc_bases; qc_items += x.qc_items; }
         std::string per_worker = "\"worker_wall_ms\": [";
-        for (int d = 0; d < n_gpus; ++d) per_worker += (d ? ", " : "") + std::to_string(wall[d]);
+        for (int d = 0; d < n_dev; ++d) per_worker += (d ? ", " : "") + std::to_string(wall[d]);
         per_worker += "], \"worker_gcells\": [";
-        for (int d = 0; d < n_gpus; ++d) per_worker += (d ? ", " : "") + std::to_string(cells[d] / 1e9);
+        for (int d = 0; d < n_dev; ++d) per_worker += (d ? ", " : "") + std::to_string(cells[d] / 1e9);
         per_worker += "], \"worker_gaps\": [";
-        for (int d = 0; d < n_gpus; ++d) { size_t cnt = 0; for (size_t g = 0; g < lines.size(); ++g) cnt += part[g] == d; per_worker += (d ? ", " : "") + std::to_string(cnt); }
+        for (int d = 0; d < n_dev; ++d) { size_t cnt = 0; for (size_t g = 0; g < L; ++g) cnt += part[g] == d; per_worker += (d ? ", " : "") + std::to_string(cnt); }
+        per_worker += "], \"worker_chunks\": [";
+        for (int d = 0; d < n_dev; ++d) per_worker += (d ? ", " : "") + std::to_string(chunks[d].size());
         per_worker += "], \"detail_ms\": {";
         { bool first = true; for (const auto& kv : t.detail) { char b[96]; snprintf(b, sizeof b, "%s\"%s\": %.3f", first ? "" : ", ", kv.first.c_str(), kv.second); per_worker += b; first = false; } }
         per_worker += "}";
-        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
+        fprintf(stderr, "{\"gaps\": %zu, \"gpus\": %d, \"workers\": %d, \"mergers_per_gpu\": %d, \"dp_gcells\": %.6f, \"pairwise_gcells\": %.6f, \"closed_gcells\": %.6f, \"merge_ms\": %.3f, "
                         "\"read_ms\": %.3f, \"pairwise_ms\": %.3f, \"graph_ms\": %.3f, \"relax_ms\": %.3f, \"relax_steps\": %u, \"output_ms\": %.3f, "
                         "\"relax_device_ms\": %.3f, \"relax_host_ms\": %.3f, \"relax_team_steps\": %u, \"relax_pairs\": %llu, "
                         "\"relax_second_passes\": %llu, \"relax_exact_retries\": %llu, \"relax_shared_pairs\": %llu, \"relax_shared_gcells\": %.6f, \"relax_call_ms\": %.3f, \"relax_pack_ms\": %.3f, "
-                        "\"qc_kernel_ms\": %.4f, \"qc_bases\": %llu, \"qc_items\": %u, \"partition_ms\": %.3f, %s}\n",
-                lines.size(), n_dev, n_gpus, tot / 1e9, ptot / 1e9, closed / 1e9, wall[slow], t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
+                        "\"qc_kernel_ms\": %.4f, \"qc_bases\": %llu, \"qc_items\": %u, \"partition_ms\": %.3f, \"setup_ms\": %.3f, %s}\n",
+                L, n_dev, n_dev, per_dev, tot / 1e9, ptot / 1e9, closed / 1e9, batch_ms, t.read_ms, t.pairwise_ms, t.graph_ms, t.relax_ms, t.relax_steps, t.output_ms,
                 t.relax_device_ms, t.relax_host_ms, t.relax_team_steps, (unsigned long long)t.relax_pairs,
                 (unsigned long long)t.relax_second_passes, (unsigned long long)t.relax_exact_retries,
                 (unsigned long long)shared_pairs, shared_cells / 1e9, t.relax_call_ms, t.relax_pack_ms,
-                qc_ms, (unsigned long long)qc_bases, qc_items, partition_ms, per_worker.c_str());
+                qc_ms, (unsigned long long)qc_bases, qc_items, partition_ms, setup_ms, per_worker.c_str());
     }
     return gap_failed ? 3 : 0;
 }

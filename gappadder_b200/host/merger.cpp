@@ -92,8 +92,16 @@ std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts)
     return std::vector<int>(part.begin(), part.end());
 }
 
+namespace {
+struct DeviceLock {             // scope of one device phase (see merge_gaps' device_lock)
+    std::unique_lock<std::mutex> l;
+    explicit DeviceLock(std::mutex* m) { if (m) l = std::unique_lock<std::mutex>(*m); }
+    void release() { if (l.owns_lock()) l.unlock(); }
+};
+} // namespace
+
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error, MergeTimings* timings)
+               std::string& error, MergeTimings* timings, std::mutex* device_lock)
 {
     using clk = std::chrono::steady_clock;
     auto t_prev = clk::now();
@@ -237,6 +245,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
     if (n_dev > 0) {
         mark("read.table");
         const uint32_t n_seq = (uint32_t)seq_ptr.size();
+        DeviceLock dl(device_lock);
+        mark("read.wait_device");
         int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
         table_resident = true;
@@ -246,6 +256,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
         rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)n_dev, opt.quick_kmer_len, hit.data(), hit.size());
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
+        dl.release();
         mark("read.quick_check");
         if (timings) {
             double ms = 0; uint64_t bases = 0; uint32_t items = 0;
@@ -277,6 +288,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
     std::vector<gp_result> res(pairs.size());
     if (!pairs.empty()) {
         int rc;
+        DeviceLock dl(device_lock);
+        mark("pairwise.wait_device");
         if (table_resident) {                                            // the table is in HBM already: pairs up, kernels, results down
             rc = gp_upload_pairs(ctx, pairs.data(), pairs.size(), &dp);
             mark("pairwise.upload_pairs");
@@ -393,7 +406,12 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         if (!steps.empty()) {
             std::vector<gp_result> rr(steps.size());
             std::vector<uint32_t> mlen(steps.size());
-            const int rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
+            int rc;
+            {
+                DeviceLock dl(device_lock);
+                mark("relax.wait_device");
+                rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
+            }
             mark("relax.device_call");
             if (rc == GP_ERR_RANGE) {
                 for (size_t g = 0; g < G; ++g) gap_on_device[g] = 0;       // outside the entry point's domain after all: step by step
@@ -499,7 +517,11 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             sl.push_back((uint32_t)nodeseq.size());
         }
         std::vector<gp_result> rr(pp.size());
-        int rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());
+        int rc;
+        {
+            DeviceLock dl(device_lock);
+            rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());
+        }
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
         if (timings) {
             uint64_t c16 = 0, sp = 0, er = 0;

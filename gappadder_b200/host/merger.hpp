@@ -5,6 +5,7 @@
 // step k of ALL merge chains is one call.
 #pragma once
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -82,8 +83,12 @@ struct MergeTimings {
 // Runs every gap (preloaded records are moved out of `in`).  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
 // here is a GPU/library failure, never an input problem (those are reported per gap like the
 // reference does, on stdout with exit code 1).
+// device_lock: when several host threads (each with its own context) drive one GPU, the mutex they share.  It is held
+// around the device phases only (table upload + quick check, pairwise launch, relax launch), so one thread's host phases
+// (nodes, graph, strings, output text) run beside another thread's kernels, and two persistent kernels never compete for
+// the SMs.
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error, MergeTimings* timings = nullptr);
+               std::string& error, MergeTimings* timings = nullptr, std::mutex* device_lock = nullptr);
 
 // Estimated DP cells of one gap's pairwise phase from contig lengths alone (all node pairs i <= j):
 // used to balance gaps over GPUs before any sequence is examined.

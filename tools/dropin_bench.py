@@ -4,8 +4,9 @@
 relax chains, output).  Checks, all by byte comparison of the output files:
   --ref-gaps K      K of the gaps also go through the reference binary (oracle/_ref/ContigsMerger, -t <cores>)
   --verify-gpus1 K  (with --gpus N > 1) the first K gaps are run again with --gpus 1
-Prints one JSON line.  gaps_per_s is whole gaps merged per second over the slowest worker's wall time
-(process start-up and CUDA context creation are reported separately as process_wall_s)."""
+Prints one JSON line.  gaps_per_s is whole gaps merged per second over merge_ms = the whole batch inside the process: from the
+parsed list to the last output file written (partition, FASTA reading, context creation, every phase, file writing);
+process start-up and module load are reported separately as process_wall_s."""
 import argparse
 import json
 import os
@@ -31,9 +32,10 @@ def write_gaps(td, config, n_gaps, seed):
     return lst
 
 
-def run_binary(binary, lst, gpus, streams, extra=()):
+def run_binary(binary, lst, gpus, streams, extra=(), chunk_gaps=512):
     t0 = time.perf_counter()
-    p = subprocess.run([binary] + FLAGS + ["-t", "5", "--batch", lst, "--gpus", str(gpus), "--streams", str(streams), "--no-gml", "--stats"] + list(extra),
+    p = subprocess.run([binary] + FLAGS + ["-t", "5", "--batch", lst, "--gpus", str(gpus), "--streams", str(streams), "--chunk-gaps", str(chunk_gaps),
+                        "--no-gml", "--stats"] + list(extra),
                        capture_output=True, text=True)
     wall = time.perf_counter() - t0
     if p.returncode != 0:
@@ -46,7 +48,8 @@ def main():
     ap.add_argument("--gaps", type=int, default=200)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=1, help="workers (host thread + context + stream) per GPU")
+    ap.add_argument("--streams", type=int, default=2, help="mergers (host thread + context + stream) per GPU; they alternate on the device")
+    ap.add_argument("--chunk-gaps", type=int, default=512, help="gaps per chunk of the batch pipeline")
     ap.add_argument("--ref-gaps", type=int, default=2, help="gaps also run through the reference binary (0: skip)")
     ap.add_argument("--verify-gpus1", type=int, default=0, help="with --gpus > 1: run the first K gaps again on one GPU and compare bytes")
     ap.add_argument("--config", default="cfg1")
@@ -60,14 +63,14 @@ def main():
         lst = write_gaps(td, args.config, args.gaps, args.seed)
         gen_s = time.perf_counter() - t0
         try:
-            runs = [run_binary(binary, lst, args.gpus, args.streams) for _ in range(max(1, args.repeat))]
+            runs = [run_binary(binary, lst, args.gpus, args.streams, chunk_gaps=args.chunk_gaps) for _ in range(max(1, args.repeat))]
         except RuntimeError as e:
             print(json.dumps({"error": str(e)}))
             return 1
         wall, stats = min(runs, key=lambda r: r[1]["merge_ms"])
         walls = stats.get("worker_wall_ms", [stats["merge_ms"]])
         busy = [w for w in walls if w > 0]
-        line = {"impl": "b200", "config": args.config, "process_wall_s": wall, "fasta_generation_s": gen_s, **stats,
+        line = {"impl": "b200", "config": args.config, "streams": args.streams, "chunk_gaps": args.chunk_gaps, "process_wall_s": wall, "fasta_generation_s": gen_s, **stats,
                 "gaps_per_s": args.gaps / (stats["merge_ms"] * 1e-3),
                 "gaps_per_s_process": args.gaps / wall,
                 "imbalance_max_over_mean": (max(busy) / (sum(busy) / len(busy))) if busy else None,
