@@ -9,5 +9,5 @@ creating a context fails when no sm_100 device is present.
 from .capi import (  # noqa: F401
     GpError, Context, DpParams, Thresholds, Pair, Result, lib, lib_path,
     pack_sequences, candidate_pairs, revcomp, estimate_gap_cells, partition_gaps, is_score_significant, merged_concat,
-    GAPPADDER_DP, gappadder_thresholds,
+    GAPPADDER_DP, gappadder_thresholds, dedup_unique_names, dedup_decide, dedup_records, DEDUP_RECORD_DTYPE,
 )

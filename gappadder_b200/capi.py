@@ -23,6 +23,7 @@ EXPORTS = [
     "gp_quick_check_stats",
     "gp_reserve", "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
     "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
+    "gp_dedup_unique_names", "gp_dedup_decide", "gp_dedup_records", "gp_quick_check_matrix",
 ]
 
 
@@ -52,6 +53,7 @@ class Thresholds(C.Structure):
 
 RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"), ("nclip", "<i4"), ("flags", "<u4")])
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
+DEDUP_RECORD_DTYPE = np.dtype([("q", "<u4"), ("r", "<u4"), ("single_m", "<u4"), ("m_len", "<u4"), ("other_len", "<u4")])
 PLACE_DTYPE = np.dtype([("score", "<i4"), ("col_start", "<i4"), ("col_end", "<i4"), ("flags", "<u4")])
 FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16, FLAG_CLOSED = 1, 2, 4, 8, 16
 KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_CLOSED, KERNEL_ALL = 1, 2, 4, 8, 15
@@ -168,6 +170,48 @@ def candidate_pairs(nodes: Sequence[bytes], k: int = 10) -> np.ndarray:
     if cnt < 0:
         raise GpError(int(cnt), "gp_candidate_pairs")
     return out[:cnt]
+
+
+def _name_array(names: Sequence[bytes]):
+    keep = [bytes(n) + b"\0" for n in names]
+    arr = (C.c_char_p * max(1, len(names)))(*[C.c_char_p(k) for k in keep])
+    return arr, keep
+
+
+def dedup_unique_names(names: Sequence[bytes]) -> np.ndarray:
+    """TERefiner_1 -U (refiner.cpp:1045-1140): keep[i] = 1 for the first record of every name."""
+    L = lib()
+    arr, _keep = _name_array(names)
+    keep = np.zeros(max(1, len(names)), dtype=np.uint8)
+    L.gp_dedup_unique_names.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    rc = L.gp_dedup_unique_names(arr, len(names), keep.ctypes.data)
+    if rc != 0:
+        raise GpError(rc, "gp_dedup_unique_names")
+    return keep[:len(names)]
+
+
+def dedup_decide(records: np.ndarray, names: Sequence[bytes], lens, cutoff: float, remove_contained: bool) -> np.ndarray:
+    """TERefiner_1 -P [-g] -c cutoff (refiner.cpp:660-801) over alignment records (DEDUP_RECORD_DTYPE) -> removed[i]."""
+    L = lib()
+    arr, _keep = _name_array(names)
+    recs = np.ascontiguousarray(records, dtype=DEDUP_RECORD_DTYPE)
+    ln = np.ascontiguousarray(lens, dtype=np.uint32)
+    removed = np.zeros(max(1, len(names)), dtype=np.uint8)
+    L.gp_dedup_decide.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_void_p]
+    rc = L.gp_dedup_decide(recs.ctypes.data, len(recs), arr, ln.ctypes.data, len(names), float(cutoff), int(bool(remove_contained)), removed.ctypes.data)
+    if rc != 0:
+        raise GpError(rc, "gp_dedup_decide")
+    return removed[:len(names)]
+
+
+def dedup_records(q: int, r: int, len_q: int, len_r: int, res, max_frac_score_loss: float = 0.4) -> np.ndarray:
+    """The two alignment records one Evaluate result stands for (builder-defined; see the header)."""
+    L = lib()
+    out = np.zeros(2, dtype=DEDUP_RECORD_DTYPE)
+    rr = Result(int(res["score"]), int(res["row_end"]), int(res["col_end"]), int(res["nclip"]), int(res["flags"]))
+    L.gp_dedup_records.argtypes = [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.c_double, C.c_void_p]
+    n = L.gp_dedup_records(q, r, len_q, len_r, C.byref(rr), float(max_frac_score_loss), out.ctypes.data)
+    return out[:n]
 
 
 def estimate_gap_cells(contig_lens) -> int:
@@ -310,6 +354,20 @@ class Context:
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._L.gp_closed_form_stats(self._h, C.byref(a), C.byref(b)))
         return dict(pairs=a.value, cells=b.value)
+
+    def quick_check_matrix(self, gap_first, k: int = 10):
+        """gp_quick_check_matrix with full_matrix = 1 -> list of (n_g, n_g) uint8 arrays: m[i, j] = 1 iff the ends of node j
+        occur in node i (every ordered pair)."""
+        gf = np.ascontiguousarray(np.asarray(gap_first, dtype=np.uint32))
+        n = (gf[1:] - gf[:-1]).astype(np.int64)
+        hit = np.zeros(max(1, int((n * n).sum())), dtype=np.uint8)
+        self._L.gp_quick_check_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_uint64, C.c_int]
+        self._check(self._L.gp_quick_check_matrix(self._h, gf.ctypes.data, len(gf) - 1, k, hit.ctypes.data, hit.nbytes, 1))
+        out, pos = [], 0
+        for ng in n:
+            out.append(hit[pos:pos + ng * ng].reshape(ng, ng).copy())
+            pos += ng * ng
+        return out
 
     def quick_check_device(self, gap_first, k: int = 10):
         """Candidate filter on the device for the gaps [gap_first[g], gap_first[g+1]) of the current sequence table.

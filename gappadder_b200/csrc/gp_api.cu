@@ -281,6 +281,11 @@ uint64_t gp_transposed_pairs(const gp_ctx* c) { return c ? c->n16c_transposed : 
 
 int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes)
 {
+    return gp_quick_check_matrix(c, gap_first, n_gaps, k, hit, hit_bytes, 0);
+}
+
+int gp_quick_check_matrix(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes, int full_matrix)
+{
     if (!c) return GP_ERR_INVALID;
     if ((!gap_first || !hit) && n_gaps) return c->fail(GP_ERR_INVALID, "null gap bounds / hit buffer");
     if (k <= 0 || k > gp::QC_MAX_K) return c->fail(GP_ERR_RANGE, "quick check on the device supports k <= %d", gp::QC_MAX_K);
@@ -353,7 +358,7 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     gp::quick_check_kernel<<<blocks, gp::QC_THREADS, smem, c->stream>>>(
         (const uint32_t*)c->d_packed.p, dm, dm + n_seq, d_chunk, d_gapfirst, (const uint64_t*)(dm + w32p),
         (const gp::QcItem*)(dmb + items_at), (uint32_t)items.size(), (unsigned int*)(dmb + queue_at), (int)k,
-        smem_probes, (uint32_t*)c->d_qc_slab.p, slab_probes, (uint8_t*)c->d_qc_hit.p);
+        smem_probes, (uint32_t*)c->d_qc_slab.p, slab_probes, (uint8_t*)c->d_qc_hit.p, full_matrix ? 1u : 0u);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->qc_ev[1], c->stream));
     c->launches += 1;

@@ -249,6 +249,76 @@ int32_t gp_overlap_size(int32_t len1, int32_t len2, const gp_result *r)
     return len1 + len2 - r->nclip - gp_merged_length(len1, len2, r);
 }
 
+/* ---- dedup stage: the reference's rules, restated (see the header) -------------------------------------------------- */
+
+/* Refiner::gnrtUniqueFa, TERefiner/refiner.cpp:1045-1140: sort (name, index), drop every record whose name equals the
+ * previous one's -- i.e. of equally named records the one with the lowest index stays. */
+int gp_dedup_unique_names(const char *const *names, uint32_t n_contigs, uint8_t *keep)
+{
+    if ((!names || !keep) && n_contigs) return GP_ERR_INVALID;
+    std::vector<uint32_t> idx(n_contigs);
+    for (uint32_t i = 0; i < n_contigs; ++i) { idx[i] = i; keep[i] = 1; }
+    std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {                       // cmp_vfa, :472-478
+        const int c = strcmp(names[a], names[b]);
+        return c != 0 ? c < 0 : a < b;
+    });
+    for (uint32_t k = 1; k < n_contigs; ++k)
+        if (strcmp(names[idx[k]], names[idx[k - 1]]) == 0) keep[idx[k]] = 0;              // :1075-1082
+    return GP_OK;
+}
+
+/* Alignment::isFullyMapped, TERefiner/Alignment.cpp:397-426 (rlength = the query contig's length). */
+static bool dedup_fully_mapped(const gp_dedup_record &a, uint32_t rlength, double cutoff)
+{
+    if (a.single_m && a.m_len <= rlength) return true;                                   // :400-403
+    const int cnt = (int)a.m_len, total_len = (int)a.m_len + (int)a.other_len;           // :408-417
+    const double percent = (double)cnt / (double)total_len;                              // :418
+    return percent > cutoff;                                                             // :420 (READ_FULL_MAPPED_CUTOFF = -c, main.cpp:165)
+}
+
+/* Refiner::removeDupRepeatsOfOneContigSet, TERefiner/refiner.cpp:660-801. */
+int gp_dedup_decide(const gp_dedup_record *recs, uint64_t n_recs, const char *const *names, const uint32_t *contig_len,
+                    uint32_t n_contigs, double cutoff_ratio, int remove_contained, uint8_t *removed)
+{
+    if ((!names || !contig_len || !removed) && n_contigs) return GP_ERR_INVALID;
+    if (!recs && n_recs) return GP_ERR_INVALID;
+    memset(removed, 0, n_contigs);
+    for (uint64_t k = 0; k < n_recs; ++k) {
+        const gp_dedup_record &a = recs[k];
+        if (a.q >= n_contigs || a.r >= n_contigs) return GP_ERR_INVALID;
+        const char *qname = names[a.q], *rname = names[a.r];
+        if (!remove_contained) {                                                          // :717-766, remove duplicate
+            const bool is_fully_map = dedup_fully_mapped(a, contig_len[a.q], cutoff_ratio);
+            if (is_fully_map && strcmp(qname, rname) > 0) {                               // qname > rname, std::string order
+                const int iq = (int)contig_len[a.q], ir = (int)contig_len[a.r];
+                if (iq == ir) removed[a.q] = 1;                                            // :726-737
+                else {
+                    const int idiff = iq > ir ? iq - ir : ir - iq, imin = iq > ir ? ir : iq;   // :741-752
+                    if (((double)idiff / (double)imin) <= (1.0 - cutoff_ratio)) removed[a.q] = 1;   // :754
+                }
+            }
+        } else {                                                                          // :768-786, remove contained
+            if (strcmp(qname, rname) == 0) continue;                                      // :770
+            if (a.single_m && a.m_len == contig_len[a.q]) removed[a.q] = 1;               // isPerfectMapped, Alignment.cpp:428-437
+        }
+    }
+    return GP_OK;
+}
+
+/* Builder-defined record synthesis (see the header): BWA parity unpinned. */
+int gp_dedup_records(uint32_t q, uint32_t r, int32_t len_q, int32_t len_r, const gp_result *res, double max_frac_score_loss,
+                     gp_dedup_record *out)
+{
+    if (!res || !out || len_q < 1 || len_r < 1) return 0;
+    const int32_t ov = gp_overlap_size(len_q, len_r, res);
+    if (ov < 1) return 0;
+    if ((double)res->score < (double)ov * (1.0 - max_frac_score_loss)) return 0;
+    const uint32_t mq = (uint32_t)std::min(ov, len_q), mr = (uint32_t)std::min(ov, len_r);
+    out[0] = gp_dedup_record{q, r, mq == (uint32_t)len_q ? 1u : 0u, mq, (uint32_t)len_q - mq};
+    out[1] = gp_dedup_record{r, q, mr == (uint32_t)len_r ? 1u : 0u, mr, (uint32_t)len_r - mr};
+    return 2;
+}
+
 /* GetComplement, GenSeqsUtils.cpp:24-61; FastaSequence::RevsereComplement, fastareader.cpp. */
 void gp_revcomp(const char *s, uint32_t len, char *out)
 {

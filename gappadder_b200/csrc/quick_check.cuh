@@ -90,14 +90,15 @@ __device__ __forceinline__ bool qc_probe(const uint32_t* __restrict__ packed, co
     return true;
 }
 
-// hit: for gap g, n_g * n_g bytes at hit_off[g] (zeroed by the caller), hit[i * n_g + j] = 1 iff (i, j), j >= i, is a candidate.
+// hit: for gap g, n_g * n_g bytes at hit_off[g] (zeroed by the caller), hit[i * n_g + j] = 1 iff (i, j), j >= i, is a candidate;
+// full_matrix != 0: also for j < i (the dedup stage asks "do the ends of j occur in i" for every ordered pair).
 // chunk_off: per table sequence, the number of 32-base chunks of all sequences before it (n_seq + 1 entries).
 // slab: per CTA, slab_probes words of global scratch for gaps whose probes do not fit shared memory (smem_probes words).
 __global__ void __launch_bounds__(QC_THREADS, 1)
 quick_check_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restrict__ seq_off, const uint32_t* __restrict__ seq_len,
                    const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ gap_first, const uint64_t* __restrict__ hit_off,
                    const QcItem* __restrict__ items, uint32_t n_items, unsigned int* __restrict__ queue, int k,
-                   uint32_t smem_probes, uint32_t* __restrict__ slab, uint32_t slab_probes, uint8_t* __restrict__ hit)
+                   uint32_t smem_probes, uint32_t* __restrict__ slab, uint32_t slab_probes, uint8_t* __restrict__ hit, uint32_t full_matrix)
 {
     extern __shared__ uint32_t qc_smem[];
     const uint32_t set_words = k >= 3 ? (1u << (2 * k)) / 32u : 4u;       // k = 1, 2: 4 / 16 bits still take whole words
@@ -189,7 +190,7 @@ quick_check_kernel(const uint32_t* __restrict__ packed, const uint32_t* __restri
                         const uint32_t h = qc_hash(v);
                         for (uint32_t p = h ? bend[h - 1] : 0u, pe = bend[h]; p < pe; ++p) {
                             const uint32_t pv = probes[p];
-                            if ((pv & 0xfffffu) == v && (pv >> 20) >= i) out[(size_t)i * n + (pv >> 20)] = 1;
+                            if ((pv & 0xfffffu) == v && ((pv >> 20) >= i || full_matrix)) out[(size_t)i * n + (pv >> 20)] = 1;
                         }
                     }
                 }

@@ -8,6 +8,9 @@
 // form runs any number of gaps through one context (and through several GPUs):
 //
 //   ContigsMerger_b200 <flags> --batch LIST [--gpus N] [--streams S] [--chunk-gaps C] [--chunk-mb M] [--no-gml]
+//   ContigsMerger_b200 <flags> --dedup IN.fa OUT.fa --cutoff C [--contained]      the dedup stage around a merge (dedup.hpp):
+//   ContigsMerger_b200 <flags> --dedup-batch LIST [--gpus N]                      MergeContigs.py:15-70 without BWA / samtools;
+//       LIST: IN.fa <TAB> OUT.fa <TAB> CUTOFF <TAB> g|p per line (g: `-P -g`, contained contigs; p: `-P`, duplicates)
 //   ContigsMerger_b200 --serve SOCKET [--gpus N] [--window-ms W]     resident service (server.hpp): thin clients -- this same
 //       binary with GAPPADDER_B200_SOCKET=SOCKET in its environment -- send one gap each; concurrent requests share a launch
 //
@@ -31,6 +34,7 @@
 #include <thread>
 #include <vector>
 
+#include "dedup.hpp"
 #include "fasta.hpp"
 #include "gappadder_b200.h"
 #include "merger.hpp"
@@ -54,6 +58,10 @@ struct Cli {
     std::string serve;          // --serve SOCKET: run as the resident service (server.hpp)
     int window_ms = 3;
     bool shutdown = false;      // --shutdown: ask the server behind GAPPADDER_B200_SOCKET to exit
+    // dedup stage (dedup.hpp): --dedup IN.fa OUT.fa --cutoff C [--contained], or --dedup-batch LIST
+    std::string dedup_in, dedup_out, dedup_batch;
+    double dedup_cutoff = 0.99;
+    bool dedup_contained = false;
 };
 
 int parse_int(const char* s, int dflt) { int v = dflt; if (s) sscanf(s, "%d", &v); return v; }
@@ -75,6 +83,10 @@ bool parse_args(int argc, char** argv, Cli& c, std::vector<char*>& ref_argv)
         if (!strcmp(a, "--chunk-gaps")) { c.chunk_gaps = parse_int(val, 512); ++pos; continue; }
         if (!strcmp(a, "--chunk-mb")) { c.chunk_mb = parse_int(val, 256); ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; continue; }
+        if (!strcmp(a, "--dedup")) { if (pos + 2 >= argc) return false; c.dedup_in = argv[pos + 1]; c.dedup_out = argv[pos + 2]; pos += 2; continue; }
+        if (!strcmp(a, "--dedup-batch")) { if (!val) return false; c.dedup_batch = val; ++pos; continue; }
+        if (!strcmp(a, "--cutoff")) { if (!val) return false; c.dedup_cutoff = atof(val); ++pos; continue; }
+        if (!strcmp(a, "--contained")) { c.dedup_contained = true; continue; }
         if (!strcmp(a, "--shutdown")) { c.shutdown = true; continue; }
         ref_argv.push_back(argv[pos]);
     }
@@ -363,6 +375,80 @@ int run_batch(const Cli& c)
     return gap_failed ? 3 : 0;
 }
 
+// The dedup stage for any number of contig sets: sets are independent, so they are dealt to the GPUs by FASTA size
+// (longest-processing-time) and every GPU runs its share as one batch.
+int run_dedup(const Cli& c)
+{
+    struct Line { DedupInput in; std::string out; };
+    std::vector<Line> lines;
+    if (!c.dedup_batch.empty()) {
+        std::ifstream f(c.dedup_batch);
+        if (!f) { fprintf(stderr, "ContigsMerger_b200: cannot open dedup list %s\n", c.dedup_batch.c_str()); return 2; }
+        std::string ln;
+        while (std::getline(f, ln)) {
+            if (ln.empty()) continue;
+            std::vector<std::string> col;
+            size_t b = 0;
+            for (;;) { const size_t t = ln.find('\t', b); col.push_back(ln.substr(b, t == std::string::npos ? t : t - b)); if (t == std::string::npos) break; b = t + 1; }
+            if (col.size() != 4 || (col[3] != "g" && col[3] != "p")) { fprintf(stderr, "ContigsMerger_b200: bad dedup line: %s\n", ln.c_str()); return 2; }
+            Line l;
+            l.in.fasta_path = col[0]; l.out = col[1]; l.in.cutoff = atof(col[2].c_str()); l.in.remove_contained = col[3] == "g";
+            lines.push_back(l);
+        }
+    } else {
+        Line l;
+        l.in.fasta_path = c.dedup_in; l.out = c.dedup_out; l.in.cutoff = c.dedup_cutoff; l.in.remove_contained = c.dedup_contained;
+        lines.push_back(l);
+    }
+    const int n_dev = std::max(1, std::min<int>(c.gpus, (int)std::max<size_t>(1, lines.size())));
+    std::vector<uint64_t> cost(lines.size(), 1);
+    for (size_t g = 0; g < lines.size(); ++g) { struct stat sb; if (stat(lines[g].in.fasta_path.c_str(), &sb) == 0) cost[g] = (uint64_t)sb.st_size * (uint64_t)sb.st_size + 1; }
+    const std::vector<int> part = partition_gaps(cost, n_dev);
+    std::vector<int> rc(n_dev, 0);
+    std::vector<std::string> err(n_dev);
+    std::vector<DedupTimings> tim(n_dev);
+    std::vector<double> wall(n_dev, 0);
+    std::vector<uint64_t> cells(n_dev, 0), npairs(n_dev, 0), removed(n_dev, 0), contigs(n_dev, 0);
+    std::atomic<bool> set_failed(false);
+    auto worker = [&](int dev) {
+        std::vector<DedupInput> in;
+        std::vector<size_t> which;
+        for (size_t g = 0; g < lines.size(); ++g) if (part[g] == dev) { in.push_back(lines[g].in); which.push_back(g); }
+        if (in.empty()) return;
+        gp_ctx* ctx = nullptr;
+        int r = gp_create(dev, &ctx);
+        if (r != GP_OK) { rc[dev] = r; err[dev] = gp_last_error(nullptr); return; }
+        std::vector<DedupOutput> out;
+        const auto w0 = std::chrono::steady_clock::now();
+        r = dedup_sets(ctx, c.opt, in, out, err[dev], &tim[dev]);
+        if (r == GP_OK)
+            for (size_t k = 0; k < which.size(); ++k) {
+                if (!out[k].error.empty()) { fprintf(stderr, "ContigsMerger_b200: %s\n", out[k].error.c_str()); set_failed = true; continue; }
+                if (!write_file(lines[which[k]].out, out[k].fasta_text)) { r = GP_ERR_INVALID; err[dev] = "cannot write " + lines[which[k]].out; break; }
+                cells[dev] += out[k].pair_cells; npairs[dev] += out[k].n_pairs; contigs[dev] += out[k].n_contigs;
+                removed[dev] += out[k].removed_names.size() + (out[k].n_contigs - out[k].n_unique);
+            }
+        wall[dev] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+        gp_destroy(ctx);
+        rc[dev] = r;
+    };
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_dev; ++d) th.emplace_back(worker, d);
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_dev; ++d)
+        if (rc[d] != 0) { fprintf(stderr, "ContigsMerger_b200: dedup worker on GPU %d failed (%d): %s\n", d, rc[d], err[d].c_str()); return 3; }
+    if (c.stats) {
+        int slow = 0; for (int d = 1; d < n_dev; ++d) if (wall[d] > wall[slow]) slow = d;
+        uint64_t tc = 0, tp = 0, tr = 0, tn = 0;
+        for (int d = 0; d < n_dev; ++d) { tc += cells[d]; tp += npairs[d]; tr += removed[d]; tn += contigs[d]; }
+        fprintf(stderr, "{\"sets\": %zu, \"gpus\": %d, \"contigs\": %llu, \"removed\": %llu, \"pairs\": %llu, \"dp_gcells\": %.6f, \"dedup_ms\": %.3f, "
+                        "\"read_ms\": %.3f, \"device_ms\": %.3f, \"rules_ms\": %.3f, \"qc_kernel_ms\": %.4f}\n",
+                lines.size(), n_dev, (unsigned long long)tn, (unsigned long long)tr, (unsigned long long)tp, tc / 1e9, wall[slow],
+                tim[slow].read_ms, tim[slow].device_ms, tim[slow].rules_ms, tim[slow].qc_kernel_ms);
+    }
+    return set_failed ? 3 : 0;
+}
+
 } // namespace
 
 int main(int argc, char** argv)
@@ -376,6 +462,7 @@ int main(int argc, char** argv)
         return serve(so);
     }
     if (!c.batch.empty()) return run_batch(c);
+    if (!c.dedup_batch.empty() || !c.dedup_in.empty()) return run_dedup(c);
     // single gap, exactly the reference's process: argv[repeatfileArgIndex] defaults to argv[1]
     if (!c.have_input && !c.shutdown) { fprintf(stderr, "usage: ContigsMerger_b200 <flags> contigs.fa\n"); return 1; }
     // A resident server (ContigsMerger_b200 --serve SOCKET) answers when GAPPADDER_B200_SOCKET names it: no CUDA context

@@ -205,6 +205,10 @@ uint64_t gp_transposed_pairs(const gp_ctx *ctx);
  * as in the reference).  k <= 10 (GAPPadder uses 10), at most 4096 nodes per gap; GP_ERR_RANGE otherwise -- the
  * host function has no such limits.  Returns 0 or a negative error. */
 int gp_quick_check_device(gp_ctx *ctx, const uint32_t *gap_first, uint32_t n_gaps, int32_t k, uint8_t *hit, uint64_t hit_bytes);
+/* The same filter for every ORDERED pair (full_matrix != 0): hit[i * n_g + j] = 1 iff a k-mer of the first or last 30 bases
+ * of node j occurs in node i, for j < i too (the dedup stage asks whether contig j may lie inside or overlap contig i).
+ * full_matrix == 0 is gp_quick_check_device. */
+int gp_quick_check_matrix(gp_ctx *ctx, const uint32_t *gap_first, uint32_t n_gaps, int32_t k, uint8_t *hit, uint64_t hit_bytes, int full_matrix);
 #define GP_QC_MAX_K 10
 #define GP_QC_MAX_NODES 4096
 /* Of the last gp_quick_check_device on this context: device time of the filter kernel (CUDA events on the context's
@@ -311,6 +315,37 @@ int32_t gp_overlap_size(int32_t len1, int32_t len2, const gp_result *r);
  * KmerUtils.cpp:22-115).  Returns the number of candidates (possibly > cap) or a negative status. */
 int64_t gp_candidate_pairs(const char *const *nodes, const uint32_t *node_len, uint32_t n_nodes,
                            int32_t kmer_len, gp_pair *pairs, uint64_t cap);
+
+/* ---- dedup stage: MergeContigs.py:15-70 around every merge --------------------------------------------
+ * The reference removes duplicate and contained contigs with `TERefiner_1 -U` (unique names, TERefiner/refiner.cpp:1045-1140),
+ * a BWA-MEM self-alignment, and `TERefiner_1 -P -c cutoff [-g]` (refiner.cpp:660-801 with Alignment.cpp:397-437): rules over
+ * (query, reference, CIGAR) of every alignment record.  The RULES are in-tree and restated exactly below (pinned to the
+ * prebuilt TERefiner_1 by tests/golden/dedup/dedup_rules.json).  The ALIGNER is BWA, not vendored and not pinned: PARITY
+ * UNPINNED there.  The records come instead from the overlap DP of this library (Evaluate, the same kernels as the merger's
+ * pairwise phase) by the documented rule of gp_dedup_records; gappadder_b200/host/dedup.cpp wires the stage together. */
+typedef struct gp_dedup_record {
+    uint32_t q, r;            /* query contig, reference contig (indices into the contig arrays) */
+    uint32_t single_m;        /* 1: the CIGAR is one M operation of m_len bases; 0: several operations */
+    uint32_t m_len;           /* sum of the M operations */
+    uint32_t other_len;       /* sum of the S, H and I operations (Alignment.cpp:408-416) */
+} gp_dedup_record;
+/* Refiner::gnrtUniqueFa (refiner.cpp:1045-1140): of records with equal names only the first stays.  keep[i] = 0 / 1. */
+int gp_dedup_unique_names(const char *const *names, uint32_t n_contigs, uint8_t *keep);
+/* Refiner::removeDupRepeatsOfOneContigSet (refiner.cpp:660-801).  remove_contained != 0 is `-g` (a contig that maps
+ * perfectly -- one M of its full length, Alignment.cpp:428-437 -- onto another is removed); 0 is the duplicate rule (a
+ * contig that is fully mapped -- Alignment.cpp:397-426, M fraction > cutoff -- onto one with a SMALLER name and a similar
+ * length is removed, :726-766).  Names must be unique (run gp_dedup_unique_names first, as MergeContigs.py does).
+ * removed[i] = 0 / 1; rmCotigs (:401-470) then writes the others in input order. */
+int gp_dedup_decide(const gp_dedup_record *recs, uint64_t n_recs, const char *const *names, const uint32_t *contig_len,
+                    uint32_t n_contigs, double cutoff, int remove_contained, uint8_t *removed);
+/* Builder-defined (BWA parity unpinned): the two records one Evaluate result stands for.  s1 = contig q (rows), s2 =
+ * contig r or its reverse complement (columns), res = Evaluate(s1, s2) with GAPPadder's scores.  With ov =
+ * gp_overlap_size (the bases the two share by the merger's own definition) the alignment counts when ov >= 1 and
+ * score >= (1 - max_frac_score_loss) * ov (IsScoreSignificant's score test, ContigsCompactor.cpp:1958-1960, -s 0.4 in
+ * GAPPadder); then out[0] is "q on r" with CIGAR {min(ov,len_q)}M{rest}S and out[1] is "r on q" likewise (a full-length
+ * cover is the single-M CIGAR).  Returns the number of records written (0 or 2). */
+int gp_dedup_records(uint32_t q, uint32_t r, int32_t len_q, int32_t len_r, const gp_result *res, double max_frac_score_loss,
+                     gp_dedup_record *out);
 
 /* Multi-GPU sharding (gaps are independent: no collective on the data path).
  * gp_estimate_gap_cells: upper bound of one gap's pairwise-phase DP cells from its contig lengths alone

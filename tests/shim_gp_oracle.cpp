@@ -89,6 +89,29 @@ int gp_quick_check_device(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     }
     return GP_OK;
 }
+// every ordered pair: hit(i, j) = "the ends of j occur in i", from the host filter on the two-node list {i, j}
+int gp_quick_check_matrix(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps, int32_t k, uint8_t* hit, uint64_t hit_bytes, int full_matrix)
+{
+    if (!full_matrix) return gp_quick_check_device(c, gap_first, n_gaps, k, hit, hit_bytes);
+    uint64_t pos = 0;
+    for (uint32_t g = 0; g < n_gaps; ++g) {
+        const uint32_t first = gap_first[g], n = gap_first[g + 1] - first;
+        if (pos + (uint64_t)n * n > hit_bytes) return GP_ERR_INVALID;
+        memset(hit + pos, 0, (size_t)n * n);
+        for (uint32_t i = 0; i < n; ++i)
+            for (uint32_t j = 0; j < n; ++j) {
+                const char* nodes[2] = {c->seqs[first + i].data(), c->seqs[first + j].data()};
+                const uint32_t lens[2] = {(uint32_t)c->seqs[first + i].size(), (uint32_t)c->seqs[first + j].size()};
+                gp_pair cand[4];
+                const int64_t np = gp_candidate_pairs(nodes, lens, 2, k, cand, 4);
+                if (np < 0) return (int)np;
+                for (int64_t q = 0; q < np; ++q) if (cand[q].row_seq == 0 && cand[q].col_seq == 1) hit[pos + (uint64_t)i * n + j] = 1;
+                if (i == j) for (int64_t q = 0; q < np; ++q) if (cand[q].row_seq == 0 && cand[q].col_seq == 0) hit[pos + (uint64_t)i * n + j] = 1;
+            }
+        pos += (uint64_t)n * n;
+    }
+    return GP_OK;
+}
 int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n, const gp_dp_params* p) { c->pairs.assign(pairs, pairs + n); c->params = *p; return GP_OK; }
 int gp_launch_resident(gp_ctx*) { return GP_OK; }
 int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n)
