@@ -300,24 +300,42 @@ int run_batch(const Cli& c)
                 if (to_write[dev].empty()) break;                 // everything written, or a failure with nothing queued
                 ch = to_write[dev].front(); to_write[dev].pop_front();
             }
-            for (size_t k = 0; k < ch->gaps.size(); ++k) {
-                const BatchLine& b = lines[ch->gaps[k]];
-                GapOutput& o = ch->out[k];
-                if (!o.error.empty()) {                          // this gap only: nothing written, the others go on
-                    fprintf(stderr, "ContigsMerger_b200: %s\n", o.error.c_str());
-                    gap_failed = true;
-                    continue;
+            // the chunk's files on a few threads (two or three small files per gap)
+            std::atomic<size_t> next_gap(0);
+            std::atomic<uint64_t> c_all(0), c_pair(0);
+            std::atomic<bool> write_failed(false);
+            std::string bad_path;
+            std::mutex bad_mu;
+            auto write_some = [&] {
+                for (size_t k = next_gap.fetch_add(1); k < ch->gaps.size(); k = next_gap.fetch_add(1)) {
+                    const BatchLine& b = lines[ch->gaps[k]];
+                    GapOutput& o = ch->out[k];
+                    if (!o.error.empty()) {                      // this gap only: nothing written, the others go on
+                        fprintf(stderr, "ContigsMerger_b200: %s\n", o.error.c_str());
+                        gap_failed = true;
+                        continue;
+                    }
+                    if (!write_file(b.out, o.stdout_text)) { write_failed = true; std::lock_guard<std::mutex> lk(bad_mu); bad_path = b.out; continue; }
+                    if (o.wrote_info) write_file(b.info, o.info_text);
+                    if (c.write_gml && o.wrote_info) write_file(b.out + ".gml", o.gml_text);
+                    c_all += o.pair_cells + o.relax_cells;
+                    c_pair += o.pair_cells;
                 }
-                if (!write_file(b.out, o.stdout_text)) {
-                    std::lock_guard<std::mutex> lk(mu);
-                    rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + b.out; failed = true; cv.notify_all();
-                    return;
-                }
-                if (o.wrote_info) write_file(b.info, o.info_text);
-                if (c.write_gml && o.wrote_info) write_file(b.out + ".gml", o.gml_text);
-                cells[dev] += o.pair_cells + o.relax_cells;
-                pcells[dev] += o.pair_cells;
+            };
+            {
+                const size_t nt = std::min<size_t>(8, std::max<size_t>(1, ch->gaps.size() / 16));
+                std::vector<std::thread> wt;
+                for (size_t t = 1; t < nt; ++t) wt.emplace_back(write_some);
+                write_some();
+                for (auto& t : wt) t.join();
             }
+            if (write_failed) {
+                std::lock_guard<std::mutex> lk(mu);
+                rc[dev] = GP_ERR_INVALID; err[dev] = "cannot write " + bad_path; failed = true; cv.notify_all();
+                return;
+            }
+            cells[dev] += c_all;
+            pcells[dev] += c_pair;
             std::vector<GapOutput>().swap(ch->out);
             wall[dev] = partition_ms + ms_since(t_run);
             { std::lock_guard<std::mutex> lk(mu); ++written[dev]; cv.notify_all(); }
