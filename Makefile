@@ -27,7 +27,7 @@ build/gp_host.o: $(CSRC)/gp_host.cpp include/gappadder_b200.h | build
 $(LIB): build/gp_api.o build/int_peak.o build/gp_host.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static
 
-build/ContigsMerger_b200: $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(HOST)/merge_graph.cpp $(HOST)/fasta.cpp $(HOST)/server.cpp $(HOST)/dedup.cpp $(HOST)/dedup.hpp $(HOST)/merger.hpp $(HOST)/merge_graph.hpp $(HOST)/fasta.hpp $(HOST)/server.hpp $(LIB)
+build/ContigsMerger_b200: $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(HOST)/merge_graph.cpp $(HOST)/fasta.cpp $(HOST)/server.cpp $(HOST)/dedup.cpp $(HOST)/dedup.hpp $(HOST)/device_gate.hpp $(HOST)/merger.hpp $(HOST)/merge_graph.hpp $(HOST)/fasta.hpp $(HOST)/server.hpp $(LIB)
 	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(HOST)/merge_graph.cpp $(HOST)/fasta.cpp $(HOST)/server.cpp $(HOST)/dedup.cpp -Lgappadder_b200 -lgappadder_b200 -Wl,-rpath,'$$ORIGIN/../gappadder_b200' -lpthread
 
 build/microbench_int: tools/microbench_int.cu | build

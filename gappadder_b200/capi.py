@@ -23,7 +23,7 @@ EXPORTS = [
     "gp_quick_check_stats",
     "gp_reserve", "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
     "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
-    "gp_dedup_unique_names", "gp_dedup_decide", "gp_dedup_records", "gp_quick_check_matrix",
+    "gp_dedup_unique_names", "gp_dedup_decide", "gp_dedup_records", "gp_quick_check_matrix", "gp_set_relax_launch_hook",
 ]
 
 

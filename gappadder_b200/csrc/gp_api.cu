@@ -81,6 +81,8 @@ struct gp_ctx {
     uint64_t rx_second_passes = 0, rx_unresolved = 0, rx_cells_bound = 0;
     double rx_kernel_ms = 0;
     cudaEvent_t rx_ev[2] = {nullptr, nullptr};
+    gp_launch_hook relax_hook = nullptr;        // gp_set_relax_launch_hook
+    void* relax_hook_user = nullptr;
     // flank placement (semi-global; flank_place.cuh)
     DeviceBuf d_fp_pairs, d_fp_order, d_fp_results, d_fp_queue, d_fp_scratch;
     HostBuf h_fp_stage;
@@ -893,6 +895,8 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
         for (uint32_t q = n; q-- > 0;) if (steps[by_prio[q]].parent < 0) roots.push_back(by_prio[q]);                  // descending priority
     }
     const uint32_t ring_slots = n + gp::RELAX_RING_SLACK;
+    uint32_t ring_total = (uint32_t)roots.size();                  // entries the ring will ever hold: roots + non-first children
+    for (uint32_t k = 0; k < n; ++k) if (steps[k].parent >= 0 && items[steps[k].parent].first_child != (int32_t)k) ++ring_total;
     (void)depth;
 
     const size_t item_bytes = (size_t)n * sizeof(gp::RelaxItem);
@@ -933,14 +937,15 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     GP_CUDA(c, cudaEventRecord(c->rx_ev[0], c->stream));
     if (pot2)
         gp::relax_chain_kernel<true><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
-            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, d_ring, ctrl,
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, ring_total, d_ring, ctrl,
             c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
     else
         gp::relax_chain_kernel<false><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
-            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, d_ring, ctrl,
+            (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, ring_total, d_ring, ctrl,
             c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->rx_ev[1], c->stream));
+    if (c->relax_hook) c->relax_hook(c->relax_hook_user);         // the kernel is enqueued: a caller may queue other work behind it
     c->launches += 1;
     char* ho = (char*)c->h_rx_out.p;
     GP_CUDA(c, cudaMemcpyAsync(ho, c->d_rx_results.p, (size_t)n * sizeof(gp::DevResult), cudaMemcpyDeviceToHost, c->stream));
@@ -965,6 +970,14 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     float ms = 0.f;
     GP_CUDA(c, cudaEventElapsedTime(&ms, c->rx_ev[0], c->rx_ev[1]));
     c->rx_kernel_ms = ms;
+    return GP_OK;
+}
+
+int gp_set_relax_launch_hook(gp_ctx* c, gp_launch_hook hook, void* user)
+{
+    if (!c) return GP_ERR_INVALID;
+    c->relax_hook = hook;
+    c->relax_hook_user = user;
     return GP_OK;
 }
 

@@ -322,20 +322,21 @@ int gp_dedup_records(uint32_t q, uint32_t r, int32_t len_q, int32_t len_r, const
 /* GetComplement, GenSeqsUtils.cpp:24-61; FastaSequence::RevsereComplement, fastareader.cpp. */
 void gp_revcomp(const char *s, uint32_t len, char *out)
 {
-    for (uint32_t i = 0; i < len; ++i) {
-        char b = s[len - 1 - i], o;
-        if (b == 'N' || b == 'n') o = b;
-        else {
-            switch (b) {
-            case 'A': case 'a': o = 'T'; break;
-            case 'T': case 't': o = 'A'; break;
-            case 'G': case 'g': o = 'C'; break;
-            case 'C': case 'c': o = 'G'; break;
-            default: o = 'N'; break;
-            }
+    struct Table {                                         // the rule as a byte table: N/n stay, A<->T, C<->G (either case -> upper), all else N
+        char t[256];
+        Table()
+        {
+            for (int b = 0; b < 256; ++b) t[b] = 'N';
+            t[(unsigned char)'n'] = 'n';
+            t[(unsigned char)'A'] = t[(unsigned char)'a'] = 'T';
+            t[(unsigned char)'T'] = t[(unsigned char)'t'] = 'A';
+            t[(unsigned char)'G'] = t[(unsigned char)'g'] = 'C';
+            t[(unsigned char)'C'] = t[(unsigned char)'c'] = 'G';
         }
-        out[i] = o;
-    }
+    };
+    static const Table T;
+    const unsigned char *p = (const unsigned char *)s + len;
+    for (uint32_t i = 0; i < len; ++i) out[i] = T.t[*--p];
     out[len] = 0;
 }
 

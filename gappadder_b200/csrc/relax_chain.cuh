@@ -84,7 +84,7 @@ __device__ __forceinline__ void relax_concat(uint32_t* __restrict__ dst, const u
 template <bool POT2>
 __global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
 relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ arena, const RelaxItem* __restrict__ items,
-                   const uint32_t* __restrict__ subtree, uint32_t n_items, uint32_t* __restrict__ ring, unsigned int* __restrict__ ctrl,
+                   const uint32_t* __restrict__ subtree, uint32_t n_items, uint32_t ring_total, uint32_t* __restrict__ ring, unsigned int* __restrict__ ctrl,
                    Wf16cParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ mlen,
                    DevResult* __restrict__ out)
 {
@@ -108,7 +108,7 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
             if (leader) {
                 const uint32_t t = atomicAdd(ctrl, 1u);
                 uint32_t v = RELAX_EXIT;
-                if (t < n_items + RELAX_RING_SLACK) {
+                if (t < ring_total) {                               // a ticket no push will ever fill: this CTA is done
                     while ((v = ld_acquire_u32(ring + t)) == RELAX_EMPTY) {
                         if (ld_acquire_u32(ctrl + 2) >= n_items) { v = RELAX_EXIT; break; }      // everything is finished
                         __nanosleep(200);

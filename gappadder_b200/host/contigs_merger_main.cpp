@@ -51,7 +51,7 @@ struct Cli {
     std::string batch;
     int gpus = 1;
     int streams = 2;            // mergers (host thread + context + stream) per GPU; they alternate on the device (run_batch)
-    int chunk_gaps = 512;       // batch pipeline: gaps per chunk at most ...
+    int chunk_gaps = 256;       // batch pipeline: gaps per chunk at most ...
     int chunk_mb = 256;         // ... and MB of FASTA per chunk at most
     bool write_gml = true;
     bool stats = false;
@@ -80,7 +80,7 @@ bool parse_args(int argc, char** argv, Cli& c, std::vector<char*>& ref_argv)
         if (!strcmp(a, "--window-ms")) { c.window_ms = parse_int(val, 3); ++pos; continue; }
         if (!strcmp(a, "--gpus")) { c.gpus = parse_int(val, 1); ++pos; continue; }
         if (!strcmp(a, "--streams")) { c.streams = parse_int(val, 2); ++pos; continue; }
-        if (!strcmp(a, "--chunk-gaps")) { c.chunk_gaps = parse_int(val, 512); ++pos; continue; }
+        if (!strcmp(a, "--chunk-gaps")) { c.chunk_gaps = parse_int(val, 256); ++pos; continue; }
         if (!strcmp(a, "--chunk-mb")) { c.chunk_mb = parse_int(val, 256); ++pos; continue; }
         if (!strcmp(a, "--stats")) { c.stats = true; continue; }
         if (!strcmp(a, "--dedup")) { if (pos + 2 >= argc) return false; c.dedup_in = argv[pos + 1]; c.dedup_out = argv[pos + 2]; pos += 2; continue; }
@@ -96,6 +96,7 @@ bool parse_args(int argc, char** argv, Cli& c, std::vector<char*>& ref_argv)
     c.input = r.input;
     c.have_input = !r.input.empty();
     c.write_gml = r.write_gml;
+    c.opt.build_gml = r.write_gml;
     if (c.opt.verbose) printf("Turn on Verbose\n");
     return true;
 }
@@ -124,9 +125,10 @@ struct Chunk {
 //              each GPU's share is cut into chunks of at most --chunk-gaps gaps / --chunk-mb MB of FASTA;
 //   readers    a pool of host threads parses the FASTA files chunk by chunk, a bounded number of chunks ahead of the GPU;
 //   mergers    --streams S host threads per GPU (default 2), each with its own context, take that GPU's chunks in order
-//              and run merge_gaps on them; they share one mutex per GPU that is held around the device phases only, so
-//              the host phases of one chunk (nodes, graph, strings, output text) run beside the kernels of another and
-//              the GPU never runs two persistent kernels at once;
+//              and run merge_gaps on them; they share one DeviceGate per GPU (device_gate.hpp) that is held around the
+//              device phases only: the host phases of one chunk (nodes, graph, strings, output text) run beside the
+//              kernels of another, two pairwise launches never compete for the SMs, and the next chunk's pairwise
+//              kernels are queued right behind a chunk's relax kernel, whose long tail leaves most SMs idle;
 //   writers    one thread per GPU writes the finished chunks' files and frees them.
 // Memory is bounded by the chunks in flight, whatever the batch size (BASELINE configs[3]: 50 000 gaps).  Results do not
 // depend on the split: every gap's bytes are what the single-gap form writes.
@@ -221,12 +223,19 @@ int run_batch(const Cli& c)
 
     const int per_dev = c.streams >= 1 ? c.streams : 1;
     const int n_workers = n_dev * per_dev;
+    // host threads of a merger's parallel phases: the machine's threads shared out over the mergers, twice over (a merger
+    // spends most of its time waiting for the device), between 2 and 16
+    MergeOptions mopt = c.opt;
+    if (mopt.host_threads <= 0) {
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        mopt.host_threads = std::max(2, std::min(16, 2 * hw / n_workers));
+    }
     std::vector<int> rc(n_workers, 0);
     std::vector<std::string> err(n_workers);
     std::vector<MergeTimings> tim(n_workers);
     std::vector<uint64_t> cells(n_dev, 0), pcells(n_dev, 0);
-    std::vector<double> wall(n_dev, 0);
-    std::vector<std::mutex> dev_mu(n_dev);
+    std::vector<double> wall(n_dev, 0), write_ms(n_dev, 0);
+    std::vector<DeviceGate> dev_gate(n_dev);
     auto add_timings = [](MergeTimings& a, const MergeTimings& b) {
         a.read_ms += b.read_ms; a.pairwise_ms += b.pairwise_ms; a.graph_ms += b.graph_ms; a.relax_ms += b.relax_ms; a.output_ms += b.output_ms;
         a.relax_steps += b.relax_steps; a.relax_team_steps += b.relax_team_steps; a.relax_pairs += b.relax_pairs;
@@ -274,6 +283,7 @@ int run_batch(const Cli& c)
         int r;
         for (;;) {
             Chunk* ch = nullptr;
+            const auto tw = clk::now();
             {
                 std::unique_lock<std::mutex> lk(mu);
                 if (failed || next_chunk[dev] >= chunks[dev].size()) break;
@@ -284,7 +294,8 @@ int run_batch(const Cli& c)
                 if (failed) break;
             }
             MergeTimings t;
-            r = merge_gaps(ctx, c.opt, ch->in, ch->out, err[w], &t, &dev_mu[dev]);
+            t.detail["pipeline.wait_for_fasta"] = ms_since(tw);
+            r = merge_gaps(ctx, mopt, ch->in, ch->out, err[w], &t, &dev_gate[dev]);
             add_timings(tim[w], t);
             if (r != GP_OK) { rc[w] = r; failed = true; std::lock_guard<std::mutex> lk(mu); cv.notify_all(); break; }
             std::vector<GapInput>().swap(ch->in);
@@ -301,6 +312,7 @@ int run_batch(const Cli& c)
                 ch = to_write[dev].front(); to_write[dev].pop_front();
             }
             // the chunk's files on a few threads (two or three small files per gap)
+            const auto tw0 = clk::now();
             std::atomic<size_t> next_gap(0);
             std::atomic<uint64_t> c_all(0), c_pair(0);
             std::atomic<bool> write_failed(false);
@@ -336,6 +348,7 @@ int run_batch(const Cli& c)
             }
             cells[dev] += c_all;
             pcells[dev] += c_pair;
+            write_ms[dev] += ms_since(tw0);
             std::vector<GapOutput>().swap(ch->out);
             wall[dev] = partition_ms + ms_since(t_run);
             { std::lock_guard<std::mutex> lk(mu); ++written[dev]; cv.notify_all(); }
@@ -361,6 +374,7 @@ int run_batch(const Cli& c)
         int slow = 0; for (int d = 1; d < n_dev; ++d) if (wall[d] > wall[slow]) slow = d;
         MergeTimings t;
         for (int w = slow; w < n_workers; w += n_dev) add_timings(t, tim[w]);
+        t.detail["pipeline.write_files"] = write_ms[slow];
         // dp_gcells / pairwise_gcells: m*n of every Evaluate the reference runs for these gaps; closed_gcells of them
         // (a node against itself) are answered in closed form here, so computed cells = dp_gcells - closed_gcells
         uint64_t closed = 0; for (const MergeTimings& x : tim) closed += x.closed_cells;

@@ -93,15 +93,23 @@ std::vector<int> partition_gaps(const std::vector<uint64_t>& cost, int n_parts)
 }
 
 namespace {
-struct DeviceLock {             // scope of one device phase (see merge_gaps' device_lock)
-    std::unique_lock<std::mutex> l;
-    explicit DeviceLock(std::mutex* m) { if (m) l = std::unique_lock<std::mutex>(*m); }
-    void release() { if (l.owns_lock()) l.unlock(); }
+struct PairwisePhase {          // scope of one device phase of the pairwise class (see device_gate.hpp)
+    DeviceGate* g;
+    bool open;
+    explicit PairwisePhase(DeviceGate* gate) : g(gate), open(gate != nullptr) { if (g) g->begin_pairwise(); }
+    void end(bool relax_follows = false) { if (open) { g->end_pairwise(relax_follows); open = false; } }
+    ~PairwisePhase() { end(false); }
 };
+struct RelaxHook { DeviceGate* g; bool fired; };
+void relax_hook_fn(void* user)
+{
+    RelaxHook* h = (RelaxHook*)user;
+    if (!h->fired) { h->fired = true; h->g->relax_launched(); }
+}
 } // namespace
 
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error, MergeTimings* timings, std::mutex* device_lock)
+               std::string& error, MergeTimings* timings, DeviceGate* gate)
 {
     using clk = std::chrono::steady_clock;
     auto t_prev = clk::now();
@@ -139,7 +147,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
     std::vector<const char*> seq_ptr;
     std::vector<uint32_t> seq_len;
     std::vector<gp_pair> pairs;
-    const unsigned host_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned host_threads = opt.host_threads > 0 ? (unsigned)opt.host_threads : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     for_each_gap(G, host_threads, [&](size_t g) {
         GapState& s = st[g];
         std::string fatal;
@@ -157,33 +165,43 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         for (const FastaRecord& r : s.contigs) {
             s.node_seq.push_back(r.seq);
             s.node_name.push_back(r.name);
-            std::string rc(r.seq.size(), 'N');
-            if (!r.seq.empty()) gp_revcomp(r.seq.data(), (uint32_t)r.seq.size(), &rc[0]);
-            s.node_seq.push_back(rc);
+            s.node_seq.emplace_back(r.seq.size(), 'N');
+            if (!r.seq.empty()) gp_revcomp(r.seq.data(), (uint32_t)r.seq.size(), &s.node_seq.back()[0]);
             s.node_name.push_back(r.name + "_R");                         // :785-787
         }
-        {   // letters besides A C G T N: rename per gap (see GapState::dp_seq)
+        {   // letters besides A C G T N: rename per gap (see GapState::dp_seq).  One pass over the bases: which letters occur
+            // (in order of first appearance) and whether everything is A/C/G/T.
             static const char placeholder[] = "BDEFHIJKLMO";
+            struct Classes {
+                unsigned char other[256], not_acgt[256];
+                Classes()
+                {
+                    for (int b = 0; b < 256; ++b) { not_acgt[b] = !(b == 'A' || b == 'C' || b == 'G' || b == 'T'); other[b] = not_acgt[b] && b != 'N'; }
+                }
+            };
+            static const Classes K;
             bool seen[256] = {false};
             int n_other = 0;
             for (int b = 0; b < 256; ++b) s.letter_map[b] = (unsigned char)b;
-            for (const FastaRecord& r : s.contigs)
-                for (unsigned char ch : r.seq)
-                    if (!seen[ch] && ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') {
+            for (const FastaRecord& r : s.contigs) {
+                if (r.seq.size() > 16382 || r.seq.empty()) s.acgt_only = false;
+                unsigned any_not_acgt = 0;
+                for (unsigned char ch : r.seq) {
+                    any_not_acgt |= K.not_acgt[ch];
+                    if (K.other[ch] && !seen[ch]) {
                         seen[ch] = true;
                         if (n_other < 11) s.letter_map[ch] = (unsigned char)placeholder[n_other];
                         ++n_other;
                     }
+                }
+                if (any_not_acgt) s.acgt_only = false;
+            }
             if (n_other > 11) {
                 out[g].error = in[g].fasta_path + ": " + std::to_string(n_other + 5) + " distinct sequence letters; this implementation "
                                "handles A C G T N plus 11 others per gap (the reference accepts any letter)";
                 out[g].exit_code = 3;
                 s.dead = true;
                 return;
-            }
-            for (const FastaRecord& r : s.contigs) {
-                if (r.seq.size() > 16382 || r.seq.empty()) s.acgt_only = false;
-                for (unsigned char ch : r.seq) if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') { s.acgt_only = false; break; }
             }
             if (n_other > 0) {
                 s.dp_seq = s.node_seq;
@@ -245,8 +263,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
     if (n_dev > 0) {
         mark("read.table");
         const uint32_t n_seq = (uint32_t)seq_ptr.size();
-        DeviceLock dl(device_lock);
-        mark("read.wait_device");
+        // Not gated: the copy runs beside any kernel, and the filter kernel (0.3 ms) simply queues behind whatever persistent
+        // kernel another merger has on the SMs -- by the time that one drains, this chunk's pair list is one step away.
         int rc = gp_upload_sequences(ctx, seq_ptr.data(), seq_len.data(), n_seq);   // packs into the context's pinned buffer
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
         table_resident = true;
@@ -256,7 +274,6 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         std::vector<uint8_t> hit(hoff.back() ? hoff.back() : 1);
         rc = gp_quick_check_device(ctx, gap_first.data(), (uint32_t)n_dev, opt.quick_kmer_len, hit.data(), hit.size());
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }
-        dl.release();
         mark("read.quick_check");
         if (timings) {
             double ms = 0; uint64_t bases = 0; uint32_t items = 0;
@@ -286,9 +303,10 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
     lap(&MergeTimings::read_ms);
     // ---- pairwise phase: one batch for all gaps (replaces runMultiThreadMergeV2, :696-721) ------
     std::vector<gp_result> res(pairs.size());
+    bool relax_announced = false;                      // end_pairwise(true) was called: begin_relax or cancel_relax must follow
     if (!pairs.empty()) {
         int rc;
-        DeviceLock dl(device_lock);
+        PairwisePhase dl(gate);
         mark("pairwise.wait_device");
         if (table_resident) {                                            // the table is in HBM already: pairs up, kernels, results down
             rc = gp_upload_pairs(ctx, pairs.data(), pairs.size(), &dp);
@@ -304,7 +322,13 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             gp_closed_form_stats(ctx, &cp, &cc);
             timings->closed_pairs += cp; timings->closed_cells += cc;
         }
+        relax_announced = gate != nullptr && !opt.host_relax;
+        dl.end(relax_announced);                                         // the relax launch comes next: nobody's pairwise phase before it
     }
+    struct CancelRelax {                                                   // whatever path leaves this function
+        DeviceGate* g; bool* on;
+        ~CancelRelax() { if (g && *on) { g->cancel_relax(); *on = false; } }
+    } cancel_relax{gate, &relax_announced};
 
     mark("pairwise.kernels_fetch");
     lap(&MergeTimings::pairwise_ms);
@@ -329,7 +353,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             else graph.add_edge(i, j, len);                                // MODE_1_2: edge i -> j
         }
         out[g].n_pairs = (uint32_t)(s.pair_end - s.pair_begin);
-        out[g].gml_text = graph.gml(s.node_name);                          // :898-899
+        if (opt.build_gml) out[g].gml_text = graph.gml(s.node_name);       // :898-899
         s.paths = remove_revcomp_duplicates(graph.find_paths(max_per_root));   // :907,:926
         for (const std::vector<int>& p : s.paths) {
             if (p.size() > 1) {
@@ -407,9 +431,17 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             std::vector<gp_result> rr(steps.size());
             std::vector<uint32_t> mlen(steps.size());
             int rc;
-            {
-                DeviceLock dl(device_lock);
+            if (gate) {
+                gate->begin_relax();
                 mark("relax.wait_device");
+                RelaxHook hook{gate, !relax_announced};                    // fires once, when the kernel is enqueued
+                gp_set_relax_launch_hook(ctx, relax_hook_fn, &hook);
+                rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
+                gp_set_relax_launch_hook(ctx, nullptr, nullptr);
+                if (!hook.fired) gate->relax_launched();                   // the call failed before launching
+                relax_announced = false;
+                gate->end_relax();
+            } else {
                 rc = gp_relax_chains(ctx, steps.data(), steps.size(), &dp, rr.data(), mlen.data());
             }
             mark("relax.device_call");
@@ -519,7 +551,8 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         std::vector<gp_result> rr(pp.size());
         int rc;
         {
-            DeviceLock dl(device_lock);
+            if (gate && relax_announced) { gate->cancel_relax(); relax_announced = false; }   // no device relax launch for these chains
+            PairwisePhase dl(gate);
             rc = gp_overlap_batch(ctx, sp.data(), sl.data(), (uint32_t)sp.size(), pp.data(), pp.size(), &dp, rr.data());
         }
         if (rc != GP_OK) { error = gp_last_error(ctx); return rc; }

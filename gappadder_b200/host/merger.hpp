@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "device_gate.hpp"
 #include "fasta.hpp"
 #include "gappadder_b200.h"
 
@@ -32,6 +33,8 @@ struct MergeOptions {
     int max_count_contig_in_path = -1;       // -p2 (default MAX_CONTIG_IN_PATH_COUNT = 20)
     bool verbose = false;                    // -V  (accepted, ignored: it pollutes stdout in the reference)
     bool host_quick_check = false;           // --host-quick-check (not a reference flag): candidate filter on the host
+    int host_threads = 0;                    // host threads of the parallel host phases; 0: min(16, hardware threads)
+    bool build_gml = true;                   // false (--no-gml in batch mode): the tmp.gml text is not even built
     bool host_relax = false;                 // --host-relax (not a reference flag): relax chains step by step from the host (round 1's form)
 };
 
@@ -83,12 +86,11 @@ struct MergeTimings {
 // Runs every gap (preloaded records are moved out of `in`).  Returns GP_OK or the failing gp_status (message via gp_last_error(ctx)); a failure
 // here is a GPU/library failure, never an input problem (those are reported per gap like the
 // reference does, on stdout with exit code 1).
-// device_lock: when several host threads (each with its own context) drive one GPU, the mutex they share.  It is held
-// around the device phases only (table upload + quick check, pairwise launch, relax launch), so one thread's host phases
-// (nodes, graph, strings, output text) run beside another thread's kernels, and two persistent kernels never compete for
-// the SMs.
+// gate: when several host threads (each with its own context) drive one GPU, the DeviceGate they share (device_gate.hpp).
+// It is held around the device phases only, so one thread's host phases (nodes, graph, strings, output text) run beside
+// another thread's kernels, and the next chunk's pairwise kernels are queued right behind this chunk's relax kernel.
 int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, std::vector<GapOutput>& out,
-               std::string& error, MergeTimings* timings = nullptr, std::mutex* device_lock = nullptr);
+               std::string& error, MergeTimings* timings = nullptr, DeviceGate* gate = nullptr);
 
 // Estimated DP cells of one gap's pairwise phase from contig lengths alone (all node pairs i <= j):
 // used to balance gaps over GPUs before any sequence is examined.

@@ -257,6 +257,13 @@ typedef struct gp_relax_step {
 #define GP_FLAG_UNRESOLVED 32u
 int gp_relax_chains(gp_ctx *ctx, const gp_relax_step *steps, uint64_t n_steps, const gp_dp_params *params,
                     gp_result *out, uint32_t *merged_len);
+/* gp_relax_chains blocks until the results are on the host.  A caller that drives one GPU from several host threads (one
+ * context each) may want to enqueue the next batch's pairwise kernels right behind the relax kernel -- its tail is a few long
+ * chains that leave most SMs idle, and idle relax CTAs exit --: the hook is called once per gp_relax_chains, on the calling
+ * thread, right after the kernel is enqueued and before the call waits (not at all when the call fails before launching).
+ * NULL removes it. */
+typedef void (*gp_launch_hook)(void *user);
+int gp_set_relax_launch_hook(gp_ctx *ctx, gp_launch_hook hook, void *user);
 /* Of the last gp_relax_chains: device time of its launch, sub-table passes, unresolved steps (descendants not counted). */
 int gp_relax_stats(const gp_ctx *ctx, double *kernel_ms, uint64_t *second_passes, uint64_t *unresolved);
 

@@ -26,6 +26,8 @@ struct gp_ctx {
     std::vector<std::string> seqs;        // the table of gp_set_sequences, unpacked again
     std::vector<gp_pair> pairs;           // gp_upload_pairs
     gp_dp_params params{};
+    gp_launch_hook hook = nullptr;
+    void* hook_user = nullptr;
 };
 
 extern "C" {
@@ -112,6 +114,7 @@ int gp_quick_check_matrix(gp_ctx* c, const uint32_t* gap_first, uint32_t n_gaps,
     }
     return GP_OK;
 }
+int gp_set_relax_launch_hook(gp_ctx* c, gp_launch_hook hook, void* user) { c->hook = hook; c->hook_user = user; return GP_OK; }
 int gp_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n, const gp_dp_params* p) { c->pairs.assign(pairs, pairs + n); c->params = *p; return GP_OK; }
 int gp_launch_resident(gp_ctx*) { return GP_OK; }
 int gp_fetch_results(gp_ctx* c, gp_result* out, uint64_t n)
@@ -131,6 +134,7 @@ int gp_reserve(gp_ctx*, uint64_t, uint32_t, uint64_t, uint64_t) { return GP_OK; 
 int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n, const gp_dp_params* p, gp_result* out, uint32_t* merged_len)
 {
     if (getenv("GP_SHIM_NO_RELAX")) return GP_ERR_RANGE;
+    if (c->hook) c->hook(c->hook_user);                   // "the kernel is enqueued"
     std::vector<std::string> merged(n);
     for (uint64_t k = 0; k < n; ++k) {
         const std::string& row = steps[k].parent < 0 ? c->seqs[steps[k].row_seq] : merged[steps[k].parent];

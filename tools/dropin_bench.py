@@ -32,7 +32,7 @@ def write_gaps(td, config, n_gaps, seed):
     return lst
 
 
-def run_binary(binary, lst, gpus, streams, extra=(), chunk_gaps=512):
+def run_binary(binary, lst, gpus, streams, extra=(), chunk_gaps=256):
     t0 = time.perf_counter()
     p = subprocess.run([binary] + FLAGS + ["-t", "5", "--batch", lst, "--gpus", str(gpus), "--streams", str(streams), "--chunk-gaps", str(chunk_gaps),
                         "--no-gml", "--stats"] + list(extra),
@@ -49,9 +49,10 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--streams", type=int, default=2, help="mergers (host thread + context + stream) per GPU; they alternate on the device")
-    ap.add_argument("--chunk-gaps", type=int, default=512, help="gaps per chunk of the batch pipeline")
+    ap.add_argument("--chunk-gaps", type=int, default=256, help="gaps per chunk of the batch pipeline")
     ap.add_argument("--ref-gaps", type=int, default=2, help="gaps also run through the reference binary (0: skip)")
     ap.add_argument("--verify-gpus1", type=int, default=0, help="with --gpus > 1: run the first K gaps again on one GPU and compare bytes")
+    ap.add_argument("--ref-procs", type=int, default=0, help="also run this many gaps through the reference binary CONCURRENTLY at -t 1 (GAPPadder's process-pool shape, SURVEY 8d)")
     ap.add_argument("--config", default="cfg1")
     ap.add_argument("--repeat", type=int, default=1, help="timed runs of the batch; the fastest is reported (the first pays page-cache and module load)")
     args = ap.parse_args()
@@ -101,6 +102,22 @@ def main():
                 t_ref += time.perf_counter() - t0
                 same = same and (r.stdout, open(info, "rb").read()) == outs[g]
             line["reference"] = {"gaps": n, "cores": cores, "seconds": t_ref, "gaps_per_s": n / t_ref, "outputs_identical": same}
+        if args.ref_procs and os.path.exists(ref):
+            n = min(args.ref_procs, args.gaps)
+            t0 = time.perf_counter()
+            ps = []
+            for g in range(n):
+                wd = os.path.join(td, "rp%d" % g)                        # the reference drops ./tmp.gml: one directory per process
+                os.makedirs(wd)
+                ps.append(subprocess.Popen([ref] + FLAGS + ["-t", "1", "-o", os.path.join(wd, "x.info"), os.path.join(td, "g%d.fa" % g)],
+                                           cwd=wd, stdout=open(os.path.join(wd, "x.out"), "wb"), stderr=subprocess.DEVNULL))
+            for q in ps:
+                q.wait()
+            t_ref = time.perf_counter() - t0
+            same = all((open(os.path.join(td, "rp%d" % g, "x.out"), "rb").read(), open(os.path.join(td, "rp%d" % g, "x.info"), "rb").read())
+                       == (open(os.path.join(td, "g%d.out" % g), "rb").read(), open(os.path.join(td, "g%d.info" % g), "rb").read()) for g in range(n))
+            line["reference_process_pool"] = {"gaps": n, "procs": n, "threads_each": 1, "cores": cores, "seconds": t_ref, "gaps_per_s": n / t_ref,
+                                              "outputs_identical": same}
         print(json.dumps(line))
     return 0
 

@@ -32,10 +32,8 @@ PY
     ncu_flank) timeout 900 ncu --set full --clock-control none --import-source on -k regex:flank_place -s 1 -c 1 -o $O/${TAG}_flank -f python bench.py --config cfg2 --steps 1 --warmup 1 --no-cpu > $O/${TAG}_ncu_flank.log 2>&1 ;;
     ncu_qc)  timeout 900 ncu --set full --clock-control none --import-source on -k regex:quick_check -s 1 -c 1 -o $O/${TAG}_qc -f python tools/quickcheck_bench.py --reps 2 > $O/${TAG}_ncu_qc.log 2>&1 ;;
     streams) for sN in 1 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --repeat 3 --streams $sN > $O/${TAG}_dropin_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_dropin_s$sN.json').read().strip().splitlines()[-1]); print('streams $sN', d['merge_ms'], d['gaps_per_s'], d.get('detail_ms'))"; done ;;
-    pipe)    for cg in 200 100 64 32; do for sN in 1 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --repeat 3 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg1 x200 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d.get('detail_ms'))"; done; done
-             for cg in 400 200 100 64; do for sN in 1 2; do timeout 300 python tools/dropin_bench.py --config cfg3 --seed 5000 --gaps 1600 --ref-gaps 0 --repeat 2 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe3_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe3_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg3 x1600 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d.get('detail_ms'))"; done; done ;;
-    dedup)   timeout 900 python -m pytest tests/test_gpu_dedup.py -q > $O/${TAG}_pytest_dedup.log 2>&1; tail -5 $O/${TAG}_pytest_dedup.log
-             timeout 600 python tools/dedup_bench.py > $O/${TAG}_dedup.json 2> $O/${TAG}_dedup.err; cat $O/${TAG}_dedup.json ;;
+    pipe)    for cg in 200 100 67 50; do for sN in 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 1 --repeat 3 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg1 x200 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d['reference']['outputs_identical'], d.get('detail_ms'))"; done; done
+             for cg in 400 200 100 64; do for sN in 2 3; do timeout 300 python tools/dropin_bench.py --config cfg3 --seed 5000 --gaps 1600 --ref-gaps 0 --repeat 2 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe3_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe3_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg3 x1600 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d.get('detail_ms'))"; done; done ;;
     ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
     *) echo "unknown: $w" ;;
