@@ -266,6 +266,16 @@ def dropin_line(args, world):
     if world == 1 and args.config == "cfg1":
         d = _dropin_tool(["--gaps", str(args.gaps), "--seed", str(args.seed), "--ref-gaps", "1", "--repeat", "2"])
         out["cfg1"] = {k: d[k] for k in DROPIN_KEEP if k in d}
+        # the dedup stage around every merge, same gaps as contig sets: sets per second for both rules
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "dedup_bench.py"), "--sets", str(args.gaps), "--repeat", "2"],
+                               capture_output=True, text=True, timeout=300)
+            dd = json.loads(p.stdout.strip().splitlines()[-1])
+            out["dedup"] = {"parity": dd.get("parity"), "sets": dd.get("sets"),
+                            "contained_rule": {k: dd["g"][k] for k in ("contigs", "removed", "pairs", "dp_gcells", "dedup_ms", "device_ms", "sets_per_s", "gcups") if k in dd.get("g", {})},
+                            "duplicate_rule": {k: dd["p"][k] for k in ("contigs", "removed", "pairs", "dp_gcells", "dedup_ms", "device_ms", "sets_per_s", "gcups") if k in dd.get("p", {})}}
+        except Exception as e:                               # the bench line must not depend on it
+            out["dedup"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     d = _dropin_tool(["--config", "cfg3", "--gaps", str(args.dropin_gaps), "--seed", "5000", "--gpus", str(world), "--ref-gaps", "0",
                       "--verify-gpus1", "32" if world > 1 else "0", "--repeat", "2"])
     out["strong"] = {k: d[k] for k in DROPIN_KEEP if k in d}

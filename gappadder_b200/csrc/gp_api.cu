@@ -933,16 +933,20 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
         GP_CUDA(c, cudaMemcpyAsync(c->d_rx_queue.p, q, 64, cudaMemcpyHostToDevice, c->stream));
     }
     unsigned int* ctrl = (unsigned int*)c->d_rx_queue.p;
+    // diagnostic: GP_RELAX_TRACE=<file> dumps every item's begin / end time (ns) and size after the launch
+    static const char* trace_path = getenv("GP_RELAX_TRACE");
+    unsigned long long* d_trace = nullptr;
+    if (trace_path) { GP_CUDA(c, cudaMalloc(&d_trace, (size_t)n * 24)); GP_CUDA(c, cudaMemsetAsync(d_trace, 0, (size_t)n * 24, c->stream)); }
     const size_t smem = gp::wf16c_smem_bytes<gp::WF16C_THREADS / 32>();
     GP_CUDA(c, cudaEventRecord(c->rx_ev[0], c->stream));
     if (pot2)
         gp::relax_chain_kernel<true><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
             (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, ring_total, d_ring, ctrl,
-            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
+            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p, d_trace);
     else
         gp::relax_chain_kernel<false><<<blocks, gp::WF16C_THREADS, smem, c->stream>>>(
             (const uint32_t*)c->d_packed.p, (uint32_t*)c->d_arena.p, (const gp::RelaxItem*)c->d_rx_items.p, d_subtree, n, ring_total, d_ring, ctrl,
-            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p);
+            c->p16c, (uint32_t*)c->d_scratch16c.p, stride, d_mlen, (gp::DevResult*)c->d_rx_results.p, d_trace);
     GP_CUDA(c, cudaGetLastError());
     GP_CUDA(c, cudaEventRecord(c->rx_ev[1], c->stream));
     if (c->relax_hook) c->relax_hook(c->relax_hook_user);         // the kernel is enqueued: a caller may queue other work behind it
@@ -952,6 +956,16 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     GP_CUDA(c, cudaMemcpyAsync(ho + (size_t)n * sizeof(gp::DevResult), d_mlen, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaMemcpyAsync((uint32_t*)c->h_queue.p + 32, c->d_rx_queue.p, 64, cudaMemcpyDeviceToHost, c->stream));
     GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (d_trace) {
+        std::vector<unsigned long long> tr((size_t)n * 3);
+        cudaMemcpy(tr.data(), d_trace, (size_t)n * 24, cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+            for (uint32_t k = 0; k < n; ++k)
+                fprintf(f, "%u %d %llu %llu %llu %llu\n", k, steps[k].parent, tr[3 * (size_t)k], tr[3 * (size_t)k + 1], tr[3 * (size_t)k + 2] >> 32, tr[3 * (size_t)k + 2] & 0xffffffffull);
+            fclose(f);
+        }
+    }
     memcpy(out, ho, (size_t)n * sizeof(gp_result));
     const uint32_t* dev_mlen = (const uint32_t*)(ho + (size_t)n * sizeof(gp::DevResult));
     c->rx_second_passes = ((const uint32_t*)c->h_queue.p)[32 + 8];

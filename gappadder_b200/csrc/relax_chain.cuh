@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(WF16C_THREADS, WF16C_CTAS_PER_SM)
 relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ arena, const RelaxItem* __restrict__ items,
                    const uint32_t* __restrict__ subtree, uint32_t n_items, uint32_t ring_total, uint32_t* __restrict__ ring, unsigned int* __restrict__ ctrl,
                    Wf16cParams P, uint32_t* __restrict__ scratch, uint32_t scratch_stride, uint32_t* __restrict__ mlen,
-                   DevResult* __restrict__ out)
+                   DevResult* __restrict__ out, unsigned long long* __restrict__ trace)
 {
     constexpr int TEAM = WF16C_THREADS / 32;
     extern __shared__ uint32_t wf16c_smem[];
@@ -124,6 +124,8 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
         }
         const uint32_t id = (uint32_t)cur;
         const RelaxItem it = items[id];
+        unsigned long long t_begin = 0;
+        if (trace && leader) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_begin));   // diagnostic (GP_RELAX_TRACE): per-item timeline
         const uint32_t* row_base = packed;
         uint32_t row_off = it.row_off, m = it.row_len;
         if (it.parent >= 0) {                                       // the parent is finished: we followed it, or its push released us
@@ -166,6 +168,11 @@ relax_chain_kernel(const uint32_t* __restrict__ packed, uint32_t* __restrict__ a
                     st_release_u32(ring + atomicAdd(ctrl + 1, 1u), (uint32_t)c);
             }
             atomicAdd(ctrl + 2, 1u);
+            if (trace) {
+                unsigned long long t_end;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+                trace[3 * (size_t)id] = t_begin; trace[3 * (size_t)id + 1] = t_end; trace[3 * (size_t)id + 2] = ((unsigned long long)m << 32) | (unsigned long long)(uint32_t)n;
+            }
         }
         cur = it.first_child;
         __syncthreads();                                             // mlen[id] is written before anyone of this CTA reads it

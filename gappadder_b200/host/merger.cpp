@@ -162,11 +162,13 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
         }
         const size_t nc = s.contigs.size();
         s.node_seq.reserve(2 * nc); s.node_name.reserve(2 * nc);
-        for (const FastaRecord& r : s.contigs) {
-            s.node_seq.push_back(r.seq);
+        for (FastaRecord& r : s.contigs) {                                // the record's letters MOVE into node 2c (no copy); contigs keep the names
+            s.node_seq.push_back(std::move(r.seq));
+            const std::string& fwd = s.node_seq.back();
             s.node_name.push_back(r.name);
-            s.node_seq.emplace_back(r.seq.size(), 'N');
-            if (!r.seq.empty()) gp_revcomp(r.seq.data(), (uint32_t)r.seq.size(), &s.node_seq.back()[0]);
+            std::string rc(fwd.size(), 'N');
+            if (!fwd.empty()) gp_revcomp(fwd.data(), (uint32_t)fwd.size(), &rc[0]);
+            s.node_seq.push_back(std::move(rc));
             s.node_name.push_back(r.name + "_R");                         // :785-787
         }
         {   // letters besides A C G T N: rename per gap (see GapState::dp_seq).  One pass over the bases: which letters occur
@@ -183,10 +185,11 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             bool seen[256] = {false};
             int n_other = 0;
             for (int b = 0; b < 256; ++b) s.letter_map[b] = (unsigned char)b;
-            for (const FastaRecord& r : s.contigs) {
-                if (r.seq.size() > 16382 || r.seq.empty()) s.acgt_only = false;
+            for (size_t c = 0; c < nc; ++c) {
+                const std::string& seq = s.node_seq[2 * c];
+                if (seq.size() > 16382 || seq.empty()) s.acgt_only = false;
                 unsigned any_not_acgt = 0;
-                for (unsigned char ch : r.seq) {
+                for (unsigned char ch : seq) {
                     any_not_acgt |= K.not_acgt[ch];
                     if (K.other[ch] && !seen[ch]) {
                         seen[ch] = true;
@@ -280,16 +283,27 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             gp_quick_check_stats(ctx, &ms, &bases, &items);
             timings->qc_kernel_ms += ms; timings->qc_bases += bases; timings->qc_items += items;
         }
-        for (size_t q = 0; q < n_dev; ++q) {
+        // the pair list off the hit matrices, row by row (the host filter's order): counts, offsets, then every gap fills its slice
+        std::vector<uint64_t> cnt(n_dev + 1, 0);
+        for_each_gap(n_dev, host_threads, [&](size_t q) {
+            const uint64_t n = gap_first[q + 1] - gap_first[q];
+            const uint8_t* h = hit.data() + hoff[q];
+            uint64_t k = 0;
+            for (uint64_t i = 0; i < n; ++i) for (uint64_t j = i; j < n; ++j) k += h[i * n + j] != 0;
+            cnt[q + 1] = k;
+        });
+        for (size_t q = 0; q < n_dev; ++q) cnt[q + 1] += cnt[q];
+        pairs.resize(cnt[n_dev]);
+        for_each_gap(n_dev, host_threads, [&](size_t q) {
             GapState& s = st[order[q]];
-            s.pair_begin = pairs.size();
+            s.pair_begin = cnt[q]; s.pair_end = cnt[q + 1];
             const uint32_t n = gap_first[q + 1] - gap_first[q];
             const uint8_t* h = hit.data() + hoff[q];
+            gp_pair* w = pairs.data() + cnt[q];
             for (uint32_t i = 0; i < n; ++i)
                 for (uint32_t j = i; j < n; ++j)
-                    if (h[(size_t)i * n + j]) pairs.push_back(gp_pair{i + s.node_base, j + s.node_base});
-            s.pair_end = pairs.size();
-        }
+                    if (h[(size_t)i * n + j]) *w++ = gp_pair{i + s.node_base, j + s.node_base};
+        });
     }
     for (size_t q = n_dev; q < order.size(); ++q) {                       // host-filtered gaps
         GapState& s = st[order[q]];
@@ -602,7 +616,7 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             append_fasta(out[g].stdout_text, name, s.merged[mi++], 60);    // printFasta(cout): DEFAULT_LINE_LENGTH
             name_to_path.insert(std::make_pair(name, sub));
         }
-        for (const FastaRecord& r : s.contigs) append_fasta(out[g].stdout_text, r.name, r.seq, opt.line_length);
+        for (size_t c = 0; c < s.contigs.size(); ++c) append_fasta(out[g].stdout_text, s.contigs[c].name, s.node_seq[2 * c], opt.line_length);
         for (const auto& kv : name_to_path) out[g].info_text += kv.first + "  " + kv.second + "\n";   // :1555-1560
         out[g].wrote_info = true;
     });

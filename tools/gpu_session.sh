@@ -34,6 +34,12 @@ PY
     streams) for sN in 1 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --repeat 3 --streams $sN > $O/${TAG}_dropin_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_dropin_s$sN.json').read().strip().splitlines()[-1]); print('streams $sN', d['merge_ms'], d['gaps_per_s'], d.get('detail_ms'))"; done ;;
     pipe)    for cg in 200 100 67 50; do for sN in 2 3; do timeout 300 python tools/dropin_bench.py --gaps 200 --ref-gaps 1 --repeat 3 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg1 x200 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d['reference']['outputs_identical'], d.get('detail_ms'))"; done; done
              for cg in 400 200 100 64; do for sN in 2 3; do timeout 300 python tools/dropin_bench.py --config cfg3 --seed 5000 --gaps 1600 --ref-gaps 0 --repeat 2 --streams $sN --chunk-gaps $cg > $O/${TAG}_pipe3_c${cg}_s$sN.json 2>/dev/null; python -c "import json; d=json.loads(open('$O/${TAG}_pipe3_c${cg}_s$sN.json').read().strip().splitlines()[-1]); print('cfg3 x1600 chunk $cg streams $sN', d['merge_ms'], round(d['gaps_per_s']), d.get('detail_ms'))"; done; done ;;
+    dedup)   timeout 900 python -m pytest tests/test_gpu_dedup.py -q > $O/${TAG}_pytest_dedup.log 2>&1; tail -5 $O/${TAG}_pytest_dedup.log
+             timeout 600 python tools/dedup_bench.py > $O/${TAG}_dedup.json 2> $O/${TAG}_dedup.err; cat $O/${TAG}_dedup.json ;;
+    cfg4)    timeout 1500 python tools/cfg4_bench.py --gpus ${CFG4_GPUS:-8,4,2,1} --gaps ${CFG4_GAPS:-50000} > $O/${TAG}_cfg4.json 2> $O/${TAG}_cfg4.err; cut -c1-3000 $O/${TAG}_cfg4.json; tail -3 $O/${TAG}_cfg4.err ;;
+    refpool) timeout 900 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --ref-procs 16 --repeat 2 > $O/${TAG}_dropin_refpool.json 2> $O/${TAG}_dropin_refpool.err; cut -c1-2500 $O/${TAG}_dropin_refpool.json ;;
+    rtrace)  timeout 600 python tools/relax_trace.py > $O/${TAG}_relax_trace.json 2> $O/${TAG}_relax_trace.err; cut -c1-600 $O/${TAG}_relax_trace.json ;;
+    lone)    timeout 600 python tools/lone_pair_bench.py > $O/${TAG}_lone_pair.json 2> $O/${TAG}_lone_pair.err; cat $O/${TAG}_lone_pair.err ;;
     ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
     *) echo "unknown: $w" ;;
