@@ -33,10 +33,15 @@ build/ContigsMerger_b200: $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(H
 build/microbench_int: tools/microbench_int.cu | build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
 
+# diagnostic library with phase stamps in the certificate kernel (tools/lone_pair_bench.py --trace); never the product
+trace: | build
+	$(NVCC) $(NVFLAGS) -DGP_WF16C_TRACE -c $(CSRC)/gp_api.cu -o build/gp_api_trace.o
+	$(NVCC) $(ARCH) -shared -o build/libgappadder_b200_trace.so build/gp_api_trace.o build/int_peak.o build/gp_host.o -cudart static
+
 oracle:
 	$(MAKE) -C oracle all
 	./oracle/build_ref.sh
 
 clean:
 	rm -rf build $(LIB)
-.PHONY: all oracle clean
+.PHONY: all oracle clean trace

@@ -8,7 +8,8 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libgappadder_b200.so")
+# GAPPADDER_B200_LIB: another build of the same library (the diagnostic `make trace` build); never a different implementation
+lib_path = os.environ.get("GAPPADDER_B200_LIB") or os.path.join(_HERE, "libgappadder_b200.so")
 
 # every symbol include/gappadder_b200.h declares (tests check that each one is exported)
 EXPORTS = [

@@ -987,6 +987,27 @@ int gp_relax_chains(gp_ctx* c, const gp_relax_step* steps, uint64_t n_steps, con
     return GP_OK;
 }
 
+#if defined(GP_WF16C_TRACE)
+// Diagnostic build: writes the stamps of gp_trace (overlap_wf16c.cuh) as "time_ns block warp tag value" lines and clears them.
+extern "C" int gp_debug_trace_dump(const char* path)
+{
+    unsigned int n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return GP_ERR_CUDA;
+    cudaMemcpyFromSymbol(&n, gp::gp_trace_n, sizeof n);
+    if (n > (1u << 16)) n = 1u << 16;
+    std::vector<unsigned long long> buf((size_t)3 * n);
+    if (n) cudaMemcpyFromSymbol(buf.data(), gp::gp_trace_buf, (size_t)24 * n);
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(gp::gp_trace_n, &zero, sizeof zero);
+    FILE* f = fopen(path, "w");
+    if (!f) return GP_ERR_INVALID;
+    for (unsigned int i = 0; i < n; ++i)
+        fprintf(f, "%llu %llu %llu %llu %llu\n", buf[3 * i], buf[3 * i + 1] >> 32, (buf[3 * i + 1] >> 16) & 0xffff, buf[3 * i + 1] & 0xffff, buf[3 * i + 2]);
+    fclose(f);
+    return (int)n;
+}
+#endif
+
 int gp_set_relax_launch_hook(gp_ctx* c, gp_launch_hook hook, void* user)
 {
     if (!c) return GP_ERR_INVALID;

@@ -225,13 +225,22 @@ GP_HD uint32_t lane16c_max(const Lane16c<K>& st)
     if (K == 8) a = p_max3_2(p_max3_2(a, st.W[4], st.W[5]), st.W[6], st.W[7]);
     return a;
 }
-// Free-moves layout: row k of either group sits 2*k higher than row 0, i.e. 4*k in V.
+// Free-moves layout: row k of either group sits 2*k higher than row 0, i.e. 4*k in V.  The offsets go on with independent
+// packed adds (the FMA-heavy pipe, which has room) and the maximum is a tree of 3-input maxima: three levels deep instead
+// of a chain of K add-max instructions on the ALU pipe.  A filter step hangs off the DP step's own K-deep max chain, so
+// the chain doubled the latency of every filter block -- 215 against 88 clocks per step for a warp that has its scheduler
+// to itself (the tail of a relax launch; tools/lone_pair_bench.py --trace) -- and cost four more ALU slots per step.
 template <int K>
 GP_HD uint32_t lane16c_max_pot2(const Lane16c<K>& st)
 {
-    uint32_t a = st.W[0];
+    uint32_t t[K];
+    t[0] = st.W[0];
 #pragma unroll
-    for (int k = 1; k < K; ++k) a = p_addmax2(st.W[k], (uint32_t)((-4 * k) & 0xffff) * 0x00010001u, a);
+    for (int k = 1; k < K; ++k) t[k] = p_add2(st.W[k], (uint32_t)((-4 * k) & 0xffff) * 0x00010001u);
+    uint32_t a = t[0];
+    if (K == 2) a = p_max2(a, t[1]);
+    if (K >= 4) a = p_max2(p_max3_2(a, t[1], t[2]), t[3]);
+    if (K == 8) a = p_max3_2(a, p_max3_2(t[4], t[5], t[6]), t[7]);
     return a;
 }
 
@@ -427,6 +436,29 @@ GP_HD Wf16Strip wf16c_next_strip(int i0, int m, int C)
 #if defined(__CUDACC__)
 // ---- device side ------------------------------------------------------------------------------
 
+// Diagnostic build only (-DGP_WF16C_TRACE, `make trace`; tools/lone_pair_bench.py --trace): lane 0 of every warp stamps the
+// phases of a pair -- probe, boundary line, every strip's set-up / first block / end -- with the SM clock.
+#if defined(GP_WF16C_TRACE)
+__device__ unsigned long long gp_trace_buf[3 * (1 << 16)];
+__device__ unsigned int gp_trace_n = 0;
+__device__ __forceinline__ void gp_trace(uint32_t tag, uint32_t val)
+{
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned int i = atomicAdd(&gp_trace_n, 1u);
+        if (i < (1u << 16)) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            gp_trace_buf[3 * i] = t;
+            gp_trace_buf[3 * i + 1] = ((unsigned long long)blockIdx.x << 32) | ((unsigned long long)(threadIdx.x >> 5) << 16) | tag;
+            gp_trace_buf[3 * i + 2] = val;
+        }
+    }
+}
+#define GP_TRACE(tag, val) gp_trace(tag, val)
+#else
+#define GP_TRACE(tag, val) ((void)0)
+#endif
+
 struct Wf16cWarp {                      // warp-uniform state of one pass
     const uint32_t* packed;             // the column sequence's table
     const uint32_t* packed_row;         // the row sequence's (the same table, or the relax chain's arena of merged contigs)
@@ -526,6 +558,7 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     const uint32_t oring_base = ring_base + 2 * WF16C_RING * 4;
     constexpr uint32_t OR_OFF = 2 * WF16C_RING * 4;                // bottom-row ring slot of the input-ring slot at the same index
     const uint32_t my_tab = tab_base + lane * LANE_BYTES;
+    GP_TRACE(10, (uint32_t)i0);
 
     // ---- increment table of this lane's rows ---------------------------------------------------
     {
@@ -576,7 +609,9 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         if constexpr (TEAM > 1) return __ldcg(bnd + jj);
         else return bnd[jj];
     };
+    GP_TRACE(11, (uint32_t)i0);
     wait_cols(32);
+    GP_TRACE(12, (uint32_t)i0);
     { const int jj = 1 + lane; ring_put(jj, bnd_load(jj <= n + 1 ? jj : n + 1)); }
     Lane16c<K> st;
     lane16c_begin<K>(st, g, itop, irel_top);
@@ -717,10 +752,13 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         }
         if (have_next) ring_put(tb + 32 + lane, next_line);
         __syncwarp();
+        if (tb == 1 || tb == 97 || tb + 32 > t_end || (tb <= n - 160 && tb + 32 > n - 160)) GP_TRACE(13, (uint32_t)tb);
     }
+    GP_TRACE(14, (uint32_t)i0);
     if (snapA != WF16C_NO_SNAP && wf16c_score_of(snapA) >= S0)
         best = wf16c_cold(snap_bufs, K, g.tr ? 3 : 1, 0u, m, n, g.C, itop, 0, S0, pot2, best);
     __syncwarp();
+    GP_TRACE(15, (uint32_t)i0);
     return best;
 }
 
@@ -742,6 +780,7 @@ __device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P,
         w.bnd[j] = wf16c_line_word(w.g, j, cj, cp);
     }
     if constexpr (TEAM > 1) { __threadfence_block(); __syncthreads(); } else __syncwarp();
+    GP_TRACE(3, (uint32_t)n);
     long long best = wf16c_initial_best(w.g);
     int i0 = 0, idx = 0;
     while (i0 < m) {
@@ -760,6 +799,7 @@ __device__ __noinline__ long long wf16c_pass(Wf16cWarp& w, const Wf16cParams& P,
         ++idx;
     }
     best = warp_max_key(best);
+    GP_TRACE(4, (uint32_t)m);
     if constexpr (TEAM > 1) {
         if (lane == 0) team_keys[w.team_warp] = best;
         __syncthreads();
@@ -819,9 +859,12 @@ __device__ __forceinline__ uint32_t wf16c_solve_pair(Wf16cWarp& w, const Wf16cPa
                                                      bool leader, unsigned int* __restrict__ counters, DevResult& r, long long& key_out, bool tr = false)
 {
     const int m = (int)w.pd.m, n = (int)w.pd.n;                           // of the computed table (tr: the reference's n, m)
+    GP_TRACE(1, (uint32_t)m);
     const int sys0 = force_sys != 0u ? (int)force_sys - 1 : wf16c_predict_system<(TEAM > 1)>(w.packed_row, w.packed, w.pd);
     w.g = wf16c_make_pass(m, n, P, sys0, false, 0, tr);
+    GP_TRACE(2, (uint32_t)sys0);
     const long long key = wf16c_pass<STD, TEAM, POT2>(w, P, team_keys);
+    GP_TRACE(5, 0u);
     uint32_t origin = wf16c_certified_origin(w.g, key);
     store_result(&r, key & ~3ll, tr ? n : m, tr ? m : n, FLAG_KERNEL16);  // exact score / ends / clip, the reference's orientation; origin still open
     for (int attempt = 1; attempt <= 2 && origin == 0u; ++attempt) {

@@ -40,6 +40,7 @@ PY
     refpool) timeout 900 python tools/dropin_bench.py --gaps 200 --ref-gaps 0 --ref-procs 16 --repeat 2 > $O/${TAG}_dropin_refpool.json 2> $O/${TAG}_dropin_refpool.err; cut -c1-2500 $O/${TAG}_dropin_refpool.json ;;
     rtrace)  timeout 600 python tools/relax_trace.py > $O/${TAG}_relax_trace.json 2> $O/${TAG}_relax_trace.err; cut -c1-600 $O/${TAG}_relax_trace.json ;;
     lone)    timeout 600 python tools/lone_pair_bench.py > $O/${TAG}_lone_pair.json 2> $O/${TAG}_lone_pair.err; cat $O/${TAG}_lone_pair.err ;;
+    lonetrace) GAPPADDER_B200_LIB=build/libgappadder_b200_trace.so timeout 600 python tools/lone_pair_bench.py --trace > /dev/null 2> $O/${TAG}_lone_trace.txt; head -150 $O/${TAG}_lone_trace.txt ;;
     ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
     *) echo "unknown: $w" ;;

@@ -17,7 +17,35 @@ def rand(rng, n):
     return bytes(rng.choice(b"ACGT") for _ in range(n))
 
 
+def trace_one(m, n, mode):
+    """Diagnostic build (make trace; GAPPADDER_B200_LIB=build/libgappadder_b200_trace.so): phase stamps of one pair."""
+    import ctypes
+    rng = random.Random(7)
+    col = rand(rng, n)
+    row = rand(rng, m - n // 2) + col[:n // 2]
+    L = g.lib()
+    with g.Context(0) as ctx:
+        ctx.set_team_mode(mode)
+        ctx.overlap_batch([row, col], [(0, 1)])
+        L.gp_debug_trace_dump(b"/dev/null")
+        ctx.overlap_batch([row, col], [(0, 1)])
+        path = os.path.join(ROOT, "gpurun_out", "wf16c_trace_%d_%d_mode%d.txt" % (m, n, mode))
+        k = L.gp_debug_trace_dump(path.encode())
+        ctx.set_team_mode(0)
+    rows = [tuple(int(x) for x in ln.split()) for ln in open(path)]
+    rows.sort()
+    t0 = rows[0][0]
+    names = {1: "pair", 2: "probed", 3: "line", 4: "strips_done", 5: "pass_done", 10: "strip", 11: "table", 12: "waited", 13: "block", 14: "blocks_done", 15: "strip_end"}
+    print("trace %d x %d mode %d: %d stamps" % (m, n, mode, k), file=sys.stderr)
+    for t, blk, warp, tag, val in rows:
+        print("  %9.2f us  warp %d  %-12s %d" % ((t - t0) / 1e3, warp, names.get(tag, str(tag)), val), file=sys.stderr)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--trace":
+        trace_one(12000, 2000, 2)
+        trace_one(12000, 2000, 1)
+        return
     rng = random.Random(7)
     out = []
     with g.Context(0) as ctx:
