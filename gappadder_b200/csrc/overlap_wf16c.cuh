@@ -632,10 +632,10 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
     uint32_t snap_idx = 0;
     snap_bufs[2 * K + 1] = (uint32_t)WF16C_NO_SNAP;
     snap_bufs[2 * K + 2] = 0u;
-    auto fire_path = [&](int jj, uint32_t acc) {                          // this lane fired at lo column jj
+    auto fire_path = [&](const uint32_t (&W)[K], int jj, uint32_t acc) { // this lane fired at lo column jj, holding registers W then
         uint32_t* cur = snap_bufs + (1u - snap_idx) * K;
 #pragma unroll
-        for (int k = 0; k < K; ++k) cur[k] = st.W[k];
+        for (int k = 0; k < K; ++k) cur[k] = W[k];
         best = wf16c_cold(snap_bufs, K, g.tr ? 2 : 0, acc, m, n, g.cell ? -1 : g.C, itop, jj, S0, pot2, best);
         snapA = (int)snap_bufs[2 * K + 1];
         snap_idx = snap_bufs[2 * K + 2];
@@ -663,7 +663,8 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         uint32_t inc[K];
         uint32_t w0 = lds32(p), w1 = lds32(p + 4);
         lds_inc<K>(inc, my_tab + (w0 >> 16));
-        auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj) {
+        // One step without the fire handling: `fire` / `acc` say whether this lane holds a candidate after it.
+        auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj, bool& fire, uint32_t& acc) {
             // Where the shuffle goes out is a scheduling matter (its result is needed a step from now): first thing
             // under the free-moves layout, whose short max chain hides less latency (ptxas otherwise parks the copy
             // of the loop-carried value right behind it: 7 % of the kernel waiting), behind the loads otherwise.
@@ -674,8 +675,8 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             lds_inc<K>(inc, my_tab + (next_word >> 16));
             if (!POT2) recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             if (lane == 0) recv = word << 16;
-            bool fire = false;
-            uint32_t acc = 0u;
+            fire = false;
+            acc = 0u;
             if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
                 lane16c_chain<K, POT2>(st, recv, d, gup, gleft);
                 if (EDGE && jj == 1) lane16c_fix_first<K>(st, g, itop, irel_top);
@@ -685,37 +686,52 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
                     fire = filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
                 }
             }
-            if (FILT) {
-                if (__any_sync(FULL, fire)) {                             // warp-uniform: every lane runs every step
-                    if (fire) fire_path(jj, acc);
-                    share_floor();
-                }
-                nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
-            }
+            if (FILT) nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
         };
         if constexpr (!EDGE && !FILT) {
             // the steady loop: full blocks (cnt == 32), four steps per iteration so that the loop-carried copies (ring
             // words, increment registers) are paid once per four steps -- they run on the same pipe as the packed adds
+            bool f;
+            uint32_t a;
 #pragma unroll 1
             do {
                 const uint32_t w2 = lds32(p + 8);
-                step(w0, w1, p + OR_OFF, j);
+                step(w0, w1, p + OR_OFF, j, f, a);
                 const uint32_t w3 = lds32(p + 12);
-                step(w1, w2, p + OR_OFF + 4, j + 1);
+                step(w1, w2, p + OR_OFF + 4, j + 1, f, a);
                 const uint32_t w4 = lds32(p + 16);
-                step(w2, w3, p + OR_OFF + 8, j + 2);
+                step(w2, w3, p + OR_OFF + 8, j + 2, f, a);
                 const uint32_t w5 = lds32(p + 20);
-                step(w3, w4, p + OR_OFF + 12, j + 3);
+                step(w3, w4, p + OR_OFF + 12, j + 3, f, a);
                 w0 = w4; w1 = w5;
                 p += 16; j += 4;
             } while (p != p_end);
         } else {
+            // Two steps per iteration and ONE vote for both: a vote after every step makes the next step wait for this
+            // step's whole max chain (no overlap between steps: 215 against 88 clocks per step for a warp alone on its
+            // scheduler).  The first step's registers are kept until the vote; its fire is resolved before the second's, so
+            // the cold function sees the steps in order.  The second step's threshold is the one before the first step's
+            // fire -- staler, i.e. lower: the fire test is a superset filter, the cold function decides.
 #pragma unroll 1
             do {
                 const uint32_t w2 = lds32(p + 8);
-                step(w0, w1, p + OR_OFF, j);
+                bool f0, f1;
+                uint32_t a0, a1;
+                step(w0, w1, p + OR_OFF, j, f0, a0);
+                CVals<K> first;
+                if (FILT) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) first.W[k] = st.W[k];
+                }
                 const uint32_t w3 = lds32(p + 12);
-                step(w1, w2, p + OR_OFF + 4, j + 1);
+                step(w1, w2, p + OR_OFF + 4, j + 1, f1, a1);
+                if (FILT) {
+                    if (__any_sync(FULL, f0 || f1)) {                     // warp-uniform: every lane runs every step
+                        if (f0) fire_path(first.W, j, a0);
+                        if (f1) fire_path(st.W, j + 1, a1);
+                        share_floor();
+                    }
+                }
                 w0 = w2; w1 = w3;
                 p += 8; j += 2;
             } while (p != p_end);
