@@ -677,13 +677,29 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             if (lane == 0) recv = word << 16;
             fire = false;
             acc = 0u;
-            if (!EDGE || (uint32_t)(jj - 1) <= (uint32_t)n) {
+            if constexpr (!EDGE) {
                 lane16c_chain<K, POT2>(st, recv, d, gup, gleft);
-                if (EDGE && jj == 1) lane16c_fix_first<K>(st, g, itop, irel_top);
                 if (do_store) sts32(oaddr, st.W[K - 1]);
                 if (FILT) {
                     acc = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr);
                     fire = filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
+                }
+            } else {
+                // Edge blocks: some lanes are outside columns 1..n+1.  Every lane computes the step and the lanes outside keep
+                // their old registers by SELECTS, not by a branch around the max chain: a branch there keeps the compiler from
+                // scheduling the step's other work (next increments, ring words, shuffles) under the chain's latency, and a
+                // warp that has its scheduler to itself ran such blocks at 184 clocks per step against 88.
+                const bool in = (uint32_t)(jj - 1) <= (uint32_t)n;
+                Lane16c<K> nx = st;
+                lane16c_chain<K, POT2>(nx, recv, d, gup, gleft);
+                if (jj == 1) lane16c_fix_first<K>(nx, g, itop, irel_top);
+#pragma unroll
+                for (int k = 0; k < K; ++k) st.W[k] = in ? nx.W[k] : st.W[k];
+                st.up0_prev = in ? nx.up0_prev : st.up0_prev;
+                if (do_store && in) sts32(oaddr, st.W[K - 1]);
+                if (FILT) {
+                    acc = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr);
+                    fire = in && filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
                 }
             }
             if (FILT) nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
