@@ -8,8 +8,8 @@ Workload (`config.workload`): BASELINE.json configs[0], the synthetic 200-gap Co
 (40 Velvet-style contigs per gap, 300-3000 bp, 8 kb locus, GAPPadder's flags -i1 -2 -i2 -2 -y 50
 -k 10): every candidate pair of the all-vs-all pairwise phase (contigs + reverse complements, k-mer
 quick check) of every gap.  configs[1] ("TERefiner contig-to-flank") has no DP in the reference
- and is not a bench line.  One step = one pass of the hot path over the whole
-200-gap batch.  Each rank gets its own 200 gaps (seeds offset by rank): weak scaling, no collective
+(SURVEY.md section 0.3); its builder-defined semi-global form is `--config cfg2`.  One step = one pass of the hot
+path over the whole 200-gap batch.  Each rank gets its own 200 gaps (seeds offset by rank): weak scaling, no collective
 on the data path.
 
   value     GCUPS with sequences and pair lists already resident in HBM (CUDA events on the library's
@@ -25,9 +25,15 @@ on the data path.
             restatement (kind "port") on the host cores, on a bounded sample of the same pair list
   parity_sample  (with cpu_baseline) 512 pairs (cfg5: 96) spread over the pair list: the timed end-to-end step's results
             against the oracle, field by field
-  dropin    (N = 1, cfg1) whole gaps per second through build/ContigsMerger_b200 --batch on the same gaps as FASTA
-            files -- read, quick check on the device, pairwise phase, graph, relax chains, output; outside
-            every timed region above (tools/dropin_bench.py)
+  dropin    whole gaps per second through build/ContigsMerger_b200 --batch (the chunk pipeline: readers, two mergers per GPU
+            behind a device gate, writers; FASTA reading and file writing inside the figure), outside every timed region
+            above (tools/dropin_bench.py): `cfg1` (N = 1) the bench workload's own gaps as FASTA files, one of them also through
+            the reference binary (bytes compared); `dedup` (N = 1) the dedup stage on the same gaps as contig sets
+            (tools/dedup_bench.py; rules pinned to TERefiner_1, alignment records builder-defined); `strong` (every N) one
+            fixed 1 600-gap cfg3-shaped job through --gpus N: gaps/s, per-GPU wall, imbalance, device-phase time of the
+            slowest GPU, first 32 gaps byte-compared with --gpus 1
+  hbm       the HBM-bound phases beside the DP: pack + upload, the quick-check kernel (bytes, ms, GB/s against
+            MEASURED_PEAKS.json), the result scatter
 
 `--impl reference` times only that CPU path (rank 0 only under torchrun).  `--config cfg3|cfg5` runs the other
 BASELINE shapes (cfg5: 10 kb contigs, 20 gaps); `--config cfg2` is BASELINE configs[1], flank placement: the semi-global kernel
