@@ -43,7 +43,11 @@ def test_fan2_modulo_allocator_order():
         B.check_paths_modulo_ties(info, out, gml, "fan2")
 
 
-@pytest.mark.parametrize("extra", [(), ("--streams", "2"), ("--host-quick-check",), ("--host-relax",)])
+@pytest.mark.parametrize("extra", [(), ("--streams", "2"), ("--host-quick-check",), ("--host-relax",),
+                                   # the chunk pipeline at its most concurrent: one gap per chunk, three mergers on the GPU, a relax
+                                   # kernel of one chunk running beside the pairwise kernel of the next (host/device_gate.hpp)
+                                   ("--chunk-gaps", "1", "--streams", "3"), ("--chunk-gaps", "2", "--streams", "2", "--no-gml"),
+                                   ("--chunk-gaps", "1", "--streams", "3", "--host-relax")])
 def test_batch_reference_bytes(extra):
     """All cases in one process (one sequence table, one pairwise launch, relax chains of all gaps together); the
     outputs must not depend on the batch, on the worker split or on where the quick check runs."""
