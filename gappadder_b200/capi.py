@@ -8,8 +8,14 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# GAPPADDER_B200_LIB: another build of the same library (the diagnostic `make trace` build); never a different implementation
-lib_path = os.environ.get("GAPPADDER_B200_LIB") or os.path.join(_HERE, "libgappadder_b200.so")
+# GAPPADDER_B200_LIB: another build of the SAME library (the diagnostic `make trace` build, build/libgappadder_b200_trace.so);
+# anything that is not a libgappadder_b200*.so is refused
+lib_path = os.path.join(_HERE, "libgappadder_b200.so")
+_override = os.environ.get("GAPPADDER_B200_LIB")
+if _override:
+    if not os.path.basename(_override).startswith("libgappadder_b200"):
+        raise ImportError("GAPPADDER_B200_LIB must name a build of libgappadder_b200 (got %r)" % _override)
+    lib_path = os.path.abspath(_override)
 
 # every symbol include/gappadder_b200.h declares (tests check that each one is exported)
 EXPORTS = [

@@ -663,8 +663,8 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
         uint32_t inc[K];
         uint32_t w0 = lds32(p), w1 = lds32(p + 4);
         lds_inc<K>(inc, my_tab + (w0 >> 16));
-        // One step without the fire handling: `fire` / `acc` say whether this lane holds a candidate after it.
-        auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj, bool& fire, uint32_t& acc) {
+        // One step of the DP, nothing else; `in`: this lane's lo column is inside 1..n+1 (always true outside edge blocks).
+        auto step = [&](uint32_t word, uint32_t next_word, uint32_t oaddr, int jj, bool& in) {
             // Where the shuffle goes out is a scheduling matter (its result is needed a step from now): first thing
             // under the free-moves layout, whose short max chain hides less latency (ptxas otherwise parks the copy
             // of the loop-carried value right behind it: 7 % of the kernel waiting), behind the loads otherwise.
@@ -675,21 +675,16 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
             lds_inc<K>(inc, my_tab + (next_word >> 16));
             if (!POT2) recv_next = __shfl_up_sync(FULL, st.W[K - 1], 1);
             if (lane == 0) recv = word << 16;
-            fire = false;
-            acc = 0u;
             if constexpr (!EDGE) {
+                in = true;
                 lane16c_chain<K, POT2>(st, recv, d, gup, gleft);
                 if (do_store) sts32(oaddr, st.W[K - 1]);
-                if (FILT) {
-                    acc = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr);
-                    fire = filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
-                }
             } else {
                 // Edge blocks: some lanes are outside columns 1..n+1.  Every lane computes the step and the lanes outside keep
                 // their old registers by SELECTS, not by a branch around the max chain: a branch there keeps the compiler from
                 // scheduling the step's other work (next increments, ring words, shuffles) under the chain's latency, and a
                 // warp that has its scheduler to itself ran such blocks at 184 clocks per step against 88.
-                const bool in = (uint32_t)(jj - 1) <= (uint32_t)n;
+                in = (uint32_t)(jj - 1) <= (uint32_t)n;
                 Lane16c<K> nx = st;
                 lane16c_chain<K, POT2>(nx, recv, d, gup, gleft);
                 if (jj == 1) lane16c_fix_first<K>(nx, g, itop, irel_top);
@@ -697,51 +692,52 @@ __device__ __noinline__ long long wf16c_strip(Wf16cWarp& w, const Wf16cParams& P
                 for (int k = 0; k < K; ++k) st.W[k] = in ? nx.W[k] : st.W[k];
                 st.up0_prev = in ? nx.up0_prev : st.up0_prev;
                 if (do_store && in) sts32(oaddr, st.W[K - 1]);
-                if (FILT) {
-                    acc = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr);
-                    fire = in && filter_fired(acc, jj >= jarm ? thrS : WF16C_UNARMED);
-                }
             }
-            if (FILT) nthr = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
         };
         if constexpr (!EDGE && !FILT) {
             // the steady loop: full blocks (cnt == 32), four steps per iteration so that the loop-carried copies (ring
             // words, increment registers) are paid once per four steps -- they run on the same pipe as the packed adds
-            bool f;
-            uint32_t a;
+            bool in;
 #pragma unroll 1
             do {
                 const uint32_t w2 = lds32(p + 8);
-                step(w0, w1, p + OR_OFF, j, f, a);
+                step(w0, w1, p + OR_OFF, j, in);
                 const uint32_t w3 = lds32(p + 12);
-                step(w1, w2, p + OR_OFF + 4, j + 1, f, a);
+                step(w1, w2, p + OR_OFF + 4, j + 1, in);
                 const uint32_t w4 = lds32(p + 16);
-                step(w2, w3, p + OR_OFF + 8, j + 2, f, a);
+                step(w2, w3, p + OR_OFF + 8, j + 2, in);
                 const uint32_t w5 = lds32(p + 20);
-                step(w3, w4, p + OR_OFF + 12, j + 3, f, a);
+                step(w3, w4, p + OR_OFF + 12, j + 3, in);
                 w0 = w4; w1 = w5;
                 p += 16; j += 4;
             } while (p != p_end);
         } else {
-            // Two steps per iteration and ONE vote for both: a vote after every step makes the next step wait for this
-            // step's whole max chain (no overlap between steps: 215 against 88 clocks per step for a warp alone on its
-            // scheduler).  The first step's registers are kept until the vote; its fire is resolved before the second's, so
-            // the cold function sees the steps in order.  The second step's threshold is the one before the first step's
-            // fire -- staler, i.e. lower: the fire test is a superset filter, the cold function decides.
+            // Two steps per iteration, then the candidate filter of BOTH steps, then ONE vote.  A filter and a vote after
+            // every step make the next step wait for this step's whole max chain (no overlap between steps: 215 against 88
+            // clocks per step for a warp alone on its scheduler); written this way the second step's chain follows the first's
+            // directly and both filters -- independent of each other -- run behind it.  The first step's registers are kept
+            // until the vote; its fire is resolved before the second's, so the cold function sees the steps in order.  The
+            // second step's threshold is the one before the first step's fire -- staler, i.e. lower: the fire test is a
+            // superset filter, the cold function decides.
 #pragma unroll 1
             do {
                 const uint32_t w2 = lds32(p + 8);
-                bool f0, f1;
-                uint32_t a0, a1;
-                step(w0, w1, p + OR_OFF, j, f0, a0);
-                CVals<K> first;
+                bool in0, in1;
+                step(w0, w1, p + OR_OFF, j, in0);
+                Lane16c<K> first;
                 if (FILT) {
 #pragma unroll
                     for (int k = 0; k < K; ++k) first.W[k] = st.W[k];
                 }
                 const uint32_t w3 = lds32(p + 12);
-                step(w1, w2, p + OR_OFF + 4, j + 1, f1, a1);
+                step(w1, w2, p + OR_OFF + 4, j + 1, in1);
                 if (FILT) {
+                    const uint32_t nthr1 = p_add2(nthr, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
+                    const uint32_t a0 = p_add2(POT2 ? lane16c_max_pot2<K>(first) : lane16c_max<K>(first), nthr);
+                    const uint32_t a1 = p_add2(POT2 ? lane16c_max_pot2<K>(st) : lane16c_max<K>(st), nthr1);
+                    const bool f0 = in0 && filter_fired(a0, j >= jarm ? thrS : WF16C_UNARMED);
+                    const bool f1 = in1 && filter_fired(a1, j + 1 >= jarm ? thrS : WF16C_UNARMED);
+                    nthr = p_add2(nthr1, POT2 ? WF16C_NSTEP_POT2 : WF16C_NSTEP);
                     if (__any_sync(FULL, f0 || f1)) {                     // warp-uniform: every lane runs every step
                         if (f0) fire_path(first.W, j, a0);
                         if (f1) fire_path(st.W, j + 1, a1);
