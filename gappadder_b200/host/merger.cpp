@@ -522,6 +522,9 @@ int merge_gaps(gp_ctx* ctx, const MergeOptions& opt, std::vector<GapInput>& in, 
             }
         }
     }
+    // no relax launch after all (no chain, host relax, nothing in the device entry point's domain): the other mergers'
+    // pairwise phases need not wait any longer
+    if (gate && relax_announced) { gate->cancel_relax(); relax_announced = false; }
     // ---- relax chains, step by step: step k of every remaining chain in one batch (gaps the device path did not take) ------
     for (;;) {
         std::vector<size_t> active;
