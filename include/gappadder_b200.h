@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 3
+#define GP_ABI_VERSION 4
 
 typedef enum gp_status {
     GP_OK = 0,
