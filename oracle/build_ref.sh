@@ -5,6 +5,8 @@
 # sources where they lie under /root/reference, into oracle/_ref/ (git-ignored):
 #   oracle/_ref/ContigsMerger   the reference binary, reference flags (-O3 -mcmodel=medium)
 #   oracle/_ref/libcm_ref.so    the same objects + oracle/ref_harness.cpp (C-ABI around Evaluate)
+#   oracle/_ref/libla_ref.so    TERefiner's affine local aligner (TERefiner/algorithms/local_alignment.cpp, unpatched,
+#                               compiled where it lies) + oracle/la_harness.cpp (C-ABI around optAlign / aln_stdaln)
 #
 # The sources are copied to a scratch directory under $TMPDIR, patched there, compiled and the
 # scratch directory is removed: no reference source is ever written into this repository.
@@ -52,4 +54,7 @@ for u in $UNITS; do $CXX -O3 -w -fPIC -c "$u.cpp" -o "$u.pic.o" & POBJS="$POBJS 
 $CXX -O3 -w -fPIC -I"$TMP" -c "$HERE/ref_harness.cpp" -o ref_harness.pic.o &
 wait
 $CXX -shared -o "$OUT/libcm_ref.so" $POBJS ref_harness.pic.o -lz -lm -lpthread
-echo "built $OUT/ContigsMerger and $OUT/libcm_ref.so"
+# (c) TERefiner's affine local aligner: one self-contained source file, no patch
+LA="$REF/TERefiner/algorithms"
+$CXX -O3 -w -fPIC -shared -I"$LA" -o "$OUT/libla_ref.so" "$LA/local_alignment.cpp" "$HERE/la_harness.cpp"
+echo "built $OUT/ContigsMerger, $OUT/libcm_ref.so and $OUT/libla_ref.so"
