@@ -15,7 +15,7 @@ all: $(LIB) build/microbench_int build/ContigsMerger_b200
 build:
 	mkdir -p build
 
-build/gp_api.o: $(CSRC)/gp_api.cu $(CSRC)/common.cuh $(CSRC)/overlap_wf32.cuh $(CSRC)/overlap_wf16.cuh $(CSRC)/overlap_wf16t.cuh $(CSRC)/overlap_wf16c.cuh include/gappadder_b200.h | build
+build/gp_api.o: $(CSRC)/gp_api.cu $(wildcard $(CSRC)/*.cuh) include/gappadder_b200.h | build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> build/gp_api.ptxas.log || (cat build/gp_api.ptxas.log; false)
 
 build/int_peak.o: $(CSRC)/int_peak.cu include/gappadder_b200.h | build

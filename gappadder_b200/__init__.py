@@ -10,4 +10,5 @@ from .capi import (  # noqa: F401
     GpError, Context, DpParams, Thresholds, Pair, Result, lib, lib_path,
     pack_sequences, candidate_pairs, revcomp, estimate_gap_cells, partition_gaps, is_score_significant, merged_concat,
     GAPPADDER_DP, gappadder_thresholds, dedup_unique_names, dedup_decide, dedup_records, DEDUP_RECORD_DTYPE,
+    AffineParams, TEREFINER_AFFINE, LOCAL_DTYPE,
 )

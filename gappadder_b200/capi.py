@@ -31,6 +31,8 @@ EXPORTS = [
     "gp_reserve", "gp_relax_chains", "gp_relax_stats", "gp_set_orientation", "gp_transposed_pairs",
     "gp_semiglobal_batch", "gp_semiglobal_upload_pairs", "gp_semiglobal_launch", "gp_semiglobal_fetch", "gp_semiglobal_stats",
     "gp_dedup_unique_names", "gp_dedup_decide", "gp_dedup_records", "gp_quick_check_matrix", "gp_set_relax_launch_hook",
+    "gp_affine_params_terefiner", "gp_local_affine_batch", "gp_local_affine_upload_pairs", "gp_local_affine_launch",
+    "gp_local_affine_fetch", "gp_local_affine_stats",
 ]
 
 
@@ -53,6 +55,11 @@ class DpParams(C.Structure):
     _fields_ = [("mismatch", C.c_int32), ("indel", C.c_int32), ("max_clip", C.c_int32)]
 
 
+class AffineParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("n_score", C.c_int32),
+                ("gap_open", C.c_int32), ("gap_ext", C.c_int32), ("band_width", C.c_int32)]
+
+
 class Thresholds(C.Structure):
     _fields_ = [("fraction_loss_score", C.c_double), ("frac_min_overlap", C.c_double),
                 ("min_overlap_len", C.c_double), ("min_overlap_len_with_scaffold", C.c_double)]
@@ -62,6 +69,10 @@ RESULT_DTYPE = np.dtype([("score", "<i4"), ("row_end", "<i4"), ("col_end", "<i4"
 PAIR_DTYPE = np.dtype([("row_seq", "<u4"), ("col_seq", "<u4")])
 DEDUP_RECORD_DTYPE = np.dtype([("q", "<u4"), ("r", "<u4"), ("single_m", "<u4"), ("m_len", "<u4"), ("other_len", "<u4")])
 PLACE_DTYPE = np.dtype([("score", "<i4"), ("col_start", "<i4"), ("col_end", "<i4"), ("flags", "<u4")])
+LOCAL_DTYPE = np.dtype([("score", "<i4"), ("start1", "<i4"), ("end1", "<i4"), ("start2", "<i4"), ("end2", "<i4"), ("flags", "<u4")])
+LOCAL_NO_MATCH, LOCAL_UNDEFINED, LOCAL_POTENTIAL_BUG = 1, 2, 4
+# aln_param_blast (TERefiner/algorithms/local_alignment.cpp:193-206), what LocalAlignment::optAlign uses
+TEREFINER_AFFINE = AffineParams(1, -3, -2, 5, 2, 50)
 FLAG_ROW0, FLAG_COL0, FLAG_CONTAINED, FLAG_KERNEL16, FLAG_CLOSED = 1, 2, 4, 8, 16
 KERNEL_TABLE16, KERNEL_PRMT16, KERNEL_CERT16, KERNEL_CLOSED, KERNEL_ALL = 1, 2, 4, 8, 15
 KERNEL_DP_ALL = KERNEL_TABLE16 | KERNEL_PRMT16 | KERNEL_CERT16      # every kernel, no closed form
@@ -140,6 +151,13 @@ def lib() -> C.CDLL:
         L.gp_semiglobal_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(DpParams), C.c_void_p]
         L.gp_semiglobal_upload_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(DpParams)]
         L.gp_semiglobal_launch.argtypes = [C.c_void_p]
+        L.gp_affine_params_terefiner.argtypes = [C.POINTER(AffineParams)]
+        L.gp_affine_params_terefiner.restype = None
+        L.gp_local_affine_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(AffineParams), C.c_void_p]
+        L.gp_local_affine_upload_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(AffineParams)]
+        L.gp_local_affine_launch.argtypes = [C.c_void_p]
+        L.gp_local_affine_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.gp_local_affine_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.gp_semiglobal_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.gp_semiglobal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         _lib = L
@@ -424,6 +442,38 @@ class Context:
         cells, t, g, ms = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_double(0)
         self._check(self._L.gp_semiglobal_stats(self._h, C.byref(cells), C.byref(t), C.byref(g), C.byref(ms)))
         return dict(cells=cells.value, table_pairs=t.value, generic_pairs=g.value, kernel_ms=ms.value)
+
+    # ---- TERefiner's affine local aligner (parity pinned: the reference's own local_alignment.cpp) ----
+    def local_affine_batch(self, seqs: Sequence[bytes], pairs, params: AffineParams = TEREFINER_AFFINE) -> np.ndarray:
+        """pairs: (sref index, ssgmt index).  -> LOCAL_DTYPE array (score, start1, end1, start2, end2, flags), 1-based."""
+        hb = HostBatch(seqs, pairs)
+        out = np.zeros(len(hb.pairs), dtype=LOCAL_DTYPE)
+        self._check(self._L.gp_local_affine_batch(self._h, hb.arr, hb.lens.ctypes.data, hb.n_seq, hb.pairs.ctypes.data, len(hb.pairs),
+                                                  C.byref(params), out.ctypes.data))
+        return out
+
+    def local_affine_host_batch(self, hb: "HostBatch", out: np.ndarray, params: AffineParams = TEREFINER_AFFINE) -> np.ndarray:
+        self._check(self._L.gp_local_affine_batch(self._h, hb.arr, hb.lens.ctypes.data, hb.n_seq, hb.pairs.ctypes.data, len(hb.pairs),
+                                                  C.byref(params), out.ctypes.data))
+        return out
+
+    def local_affine_upload_pairs(self, pairs: np.ndarray, params: AffineParams = TEREFINER_AFFINE):
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        self._check(self._L.gp_local_affine_upload_pairs(self._h, pairs.ctypes.data, len(pairs), C.byref(params)))
+        self._n_local = len(pairs)
+
+    def local_affine_launch(self):
+        self._check(self._L.gp_local_affine_launch(self._h))
+
+    def local_affine_fetch(self) -> np.ndarray:
+        out = np.zeros(self._n_local, dtype=LOCAL_DTYPE)
+        self._check(self._L.gp_local_affine_fetch(self._h, out.ctypes.data, self._n_local))
+        return out
+
+    def local_affine_stats(self) -> dict:
+        cells, f, e = C.c_uint64(0), C.c_double(0), C.c_double(0)
+        self._check(self._L.gp_local_affine_stats(self._h, C.byref(cells), C.byref(f), C.byref(e)))
+        return dict(cells=cells.value, forward_ms=f.value, epilogue_ms=e.value)
 
     def quick_check_stats(self) -> dict:
         """Of the last quick_check_device: kernel ms (CUDA events), bases scanned, work items."""

@@ -56,7 +56,7 @@ struct DevLocal {                                 // same layout as gp_local_res
 inline bool aff_params_ok(const AffParams& P)
 {
     return P.match >= 1 && P.match <= 64 && P.mismatch <= 0 && P.mismatch >= -1024 && P.nscore <= 0 && P.nscore >= -1024 &&
-           P.q >= 0 && P.q <= 1024 && P.r >= 1 && P.r <= 1024 && P.band >= 1 && P.band <= (1 << 20);
+           P.q >= 0 && P.q <= 1024 && P.r >= 1 && P.r <= 64 && P.band >= 1 && P.band <= (1 << 20);
 }
 inline bool aff_pair_ok(uint32_t len1, uint32_t len2, const AffParams& P)
 {
@@ -491,25 +491,295 @@ __host__ __device__ inline void aff_epilogue(const AffSeq& s1, const AffSeq& s2,
     res->start2 = pj ? pj : 1;
 }
 
-#ifdef __CUDACC__
-constexpr int AE_THREADS = 64;
+// ---- passes 2 and 3, one WARP per pair ----------------------------------------------------------------------------------
+//
+// aff_epilogue above is the reference's order of evaluation, one cell after the other; with one thread per pair a batch
+// waits for its longest pair's half a million dependent cells.  aff_epilogue_warp computes the very same values column
+// by column with the 32 lanes spread over a column's band:
+//   * a cell's score without its vertical gap state depends on the previous column only: all cells at once;
+//   * the vertical state is a running maximum down the column, F(i) = max over cells k already passed of
+//     (h'(k) - q - |k - i| r), h' = the score without F (an F-derived score never opens a better gap than the score it
+//     came from, q >= 0): a prefix maximum of h'(k) - q -/+ k r -- per-lane segments, one 32-entry scan, per-lane fix-up.
+//     The reference's ties go to the EXTENSION (:262, :285), i.e. to the earliest origin, which the scan keeps;
+//   * the column's effect on the running best (first strict maximum while walking the column, stop at the first record
+//     equal to score + q + r, :667-672) is a reduction: the column maximum at its first position, and the first cell
+//     that reaches the stop value.
+// The band edges of the next column are set by lane 0 exactly as the reference sets them, and exactly the array entries the
+// reference writes are written (entries outside the band keep their stale values for the time the band widens again).
+// Lanes talk through memory only (AffWarp, the work arrays) with a warp barrier between phases, so the same text runs on
+// the host with a loop over the lanes in every phase: that is what the CPU tests compare with aff_epilogue and with
+// the reference.
+#ifdef __CUDA_ARCH__
+#define AFF_LANES(l) for (int l = (int)(threadIdx.x & 31u), aff_once_ = 1; aff_once_; aff_once_ = 0)
+#define AFF_SYNC() __syncwarp()
+#else
+#define AFF_LANES(l) for (int l = 0; l < 32; ++l)
+#define AFF_SYNC() ((void)0)
+#endif
 
-// One thread per pair (pulled from a queue), scratch_stride ints of scratch per thread.
+struct AffWarp {                                  // one per warp, shared memory on the device
+    int segA[32], segTag[32], exA[32], exTag[32];
+    int segM[32], segP[32], segT[32];
+    int score_r, start_i, start_j, hi, lo, stop, undefined;
+    int gl_score, gl_first;
+};
+constexpr int AFF_NEG_BIG = -(1 << 29);
+
+// Reverse pass (:617-690).  Hh[k] / Ee[k]: the score of row k and the horizontal gap state of row k at the last column
+// that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff); tH / tE: this column's values before F.
+__host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq& s2, const AffParams& P, int score_f, int end_i, int end_j,
+                                                 int* Hh, int* Ee, int* tH, int* tE, AffWarp* w)
+{
+    const int q = P.q, r = P.r, qr = q + r;
+    AFF_LANES(l) { for (int k = l; k <= end_i + 1; k += 32) { Hh[k] = 0; Ee[k] = 0; } }
+    AFF_SYNC();
+    AFF_LANES(l) {
+        if (l == 0) {
+            const int sr = aff_sc(s1.at1(end_i), s2.at1(end_j), P);
+            w->score_r = sr; w->start_i = end_i; w->start_j = end_j;
+            Hh[end_i] = qr + sr;                                                  // :627
+            w->hi = end_i - 1;
+            w->lo = end_i - 3 > 0 ? end_i - 3 : 0;
+            w->stop = 0; w->undefined = 0;
+        }
+    }
+    AFF_SYNC();
+    const int T = score_f + qr;
+    for (int j = end_j - 1; j != 0; --j) {
+        const int hi = w->hi, lo = w->lo;
+        if (hi < lo) {
+            AFF_SYNC();
+            AFF_LANES(l) { if (l == 0) w->undefined = 1; }
+            AFF_SYNC();
+            break;
+        }
+        const int S = (hi - lo + 31) / 32;
+        const uint32_t c2 = s2.at1(j);
+        AFF_LANES(l) {                                                            // scores without F
+            const int top = hi - l * S;
+            int bot = top - S + 1;
+            if (bot < lo + 1) bot = lo + 1;
+            int best = AFF_NEG_BIG;
+            for (int i = top; i >= bot; --i) {
+                const int hl = Hh[i], eo = Ee[i];
+                int h = Hh[i + 1] + aff_sc(s1.at1(i), c2, P);
+                if (h < 0) h = 0;
+                int e = (eo > hl - q) ? eo - r : hl - qr;
+                if (e < 0) e = 0;
+                if (h < e) h = e;
+                tH[i] = h; tE[i] = e;
+                const int a = h - q - i * r;                                      // as F of a row i' < i: a + i' r
+                best = a > best ? a : best;
+            }
+            w->segA[l] = best;
+        }
+        AFF_SYNC();
+        AFF_LANES(l) {
+            if (l == 0) {
+                int run = AFF_NEG_BIG;
+                for (int k = 0; k < 32; ++k) { w->exA[k] = run; run = w->segA[k] > run ? w->segA[k] : run; }
+            }
+        }
+        AFF_SYNC();
+        AFF_LANES(l) {                                                            // F, final scores, this column's records
+            const int top = hi - l * S;
+            int bot = top - S + 1;
+            if (bot < lo + 1) bot = lo + 1;
+            int run = w->exA[l], bm = -1, bp = 0, tp = 0;
+            for (int i = top; i >= bot; --i) {
+                const int hp = tH[i];
+                const int f = run + i * r;                                        // max over k > i of h'(k) - q - (k - i) r
+                const int h = hp > f ? hp : f;
+                Hh[i] = h; Ee[i] = tE[i];
+                const int a = hp - q - i * r;
+                run = a > run ? a : run;
+                if (h > bm) { bm = h; bp = i; }
+                if (tp == 0 && h >= T) tp = i;
+            }
+            w->segM[l] = bm; w->segP[l] = bp; w->segT[l] = tp;
+            if (l == 0) { Hh[hi + 1] = 0; Ee[lo] = 0; }                           // :665 of the first cell, :674
+        }
+        AFF_SYNC();
+        AFF_LANES(l) {
+            if (l == 0) {
+                int M = -1, Mp = 0, tpos = 0;
+                for (int k = 0; k < 32; ++k) {
+                    if (w->segM[k] > M) { M = w->segM[k]; Mp = w->segP[k]; }
+                    if (tpos == 0 && w->segT[k]) tpos = w->segT[k];
+                }
+                bool stop = false;
+                if (w->score_r < T && tpos != 0 && Hh[tpos] == T) {                // the first record that reaches T is T itself
+                    w->score_r = T; w->start_i = tpos; w->start_j = j; stop = true;
+                }
+                if (stop) w->stop = 1;
+                else {
+                    if (M > w->score_r) { w->score_r = M; w->start_i = Mp; w->start_j = j; }
+                    int nh = hi;
+                    if (Hh[nh] <= qr) --nh;                                        // :676-677
+                    if (nh <= 0) nh = 0;
+                    int nl = w->start_i - (w->start_j - j) - (w->score_r + (w->start_j - j) * P.match) / r - 1;      // :678
+                    if (nl <= 0) nl = 0;
+                    w->hi = nh; w->lo = nl;
+                }
+            }
+        }
+        AFF_SYNC();
+        if (w->stop) break;
+    }
+}
+
+// aln_global_core (:328-508), as aff_global: returns through w->gl_score / w->gl_first.  work: 8*(len1+1) ints.
+__host__ __device__ inline void aff_global_warp(const AffSeq& s1, int o1, int len1, const AffSeq& s2, int o2, int len2, const AffParams& P,
+                                                int b, int* work, AffWarp* w)
+{
+    const int q = P.q, r = P.r;
+    int b1, b2;
+    if (len1 > len2) { b1 = len1 - len2 + b; b2 = b; } else { b1 = b; b2 = len2 - len1 + b; }
+    if (b1 > len1) b1 = len1;
+    if (b2 > len2) b2 = len2;
+    const int wd = len1 + 1;
+    AffCol curr{work, work + wd, work + 2 * wd, work + 3 * wd}, last{work + 4 * wd, work + 5 * wd, work + 6 * wd, work + 7 * wd};
+    AFF_SYNC();
+    AFF_LANES(l) {
+        for (int i = l; i < wd; i += 32) {
+            curr.M[i] = curr.I[i] = curr.D[i] = AFF_MINOR_INF; curr.tag[i] = 0;
+            last.M[i] = last.I[i] = last.D[i] = AFF_MINOR_INF; last.tag[i] = 0;
+        }
+    }
+    AFF_SYNC();
+    // first row (:375-381): D(i) = -q - i r, its path leaves the corner downwards
+    AFF_LANES(l) {
+        if (l == 0) curr.M[0] = 0;
+        for (int i = 1 + l; i < b1; i += 32) { curr.D[i] = -q - i * r; curr.tag[i] = AFF_FROM_D << 4; }
+    }
+    AFF_SYNC();
+    { const AffCol t = curr; curr = last; last = t; }
+
+    // One column.  e0: the band's lower edge cell (row 0 while the band touches it, INF otherwise), end: its top cell.
+    auto column = [&](int j, int e0, int end, bool top_I_inf) {
+        const int n = end - e0;                                                   // cells e0+1 .. end
+        const int S = (n + 31) / 32;
+        const uint32_t c2 = s2.at1(o2 + j);
+        AFF_LANES(l) {
+            if (l == 0) {                                                         // the edge cell
+                curr.M[e0] = AFF_MINOR_INF; curr.D[e0] = AFF_MINOR_INF;
+                if (e0 == 0) aff_set_I(curr, 0, last, 0, q, r, j == 1); else curr.I[e0] = AFF_MINOR_INF;
+            }
+            const int first = e0 + 1 + l * S;
+            int lastc = first + S - 1;
+            if (lastc > end) lastc = end;
+            int best = AFF_MINOR_INF * 2 + 2, btag = 0;                           // below anything a cell can hold
+            for (int i = first; i <= lastc; ++i) {
+                aff_set_M(curr, i, last, i - 1, aff_sc(s1.at1(o1 + i), c2, P), i == 1 && j == 1);
+                if (i == end && top_I_inf) curr.I[i] = AFF_MINOR_INF; else aff_set_I(curr, i, last, i, q, r, false);
+                const int a = curr.M[i] - q + i * r;                              // as D of a row i' > i: a - i' r
+                if (a > best) { best = a; btag = curr.tag[i] & 3; }               // ties: the earlier origin (:285)
+            }
+            w->segA[l] = best; w->segTag[l] = btag;
+        }
+        AFF_SYNC();
+        AFF_LANES(l) {
+            if (l == 0) {
+                // the chain starts from the edge cell: D(e0) extended, or M(e0) opened (both INF-like, the reference's order)
+                int run, rtag;
+                if (curr.M[e0] - q > curr.D[e0]) { run = curr.M[e0] - q + e0 * r; rtag = curr.tag[e0] & 3; }
+                else { run = curr.D[e0] + e0 * r; rtag = (curr.tag[e0] >> 4) & 3; }
+                for (int k = 0; k < 32; ++k) {
+                    w->exA[k] = run; w->exTag[k] = rtag;
+                    if (w->segA[k] > run) { run = w->segA[k]; rtag = w->segTag[k]; }
+                }
+            }
+        }
+        AFF_SYNC();
+        AFF_LANES(l) {
+            const int first = e0 + 1 + l * S;
+            int lastc = first + S - 1;
+            if (lastc > end) lastc = end;
+            int run = w->exA[l], rtag = w->exTag[l];
+            for (int i = first; i <= lastc; ++i) {
+                curr.D[i] = run - i * r;
+                curr.tag[i] = (curr.tag[i] & ~48) | (rtag << 4);
+                const int a = curr.M[i] - q + i * r;
+                if (a > run) { run = a; rtag = curr.tag[i] & 3; }
+            }
+        }
+        AFF_SYNC();
+        { const AffCol t = curr; curr = last; last = t; }
+    };
+
+    int j;
+    const int tmp_end = b2 < len2 ? b2 : len2 - 1;
+    for (j = 1; j <= tmp_end; ++j) column(j, 0, (j + b1 <= len1 + 1) ? (j + b1 - 1) : len1, !(j + b1 - 1 > len1));      // part 1
+    if (j == len2 && b2 != len2 - 1) { column(j, 0, (j + b1 <= len1 + 1) ? (j + b1 - 1) : len1, !(j + b1 - 1 > len1)); ++j; }
+    for (; j <= len2 - b2 + 1; ++j) column(j, j - b2, j + b1 - 1, true);                                                  // part 2
+    for (; j < len2; ++j) column(j, j - b2, len1, false);                                                                 // part 3
+    if (j == len2) column(j, j - b2, len1, false);
+    AFF_LANES(l) {
+        if (l == 0) {
+            int mx = last.M[len1], t = last.tag[len1] & 3;
+            if (last.I[len1] > mx) { mx = last.I[len1]; t = (last.tag[len1] >> 2) & 3; }
+            if (last.D[len1] > mx) { mx = last.D[len1]; t = (last.tag[len1] >> 4) & 3; }
+            w->gl_score = mx; w->gl_first = t;
+        }
+    }
+    AFF_SYNC();
+}
+
+// Passes 2 and 3 for one pair by one warp (host: by a loop over the lanes); same contract as aff_epilogue.  Lane 0's *res
+// is the result.
+__host__ __device__ inline void aff_epilogue_warp(const AffSeq& s1, const AffSeq& s2, const AffParams& P, int score_f, int end_i, int end_j,
+                                                  int* work, AffWarp* w, DevLocal* res)
+{
+    const int qr = P.q + P.r;
+    const int stride = end_i + 2;
+    aff_reverse_warp(s1, s2, P, score_f, end_i, end_j, work, work + stride, work + 2 * stride, work + 3 * stride, w);
+    res->end1 = end_i; res->end2 = end_j; res->flags = 0;
+    if (w->undefined) { res->flags |= AFF_FLAG_UNDEFINED; res->start1 = 0; res->start2 = 0; res->score = score_f; return; }
+    const int score_r = w->score_r - qr, start_i = w->start_i, start_j = w->start_j;
+    const int len1 = end_i - start_i + 1, len2 = end_j - start_j + 1;
+    int jmax = (end_i - start_i > end_j - start_j) ? end_i - start_i : end_j - start_j;
+    ++jmax;
+    int score_g = 0, first = AFF_FROM_M;
+    for (int b = P.band;; b <<= 1) {
+        aff_global_warp(s1, start_i - 1, len1, s2, start_j - 1, len2, P, b, work, w);
+        score_g = w->gl_score; first = w->gl_first;
+        if (score_g == score_r || score_f == score_g) break;
+        if (b > jmax) break;
+    }
+    if (score_r > score_g && score_f > score_g) { res->score = -1; res->flags |= AFF_FLAG_POTENTIAL_BUG; }
+    else res->score = score_g;
+    const int pi = (first == AFF_FROM_I ? 0 : 1) + start_i - 1, pj = (first == AFF_FROM_D ? 0 : 1) + start_j - 1;
+    res->start1 = pi ? pi : 1;
+    res->start2 = pj ? pj : 1;
+}
+
+#ifdef __CUDACC__
+constexpr int AE_THREADS = 128;                  // 4 warps per CTA, one pair per warp at a time
+
+// One warp per pair (pulled from a queue in the forward kernel's order), scratch_stride ints of scratch per warp.
 __global__ void __launch_bounds__(AE_THREADS)
-affine_epilogue_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
-                       unsigned int* __restrict__ queue, AffParams P, int* __restrict__ scratch, size_t scratch_stride,
+affine_epilogue_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ order,
+                       uint32_t n_work, unsigned int* __restrict__ queue, AffParams P, int* __restrict__ scratch, size_t scratch_stride,
                        DevLocal* __restrict__ out)
 {
-    int* const work = scratch + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * scratch_stride;
+    __shared__ AffWarp warp_area[AE_THREADS / 32];
+    AffWarp* const w = &warp_area[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    int* const work = scratch + (size_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * scratch_stride;
     for (;;) {
-        const uint32_t pid = atomicAdd(queue, 1u);
-        if (pid >= n_pairs) break;
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(queue, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= n_work) break;
+        const uint32_t pid = order[qi];
         DevLocal res = out[pid];
+        __syncwarp();
         if (res.score <= 0 || (res.flags & AFF_FLAG_NO_MATCH)) continue;
         const PairDesc pd = pairs[pid];
         const AffSeq s1{packed + pd.row_off}, s2{packed + pd.col_off};
-        aff_epilogue(s1, s2, P, res.score, res.end1, res.end2, work, &res);
-        out[pid] = res;
+        aff_epilogue_warp(s1, s2, P, res.score, res.end1, res.end2, work, w, &res);
+        if (lane == 0) out[pid] = res;
+        __syncwarp();
     }
 }
 

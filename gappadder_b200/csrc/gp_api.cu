@@ -10,6 +10,7 @@
 #include "quick_check.cuh"
 #include "flank_place.cuh"
 #include "relax_chain.cuh"
+#include "affine_local.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -36,6 +37,14 @@ struct DeviceBuf {
                                               // (pinned) reallocation costs about a millisecond
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    cudaError_t reserve_exact(size_t bytes)     // for the few buffers that are large and do not creep
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -92,6 +101,15 @@ struct gp_ctx {
     gp_dp_params fp_params{};
     cudaEvent_t fp_ev[2] = {nullptr, nullptr};
     bool fp_ev_valid = false;
+    // affine local aligner (affine_local.cuh)
+    DeviceBuf d_af_pairs, d_af_order, d_af_results, d_af_queue, d_af_scratch, d_ae_scratch;
+    HostBuf h_af_stage;
+    uint64_t af_pairs = 0, af_work = 0, af_cells = 0;
+    uint32_t af_max_m = 0, af_max_n = 0;
+    std::vector<uint32_t> af_host_ids;         // pairs with an empty sequence: answered on the host
+    gp::AffParams af_params{};
+    cudaEvent_t af_ev[3] = {nullptr, nullptr, nullptr};
+    bool af_ev_valid = false;
     cudaEvent_t qc_ev[2] = {nullptr, nullptr};
     double qc_kernel_ms = 0;
     uint64_t qc_bases = 0;
@@ -166,10 +184,11 @@ int gp_create(int device, gp_ctx** out)
     }
     for (auto& ev : c->qc_ev) cudaEventCreate(&ev);
     for (auto& ev : c->fp_ev) cudaEventCreate(&ev);
+    for (auto& ev : c->af_ev) cudaEventCreate(&ev);
     for (auto& ev : c->rx_ev) cudaEventCreate(&ev);
     for (auto& ev : c->kev)
         if ((e = cudaEventCreate(&ev)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->stream); delete c; return GP_ERR_CUDA; }
-    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess || (e = gp::fp_configure()) != cudaSuccess || (e = gp::relax_configure()) != cudaSuccess ||
+    if ((e = gp::wf16_configure()) != cudaSuccess || (e = gp::wf16t_configure()) != cudaSuccess || (e = gp::wf16c_configure()) != cudaSuccess || (e = gp::fp_configure()) != cudaSuccess || (e = gp::affine_configure()) != cudaSuccess || (e = gp::relax_configure()) != cudaSuccess ||
         // set once, to the maximum: function attributes are per device, and several contexts (workers) may launch concurrently
         (e = cudaFuncSetAttribute(gp::quick_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gp::QC_SMEM_MAX)) != cudaSuccess) {
         g_create_error = std::string("kernel attribute setup failed: ") + cudaGetErrorString(e);
@@ -187,9 +206,11 @@ void gp_destroy(gp_ctx* c)
     for (auto& ev : c->kev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->qc_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->fp_ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->af_ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->rx_ev) if (ev) cudaEventDestroy(ev);
     c->d_arena.release(); c->d_rx_items.release(); c->d_rx_order.release(); c->d_rx_status.release(); c->d_rx_results.release(); c->d_rx_queue.release(); c->h_rx_stage.release(); c->h_rx_out.release();
     c->d_fp_pairs.release(); c->d_fp_order.release(); c->d_fp_results.release(); c->d_fp_queue.release(); c->d_fp_scratch.release(); c->h_fp_stage.release();
+    c->d_af_pairs.release(); c->d_af_order.release(); c->d_af_results.release(); c->d_af_queue.release(); c->d_af_scratch.release(); c->d_ae_scratch.release(); c->h_af_stage.release();
     c->d_qc_slab.release();
     c->d_packed.release(); c->d_pairs.release(); c->d_order16t.release(); c->d_order16.release(); c->d_order32.release();
     c->d_scratch16t.release(); c->d_scratch16c.release(); c->d_order16c.release(); c->h_queue.release();
@@ -1153,6 +1174,154 @@ int gp_semiglobal_stats(gp_ctx* c, uint64_t* cells, uint64_t* table_pairs, uint6
             GP_CUDA(c, cudaEventElapsedTime(&t, c->fp_ev[0], c->fp_ev[1]));
             *kernel_ms = t;
         }
+    }
+    return GP_OK;
+}
+
+// ---- TERefiner's affine local aligner (affine_local.cuh) ---------------------------------------------------------------
+
+void gp_affine_params_terefiner(gp_affine_params* p)
+{
+    if (!p) return;
+    p->match = 1; p->mismatch = -3; p->n_score = -2; p->gap_open = 5; p->gap_ext = 2; p->band_width = 50;      // aln_param_blast, local_alignment.cpp:193-206
+}
+
+int gp_local_affine_upload_pairs(gp_ctx* c, const gp_pair* pairs, uint64_t n_pairs, const gp_affine_params* params)
+{
+    if (!c) return GP_ERR_INVALID;
+    c->af_pairs = 0; c->af_work = 0; c->af_cells = 0; c->af_max_m = c->af_max_n = 0; c->af_host_ids.clear(); c->af_ev_valid = false;
+    if (!pairs && n_pairs) return c->fail(GP_ERR_INVALID, "null pairs");
+    gp_affine_params dflt;
+    gp_affine_params_terefiner(&dflt);
+    if (!params) params = &dflt;
+    const gp::AffParams P{params->match, params->mismatch, params->n_score, params->gap_open, params->gap_ext, params->band_width};
+    if (!gp::aff_params_ok(P)) return c->fail(GP_ERR_INVALID, "affine parameters out of range (match 1..64, mismatch / n_score -1024..0, gap_open 0..1024, gap_ext 1..64, band_width >= 1)");
+    if (n_pairs > 0xfffffff0ull) return c->fail(GP_ERR_RANGE, "too many pairs in one batch");
+    c->af_params = P;
+    if (n_pairs == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t n_seq = (uint32_t)c->seq_len.size();
+    const size_t desc_bytes = n_pairs * sizeof(gp::PairDesc);
+    GP_CUDA(c, c->h_af_stage.reserve(desc_bytes + n_pairs * sizeof(uint32_t)));
+    gp::PairDesc* hd = (gp::PairDesc*)c->h_af_stage.p;
+    uint32_t* ord = (uint32_t*)((char*)c->h_af_stage.p + desc_bytes);
+    uint64_t n_work = 0, cells = 0;
+    uint32_t max_m = 0, max_n = 0;
+    for (uint64_t i = 0; i < n_pairs; ++i) {
+        const uint32_t a = pairs[i].row_seq, b = pairs[i].col_seq;
+        if (a >= n_seq || b >= n_seq) return c->fail(GP_ERR_INVALID, "pair %llu references sequence out of range", (unsigned long long)i);
+        const uint32_t m = c->seq_len[a], n = c->seq_len[b];
+        hd[i] = gp::PairDesc{c->seq_off[a], m, c->seq_off[b], n};
+        if (m == 0 || n == 0) { c->af_host_ids.push_back((uint32_t)i); continue; }
+        if (!gp::aff_pair_ok(m, n, P))
+            return c->fail(GP_ERR_RANGE, "pair %llu (%u x %u bases) exceeds the affine aligner's range (min(len1, len2) * match + gap_open + gap_ext <= %d, lengths < 2^20)",
+                           (unsigned long long)i, m, n, gp::AFF_OVERFLOW);
+        cells += (uint64_t)m * n;
+        max_m = std::max(max_m, m);
+        max_n = std::max(max_n, n);
+        ord[n_work++] = (uint32_t)i;
+    }
+    sort_longest_first(hd, ord, n_work);
+    GP_CUDA(c, c->d_af_pairs.reserve(desc_bytes));
+    GP_CUDA(c, c->d_af_order.reserve(n_pairs * sizeof(uint32_t)));
+    GP_CUDA(c, c->d_af_results.reserve(n_pairs * sizeof(gp::DevLocal)));
+    GP_CUDA(c, c->d_af_queue.reserve(64));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_af_pairs.p, hd, desc_bytes, cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaMemcpyAsync(c->d_af_order.p, ord, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->af_pairs = n_pairs; c->af_work = n_work; c->af_cells = cells; c->af_max_m = max_m; c->af_max_n = max_n;
+    return GP_OK;
+}
+
+int gp_local_affine_launch(gp_ctx* c)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (c->af_work == 0) return GP_OK;
+    GP_CUDA(c, cudaSetDevice(c->device));
+    const int blocks = c->sm_count * gp::AF_CTAS_PER_SM;
+    const uint32_t warps = (uint32_t)blocks * (gp::AF_THREADS / 32);
+    const uint32_t stride = (c->af_max_n + 1 + 64 + 31) & ~31u;
+    GP_CUDA(c, c->d_af_scratch.reserve((size_t)warps * stride * sizeof(uint32_t)));
+    // start recovery: one warp per pair, 8 ints of scratch per row of the longest row sequence and warp, 4 GB at most
+    const size_t per_warp = (gp::aff_epilogue_words((int)c->af_max_m) + 31) & ~(size_t)31;
+    const size_t budget_words = (size_t)1 << 30;
+    constexpr size_t ae_warps_per_block = gp::AE_THREADS / 32;
+    size_t ae_blocks = std::min<size_t>((size_t)c->sm_count * 8, (c->af_work + ae_warps_per_block - 1) / ae_warps_per_block);
+    ae_blocks = std::max<size_t>(1, std::min(ae_blocks, budget_words / (per_warp * ae_warps_per_block)));
+    GP_CUDA(c, c->d_ae_scratch.reserve_exact(ae_blocks * ae_warps_per_block * per_warp * sizeof(int)));
+    GP_CUDA(c, cudaMemsetAsync(c->d_af_queue.p, 0, 64, c->stream));
+    unsigned int* queue = (unsigned int*)c->d_af_queue.p;
+    GP_CUDA(c, cudaEventRecord(c->af_ev[0], c->stream));
+    gp::affine_forward_kernel<<<blocks, gp::AF_THREADS, gp::AF_SMEM_BYTES, c->stream>>>(
+        (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_af_pairs.p, (const uint32_t*)c->d_af_order.p, (uint32_t)c->af_work, queue,
+        c->af_params, (uint32_t*)c->d_af_scratch.p, stride, (gp::DevLocal*)c->d_af_results.p);
+    GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->af_ev[1], c->stream));
+    gp::affine_epilogue_kernel<<<(unsigned)ae_blocks, gp::AE_THREADS, 0, c->stream>>>(
+        (const uint32_t*)c->d_packed.p, (const gp::PairDesc*)c->d_af_pairs.p, (const uint32_t*)c->d_af_order.p, (uint32_t)c->af_work, queue + 8,
+        c->af_params, (int*)c->d_ae_scratch.p, per_warp, (gp::DevLocal*)c->d_af_results.p);
+    GP_CUDA(c, cudaGetLastError());
+    GP_CUDA(c, cudaEventRecord(c->af_ev[2], c->stream));
+    c->launches += 2;
+    c->af_ev_valid = true;
+    return GP_OK;
+}
+
+int gp_local_affine_fetch(gp_ctx* c, gp_local_result* out, uint64_t n_pairs)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (n_pairs != c->af_pairs) return c->fail(GP_ERR_INVALID, "n_pairs does not match the uploaded batch");
+    if (n_pairs == 0) return GP_OK;
+    if (!out) return c->fail(GP_ERR_INVALID, "null output");
+    static_assert(sizeof(gp_local_result) == sizeof(gp::DevLocal), "result layouts must match");
+    GP_CUDA(c, cudaSetDevice(c->device));
+    GP_CUDA(c, cudaMemcpyAsync(out, c->d_af_results.p, n_pairs * sizeof(gp_local_result), cudaMemcpyDeviceToHost, c->stream));
+    GP_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (uint32_t id : c->af_host_ids) {            // aln_local_core returns -1 for an empty sequence (local_alignment.cpp:545)
+        out[id].score = -1; out[id].start1 = out[id].end1 = out[id].start2 = out[id].end2 = 0; out[id].flags = GP_LOCAL_NO_MATCH;
+    }
+    return GP_OK;
+}
+
+int gp_local_affine_batch(gp_ctx* c, const char* const* seqs, const uint32_t* seq_len, uint32_t n_seq,
+                          const gp_pair* pairs, uint64_t n_pairs, const gp_affine_params* params, gp_local_result* out)
+{
+    if (!c) return GP_ERR_INVALID;
+    if ((!seqs || !seq_len) && n_seq) return c->fail(GP_ERR_INVALID, "null sequences");
+    // the reference's letter classes (aln_nt4_table, local_alignment.cpp:32-49): a/A c/C g/G t/T, everything else one class
+    static const struct Nt4 { char t[256]; Nt4() { memset(t, 'N', sizeof t); for (const char* p = "ACGT"; *p; ++p) { t[(unsigned char)*p] = *p; t[(unsigned char)(*p + 32)] = *p; } } } nt4;
+    uint64_t total = 0;
+    for (uint32_t s = 0; s < n_seq; ++s) { if (!seqs[s] && seq_len[s]) return c->fail(GP_ERR_INVALID, "null sequence %u", s); total += seq_len[s]; }
+    std::vector<char> norm(total ? total : 1);
+    std::vector<const char*> ptr(n_seq);
+    uint64_t at = 0;
+    for (uint32_t s = 0; s < n_seq; ++s) {
+        ptr[s] = norm.data() + at;
+        const unsigned char* src = (const unsigned char*)seqs[s];
+        for (uint32_t i = 0; i < seq_len[s]; ++i) norm[at + i] = nt4.t[src[i]];
+        at += seq_len[s];
+    }
+    int rc = gp_upload_sequences(c, ptr.data(), seq_len, n_seq);
+    if (rc == GP_OK) rc = gp_local_affine_upload_pairs(c, pairs, n_pairs, params);
+    if (rc == GP_OK) rc = gp_local_affine_launch(c);
+    if (rc == GP_OK) rc = gp_local_affine_fetch(c, out, n_pairs);
+    return rc;
+}
+
+int gp_local_affine_stats(gp_ctx* c, uint64_t* cells, double* forward_ms, double* epilogue_ms)
+{
+    if (!c) return GP_ERR_INVALID;
+    if (cells) *cells = c->af_cells;
+    if (forward_ms) *forward_ms = 0.0;
+    if (epilogue_ms) *epilogue_ms = 0.0;
+    if ((forward_ms || epilogue_ms) && c->af_ev_valid) {
+        GP_CUDA(c, cudaSetDevice(c->device));
+        GP_CUDA(c, cudaEventSynchronize(c->af_ev[2]));
+        float t = 0.f;
+        GP_CUDA(c, cudaEventElapsedTime(&t, c->af_ev[0], c->af_ev[1]));
+        if (forward_ms) *forward_ms = t;
+        GP_CUDA(c, cudaEventElapsedTime(&t, c->af_ev[1], c->af_ev[2]));
+        if (epilogue_ms) *epilogue_ms = t;
     }
     return GP_OK;
 }

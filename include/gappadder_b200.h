@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GP_ABI_VERSION 4
+#define GP_ABI_VERSION 5
 
 typedef enum gp_status {
     GP_OK = 0,
@@ -295,6 +295,50 @@ int gp_semiglobal_launch(gp_ctx *ctx);
 int gp_semiglobal_fetch(gp_ctx *ctx, gp_place_result *out, uint64_t n_pairs);
 /* Of the uploaded batch: DP cells (sum of m*n), pairs per kernel; of the last launch: device time (CUDA events). */
 int gp_semiglobal_stats(gp_ctx *ctx, uint64_t *cells, uint64_t *table_pairs, uint64_t *generic_pairs, double *kernel_ms);
+
+/* ---- TERefiner's affine-gap local aligner (LocalAlignment::optAlign) ------------------------------------------------------
+ * Replaces TERefiner/algorithms/local_alignment.cpp:1036-1049, i.e. aln_stdaln(ref, sgmt, &aln_param_blast, 0, 1)
+ * (aln_local_core :512-745 followed by aln_global_core :328-508; callers: TERefiner/main.cpp:209-212,
+ * scaffolding.cpp:103-105, RepeatsClassifier.cpp:50-57).  The aligner's source is part of the reference tree, so parity
+ * is PINNED: results are identical to that code (oracle/_ref/libla_ref.so is compiled from it), including its tie rules
+ * and its two departures from the textbook recurrence (csrc/affine_local.cuh).  row_seq is the reference's `sref`
+ * (seq1), col_seq its `ssgmt` (seq2).
+ *   score            the local score (the reference's AlnAln::score)
+ *   start1, end1     1-based first / last aligned position in row_seq  (optm_start_ref, optm_end_ref)
+ *   start2, end2     the same in col_seq                               (optm_start_sgmt, optm_end_sgmt)
+ *   flags            GP_LOCAL_NO_MATCH: nothing aligns (no positive cell, or an empty sequence: score 0 resp. -1,
+ *                    coordinates 0; the reference reads path[-1] there); GP_LOCAL_UNDEFINED: the reference's reverse band
+ *                    collapsed (its loop :654 would leave its array): end1/end2/score of the forward pass only;
+ *                    GP_LOCAL_POTENTIAL_BUG: the reference prints "Potential bug" and reports score -1 (:727-730), as here.
+ * Letters: A C G T (either case in the one-call form) are the four bases, every other byte is the reference's N class
+ * (aln_nt4_table :32-49).  The split form works on the context's current sequence table, where only upper-case A C G T
+ * are bases.  Limits: both sequences < 2^20 bases and min(len1, len2) * match + gap_open + gap_ext <= 32000 (the reference
+ * rescales its 16-bit scores beyond that, :573-588); GP_ERR_RANGE otherwise. */
+typedef struct gp_affine_params {
+    int32_t match, mismatch, n_score;     /* equal bases, unequal bases, anything against a non-base (aln_sm_blast :193-199) */
+    int32_t gap_open, gap_ext;            /* a gap of g letters costs gap_open + g * gap_ext                               */
+    int32_t band_width;                   /* first band of the global fill (:717); it is doubled until the score agrees    */
+} gp_affine_params;
+/* aln_param_blast (:206), what LocalAlignment uses: 1, -3, -2, 5, 2, 50.  params == NULL means these. */
+void gp_affine_params_terefiner(gp_affine_params *p);
+typedef struct gp_local_result {
+    int32_t score;
+    int32_t start1, end1, start2, end2;
+    uint32_t flags;
+} gp_local_result;
+#define GP_LOCAL_NO_MATCH 1u
+#define GP_LOCAL_UNDEFINED 2u
+#define GP_LOCAL_POTENTIAL_BUG 4u
+/* One call on host ASCII sequences: pack + upload + kernels + results.  Blocking. */
+int gp_local_affine_batch(gp_ctx *ctx, const char *const *seqs, const uint32_t *seq_len, uint32_t n_seq,
+                          const gp_pair *pairs, uint64_t n_pairs, const gp_affine_params *params, gp_local_result *out);
+/* Split form on the context's current sequence table: upload once, launch any number of times (only enqueues on
+ * gp_stream(ctx): the forward kernel, then the start-recovery kernel), fetch once. */
+int gp_local_affine_upload_pairs(gp_ctx *ctx, const gp_pair *pairs, uint64_t n_pairs, const gp_affine_params *params);
+int gp_local_affine_launch(gp_ctx *ctx);
+int gp_local_affine_fetch(gp_ctx *ctx, gp_local_result *out, uint64_t n_pairs);
+/* Of the uploaded batch: forward-pass cells (sum of len1*len2); of the last launch: device time of each kernel. */
+int gp_local_affine_stats(gp_ctx *ctx, uint64_t *cells, double *forward_ms, double *epilogue_ms);
 
 /* Diagnostic: measures the chip's integer issue ceiling on the context's stream (a few ms):
  * thread-level instructions per second of VIADDMNMX.S16x2 alone (ALU pipe) and of the

@@ -157,3 +157,36 @@ def ref_evaluate(s1: bytes, s2: bytes, relax: bool):
 def ref_binary() -> Optional[str]:
     p = os.path.join(ORACLE_DIR, "_ref", "ContigsMerger")
     return p if os.path.exists(p) else None
+
+
+# ---- TERefiner's affine local aligner: the reference's own code (oracle/_ref/libla_ref.so, oracle/la_harness.cpp) ----
+_la_ref = None
+_la_tried = False
+
+
+def la_ref_lib() -> Optional[C.CDLL]:
+    global _la_ref, _la_tried
+    if not _la_tried:
+        _la_tried = True
+        so = os.path.join(ORACLE_DIR, "_ref", "libla_ref.so")
+        if os.path.exists(so):
+            lib = C.CDLL(so)
+            lib.laref_opt_align.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
+            lib.laref_opt_align.restype = None
+            lib.laref_stdaln_local.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32)]
+            lib.laref_stdaln_local.restype = None
+            lib.laref_forward_score.argtypes = [C.c_char_p, C.c_char_p]
+            lib.laref_forward_score.restype = C.c_int32
+            _la_ref = lib
+    return _la_ref
+
+
+def ref_local_affine(s1: bytes, s2: bytes):
+    """(score, start1, end1, start2, end2) of the reference's aln_stdaln(s1, s2, &aln_param_blast, LOCAL, 1), or None when
+    nothing aligns (the reference reads path[-1] there)."""
+    lib = la_ref_lib()
+    if not s1 or not s2 or lib.laref_forward_score(s1, s2) < 1:
+        return None
+    o = (C.c_int32 * 6)()
+    lib.laref_stdaln_local(s1, s2, o)
+    return (o[0], o[1], o[2], o[3], o[4])

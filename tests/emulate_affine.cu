@@ -84,4 +84,19 @@ int aff_host_epilogue(const uint8_t* c1, int m, const uint8_t* c2, int n, const 
     return 0;
 }
 
+// The same two passes as ONE WARP computes them (aff_epilogue_warp; on the host every phase loops over the 32 lanes).
+int aff_host_epilogue_warp(const uint8_t* c1, int m, const uint8_t* c2, int n, const int* params, int score, int end1, int end2, int32_t* out)
+{
+    const AffParams P{params[0], params[1], params[2], params[3], params[4], params[5]};
+    if (!aff_params_ok(P) || score <= 0 || end1 < 1 || end1 > m || end2 < 1 || end2 > n) return 1;
+    const std::vector<uint32_t> w1 = pack_codes(c1, m), w2 = pack_codes(c2, n);
+    std::vector<int> work(aff_epilogue_words(end1), 0x5a5a5a5a);
+    AffWarp area;
+    memset(&area, 0x5a, sizeof area);
+    DevLocal res{};
+    aff_epilogue_warp(AffSeq{w1.data()}, AffSeq{w2.data()}, P, score, end1, end2, work.data(), &area, &res);
+    out[0] = res.score; out[1] = res.start1; out[2] = res.end1; out[3] = res.start2; out[4] = res.end2; out[5] = (int32_t)res.flags;
+    return 0;
+}
+
 } // extern "C"

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     L = g.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.gp_abi_version() == 4
+    assert L.gp_abi_version() == 5
 
 
 def test_no_cpu_fallback_without_gpu():
