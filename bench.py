@@ -39,7 +39,9 @@ on the data path.
 BASELINE shapes (cfg5: 10 kb contigs, 20 gaps); `--config cfg2` is BASELINE configs[1], flank placement: the semi-global kernel
 (gp_semiglobal_batch) on 2 flanks x 80 nodes per gap, bit-exact against the oracle's builder-written definition -- the reference's
 own arithmetic there is BWA's, absent from the reference tree (parity unpinned), so its CPU arm is the oracle port; `--cert-layout 1` forces the certificate kernel's
-column-potential layout (A/B); the bench line the driver reads is the default cfg1 run.
+column-potential layout (A/B); `--config affine` is TERefiner's affine-gap local aligner (gp_local_affine_batch) on cfg1's pair list,
+identical to the reference's own local_alignment.cpp, which is also its CPU arm (kind "reference"); the bench line the driver reads is
+the default cfg1 run.
 """
 from __future__ import annotations
 
@@ -335,6 +337,8 @@ def run_reference(args):
 
 
 WORKLOADS = {
+    "affine": "affine (TERefiner's LocalAlignment::optAlign on ContigsMerger's pairs): %d synthetic cfg1 gaps/GPU x 40 contigs and their reverse "
+              "complements (300-3000 bp), affine-gap local alignment 1/-3/-2, open 5, ext 2 (aln_param_blast), score + start/end coordinates",
     "cfg2": "cfg2 (BASELINE configs[1], flank placement): %d synthetic gaps/GPU x 2 flanks (995 bp) x 40 contigs and their reverse "
             "complements (300-3000 bp), semi-global (flank end to end inside the contig); BWA parity unpinned",
     "cfg1": "cfg1: %d synthetic gaps/GPU x 40 contigs (300-3000 bp, 8 kb locus, 0.2%% subst, 50%% RC)",
@@ -367,8 +371,9 @@ def measured_hbm_peak():
 
 def workload_config(args):
     return {"workload": WORKLOADS[args.config] % args.gaps +
-                        (", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)" if args.config != "cfg2"
-                         else ", every flank against every node, scores +1 / -2 / -2"),
+                        (", every flank against every node, scores +1 / -2 / -2" if args.config == "cfg2"
+                         else ", all candidate pairs of the k = 10 quick check" if args.config == "affine"
+                         else ", all candidate pairs of ContigsMerger's pairwise phase (-i1 -2 -i2 -2 -y 50 -k 10)"),
             "gaps_per_gpu": args.gaps, "first_seed": args.seed, "l2": "flushed between timed steps (256 MiB write)",
             "parallelism": "gaps sharded by rank, no collective"}
 
@@ -547,6 +552,180 @@ def run_gpu_cfg2(args):
             line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": "first %d flank-node pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
             line["parity_sample"] = flank_parity_sample(seqs, pairs, out, cores)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# affine: TERefiner's affine-gap local aligner (LocalAlignment::optAlign, TERefiner/algorithms/local_alignment.cpp) on the pair
+# list of ContigsMerger's pairwise phase.  Parity is PINNED: the CPU arm is that file compiled as it lies
+# (oracle/_ref/libla_ref.so, kind "reference").  GCUPS counts the forward table (len1 * len2 cells per pair); the start
+# recovery (reverse pass + banded global fill) is inside every timed figure but adds no cells to the count.
+
+def cpu_affine_path():
+    import ctypes as C
+    import _oracle
+    lib = _oracle.la_ref_lib()
+    if lib is None:
+        return None, None
+
+    def run(a, b):
+        if lib.laref_forward_score(a, b) >= 1:          # the reference reads path[-1] when nothing aligns
+            o = (C.c_int32 * 6)()
+            lib.laref_stdaln_local(a, b, o)
+            return (o[0], o[1], o[2], o[3], o[4])
+        return None
+    return "reference", run
+
+
+def affine_parity_sample(seqs, pairs, res, cores, n=512):
+    _, run = cpu_affine_path()
+    idx = np.unique(np.linspace(0, len(pairs) - 1, num=min(n, len(pairs)), dtype=np.int64))
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(k):
+        w = run(seqs[int(pairs["row_seq"][k])], seqs[int(pairs["col_seq"][k])])
+        r = res[k]
+        if w is None:
+            return bool(int(r["flags"]) & 1)
+        return w == (int(r["score"]), int(r["start1"]), int(r["end1"]), int(r["start2"]), int(r["end2"]))
+    with ThreadPoolExecutor(max_workers=max(1, cores)) as ex:
+        ok = list(ex.map(one, idx))
+    bad = [int(k) for k, good in zip(idx, ok) if not good]
+    return {"pairs": int(len(idx)), "mismatches": len(bad), "first_bad": bad[:4],
+            "against": "the reference's own aln_stdaln(.., &aln_param_blast, LOCAL, 1) (oracle/_ref/libla_ref.so): score, start1, end1, start2, end2"}
+
+
+def run_reference_affine(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    kind, run = cpu_affine_path()
+    if run is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libla_ref.so not built (oracle/build_ref.sh needs /root/reference)"}))
+        return 0
+    cores = min(host_cores(), 64)
+    seqs, pairs, _, _, _ = build_workload(max(1, min(args.gaps, 4)), args.seed, "cfg1")
+    sample, cells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+    for _ in range(min(args.warmup, 1)):
+        cpu_run_pairs(run, seqs, sample[:max(cores, len(sample) // 8)], cores)
+    t = float(np.mean([cpu_run_pairs(run, seqs, sample, cores) for _ in range(args.steps)]))
+    v = cells / t / 1e9
+    desc = "first %d pairs (%.3f Gcells) of the pair list, seeds %d.., per step" % (len(sample), cells / 1e9, args.seed)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def run_gpu_affine(args):
+    import torch
+    import gappadder_b200 as g
+    from gappadder_b200.capi import HostBatch, LOCAL_DTYPE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = g.Context(local_rank)
+    seqs, pairs, cells, _, _ = build_workload(args.gaps, rank_first_seed(args.seed, rank, args.gaps), "cfg1")
+    hb = HostBatch(seqs, pairs)
+    ctx.upload_host_sequences(hb)
+    ctx.local_affine_upload_pairs(pairs)
+    assert ctx.local_affine_stats()["cells"] == cells
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        ctx.local_affine_launch()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    f_ms = e_ms = 0.0
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        ctx.local_affine_launch()
+        e1.record(stream)
+        stream.synchronize()
+        st = ctx.local_affine_stats()
+        f_ms += st["forward_ms"]
+        e_ms += st["epilogue_ms"]
+    barrier()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev]))
+    f_ms /= args.steps
+    e_ms /= args.steps
+    # end to end: the blocking C call on host ASCII buffers (letter classes, pack into pinned memory, H2D, kernels, D2H)
+    out = np.zeros(len(pairs), dtype=LOCAL_DTYPE)
+    for _ in range(min(args.warmup, 2)):
+        ctx.local_affine_host_batch(hb, out)
+    barrier()
+    e2e_t = []
+    for _ in range(args.steps):
+        out[:] = 0
+        t0 = time.perf_counter()
+        ctx.local_affine_host_batch(hb, out)
+        e2e_t.append(time.perf_counter() - t0)
+    barrier()
+    my_e2e_ms = float(np.mean(e2e_t)) * 1e3
+    n_bases = int(sum(len(x) for x in seqs))
+    h2d = int(n_bases // 2 + len(pairs) * (16 + 4))
+    d2h = int(len(pairs) * 24)
+    tot_cells, tot_gaps, max_ms, max_e2e_ms = reduce_over_ranks(dist, dev, cells, args.gaps, my_ms, my_e2e_ms)
+    if rank == 0:
+        alu, dual = ctx.int_peak()
+        ops = 10                                    # per forward cell: 2 gap-state updates (2 add + max each), guard compare + select, add + max3/relu
+        achieved = cells / (f_ms * 1e-3) * ops
+        line = {
+            "metric": METRIC, "value": tot_cells / (max_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s32", "data": "synthetic",
+            "config": workload_config(args), "pairs_per_step": int(len(pairs)) * world, "gcells_per_step": tot_cells / 1e9,
+            "parity_status": "pinned: identical to the reference's TERefiner/algorithms/local_alignment.cpp (score and the four coordinates)",
+            "kernel_ms": {"affine_forward_kernel": f_ms, "affine_epilogue_kernel": e_ms},
+            "e2e": {"value": tot_cells / (max_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": max_e2e_ms, "timing": "wall clock of the blocking gp_local_affine_batch call"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": alu / 1e12, "unit": "Tintop/s", "frac": achieved / alu,
+                         "traffic": None, "kernel": "affine_forward_kernel", "kernel_ms": f_ms, "kernel_gcells": cells / 1e9, "ops_per_cell": ops,
+                         "peak_source": "measured live (gp_int_peak): single-pipe 32-bit integer instruction rate; this kernel computes one 32-bit "
+                                        "cell per lane (three states per cell, 16-bit packing is the next step)"},
+            "mean_score": float(out["score"].mean()), "flagged_pairs": int((out["flags"] != 0).sum()),
+            "result_checksum": int(out["score"].astype(np.int64).sum() + out["start1"].astype(np.int64).sum() + out["start2"].astype(np.int64).sum()),
+        }
+        if world == 1 and not args.no_cpu:
+            kind, run = cpu_affine_path()
+            if run is not None:
+                cores = min(host_cores(), 64)
+                sample, scells = cpu_sample(seqs, pairs, cores, args.cpu_budget, run)
+                t = cpu_run_pairs(run, seqs, sample, cores)
+                line["cpu_baseline"] = {"value": scells / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                        "sample": "first %d pairs (%.3f Gcells) of this run's pair list, %.1f s" % (len(sample), scells / 1e9, t)}
+                line["parity_sample"] = affine_parity_sample(seqs, pairs, out, cores)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
@@ -780,9 +959,11 @@ def main():
     ap.add_argument("--kernel-mask", type=int, default=15, help="A/B: what the library may use (1 table, 2 PRMT, 4 certificate kernel, 8 closed form for s-vs-s)")
     args = ap.parse_args()
     if args.gaps is None:
-        args.gaps = 20 if args.config == "cfg5" else 200
+        args.gaps = 20 if args.config == "cfg5" else 50 if args.config == "affine" else 200
     if args.config == "cfg2":
         return run_reference_cfg2(args) if args.impl == "reference" else run_gpu_cfg2(args)
+    if args.config == "affine":
+        return run_reference_affine(args) if args.impl == "reference" else run_gpu_affine(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

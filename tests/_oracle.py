@@ -190,3 +190,28 @@ def ref_local_affine(s1: bytes, s2: bytes):
     o = (C.c_int32 * 6)()
     lib.laref_stdaln_local(s1, s2, o)
     return (o[0], o[1], o[2], o[3], o[4])
+
+
+_la_oracle = None
+
+
+def la_oracle_lib() -> C.CDLL:
+    """oracle/local_affine_oracle.c (the C restatement of the affine local aligner), built on demand with gcc."""
+    global _la_oracle
+    if _la_oracle is None:
+        so = os.path.join(ORACLE_DIR, "_build", "liblocal_affine_oracle.so")
+        src = os.path.join(ORACLE_DIR, "local_affine_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "all"])
+        lib = C.CDLL(so)
+        lib.lao_local_affine.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
+        _la_oracle = lib
+    return _la_oracle
+
+
+def oracle_local_affine(s1: bytes, s2: bytes):
+    """(score, start1, end1, start2, end2) by the oracle restatement, or None when nothing aligns."""
+    o = (C.c_int32 * 5)()
+    rc = la_oracle_lib().lao_local_affine(s1, len(s1), s2, len(s2), o)
+    assert rc in (0, 1), "reverse band collapsed (the reference is undefined there)"
+    return None if rc == 1 else tuple(o)
