@@ -521,14 +521,92 @@ struct AffWarp {                                  // one per warp, shared memory
     int segA[32], segTag[32], exA[32], exTag[32];
     int segM[32], segP[32], segT[32];
     int score_r, start_i, start_j, hi, lo, stop, undefined;
+    int colM, colP, colT, run0, tag0;
     int gl_score, gl_first;
 };
 constexpr int AFF_NEG_BIG = -(1 << 29);
 
+// The three places where the lanes' partial results meet.  On the host: the plain loops that define them.  On the device:
+// the same functions of the same 32 inputs by warp shuffles (a 32-step loop on one lane is most of a column's latency).
+//
+// exA[l] = max(segA[0 .. l-1]), AFF_NEG_BIG for l = 0.  All lanes call it.
+__host__ __device__ __forceinline__ void aff_meet_prefix_max(AffWarp* w)
+{
+#ifdef __CUDA_ARCH__
+    const int l = (int)(threadIdx.x & 31u);
+    int x = w->segA[l];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (l >= o && y > x) x = y;
+    }
+    const int ex = __shfl_up_sync(0xffffffffu, x, 1);
+    w->exA[l] = l ? ex : AFF_NEG_BIG;
+#else
+    int run = AFF_NEG_BIG;
+    for (int k = 0; k < 32; ++k) { w->exA[k] = run; run = w->segA[k] > run ? w->segA[k] : run; }
+#endif
+}
+
+// colM / colP = the largest segM and the segP of the FIRST lane that holds it; colT = segT of the first lane where it is
+// not 0 (0 if none).  segM >= -1.
+__host__ __device__ __forceinline__ void aff_meet_column_best(AffWarp* w)
+{
+#ifdef __CUDA_ARCH__
+    const int l = (int)(threadIdx.x & 31u);
+    int key = ((w->segM[l] + 1) << 5) | (31 - l);                                 // larger score first, then the earlier lane
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, key, o);
+        key = y > key ? y : key;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, w->segT[l] != 0);
+    if (l == 0) {
+        w->colM = (key >> 5) - 1;
+        w->colP = w->segP[31 - (key & 31)];
+        w->colT = hit ? w->segT[__ffs((int)hit) - 1] : 0;
+    }
+#else
+    int M = -1, Mp = 0, tpos = 0;
+    for (int k = 0; k < 32; ++k) {
+        if (w->segM[k] > M) { M = w->segM[k]; Mp = w->segP[k]; }
+        if (tpos == 0 && w->segT[k]) tpos = w->segT[k];
+    }
+    w->colM = M; w->colP = Mp; w->colT = tpos;
+#endif
+}
+
+// exA[l] / exTag[l] = the best of (run0, tag0) followed by (segA[k], segTag[k]) for k < l, where a later entry replaces an
+// earlier one only if it is strictly larger.  All lanes call it with the same run0 / tag0.
+__host__ __device__ __forceinline__ void aff_meet_prefix_best(AffWarp* w, int run0, int tag0)
+{
+#ifdef __CUDA_ARCH__
+    const int l = (int)(threadIdx.x & 31u);
+    // value in the high bits, then "earlier wins" (the start entry is the earliest), the tag rides along
+    long long x = (long long)w->segA[l] * 256 + ((31 - l) << 2) + w->segTag[l];
+    const long long x0 = (long long)run0 * 256 + (32 << 2) + tag0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (l >= o && y > x) x = y;
+    }
+    long long ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (l == 0 || x0 > ex) ex = x0;
+    w->exA[l] = (int)(ex >> 8);
+    w->exTag[l] = (int)(ex & 3);
+#else
+    int run = run0, rtag = tag0;
+    for (int k = 0; k < 32; ++k) {
+        w->exA[k] = run; w->exTag[k] = rtag;
+        if (w->segA[k] > run) { run = w->segA[k]; rtag = w->segTag[k]; }
+    }
+#endif
+}
+
 // Reverse pass (:617-690).  Hh[k] / Ee[k]: the score of row k and the horizontal gap state of row k at the last column
 // that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff); tH / tE: this column's values before F.
 __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq& s2, const AffParams& P, int score_f, int end_i, int end_j,
-                                                 int* Hh, int* Ee, int* tH, int* tE, AffWarp* w)
+                                                 int* __restrict__ Hh, int* __restrict__ Ee, int* __restrict__ tH, int* __restrict__ tE, AffWarp* w)
 {
     const int q = P.q, r = P.r, qr = q + r;
     AFF_LANES(l) { for (int k = l; k <= end_i + 1; k += 32) { Hh[k] = 0; Ee[k] = 0; } }
@@ -574,12 +652,7 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
             w->segA[l] = best;
         }
         AFF_SYNC();
-        AFF_LANES(l) {
-            if (l == 0) {
-                int run = AFF_NEG_BIG;
-                for (int k = 0; k < 32; ++k) { w->exA[k] = run; run = w->segA[k] > run ? w->segA[k] : run; }
-            }
-        }
+        aff_meet_prefix_max(w);
         AFF_SYNC();
         AFF_LANES(l) {                                                            // F, final scores, this column's records
             const int top = hi - l * S;
@@ -600,13 +673,11 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
             if (l == 0) { Hh[hi + 1] = 0; Ee[lo] = 0; }                           // :665 of the first cell, :674
         }
         AFF_SYNC();
+        aff_meet_column_best(w);
+        AFF_SYNC();
         AFF_LANES(l) {
             if (l == 0) {
-                int M = -1, Mp = 0, tpos = 0;
-                for (int k = 0; k < 32; ++k) {
-                    if (w->segM[k] > M) { M = w->segM[k]; Mp = w->segP[k]; }
-                    if (tpos == 0 && w->segT[k]) tpos = w->segT[k];
-                }
+                const int M = w->colM, Mp = w->colP, tpos = w->colT;
                 bool stop = false;
                 if (w->score_r < T && tpos != 0 && Hh[tpos] == T) {                // the first record that reaches T is T itself
                     w->score_r = T; w->start_i = tpos; w->start_j = j; stop = true;
@@ -681,15 +752,12 @@ __host__ __device__ inline void aff_global_warp(const AffSeq& s1, int o1, int le
         AFF_LANES(l) {
             if (l == 0) {
                 // the chain starts from the edge cell: D(e0) extended, or M(e0) opened (both INF-like, the reference's order)
-                int run, rtag;
-                if (curr.M[e0] - q > curr.D[e0]) { run = curr.M[e0] - q + e0 * r; rtag = curr.tag[e0] & 3; }
-                else { run = curr.D[e0] + e0 * r; rtag = (curr.tag[e0] >> 4) & 3; }
-                for (int k = 0; k < 32; ++k) {
-                    w->exA[k] = run; w->exTag[k] = rtag;
-                    if (w->segA[k] > run) { run = w->segA[k]; rtag = w->segTag[k]; }
-                }
+                if (curr.M[e0] - q > curr.D[e0]) { w->run0 = curr.M[e0] - q + e0 * r; w->tag0 = curr.tag[e0] & 3; }
+                else { w->run0 = curr.D[e0] + e0 * r; w->tag0 = (curr.tag[e0] >> 4) & 3; }
             }
         }
+        AFF_SYNC();
+        aff_meet_prefix_best(w, w->run0, w->tag0);
         AFF_SYNC();
         AFF_LANES(l) {
             const int first = e0 + 1 + l * S;
