@@ -495,12 +495,13 @@ __host__ __device__ inline void aff_epilogue(const AffSeq& s1, const AffSeq& s2,
 //
 // aff_epilogue above is the reference's order of evaluation, one cell after the other; with one thread per pair a batch
 // waits for its longest pair's half a million dependent cells.  aff_epilogue_warp computes the very same values column
-// by column with the 32 lanes spread over a column's band:
+// by column with the 32 lanes spread over a column's band, lane l on the cells l, 32 + l, 64 + l, ... of the column (so
+// that a warp's loads and stores are whole cache lines):
 //   * a cell's score without its vertical gap state depends on the previous column only: all cells at once;
 //   * the vertical state is a running maximum down the column, F(i) = max over cells k already passed of
 //     (h'(k) - q - |k - i| r), h' = the score without F (an F-derived score never opens a better gap than the score it
-//     came from, q >= 0): a prefix maximum of h'(k) - q -/+ k r -- per-lane segments, one 32-entry scan, per-lane fix-up.
-//     The reference's ties go to the EXTENSION (:262, :285), i.e. to the earliest origin, which the scan keeps;
+//     came from, q >= 0): a prefix maximum of h'(k) - q -/+ k r, AFF_G chunks of 32 cells per meeting of the lanes.
+//     The reference's ties go to the EXTENSION (:262, :285), i.e. to the earliest origin, which the prefix keeps;
 //   * the column's effect on the running best (first strict maximum while walking the column, stop at the first record
 //     equal to score + q + r, :667-672) is a reduction: the column maximum at its first position, and the first cell
 //     that reaches the stop value.
@@ -508,7 +509,8 @@ __host__ __device__ inline void aff_epilogue(const AffSeq& s1, const AffSeq& s2,
 // reference writes are written (entries outside the band keep their stale values for the time the band widens again).
 // Lanes talk through memory only (AffWarp, the work arrays) with a warp barrier between phases, so the same text runs on
 // the host with a loop over the lanes in every phase: that is what the CPU tests compare with aff_epilogue and with
-// the reference.
+// the reference.  The two places where the lanes' partial results meet are functions with a plain-loop definition (host)
+// and the same function of the same inputs by warp shuffles (device).
 #ifdef __CUDA_ARCH__
 #define AFF_LANES(l) for (int l = (int)(threadIdx.x & 31u), aff_once_ = 1; aff_once_; aff_once_ = 0)
 #define AFF_SYNC() __syncwarp()
@@ -517,89 +519,80 @@ __host__ __device__ inline void aff_epilogue(const AffSeq& s1, const AffSeq& s2,
 #define AFF_SYNC() ((void)0)
 #endif
 
+constexpr int AFF_G = 4;                          // chunks of 32 cells per meeting
+constexpr int AFF_NEG_BIG = -(1 << 29);
+constexpr int AFF_NEVER = AFF_MINOR_INF * 2 + 2;  // below anything a state can hold
+
 struct AffWarp {                                  // one per warp, shared memory on the device
-    int segA[32], segTag[32], exA[32], exTag[32];
-    int segM[32], segP[32], segT[32];
+    int gA[AFF_G][32], gTag[AFF_G][32];           // in: candidates in column order (chunk, lane), with the tag that rides along
+    int gExA[AFF_G][32], gExTag[AFF_G][32];       // out: the best candidate before each position
+    int run0, tag0;                               // the best candidate before this meeting / after it
+    int segM[32], segP[32], segT[32];             // per lane: best score of the column so far, its row, first row that reaches T
+    int colM, colP, colT;
     int score_r, start_i, start_j, hi, lo, stop, undefined;
-    int colM, colP, colT, run0, tag0;
     int gl_score, gl_first;
 };
-constexpr int AFF_NEG_BIG = -(1 << 29);
 
-// The three places where the lanes' partial results meet.  On the host: the plain loops that define them.  On the device:
-// the same functions of the same 32 inputs by warp shuffles (a 32-step loop on one lane is most of a column's latency).
-//
-// exA[l] = max(segA[0 .. l-1]), AFF_NEG_BIG for l = 0.  All lanes call it.
-__host__ __device__ __forceinline__ void aff_meet_prefix_max(AffWarp* w)
+// gEx[g][l] = the best of (run0, tag0), gA[0][0..31], gA[1][0..31], ... up to but not including gA[g][l], where a later
+// candidate replaces an earlier one only if it is strictly larger; (run0, tag0) = the best after the last position.
+__host__ __device__ __forceinline__ void aff_meet_prefix_best(AffWarp* w)
 {
 #ifdef __CUDA_ARCH__
     const int l = (int)(threadIdx.x & 31u);
-    int x = w->segA[l];
+    // one key per candidate: value, then "earlier wins" (bits 2-7: 32 for what came before, 31 - lane inside a chunk), then the tag
+    long long carry = (long long)w->run0 * 256 + (32 << 2) + w->tag0;
+    long long ex[AFF_G];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if (l >= o && y > x) x = y;
+    for (int g = 0; g < AFF_G; ++g) {
+        long long x = (long long)w->gA[g][l] * 256 + ((31 - l) << 2) + w->gTag[g][l];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (l >= o && y > x) x = y;
+        }
+        const long long before = __shfl_up_sync(0xffffffffu, x, 1);
+        const long long total = __shfl_sync(0xffffffffu, x, 31);
+        ex[g] = (l == 0 || carry > before) ? carry : before;
+        if (total > carry) carry = (total & ~0xfcll) | (32 << 2);
     }
-    const int ex = __shfl_up_sync(0xffffffffu, x, 1);
-    w->exA[l] = l ? ex : AFF_NEG_BIG;
+#pragma unroll
+    for (int g = 0; g < AFF_G; ++g) { w->gExA[g][l] = (int)(ex[g] >> 8); w->gExTag[g][l] = (int)(ex[g] & 3); }
+    __syncwarp();
+    if (l == 0) { w->run0 = (int)(carry >> 8); w->tag0 = (int)(carry & 3); }
 #else
-    int run = AFF_NEG_BIG;
-    for (int k = 0; k < 32; ++k) { w->exA[k] = run; run = w->segA[k] > run ? w->segA[k] : run; }
+    int run = w->run0, rtag = w->tag0;
+    for (int g = 0; g < AFF_G; ++g)
+        for (int k = 0; k < 32; ++k) {
+            w->gExA[g][k] = run; w->gExTag[g][k] = rtag;
+            if (w->gA[g][k] > run) { run = w->gA[g][k]; rtag = w->gTag[g][k]; }
+        }
+    w->run0 = run; w->tag0 = rtag;
 #endif
 }
 
-// colM / colP = the largest segM and the segP of the FIRST lane that holds it; colT = segT of the first lane where it is
-// not 0 (0 if none).  segM >= -1.
+// colM = the largest segM, colP = the largest segP among the lanes that hold it, colT = the largest segT.
+// segM >= -1, 0 <= segP, segT < 2^20.
 __host__ __device__ __forceinline__ void aff_meet_column_best(AffWarp* w)
 {
 #ifdef __CUDA_ARCH__
     const int l = (int)(threadIdx.x & 31u);
-    int key = ((w->segM[l] + 1) << 5) | (31 - l);                                 // larger score first, then the earlier lane
+    long long key = ((long long)(w->segM[l] + 1) << 20) | (long long)w->segP[l];
+    int t = w->segT[l];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const int y = __shfl_xor_sync(0xffffffffu, key, o);
+        const long long y = __shfl_xor_sync(0xffffffffu, key, o);
+        const int z = __shfl_xor_sync(0xffffffffu, t, o);
         key = y > key ? y : key;
+        t = z > t ? z : t;
     }
-    const unsigned hit = __ballot_sync(0xffffffffu, w->segT[l] != 0);
-    if (l == 0) {
-        w->colM = (key >> 5) - 1;
-        w->colP = w->segP[31 - (key & 31)];
-        w->colT = hit ? w->segT[__ffs((int)hit) - 1] : 0;
-    }
+    if (l == 0) { w->colM = (int)(key >> 20) - 1; w->colP = (int)(key & 0xfffff); w->colT = t; }
 #else
     int M = -1, Mp = 0, tpos = 0;
     for (int k = 0; k < 32; ++k) {
-        if (w->segM[k] > M) { M = w->segM[k]; Mp = w->segP[k]; }
-        if (tpos == 0 && w->segT[k]) tpos = w->segT[k];
+        if (w->segM[k] > M || (w->segM[k] == M && w->segP[k] > Mp)) { M = w->segM[k]; Mp = w->segP[k]; }
+        if (w->segT[k] > tpos) tpos = w->segT[k];
     }
     w->colM = M; w->colP = Mp; w->colT = tpos;
-#endif
-}
-
-// exA[l] / exTag[l] = the best of (run0, tag0) followed by (segA[k], segTag[k]) for k < l, where a later entry replaces an
-// earlier one only if it is strictly larger.  All lanes call it with the same run0 / tag0.
-__host__ __device__ __forceinline__ void aff_meet_prefix_best(AffWarp* w, int run0, int tag0)
-{
-#ifdef __CUDA_ARCH__
-    const int l = (int)(threadIdx.x & 31u);
-    // value in the high bits, then "earlier wins" (the start entry is the earliest), the tag rides along
-    long long x = (long long)w->segA[l] * 256 + ((31 - l) << 2) + w->segTag[l];
-    const long long x0 = (long long)run0 * 256 + (32 << 2) + tag0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long y = __shfl_up_sync(0xffffffffu, x, o);
-        if (l >= o && y > x) x = y;
-    }
-    long long ex = __shfl_up_sync(0xffffffffu, x, 1);
-    if (l == 0 || x0 > ex) ex = x0;
-    w->exA[l] = (int)(ex >> 8);
-    w->exTag[l] = (int)(ex & 3);
-#else
-    int run = run0, rtag = tag0;
-    for (int k = 0; k < 32; ++k) {
-        w->exA[k] = run; w->exTag[k] = rtag;
-        if (w->segA[k] > run) { run = w->segA[k]; rtag = w->segTag[k]; }
-    }
 #endif
 }
 
@@ -631,14 +624,11 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
             AFF_SYNC();
             break;
         }
-        const int S = (hi - lo + 31) / 32;
+        const int W = hi - lo;                                                    // the column's cells: rows hi - t, t = 0 .. W-1
         const uint32_t c2 = s2.at1(j);
         AFF_LANES(l) {                                                            // scores without F
-            const int top = hi - l * S;
-            int bot = top - S + 1;
-            if (bot < lo + 1) bot = lo + 1;
-            int best = AFF_NEG_BIG;
-            for (int i = top; i >= bot; --i) {
+            for (int t = l; t < W; t += 32) {
+                const int i = hi - t;
                 const int hl = Hh[i], eo = Ee[i];
                 int h = Hh[i + 1] + aff_sc(s1.at1(i), c2, P);
                 if (h < 0) h = 0;
@@ -646,33 +636,40 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
                 if (e < 0) e = 0;
                 if (h < e) h = e;
                 tH[i] = h; tE[i] = e;
-                const int a = h - q - i * r;                                      // as F of a row i' < i: a + i' r
-                best = a > best ? a : best;
             }
-            w->segA[l] = best;
+            w->segM[l] = -1; w->segP[l] = 0; w->segT[l] = 0;
+            if (l == 0) { w->run0 = AFF_NEG_BIG; w->tag0 = 0; }
         }
         AFF_SYNC();
-        aff_meet_prefix_max(w);
-        AFF_SYNC();
-        AFF_LANES(l) {                                                            // F, final scores, this column's records
-            const int top = hi - l * S;
-            int bot = top - S + 1;
-            if (bot < lo + 1) bot = lo + 1;
-            int run = w->exA[l], bm = -1, bp = 0, tp = 0;
-            for (int i = top; i >= bot; --i) {
-                const int hp = tH[i];
-                const int f = run + i * r;                                        // max over k > i of h'(k) - q - (k - i) r
-                const int h = hp > f ? hp : f;
-                Hh[i] = h; Ee[i] = tE[i];
-                const int a = hp - q - i * r;
-                run = a > run ? a : run;
-                if (h > bm) { bm = h; bp = i; }
-                if (tp == 0 && h >= T) tp = i;
+        for (int t0 = 0; t0 < W; t0 += 32 * AFF_G) {                              // F, final scores, this column's records
+            AFF_LANES(l) {
+                for (int g = 0; g < AFF_G; ++g) {
+                    const int t = t0 + 32 * g + l, i = hi - t;
+                    w->gA[g][l] = t < W ? tH[i] - q - i * r : AFF_NEG_BIG;        // as F of a row i' < i: this + i' r
+                    w->gTag[g][l] = 0;
+                }
             }
-            w->segM[l] = bm; w->segP[l] = bp; w->segT[l] = tp;
-            if (l == 0) { Hh[hi + 1] = 0; Ee[lo] = 0; }                           // :665 of the first cell, :674
+            AFF_SYNC();
+            aff_meet_prefix_best(w);
+            AFF_SYNC();
+            AFF_LANES(l) {
+                int bm = w->segM[l], bp = w->segP[l], tp = w->segT[l];
+                for (int g = 0; g < AFF_G; ++g) {
+                    const int t = t0 + 32 * g + l, i = hi - t;
+                    if (t < W) {
+                        const int hp = tH[i];
+                        const int f = w->gExA[g][l] + i * r;                      // max over k > i of h'(k) - q - (k - i) r
+                        const int h = hp > f ? hp : f;
+                        Hh[i] = h; Ee[i] = tE[i];
+                        if (h > bm) { bm = h; bp = i; }
+                        if (tp == 0 && h >= T) tp = i;
+                    }
+                }
+                w->segM[l] = bm; w->segP[l] = bp; w->segT[l] = tp;
+            }
+            AFF_SYNC();
         }
-        AFF_SYNC();
+        AFF_LANES(l) { if (l == 0) { Hh[hi + 1] = 0; Ee[lo] = 0; } }              // :665 of the first cell, :674
         aff_meet_column_best(w);
         AFF_SYNC();
         AFF_LANES(l) {
@@ -726,52 +723,48 @@ __host__ __device__ inline void aff_global_warp(const AffSeq& s1, int o1, int le
     AFF_SYNC();
     { const AffCol t = curr; curr = last; last = t; }
 
-    // One column.  e0: the band's lower edge cell (row 0 while the band touches it, INF otherwise), end: its top cell.
+    // One column.  e0: the band's lower edge cell (row 0 while the band touches it, INF otherwise), end: its top cell;
+    // the cells in between are rows e0 + 1 + t, t = 0 .. n-1.
     auto column = [&](int j, int e0, int end, bool top_I_inf) {
-        const int n = end - e0;                                                   // cells e0+1 .. end
-        const int S = (n + 31) / 32;
+        const int n = end - e0;
         const uint32_t c2 = s2.at1(o2 + j);
         AFF_LANES(l) {
             if (l == 0) {                                                         // the edge cell
                 curr.M[e0] = AFF_MINOR_INF; curr.D[e0] = AFF_MINOR_INF;
                 if (e0 == 0) aff_set_I(curr, 0, last, 0, q, r, j == 1); else curr.I[e0] = AFF_MINOR_INF;
-            }
-            const int first = e0 + 1 + l * S;
-            int lastc = first + S - 1;
-            if (lastc > end) lastc = end;
-            int best = AFF_MINOR_INF * 2 + 2, btag = 0;                           // below anything a cell can hold
-            for (int i = first; i <= lastc; ++i) {
-                aff_set_M(curr, i, last, i - 1, aff_sc(s1.at1(o1 + i), c2, P), i == 1 && j == 1);
-                if (i == end && top_I_inf) curr.I[i] = AFF_MINOR_INF; else aff_set_I(curr, i, last, i, q, r, false);
-                const int a = curr.M[i] - q + i * r;                              // as D of a row i' > i: a - i' r
-                if (a > best) { best = a; btag = curr.tag[i] & 3; }               // ties: the earlier origin (:285)
-            }
-            w->segA[l] = best; w->segTag[l] = btag;
-        }
-        AFF_SYNC();
-        AFF_LANES(l) {
-            if (l == 0) {
-                // the chain starts from the edge cell: D(e0) extended, or M(e0) opened (both INF-like, the reference's order)
+                // the D chain starts from it: D(e0) extended, or M(e0) opened (both INF-like here; the reference's order, :280)
                 if (curr.M[e0] - q > curr.D[e0]) { w->run0 = curr.M[e0] - q + e0 * r; w->tag0 = curr.tag[e0] & 3; }
                 else { w->run0 = curr.D[e0] + e0 * r; w->tag0 = (curr.tag[e0] >> 4) & 3; }
             }
-        }
-        AFF_SYNC();
-        aff_meet_prefix_best(w, w->run0, w->tag0);
-        AFF_SYNC();
-        AFF_LANES(l) {
-            const int first = e0 + 1 + l * S;
-            int lastc = first + S - 1;
-            if (lastc > end) lastc = end;
-            int run = w->exA[l], rtag = w->exTag[l];
-            for (int i = first; i <= lastc; ++i) {
-                curr.D[i] = run - i * r;
-                curr.tag[i] = (curr.tag[i] & ~48) | (rtag << 4);
-                const int a = curr.M[i] - q + i * r;
-                if (a > run) { run = a; rtag = curr.tag[i] & 3; }
+            for (int t = l; t < n; t += 32) {
+                const int i = e0 + 1 + t;
+                aff_set_M(curr, i, last, i - 1, aff_sc(s1.at1(o1 + i), c2, P), i == 1 && j == 1);
+                if (i == end && top_I_inf) curr.I[i] = AFF_MINOR_INF; else aff_set_I(curr, i, last, i, q, r, false);
             }
         }
         AFF_SYNC();
+        for (int t0 = 0; t0 < n; t0 += 32 * AFF_G) {                              // D: a prefix over the M states of the rows below
+            AFF_LANES(l) {
+                for (int g = 0; g < AFF_G; ++g) {
+                    const int t = t0 + 32 * g + l, i = e0 + 1 + t;
+                    w->gA[g][l] = t < n ? curr.M[i] - q + i * r : AFF_NEVER;      // as D of a row i' > i: this - i' r
+                    w->gTag[g][l] = t < n ? curr.tag[i] & 3 : 0;
+                }
+            }
+            AFF_SYNC();
+            aff_meet_prefix_best(w);                                              // ties: the earlier origin (:285)
+            AFF_SYNC();
+            AFF_LANES(l) {
+                for (int g = 0; g < AFF_G; ++g) {
+                    const int t = t0 + 32 * g + l, i = e0 + 1 + t;
+                    if (t < n) {
+                        curr.D[i] = w->gExA[g][l] - i * r;
+                        curr.tag[i] = (curr.tag[i] & ~48) | (w->gExTag[g][l] << 4);
+                    }
+                }
+            }
+            AFF_SYNC();
+        }
         { const AffCol t = curr; curr = last; last = t; }
     };
 
