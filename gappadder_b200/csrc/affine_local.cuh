@@ -570,6 +570,41 @@ __host__ __device__ __forceinline__ void aff_meet_prefix_best(AffWarp* w)
 #endif
 }
 
+// The same for plain maxima (no tag, ties are immaterial): gExA[g][l] = max(run0, every gA before position (g, l)).
+__host__ __device__ __forceinline__ void aff_meet_prefix_max(AffWarp* w)
+{
+#ifdef __CUDA_ARCH__
+    const int l = (int)(threadIdx.x & 31u);
+    int carry = w->run0;
+    int ex[AFF_G];
+#pragma unroll
+    for (int g = 0; g < AFF_G; ++g) {
+        int x = w->gA[g][l];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (l >= o && y > x) x = y;
+        }
+        const int before = __shfl_up_sync(0xffffffffu, x, 1);
+        const int total = __shfl_sync(0xffffffffu, x, 31);
+        ex[g] = (l == 0 || carry > before) ? carry : before;
+        carry = total > carry ? total : carry;
+    }
+#pragma unroll
+    for (int g = 0; g < AFF_G; ++g) w->gExA[g][l] = ex[g];
+    __syncwarp();
+    if (l == 0) w->run0 = carry;
+#else
+    int run = w->run0;
+    for (int g = 0; g < AFF_G; ++g)
+        for (int k = 0; k < 32; ++k) {
+            w->gExA[g][k] = run;
+            if (w->gA[g][k] > run) run = w->gA[g][k];
+        }
+    w->run0 = run;
+#endif
+}
+
 // colM = the largest segM, colP = the largest segP among the lanes that hold it, colT = the largest segT.
 // segM >= -1, 0 <= segP, segT < 2^20.
 __host__ __device__ __forceinline__ void aff_meet_column_best(AffWarp* w)
@@ -597,9 +632,9 @@ __host__ __device__ __forceinline__ void aff_meet_column_best(AffWarp* w)
 }
 
 // Reverse pass (:617-690).  Hh[k] / Ee[k]: the score of row k and the horizontal gap state of row k at the last column
-// that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff); tH / tE: this column's values before F.
+// that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff); tH: this column's scores before F.
 __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq& s2, const AffParams& P, int score_f, int end_i, int end_j,
-                                                 int* __restrict__ Hh, int* __restrict__ Ee, int* __restrict__ tH, int* __restrict__ tE, AffWarp* w)
+                                                 int* __restrict__ Hh, int* __restrict__ Ee, int* __restrict__ tH, AffWarp* w)
 {
     const int q = P.q, r = P.r, qr = q + r;
     AFF_LANES(l) { for (int k = l; k <= end_i + 1; k += 32) { Hh[k] = 0; Ee[k] = 0; } }
@@ -635,10 +670,11 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
                 int e = (eo > hl - q) ? eo - r : hl - qr;
                 if (e < 0) e = 0;
                 if (h < e) h = e;
-                tH[i] = h; tE[i] = e;
+                tH[i] = h;
+                Ee[i] = e;                                                        // read by this cell only: in place
             }
             w->segM[l] = -1; w->segP[l] = 0; w->segT[l] = 0;
-            if (l == 0) { w->run0 = AFF_NEG_BIG; w->tag0 = 0; }
+            if (l == 0) w->run0 = AFF_NEG_BIG;
         }
         AFF_SYNC();
         for (int t0 = 0; t0 < W; t0 += 32 * AFF_G) {                              // F, final scores, this column's records
@@ -646,11 +682,10 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
                 for (int g = 0; g < AFF_G; ++g) {
                     const int t = t0 + 32 * g + l, i = hi - t;
                     w->gA[g][l] = t < W ? tH[i] - q - i * r : AFF_NEG_BIG;        // as F of a row i' < i: this + i' r
-                    w->gTag[g][l] = 0;
                 }
             }
             AFF_SYNC();
-            aff_meet_prefix_best(w);
+            aff_meet_prefix_max(w);
             AFF_SYNC();
             AFF_LANES(l) {
                 int bm = w->segM[l], bp = w->segP[l], tp = w->segT[l];
@@ -660,7 +695,7 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
                         const int hp = tH[i];
                         const int f = w->gExA[g][l] + i * r;                      // max over k > i of h'(k) - q - (k - i) r
                         const int h = hp > f ? hp : f;
-                        Hh[i] = h; Ee[i] = tE[i];
+                        Hh[i] = h;
                         if (h > bm) { bm = h; bp = i; }
                         if (tp == 0 && h >= T) tp = i;
                     }
@@ -793,7 +828,7 @@ __host__ __device__ inline void aff_epilogue_warp(const AffSeq& s1, const AffSeq
 {
     const int qr = P.q + P.r;
     const int stride = end_i + 2;
-    aff_reverse_warp(s1, s2, P, score_f, end_i, end_j, work, work + stride, work + 2 * stride, work + 3 * stride, w);
+    aff_reverse_warp(s1, s2, P, score_f, end_i, end_j, work, work + stride, work + 2 * stride, w);
     res->end1 = end_i; res->end2 = end_j; res->flags = 0;
     if (w->undefined) { res->flags |= AFF_FLAG_UNDEFINED; res->start1 = 0; res->start2 = 0; res->score = score_f; return; }
     const int score_r = w->score_r - qr, start_i = w->start_i, start_j = w->start_j;
