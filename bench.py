@@ -710,10 +710,11 @@ def run_gpu_affine(args):
             "e2e": {"value": tot_cells / (max_e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": max_e2e_ms, "timing": "wall clock of the blocking gp_local_affine_batch call"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": alu / 1e12, "unit": "Tintop/s", "frac": achieved / alu,
+            "roofline": {"bound": "int", "achieved": achieved / 1e12, "peak": dual / 1e12, "unit": "Tintop/s", "frac": achieved / dual,
                          "traffic": None, "kernel": "affine_forward_kernel", "kernel_ms": f_ms, "kernel_gcells": cells / 1e9, "ops_per_cell": ops,
-                         "peak_source": "measured live (gp_int_peak): single-pipe 32-bit integer instruction rate; this kernel computes one 32-bit "
-                                        "cell per lane (three states per cell, 16-bit packing is the next step)"},
+                         "peak_source": "measured live (gp_int_peak): thread-level integer instruction rate with both pipes busy (%.2f Tinst/s; ALU pipe "
+                                        "alone %.2f); this kernel computes ONE 32-bit cell per instruction (three states per cell), so no factor 2 "
+                                        "for packed lanes as in the overlap kernels" % (dual / 1e12, alu / 1e12)},
             "mean_score": float(out["score"].mean()), "flagged_pairs": int((out["flags"] != 0).sum()),
             "result_checksum": int(out["score"].astype(np.int64).sum() + out["start1"].astype(np.int64).sum() + out["start2"].astype(np.int64).sum()),
         }
