@@ -100,6 +100,7 @@ __host__ __device__ __forceinline__ long long aff_key(int score, int i, int j)
 template <int R>
 struct AffLane {
     int H[R];          // H(i, j) of my rows at the column of my previous step
+    int Hq[R];         // H - (q + r): what a gap opened from that cell starts with (used twice: by the row below, by the next column)
     int E[R];          // the horizontal gap state stored with it (what the reference keeps in the low half of eh[], :597)
     int up_prev;       // H(row above my first, j-1): the diagonal of my first row
     int bscore;        // score of `best`
@@ -107,10 +108,10 @@ struct AffLane {
 };
 
 template <int R>
-__host__ __device__ __forceinline__ void aff_lane_begin(AffLane<R>& st)
+__host__ __device__ __forceinline__ void aff_lane_begin(AffLane<R>& st, int q, int r)
 {
 #pragma unroll
-    for (int x = 0; x < R; ++x) { st.H[x] = 0; st.E[x] = 0; }       // column 0 (:566)
+    for (int x = 0; x < R; ++x) { st.H[x] = 0; st.Hq[x] = -(q + r); st.E[x] = 0; }       // column 0 (:566)
     st.up_prev = 0;
 }
 
@@ -132,8 +133,13 @@ __host__ __device__ __forceinline__ int aff_max3_relu(int a, int b, int c)
 //     if H(i,j-1) >= q + r + 1:  e = max(E(i,j-1) - r, H(i,j-1) - q - r);  h = max(h, e)      else e = 0
 // The `if` around f changes nothing: a stale f is <= 0 when the guard first fails (h >= f held one row up and h = 0
 // there) and only decreases until it is replaced, so skipped or not, a non-positive f never shows in h; the plain
-// recurrence f = max(f - r, H(i-1,j) - q - r) has the same positive part.  The guard around e does change values and
-// is kept as it is.
+// recurrence f = max(f - r, H(i-1,j) - q - r) has the same positive part.
+// The guard around e does change values and is kept, in this form: with t = H(i,j-1) - q - r the guard is t >= 1, and
+//     e = min(max(E(i,j-1) - r, t), t * 2^15)
+// is the reference's e when the guard holds (t * 2^15 >= 2^15 exceeds every score) and some value <= 0 when it does not.
+// A stored state <= 0 is as good as the reference's 0: it never shows in h (clamped at 0), and one column on it is either
+// discarded again or loses against t' >= 1 (e' = max(E - r, t') = t' for every E <= r + 1).  One min on the ALU pipe and one
+// multiply on the other pipe instead of a compare and a select, both on the ALU pipe, which is this kernel's bound.
 template <int R>
 __host__ __device__ __forceinline__ uint32_t aff_lane_step(AffLane<R>& st, uint32_t recv, const int* inc, int q, int r, int j, int itop)
 {
@@ -144,19 +150,22 @@ __host__ __device__ __forceinline__ uint32_t aff_lane_step(AffLane<R>& st, uint3
     for (int x = 1; x < R; ++x) d[x] = st.H[x - 1] + inc[x];
     int hu = aff_h(recv), f = aff_f(recv);
     st.up_prev = hu;
+    int huq = hu - qr;
     int colmax = 0;
 #pragma unroll
     for (int x = 0; x < R; ++x) {
-        const int a = f - r, b = hu - qr;
-        f = a > b ? a : b;
-        const int hl = st.H[x];
-        const int e1 = st.E[x] - r, e2 = hl - qr;
-        int e = e1 > e2 ? e1 : e2;
-        e = hl > qr ? e : 0;
+        const int a = f - r;
+        f = a > huq ? a : huq;
+        const int t = st.Hq[x];
+        const int e1 = st.E[x] - r;
+        int e = e1 > t ? e1 : t;
+        const int cap = t * 32768;
+        e = e < cap ? e : cap;
         const int h = aff_max3_relu(d[x], e, f);
         st.E[x] = e;
         st.H[x] = h;
-        hu = h;
+        huq = h - qr;
+        st.Hq[x] = huq;
         colmax = h > colmax ? h : colmax;
     }
     if (colmax >= st.bscore && colmax > 0) {
@@ -166,7 +175,7 @@ __host__ __device__ __forceinline__ uint32_t aff_lane_step(AffLane<R>& st, uint3
         const long long k = aff_key(colmax, itop + x0 + 1, j);
         if (k > st.best) { st.best = k; st.bscore = colmax; }
     }
-    return aff_pack(hu, f);
+    return aff_pack(st.H[R - 1], f);
 }
 
 #ifdef __CUDACC__
@@ -227,7 +236,7 @@ affine_forward_kernel(const uint32_t* __restrict__ packed, const PairDesc* __res
                     }
                 }
             }
-            aff_lane_begin<R>(st);
+            aff_lane_begin<R>(st, P.q, P.r);
             uint32_t bottom = row0;                                  // my last row at the column of my previous step
             uint32_t mysym = 0;                                      // that column's symbol class
             uint32_t recv_next = row0;
@@ -526,6 +535,8 @@ constexpr int AFF_NEVER = AFF_MINOR_INF * 2 + 2;  // below anything a state can 
 struct AffWarp {                                  // one per warp, shared memory on the device
     int gA[AFF_G][32], gTag[AFF_G][32];           // in: candidates in column order (chunk, lane), with the tag that rides along
     int gExA[AFF_G][32], gExTag[AFF_G][32];       // out: the best candidate before each position
+    int gH[AFF_G][32];                            // reverse pass: the group's scores before F
+    int carryH[2];                                // reverse pass: old score of the previous group's last row
     int run0, tag0;                               // the best candidate before this meeting / after it
     int segM[32], segP[32], segT[32];             // per lane: best score of the column so far, its row, first row that reaches T
     int colM, colP, colT;
@@ -632,9 +643,9 @@ __host__ __device__ __forceinline__ void aff_meet_column_best(AffWarp* w)
 }
 
 // Reverse pass (:617-690).  Hh[k] / Ee[k]: the score of row k and the horizontal gap state of row k at the last column
-// that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff); tH: this column's scores before F.
+// that touched them (the reference's eh[k] >> 16 and eh[k+1] & 0xffff).
 __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq& s2, const AffParams& P, int score_f, int end_i, int end_j,
-                                                 int* __restrict__ Hh, int* __restrict__ Ee, int* __restrict__ tH, AffWarp* w)
+                                                 int* __restrict__ Hh, int* __restrict__ Ee, AffWarp* w)
 {
     const int q = P.q, r = P.r, qr = q + r;
     AFF_LANES(l) { for (int k = l; k <= end_i + 1; k += 32) { Hh[k] = 0; Ee[k] = 0; } }
@@ -661,27 +672,32 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
         }
         const int W = hi - lo;                                                    // the column's cells: rows hi - t, t = 0 .. W-1
         const uint32_t c2 = s2.at1(j);
-        AFF_LANES(l) {                                                            // scores without F
-            for (int t = l; t < W; t += 32) {
-                const int i = hi - t;
-                const int hl = Hh[i], eo = Ee[i];
-                int h = Hh[i + 1] + aff_sc(s1.at1(i), c2, P);
-                if (h < 0) h = 0;
-                int e = (eo > hl - q) ? eo - r : hl - qr;
-                if (e < 0) e = 0;
-                if (h < e) h = e;
-                tH[i] = h;
-                Ee[i] = e;                                                        // read by this cell only: in place
-            }
+        AFF_LANES(l) {
             w->segM[l] = -1; w->segP[l] = 0; w->segT[l] = 0;
             if (l == 0) w->run0 = AFF_NEG_BIG;
         }
-        AFF_SYNC();
-        for (int t0 = 0; t0 < W; t0 += 32 * AFF_G) {                              // F, final scores, this column's records
+        // AFF_G chunks of 32 cells at a time: scores without F from the previous column's values (all reads of a group come
+        // before its writes; the one value a group needs from a row the group before has already overwritten, the old
+        // score of that group's last row, is handed over in carryH), F by a prefix maximum, final scores and records.
+        for (int t0 = 0, k = 0; t0 < W; t0 += 32 * AFF_G, ++k) {
             AFF_LANES(l) {
                 for (int g = 0; g < AFF_G; ++g) {
                     const int t = t0 + 32 * g + l, i = hi - t;
-                    w->gA[g][l] = t < W ? tH[i] - q - i * r : AFF_NEG_BIG;        // as F of a row i' < i: this + i' r
+                    int h = 0, a = AFF_NEG_BIG;
+                    if (t < W) {
+                        const int hl = Hh[i], eo = Ee[i];
+                        const int hd = (t == t0 && t0 > 0) ? w->carryH[(k + 1) & 1] : Hh[i + 1];
+                        h = hd + aff_sc(s1.at1(i), c2, P);
+                        if (h < 0) h = 0;
+                        int e = (eo > hl - q) ? eo - r : hl - qr;
+                        if (e < 0) e = 0;
+                        if (h < e) h = e;
+                        Ee[i] = e;                                                // read by this cell only: in place
+                        a = h - q - i * r;                                        // as F of a row i' < i: this + i' r
+                        if (t == t0 + 32 * AFF_G - 1) w->carryH[k & 1] = hl;
+                    }
+                    w->gH[g][l] = h;
+                    w->gA[g][l] = a;
                 }
             }
             AFF_SYNC();
@@ -692,7 +708,7 @@ __host__ __device__ inline void aff_reverse_warp(const AffSeq& s1, const AffSeq&
                 for (int g = 0; g < AFF_G; ++g) {
                     const int t = t0 + 32 * g + l, i = hi - t;
                     if (t < W) {
-                        const int hp = tH[i];
+                        const int hp = w->gH[g][l];
                         const int f = w->gExA[g][l] + i * r;                      // max over k > i of h'(k) - q - (k - i) r
                         const int h = hp > f ? hp : f;
                         Hh[i] = h;
@@ -828,7 +844,7 @@ __host__ __device__ inline void aff_epilogue_warp(const AffSeq& s1, const AffSeq
 {
     const int qr = P.q + P.r;
     const int stride = end_i + 2;
-    aff_reverse_warp(s1, s2, P, score_f, end_i, end_j, work, work + stride, work + 2 * stride, w);
+    aff_reverse_warp(s1, s2, P, score_f, end_i, end_j, work, work + stride, w);
     res->end1 = end_i; res->end2 = end_j; res->flags = 0;
     if (w->undefined) { res->flags |= AFF_FLAG_UNDEFINED; res->start1 = 0; res->start2 = 0; res->score = score_f; return; }
     const int score_r = w->score_r - qr, start_i = w->start_i, start_j = w->start_j;
@@ -851,9 +867,10 @@ __host__ __device__ inline void aff_epilogue_warp(const AffSeq& s1, const AffSeq
 
 #ifdef __CUDACC__
 constexpr int AE_THREADS = 128;                  // 4 warps per CTA, one pair per warp at a time
+constexpr int AE_CTAS_PER_SM = 8;                // 64 registers: the kernel waits on memory and on its meetings, more warps hide more
 
 // One warp per pair (pulled from a queue in the forward kernel's order), scratch_stride ints of scratch per warp.
-__global__ void __launch_bounds__(AE_THREADS)
+__global__ void __launch_bounds__(AE_THREADS, AE_CTAS_PER_SM)
 affine_epilogue_kernel(const uint32_t* __restrict__ packed, const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ order,
                        uint32_t n_work, unsigned int* __restrict__ queue, AffParams P, int* __restrict__ scratch, size_t scratch_stride,
                        DevLocal* __restrict__ out)

@@ -38,7 +38,7 @@ int aff_emulate_forward(const uint8_t* c1, int m, const uint8_t* c2, int n, cons
     for (int s = 0; s < n_strips; ++s) {
         const bool last = s == n_strips - 1;
         uint32_t bottom[32], mysym[32], recv_next[32], sym_next[32];
-        for (int l = 0; l < 32; ++l) { aff_lane_begin<R>(st[l]); bottom[l] = row0; mysym[l] = 0; recv_next[l] = row0; sym_next[l] = 0; }
+        for (int l = 0; l < 32; ++l) { aff_lane_begin<R>(st[l], P.q, P.r); bottom[l] = row0; mysym[l] = 0; recv_next[l] = row0; sym_next[l] = 0; }
         const int steps = n + D * 31;
         for (int t = 1; t <= steps; ++t) {
             uint32_t recv[32], csym[32], shb[32], shs[32];
