@@ -1,5 +1,5 @@
 # Builds the C-ABI library (CUDA kernels for sm_100a + host half) and the host tools, in-tree.
-#   make            -> gappadder_b200/libgappadder_b200.so, build/ContigsMerger_b200, build/microbench_int
+#   make            -> gappadder_b200/libgappadder_b200.so, build/ContigsMerger_b200, build/TERefiner_b200, build/microbench_int
 #   make oracle     -> oracle/_build/liboverlap_oracle.so (+ oracle/_ref/ when /root/reference exists)
 NVCC ?= nvcc
 CXX ?= g++
@@ -10,7 +10,7 @@ CSRC := gappadder_b200/csrc
 LIB := gappadder_b200/libgappadder_b200.so
 
 HOST := gappadder_b200/host
-all: $(LIB) build/microbench_int build/ContigsMerger_b200
+all: $(LIB) build/microbench_int build/ContigsMerger_b200 build/TERefiner_b200
 
 build:
 	mkdir -p build
@@ -29,6 +29,9 @@ $(LIB): build/gp_api.o build/int_peak.o build/gp_host.o
 
 build/ContigsMerger_b200: $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(HOST)/merge_graph.cpp $(HOST)/fasta.cpp $(HOST)/server.cpp $(HOST)/dedup.cpp $(HOST)/dedup.hpp $(HOST)/device_gate.hpp $(HOST)/merger.hpp $(HOST)/merge_graph.hpp $(HOST)/fasta.hpp $(HOST)/server.hpp $(LIB)
 	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/contigs_merger_main.cpp $(HOST)/merger.cpp $(HOST)/merge_graph.cpp $(HOST)/fasta.cpp $(HOST)/server.cpp $(HOST)/dedup.cpp -Lgappadder_b200 -lgappadder_b200 -Wl,-rpath,'$$ORIGIN/../gappadder_b200' -lpthread
+
+build/TERefiner_b200: $(HOST)/terefiner_main.cpp $(HOST)/local_alignment.cpp $(HOST)/local_alignment.hpp $(LIB)
+	$(CXX) $(CXXFLAGS) -o $@ $(HOST)/terefiner_main.cpp $(HOST)/local_alignment.cpp -Lgappadder_b200 -lgappadder_b200 -Wl,-rpath,'$$ORIGIN/../gappadder_b200' -lpthread
 
 build/microbench_int: tools/microbench_int.cu | build
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $<
