@@ -11,7 +11,7 @@
 //      FIRST strict maximum in column-major order (seq2 outer, seq1 inner).  Two details differ from the textbook
 //      recurrence and are reproduced: the horizontal gap state of a cell is dropped unless the cell to its left scores
 //      more than gap_open + gap_ext (:594-599), and the vertical one is only looked at below a positive cell (:590-593;
-//      that one changes no value, see aff_cell).  This is the O(len1*len2) part: `affine_forward_kernel`, an anti-diagonal
+//      that one changes no value, see aff_lane_step).  This is the O(len1*len2) part: `affine_forward_kernel`, an anti-diagonal
 //      wavefront with one warp per pair, 512-row strips, 16 rows per lane in registers, the lane-to-lane hand-over by
 //      shuffle one step ahead, the strip-to-strip hand-over through a boundary line in L2, the substitution scores from
 //      a per-warp shared-memory table read with conflict-free LDS.128 (the machinery of flank_place.cuh).
@@ -21,13 +21,16 @@
 //   3. a banded GLOBAL alignment of the sub-rectangle (:715-739, aln_global_core :328-508), band 50, doubled until its
 //      score agrees; the reference walks its traceback matrix only to report where the path starts, which is a
 //      two-bit tag carried forward with each state here (no traceback matrix).
-//   Passes 2 and 3 are `aff_epilogue`, ONE __host__ __device__ function that follows the reference statement by
-//   statement; `affine_epilogue_kernel` runs it with one thread per pair (their cost is the square of the ALIGNED
-//   length, not of the sequence lengths).  The very same function compiled for the host is what the CPU tests
-//   compare with the reference (tests/emulate_affine.cu), so the device path carries no arithmetic of its own.
+//   Passes 2 and 3 exist twice.  `aff_epilogue` follows the reference statement by statement (one cell after the other);
+//   `aff_epilogue_warp` computes the same values column by column with the 32 lanes of a warp spread over a column's band,
+//   and is what `affine_epilogue_kernel` runs, one warp per pair (the cost of these passes is the square of the ALIGNED
+//   length, not of the sequence lengths).  Both are __host__ __device__ text: compiled for the host they are what the CPU
+//   tests compare with each other and with the reference (tests/emulate_affine.cu), so the device path carries no
+//   arithmetic of its own.
 //
 // Domain: min(len1, len2) * match + open + ext <= 32000 (below the reference's 16-bit overflow rescaling, :573-588), both
-// lengths < 2^20, gap penalties and scores small positive / negative integers (aff_params_ok).
+// lengths < 2^20, gap penalties and scores small positive / negative integers (aff_params_ok).  Everything this file does has
+// been measured step by step: DESIGN.md section 4 "Affine local aligner", profiles/affine_*.
 #pragma once
 #include "common.cuh"
 
