@@ -29,7 +29,8 @@ on the data path.
             behind a device gate, writers; FASTA reading and file writing inside the figure), outside every timed region
             above (tools/dropin_bench.py): `cfg1` (N = 1) the bench workload's own gaps as FASTA files, one of them also through
             the reference binary (bytes compared); `dedup` (N = 1) the dedup stage on the same gaps as contig sets
-            (tools/dedup_bench.py; rules pinned to TERefiner_1, alignment records builder-defined); `strong` (every N) one
+            (tools/dedup_bench.py; rules pinned to TERefiner_1, alignment records builder-defined); `affine` (N = 1) TERefiner's
+            affine local aligner on 20 of the gaps (tools/affine_bench.py, 64 pairs against the reference's own code); `strong` (every N) one
             fixed 1 600-gap cfg3-shaped job through --gpus N: gaps/s, per-GPU wall, imbalance, device-phase time of the
             slowest GPU, first 32 gaps byte-compared with --gpus 1
   hbm       the HBM-bound phases beside the DP: pack + upload, the quick-check kernel (bytes, ms, GB/s against
@@ -284,6 +285,16 @@ def dropin_line(args, world):
                             "duplicate_rule": {k: dd["p"][k] for k in ("contigs", "removed", "pairs", "dp_gcells", "dedup_ms", "device_ms", "sets_per_s", "gcups") if k in dd.get("p", {})}}
         except Exception as e:                               # the bench line must not depend on it
             out["dedup"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+        # TERefiner's affine local aligner on 20 of these gaps (tools/affine_bench.py: the two kernels by CUDA events, 64 sampled
+        # pairs against the reference's own aligner); `bench.py --config affine` is the full line for it
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "affine_bench.py"), "--gaps", "20", "--reps", "3", "--check", "64"],
+                               capture_output=True, text=True, timeout=180)
+            da = json.loads(p.stdout.strip().splitlines()[-1])
+            out["affine"] = {k: da[k] for k in ("workload", "gaps", "pairs", "cells", "forward_ms", "epilogue_ms", "forward_gcups", "total_gcups",
+                                                "mean_score", "flagged", "parity_sample") if k in da}
+        except Exception as e:                               # the bench line must not depend on it
+            out["affine"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     d = _dropin_tool(["--config", "cfg3", "--gaps", str(args.dropin_gaps), "--seed", "5000", "--gpus", str(world), "--ref-gaps", "0",
                       "--verify-gpus1", "32" if world > 1 else "0", "--repeat", "2"])
     out["strong"] = {k: d[k] for k in DROPIN_KEEP if k in d}

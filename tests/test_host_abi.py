@@ -2,6 +2,7 @@
 host-side half (packing, candidate filter, significance, merged strings, reverse complement)
 matches the golden vectors / the oracle.  No compute calls that need a GPU."""
 import json
+import ctypes as C
 import os
 import re
 
@@ -26,6 +27,18 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert L.gp_abi_version() == 5
+
+
+def test_affine_defaults_are_the_reference_parameters():
+    """gp_affine_params_terefiner = aln_param_blast (TERefiner/algorithms/local_alignment.cpp:193-206); layouts of the two
+    affine structs as the header declares them."""
+    p = capi.AffineParams()
+    g.lib().gp_affine_params_terefiner(C.byref(p))
+    assert (p.match, p.mismatch, p.n_score, p.gap_open, p.gap_ext, p.band_width) == (1, -3, -2, 5, 2, 50)
+    t = capi.TEREFINER_AFFINE
+    assert (t.match, t.mismatch, t.n_score, t.gap_open, t.gap_ext, t.band_width) == (1, -3, -2, 5, 2, 50)
+    assert C.sizeof(capi.AffineParams) == 24 and capi.LOCAL_DTYPE.itemsize == 24
+    assert capi.LOCAL_DTYPE.names == ("score", "start1", "end1", "start2", "end2", "flags")
 
 
 def test_no_cpu_fallback_without_gpu():
