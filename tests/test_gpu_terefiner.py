@@ -13,6 +13,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "build", "TERefiner_b200")
 
 
+def _n_gpus():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "terefiner_modes.json")) as f:
         return json.load(f)["cases"]
@@ -39,3 +47,18 @@ def test_one_pair_per_process():
     r = golden()[0]
     p = subprocess.run([BIN, "-M", "-r", r["s1"], "-s", r["s2"]], capture_output=True, timeout=300)
     assert p.returncode == 0 and p.stdout.decode() == r["M"]
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
+def test_pairs_dealt_to_two_gpus():
+    if not os.path.exists(BIN):
+        pytest.skip("build/TERefiner_b200 not built")
+    recs = [r for r in golden() if "M" in r]
+    with tempfile.TemporaryDirectory() as td:
+        lst = os.path.join(td, "pairs.tsv")
+        with open(lst, "w") as f:
+            for r in recs:
+                f.write(r["s1"] + "\t" + r["s2"] + "\n")
+        p = subprocess.run([BIN, "-M", "--batch", lst, "--gpus", "2"], capture_output=True, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()
+    assert p.stdout.decode() == "".join(r["M"] for r in recs)

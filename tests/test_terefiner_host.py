@@ -33,13 +33,13 @@ def hosttest_binary():
     return out
 
 
-def run_batch(binary, mode, recs):
+def run_batch(binary, mode, recs, extra=()):
     with tempfile.TemporaryDirectory() as td:
         lst = os.path.join(td, "pairs.tsv")
         with open(lst, "w") as f:
             for r in recs:
                 f.write(r["s1"] + "\t" + r["s2"] + "\n")
-        p = subprocess.run([binary, "-" + mode, "--batch", lst], capture_output=True)
+        p = subprocess.run([binary, "-" + mode, "--batch", lst] + list(extra), capture_output=True)
     return p.returncode, p.stdout.decode(), p.stderr.decode()
 
 
@@ -48,6 +48,15 @@ def test_batch_list_equals_the_prebuilt_binary(hosttest_binary, mode):
     recs = [r for r in golden() if mode in r]
     assert len(recs) > 100
     rc, out, err = run_batch(hosttest_binary, mode, recs)
+    assert rc == 0, err
+    assert out == "".join(r[mode] for r in recs)
+
+
+@pytest.mark.parametrize("mode", ["M", "A"])
+def test_pairs_dealt_to_three_gpus_come_back_in_list_order(hosttest_binary, mode):
+    """--gpus N: one host thread and one context per GPU, pairs dealt longest first, no exchange; same bytes."""
+    recs = [r for r in golden() if mode in r]
+    rc, out, err = run_batch(hosttest_binary, mode, recs, ["--gpus", "3"])
     assert rc == 0, err
     assert out == "".join(r[mode] for r in recs)
 
