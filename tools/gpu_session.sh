@@ -1,6 +1,6 @@
 #!/bin/bash
 # tools/gpu_session.sh TAG [what...] -- one gpurun call's worth of work on the GPU box; everything lands in gpurun_out/TAG_*.
-# what: tests bench ref cfg3 cfg5 ncu_pair ncu_relax launches dropin qc   (default: tests bench)
+# what: tests bench ref cfg3 cfg5 ncu_pair ncu_relax launches dropin qc affine ncu_affine ...   (default: tests bench)
 TAG=$1; shift
 WHAT="${*:-tests bench}"
 O=gpurun_out
@@ -43,6 +43,11 @@ PY
     lonetrace) GAPPADDER_B200_LIB=build/libgappadder_b200_trace.so timeout 600 python tools/lone_pair_bench.py --trace > /dev/null 2> $O/${TAG}_lone_trace.txt; head -150 $O/${TAG}_lone_trace.txt ;;
     ppg)     timeout 600 python tools/process_per_gap_bench.py > $O/${TAG}_process_per_gap.json 2> $O/${TAG}_process_per_gap.err; cat $O/${TAG}_process_per_gap.json ;;
     qc)      timeout 600 python tools/quickcheck_bench.py > $O/${TAG}_quickcheck.json 2> $O/${TAG}_quickcheck.err; cat $O/${TAG}_quickcheck.json ;;
+    affine)  timeout 300 python -m pytest tests/test_gpu_affine.py tests/test_gpu_terefiner.py -m gpu -q > $O/${TAG}_pytest_affine.log 2>&1; tail -3 $O/${TAG}_pytest_affine.log
+             timeout 120 python tools/affine_bench.py --gaps 20 > $O/${TAG}_affine_kernels.json 2> $O/${TAG}_affine_kernels.err; cut -c1-400 $O/${TAG}_affine_kernels.json
+             timeout 300 python bench.py --config affine > $O/${TAG}_bench_affine.json 2> $O/${TAG}_bench_affine.err; tail -c 500 $O/${TAG}_bench_affine.json ;;
+    ncu_affine) timeout 300 ncu --set full --clock-control none --import-source on -k regex:affine_forward -c 1 -o $O/${TAG}_affine_forward -f python tools/affine_bench.py --gaps 20 --reps 1 --check 0 > $O/${TAG}_ncu_affine_forward.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:affine_epilogue -c 1 -o $O/${TAG}_affine_epilogue -f python tools/affine_bench.py --gaps 6 --reps 1 --check 0 > $O/${TAG}_ncu_affine_epilogue.log 2>&1 ;;
     *) echo "unknown: $w" ;;
   esac
 done
