@@ -1273,6 +1273,7 @@ int gp_local_affine_fetch(gp_ctx* c, gp_local_result* out, uint64_t n_pairs)
     if (n_pairs != c->af_pairs) return c->fail(GP_ERR_INVALID, "n_pairs does not match the uploaded batch");
     if (n_pairs == 0) return GP_OK;
     if (!out) return c->fail(GP_ERR_INVALID, "null output");
+    if (c->af_work && !c->af_ev_valid) return c->fail(GP_ERR_INVALID, "gp_local_affine_fetch before gp_local_affine_launch");
     static_assert(sizeof(gp_local_result) == sizeof(gp::DevLocal), "result layouts must match");
     GP_CUDA(c, cudaSetDevice(c->device));
     GP_CUDA(c, cudaMemcpyAsync(out, c->d_af_results.p, n_pairs * sizeof(gp_local_result), cudaMemcpyDeviceToHost, c->stream));
