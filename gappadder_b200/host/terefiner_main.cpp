@@ -5,6 +5,8 @@
 // and, because one pair per process leaves a GPU idle,
 //   -M|-A --batch LIST     LIST holds one pair per line, "SEQ1<TAB>SEQ2"; one output line per pair, in order; every pair of
 //                          the list goes through the same launches.
+//   --align -r SEQ1 -s SEQ2   (no TERefiner_1 mode; for tests) LocalAlignment::align: twelve numbers, the best alignment and the
+//                          ones before and after it, -1 where the reference leaves its outputs untouched
 //   --gpus N               (with --batch) pairs are independent: they are dealt to N GPUs of the box, longest first, one host
 //                          thread and one context per GPU, no exchange between them; output order is the list's.
 // The modes GAPPadder itself uses (-U, -P: the dedup stage) are `ContigsMerger_b200 --dedup`; the BAM classifiers have no
@@ -24,7 +26,7 @@
 
 int main(int argc, char** argv)
 {
-    bool bm = false, ba = false;
+    bool bm = false, ba = false, b_align = false;
     std::string ref, sgmt, batch;
     bool have_r = false, have_s = false;
     int gpu = 0, gpus = 1;
@@ -32,6 +34,7 @@ int main(int argc, char** argv)
         const std::string a = argv[i];
         if (a == "-M") bm = true;
         else if (a == "-A") ba = true;
+        else if (a == "--align") b_align = true;
         else if (a == "-r" && i + 1 < argc) { ref = argv[++i]; have_r = true; }
         else if (a == "-s" && i + 1 < argc) { sgmt = argv[++i]; have_s = true; }
         else if (a == "--batch" && i + 1 < argc) batch = argv[++i];
@@ -41,6 +44,19 @@ int main(int argc, char** argv)
             fprintf(stderr, "TERefiner_b200: mode %s is not the alignment path (the dedup stage -U / -P is ContigsMerger_b200 --dedup)\n", a.c_str());
             return 2;
         } else { fprintf(stderr, "TERefiner_b200: unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (b_align) {
+        if (!(have_r && have_s)) { fprintf(stderr, "usage: TERefiner_b200 --align -r SEQ1 -s SEQ2\n"); return 2; }
+        gp_ctx* ctx = nullptr;
+        if (gp_create(gpu, &ctx) != GP_OK) { fprintf(stderr, "TERefiner_b200: %s\n", gp_last_error(nullptr)); return 3; }
+        gpm::LocalAlignment la(ctx);
+        int v[12];
+        for (int& x : v) x = -1;
+        const bool ok = la.align(ref, sgmt, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+        if (!ok) fprintf(stderr, "TERefiner_b200: %s\n", la.error().c_str());
+        else for (int k = 0; k < 12; ++k) printf("%d%c", v[k], k == 11 ? '\n' : ' ');
+        gp_destroy(ctx);
+        return ok ? 0 : 3;
     }
     if (bm == ba || (batch.empty() && !(have_r && have_s))) {
         fprintf(stderr, "usage: TERefiner_b200 -M|-A -r SEQ1 -s SEQ2   |   TERefiner_b200 -M|-A --batch LIST [--gpus N]\n");

@@ -37,6 +37,19 @@ void laref_stdaln_local(const char *ref, const char *sgmt, int32_t *out)
     aln_free_AlnAln(aa);
 }
 
+// LocalAlignment::align (:1053-1090): the best alignment and the two beside it.  out[12], every entry starts at -1 as in
+// the reference's callers; entries the method leaves untouched stay -1.  The method reads path[-1] when one of its
+// alignments finds nothing: the caller must keep such pairs away (check the three inputs with laref_forward_score).
+void laref_align(const char *ref, const char *sgmt, int32_t *out)
+{
+    std::string a(ref), b(sgmt);
+    LocalAlignment la;
+    int v[12];
+    for (int k = 0; k < 12; ++k) v[k] = -1;
+    la.align(a, b, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11]);
+    for (int k = 0; k < 12; ++k) out[k] = v[k];
+}
+
 // Forward pass only (aln_local_core with path == 0, :615): the local score.
 int32_t laref_forward_score(const char *ref, const char *sgmt)
 {

@@ -8,7 +8,9 @@
 The binary is /root/reference/TERefiner/TERefiner_1 (or /root/reference/TERefiner_1), run from an executable copy in a
 temporary directory.  Pairs on which one of the alignments involved finds nothing are left out: the reference reads
 path[-1] there (local_alignment.cpp:611-614, :817) and prints whatever the heap holds.  Which pairs those are is decided
-with the reference's own forward pass (oracle/_ref/libla_ref.so).  Needs /root/reference (this container only).
+with the reference's own forward pass (oracle/_ref/libla_ref.so).  "align" holds LocalAlignment::align's twelve outputs (-1 where
+the method leaves them untouched) from the reference class compiled into that library: no TERefiner_1 mode prints them.
+Needs /root/reference (this container only).
 
     python tests/golden/make_golden_terefiner.py
 """
@@ -100,13 +102,19 @@ def main():
             rec = {"s1": a.decode(), "s2": b.decode()}
             if aligned(a, b):
                 rec["M"] = subprocess.run([exe, "-M", "-r", a, "-s", b], capture_output=True, check=True).stdout.decode()
+                s1, e1, s2, e2 = local(a, b)         # LocalAlignment::align (no TERefiner_1 mode prints it): the compiled reference class
+                if ((not (s1 > 1 and s2 > 1)) or aligned(a[:s1 - 1], b[:s2 - 1])) and ((not (e1 < len(a) and e2 < len(b))) or aligned(a[e1:], b[e2:])):
+                    w = (C.c_int32 * 12)()
+                    L.laref_align(a, b, w)
+                    rec["align"] = list(w)
             if rest_defined(a, b) and rest_defined(a, supplementary(b)):
                 rec["A"] = subprocess.run([exe, "-A", "-r", a, "-s", b], capture_output=True, check=True).stdout.decode()
             recs.append(rec)
     path = os.path.join(HERE, "terefiner_modes.json")
     with open(path, "w") as f:
         json.dump({"generator": "tests/golden/make_golden_terefiner.py", "binary": src, "cases": recs}, f, separators=(",", ":"))
-    print(len(recs), "pairs,", sum("M" in r for r in recs), "with -M,", sum("A" in r for r in recs), "with -A ->", path, os.path.getsize(path), "bytes")
+    print(len(recs), "pairs,", sum("M" in r for r in recs), "with -M,", sum("A" in r for r in recs), "with -A,", sum("align" in r for r in recs),
+          "with align ->", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

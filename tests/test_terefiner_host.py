@@ -69,6 +69,15 @@ def test_one_pair_per_process_as_the_reference_is_called(hosttest_binary):
                 assert p.returncode == 0 and p.stdout.decode() == r[mode]
 
 
+def test_align_with_the_alignments_before_and_after(hosttest_binary):
+    """LocalAlignment::align (TERefiner/algorithms/local_alignment.cpp:1053-1090) through the host mirror's batch form."""
+    recs = [r for r in golden() if "align" in r]
+    assert len(recs) > 90
+    for r in recs[::3]:
+        p = subprocess.run([hosttest_binary, "--align", "-r", r["s1"], "-s", r["s2"]], capture_output=True)
+        assert p.returncode == 0 and [int(x) for x in p.stdout.split()] == r["align"]
+
+
 def test_nothing_aligns_and_usage_errors(hosttest_binary):
     p = subprocess.run([hosttest_binary, "-M", "-r", "AAAA", "-s", "CCCC"], capture_output=True)
     assert p.returncode == 0 and p.stdout == b"0 0 0 0\n"           # the reference reads path[-1] here
